@@ -1,0 +1,483 @@
+"""CPU oracle for the VQ-VAE-WaveNet inference hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a NumPy restatement of the reference's algorithm for the path named in
+BASELINE.json (VQ nearest-codebook lookup -> conditioning -> WaveNet fast generation ->
+mu-law softmax draw).  It is imported only by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product path (the CUDA library
+behind include/vqwn.h) never routes through it.
+
+PARITY UNPINNED: the reference is TensorFlow-1.x graph code, TensorFlow is not installed
+in this image (nor in /opt/wheelhouse), the reference ships no tests, golden vectors or
+checkpoint, so this restatement cannot be checked against reference outputs.  What pins it
+instead (tests/test_oracle.py):
+  * the five shipped WAVs (results/VCTK/p225_001/*.wav) lie on the mu-law decode grid
+    (fixture tests/golden/wav_grid.npz) -> pins mu_law_decode_np and the float32 WAV format;
+  * the reference holds two independent formulations of the decoder (queue form
+    wavenet.py:103-172 and padded dilated-conv form wavenet.py:24-100): both are restated
+    here and must agree;
+  * two VQ distance formulations (model.py:60-65 direct, Magenta/sonnet.py:91-95 expanded);
+  * an independent torch.nn.functional.conv1d witness of the conv form.
+
+All citations are file:line relative to /root/reference.
+Everything is float32 unless the reference itself uses another type at that point.
+"""
+from __future__ import annotations
+
+import json
+from collections import deque
+
+import numpy as np
+
+F32 = np.float32
+
+
+# --------------------------------------------------------------------------------------
+# Configuration (model_parameters.json / wavenet_parameters.json, read as generate.py:63-64
+# and wavenet.py:10-21 do)
+# --------------------------------------------------------------------------------------
+class Config:
+    """Hyper-parameters of the path.  Defaults = the two JSON files of the reference."""
+
+    def __init__(self, wavenet=None, model=None, num_speakers=109):
+        w = dict(
+            quantization_channels=256, num_cycles=3, num_cycle_layers=10,
+            dilation_rates=[2 ** i for i in range(10)] * 3, kernel_size=3,
+            dilation_filters=256, skip_filters=512, residual_filters=256,
+            preprocess=dict(kernel_size=32, filters=256))
+        if wavenet:
+            w.update(wavenet)
+        m = dict(encoder="64", use_vq=True, speaker_embedding=64, k=512, latent_dim=64, beta=0.25)
+        if model:
+            m.update(model)
+        # wavenet.py:13
+        assert len(w["dilation_rates"]) == w["num_cycles"] * w["num_cycle_layers"]
+        self.wavenet = w
+        self.model = m
+        self.num_speakers = num_speakers
+        self.q = w["quantization_channels"]
+        self.dilations = list(w["dilation_rates"])
+        self.ksize = w["kernel_size"]
+        self.R = w["residual_filters"]
+        self.G = w["dilation_filters"]            # gate width; conv makes 2*G channels
+        self.S = w["skip_filters"]
+        self.pre_k = w["preprocess"]["kernel_size"]
+        self.pre_f = w["preprocess"]["filters"]
+        self.K = m["k"]
+        self.D = m["latent_dim"]
+        self.spk_dim = m["speaker_embedding"]
+        self.C = self.D + self.spk_dim            # decoder.py:49-50 concat
+        # wavenet.py:15-17
+        self.receptive_field = sum(self.dilations) * (self.ksize - 1) + 1 + self.pre_k - 1
+
+    @classmethod
+    def from_files(cls, model_path, num_speakers=109):
+        with open(model_path) as f:
+            m = json.load(f)
+        import os
+        wp = m["wavenet_parameters"]
+        if not os.path.isabs(wp) and not os.path.exists(wp):
+            wp = os.path.join(os.path.dirname(model_path), wp)
+        with open(wp) as f:
+            w = json.load(f)
+        return cls(w, m, num_speakers)
+
+    def layer_scope(self, i):
+        # wavenet.py:134-135
+        n = self.wavenet["num_cycle_layers"]
+        return "decoder/cycle_%d/layer_%d" % (1 + i // n, 1 + i % n)
+
+
+def tensor_specs(cfg):
+    """(tf_variable_name, shape) in the fixed order used for synthetic weights."""
+    R, G, S, C, q = cfg.R, cfg.G, cfg.S, cfg.C, cfg.q
+    specs = [
+        ("embedding/embedding", (cfg.K, cfg.D)),                       # model.py:47-49
+        ("speaker_embedding", (cfg.num_speakers, cfg.spk_dim)),        # model.py:23-26
+        ("decoder/preprocess/kernel", (cfg.pre_k, 1, cfg.pre_f)),      # wavenet_ops.py:173-176
+        ("decoder/preprocess/bias", (cfg.pre_f,)),
+        ("decoder/skip/kernel", (1, cfg.pre_f, S)),                    # wavenet.py:127-128
+        ("decoder/skip/bias", (S,)),
+    ]
+    for i in range(len(cfg.dilations)):
+        s = cfg.layer_scope(i)
+        specs += [
+            (s + "/gated/kernel", (cfg.ksize, R, 2 * G)),
+            (s + "/gated/bias", (2 * G,)),
+            (s + "/gated/local_condition/kernel", (1, C, 2 * G)),
+            (s + "/skip/kernel", (1, G, S)),
+            (s + "/skip/bias", (S,)),
+            (s + "/residual/kernel", (1, G, R)),
+            (s + "/residual/bias", (R,)),
+        ]
+    specs += [
+        ("decoder/postprocess1/kernel", (1, S, S)),
+        ("decoder/postprocess1/bias", (S,)),
+        ("decoder/postprocess1/local_condition/kernel", (1, C, S)),
+        ("decoder/postprocess2/kernel", (1, S, q)),
+        ("decoder/postprocess2/bias", (q,)),
+    ]
+    return specs
+
+
+def make_weights(cfg, seed=1234, peaked=False):
+    """Seeded synthetic weights keyed by reference variable name.
+
+    kernels U(+-sqrt(3/fan_in)) as tf.uniform_unit_scaling_initializer(1.0) (wavenet_ops.py:69),
+    biases U(+-0.05) (reference inits 0; non-zero so bias paths are exercised),
+    codebook factor 1.7 (model.py:49), speaker table factor 2.0 (model.py:26).
+    peaked=True scales postprocess2/kernel by 8 so the softmax is peaked (greedy tests)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in tensor_specs(cfg):
+        if name.endswith("bias"):
+            a = rng.uniform(-0.05, 0.05, size=shape)
+        else:
+            fan_in = int(np.prod(shape[:-1]))
+            lim = np.sqrt(3.0 / fan_in)
+            if name == "embedding/embedding":
+                lim *= 1.7
+            elif name == "speaker_embedding":
+                lim *= 2.0
+            a = rng.uniform(-lim, lim, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=F32)
+    if peaked:
+        out["decoder/postprocess2/kernel"] = (out["decoder/postprocess2/kernel"] * F32(8)).astype(F32)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# mu-law codec (mu_law_ops.py) and sampling (utils.py:13-46)
+# --------------------------------------------------------------------------------------
+def mu_law_encode(x, quantization_channels=256, to_int=False):
+    """mu_law_ops.py:5-15 (float path :6-8, int path :9-11).  float32 arithmetic."""
+    mu = F32(quantization_channels - 1)
+    x = np.clip(np.asarray(x, dtype=F32), F32(-1.0), F32(1.0))
+    y = (np.sign(x) * np.log1p(mu * np.abs(x)) / np.log1p(mu)).astype(F32)
+    if to_int:
+        # tf.cast(float->int32) truncates toward zero; argument is >= 0.5 here
+        y = ((y + F32(1)) / F32(2) * mu + F32(0.5)).astype(F32).astype(np.int32)
+    return y
+
+
+def mu_law_decode_np(y, quantization_channels=256):
+    """mu_law_ops.py:26-31, float32 NumPy."""
+    mu = np.asarray(quantization_channels - 1, dtype=F32)
+    y = (2 * np.asarray(y, dtype=F32) / mu) - 1
+    x = np.sign(y) * ((1 + mu) ** abs(y) - 1) / mu
+    return x.astype(F32)
+
+
+def decode_lut(quantization_channels=256):
+    """audio value for every index the draw can return: 0..q (q itself happens in sample mode
+    when the float32 cdf ends below the uniform draw, utils.py:20-25)."""
+    return mu_law_decode_np(np.arange(quantization_channels + 1), quantization_channels)
+
+
+def encode_lut(quantization_channels=256):
+    """network input for every index: mu_law_encode(decode(k)) (generate.py:112-113 feeds the
+    decoded float back; wavenet.py:113 re-encodes it, clipping entry q to 1.0)."""
+    return mu_law_encode(decode_lut(quantization_channels), quantization_channels)
+
+
+def sample_indices(pdf, uniforms):
+    """utils.py:19-25 with the np.random.rand(batch) draw made injectable.
+    cdf is a sequential float32 running sum; the comparison happens in float64."""
+    cdf = np.cumsum(np.asarray(pdf, dtype=F32), axis=1)
+    pred = np.zeros(cdf.shape[0], dtype=F32)
+    for i, prob in enumerate(np.asarray(uniforms, dtype=np.float64)):
+        pred[i] = cdf[i].searchsorted(prob)
+    return pred
+
+
+def decode_indices(predictions, mode="sample", uniforms=None):
+    """utils.py:30-46 up to (not including) the mu-law decode: returns indices [B]."""
+    if mode == "sample":
+        return sample_indices(predictions, uniforms).astype(np.int32)
+    elif mode == "greedy":
+        return np.argmax(predictions, axis=-1).astype(np.int32)
+    raise NotImplementedError("decode mode %s not implemented" % mode)
+
+
+def decode(predictions, mode="sample", quantization_channels=256, uniforms=None):
+    """utils.py:30-46.  NB sample() ignores quantization_channels (utils.py:41)."""
+    idx = decode_indices(predictions, mode, uniforms)
+    qc = 256 if mode == "sample" else quantization_channels
+    return mu_law_decode_np(idx.astype(F32), qc)
+
+
+# --------------------------------------------------------------------------------------
+# VQ bottleneck (model.py:45-74) + speaker condition (model.py:19-27) + concat
+# --------------------------------------------------------------------------------------
+def vq_distances(z_e, embedding):
+    """model.py:60-61 direct form, float32, materialising [..., K, D] like the reference."""
+    z = np.asarray(z_e, dtype=F32)
+    e = np.asarray(embedding, dtype=F32)
+    diff = z[..., None, :] - e
+    return np.sum(diff * diff, axis=-1, dtype=F32)
+
+
+def vq_discretise(z_e, embedding, chunk=2048):
+    """model.py:57-74: returns (q_z_x int64, e_k, z_q) with z_q = z_e + (e_k - z_e)."""
+    z = np.asarray(z_e, dtype=F32)
+    flat = z.reshape(-1, z.shape[-1])
+    idx = np.empty(flat.shape[0], dtype=np.int64)
+    for s in range(0, flat.shape[0], chunk):           # chunked only to bound memory
+        idx[s:s + chunk] = np.argmin(vq_distances(flat[s:s + chunk], embedding), axis=-1)
+    e_k = np.asarray(embedding, dtype=F32)[idx]
+    z_q = (flat + (e_k - flat)).astype(F32)
+    shp = z.shape[:-1]
+    return idx.reshape(shp), e_k.reshape(z.shape), z_q.reshape(z.shape)
+
+
+def vq_distances_f64(z_e, embedding):
+    """float64 distances, used by tests to decide whether an index mismatch is a near-tie."""
+    z = np.asarray(z_e, dtype=np.float64)
+    e = np.asarray(embedding, dtype=np.float64)
+    return (z * z).sum(-1, keepdims=True) - 2.0 * z @ e.T + (e * e).sum(-1)[None, :]
+
+
+def vq_discretise_expanded(z_e, embedding):
+    """Magenta/sonnet.py:91-98: ||z||^2 - 2 z.W + ||w||^2, argmax(-d)."""
+    z = np.asarray(z_e, dtype=F32)
+    flat = z.reshape(-1, z.shape[-1])
+    w = np.asarray(embedding, dtype=F32).T
+    d = (np.sum(flat ** 2, 1, keepdims=True, dtype=F32) - F32(2) * (flat @ w)
+         + np.sum(w ** 2, 0, keepdims=True, dtype=F32))
+    return np.argmax(-d, 1).reshape(z.shape[:-1])
+
+
+def speaker_rows(speaker_onehot, speaker_embedding):
+    """model.py:19-27: argmax over the one-hot (all-zero row -> index 0) then gather.
+    speaker_onehot [B,1,N] -> h [B,1,spk_dim]."""
+    idx = np.argmax(np.asarray(speaker_onehot), axis=-1)
+    return np.asarray(speaker_embedding, dtype=F32)[idx]
+
+
+def concat_condition(net, global_condition):
+    """Decoder/decoder_ops.py:39-43: tile speaker row over frames, concat on channels."""
+    g = np.tile(global_condition, [1, net.shape[1], 1])
+    return np.concatenate([net, g], axis=-1).astype(F32)
+
+
+def encode_condition(z_e, speaker_idx, weights):
+    """model.py:133-142 + model.py:85-87 + decoder.py:49-50: what generate.py:92 evaluates
+    as model.encoding ([B,F,D+spk])."""
+    idx, _, z_q = vq_discretise(z_e, weights["embedding/embedding"])
+    h = weights["speaker_embedding"][np.asarray(speaker_idx)][:, None, :]
+    return idx, concat_condition(z_q, h)
+
+
+# --------------------------------------------------------------------------------------
+# Fast generation (Decoder/WaveNet/wavenet.py:103-172, wavenet_ops.py:147-267)
+# --------------------------------------------------------------------------------------
+class _FastConv:
+    """wavenet_ops.py:163-195: one stride of a dilated causal conv with (k-1) chained
+    FIFO queues of capacity d, pre-filled with d zero items (:181-184)."""
+
+    def __init__(self, kernel, bias, dilation, batch):
+        self.kernel = kernel
+        self.bias = bias
+        self.k = kernel.shape[0]
+        self.d = dilation
+        self.batch = batch
+        self.cin = kernel.shape[1]
+        self.queues = None
+
+    def init(self):
+        z = np.zeros((self.batch, self.cin), dtype=F32)
+        self.queues = [deque([z] * self.d) for _ in range(self.k - 1)]
+
+    def __call__(self, current):
+        k = self.k
+        new_state = current @ self.kernel[k - 1] + self.bias          # :178
+        for i in range(1, k):
+            q = self.queues[i - 1]
+            past = q.popleft()                                        # :187
+            q.append(current)                                         # :188
+            current = past                                            # :189
+            new_state = new_state + past @ self.kernel[k - i - 1]      # :193
+        return new_state.astype(F32)
+
+
+def _sigmoid(x):
+    return (F32(1) / (F32(1) + np.exp(-x))).astype(F32)
+
+
+def softmax(x):
+    m = np.max(x, axis=-1, keepdims=True)
+    e = np.exp((x - m).astype(F32)).astype(F32)
+    return (e / np.sum(e, axis=-1, keepdims=True, dtype=F32)).astype(F32)
+
+
+class FastWavenet:
+    """wavenet.py:103-172.  step() == sess.run([predictions, push_ops]) (generate.py:109)."""
+
+    def __init__(self, cfg, weights, batch):
+        self.cfg, self.w, self.batch = cfg, weights, batch
+        w = weights
+        self.pre = _FastConv(w["decoder/preprocess/kernel"], w["decoder/preprocess/bias"], 1, batch)
+        self.layers = []
+        for i, d in enumerate(cfg.dilations):
+            s = cfg.layer_scope(i)
+            self.layers.append(_FastConv(w[s + "/gated/kernel"], w[s + "/gated/bias"], d, batch))
+        self.init_ops()
+
+    def init_ops(self):
+        """generate.py:105"""
+        self.pre.init()
+        for c in self.layers:
+            c.init()
+
+    def step(self, input_t, local_condition_t):
+        """input_t [B,1] float audio in [-1,1]; local_condition_t [B,C] -> (probs, logits)"""
+        cfg, w = self.cfg, self.w
+        x = mu_law_encode(np.asarray(input_t, dtype=F32).reshape(self.batch, 1))   # wavenet.py:113 (always 256)
+        lc = np.asarray(local_condition_t, dtype=F32)
+        current = self.pre(x)                                                       # :119-124
+        skip = current @ w["decoder/skip/kernel"][0] + w["decoder/skip/bias"]       # :127-128
+        G = cfg.G
+        for i, conv in enumerate(self.layers):
+            s = cfg.layer_scope(i)
+            net = conv(current)                                                     # wavenet_ops.py:228-229
+            net = net + lc @ w[s + "/gated/local_condition/kernel"][0]              # :230-231, :208
+            gated = (np.tanh(net[:, :G]) * _sigmoid(net[:, G:])).astype(F32)        # :235-236
+            skip = skip + (gated @ w[s + "/skip/kernel"][0] + w[s + "/skip/bias"])  # :261-262; wavenet.py:144
+            current = current + (gated @ w[s + "/residual/kernel"][0] + w[s + "/residual/bias"])  # :264-265; :145
+        net = np.maximum(skip, 0)                                                   # wavenet.py:153
+        net = net @ w["decoder/postprocess1/kernel"][0] + w["decoder/postprocess1/bias"]
+        net = net + lc @ w["decoder/postprocess1/local_condition/kernel"][0]        # :157-159
+        net = np.maximum(net, 0)
+        logits = (net @ w["decoder/postprocess2/kernel"][0] + w["decoder/postprocess2/bias"]).astype(F32)
+        return softmax(logits), logits
+
+
+def draw_margin(probs, mode, uniforms=None):
+    """How far each stream's draw is from flipping: greedy -> (p1 - p2) / p1 of the two largest
+    probabilities; sample -> distance from the uniform to the nearest float32 cdf boundary.
+    Tests use it to tell a near-tie (documented tolerance) from a real divergence."""
+    if mode == "greedy":
+        s = np.sort(np.asarray(probs, dtype=np.float64), axis=-1)
+        return ((s[:, -1] - s[:, -2]) / s[:, -1]).astype(F32)
+    cdf = np.cumsum(np.asarray(probs, dtype=F32), axis=1).astype(np.float64)
+    return np.min(np.abs(cdf - np.asarray(uniforms, dtype=np.float64)[:, None]), axis=1).astype(F32)
+
+
+def generate(cfg, weights, encoding, length, mode="greedy", uniforms=None, teacher=None,
+             return_logits=False, return_margins=False):
+    """generate.py:103-113.  encoding [B,F,C]; returns (audio [B,T] float32, idx [B,T] int32
+    [, logits [B,T,q]]).  teacher [B,T]: feed teacher[:, i-1] instead of the model's own draw
+    (per-step logit parity; first input is 0 as shift_right does, wavenet_ops.py:9-14).
+    uniforms [T,B] float64 replaces the unseeded np.random.rand(B) of utils.py:22."""
+    B = encoding.shape[0]
+    net = FastWavenet(cfg, weights, B)
+    audio = np.zeros([B, 1], dtype=F32)
+    to_write = np.zeros([B, length], dtype=F32)
+    idx_out = np.zeros([B, length], dtype=np.int32)
+    logits_out = np.zeros([B, length, cfg.q], dtype=F32) if return_logits else None
+    margins = np.zeros([B, length], dtype=F32) if return_margins else None
+    ratio = length // encoding.shape[1]                                             # generate.py:107
+    for i in range(length):
+        probs, logits = net.step(audio, encoding[:, i // ratio])
+        u = None if uniforms is None else uniforms[i]
+        idx = decode_indices(probs, mode, u)
+        if return_margins:
+            margins[:, i] = draw_margin(probs, mode, u)
+        decoded = mu_law_decode_np(idx.astype(F32), 256 if mode == "sample" else cfg.q)
+        to_write[:, i] = decoded
+        idx_out[:, i] = idx
+        if return_logits:
+            logits_out[:, i] = logits
+        if teacher is None:
+            audio = np.expand_dims(decoded, -1)
+        else:
+            audio = np.asarray(teacher[:, i:i + 1], dtype=F32)
+    out = (to_write, idx_out)
+    if return_logits:
+        out = out + (logits_out,)
+    if return_margins:
+        out = out + (margins,)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Teacher-forced conv form (wavenet.py:24-100, wavenet_ops.py:9-14,59-138) -- second witness
+# --------------------------------------------------------------------------------------
+def shift_right(x):
+    """wavenet_ops.py:9-14"""
+    return np.concatenate([np.zeros_like(x[:, :1]), x[:, :-1]], axis=1)
+
+
+def conv1d_v2(net, kernel, bias=None, dilations=1):
+    """wavenet_ops.py:59-90 with padding='CAUSAL': left-pad d*(k-1) zeros, VALID dilated conv."""
+    k = kernel.shape[0]
+    T = net.shape[1]
+    pad = dilations * (k - 1)
+    xp = np.concatenate([np.zeros((net.shape[0], pad, net.shape[2]), dtype=F32), net], axis=1)
+    out = None
+    for j in range(k):
+        term = xp[:, j * dilations: j * dilations + T] @ kernel[j]
+        out = term if out is None else out + term
+    if bias is not None:
+        out = out + bias
+    return out.astype(F32)
+
+
+def add_condition(net, condition, kernel):
+    """wavenet_ops.py:93-101: bias-free 1x1 on [B,F,C], each frame broadcast over T//F samples."""
+    B, T, C = net.shape
+    F = condition.shape[1]
+    enc = condition @ kernel[0]
+    net = net.reshape(B, F, T // F, C) + enc[:, :, None, :]
+    return net.reshape(B, T, C).astype(F32)
+
+
+def wavenet_teacher_forced(cfg, weights, x, local_condition):
+    """wavenet.py:24-100.  x [B,T,1] float audio, local_condition [B,F,C] -> (logits [B*T,q],
+    labels [B*T])."""
+    w = weights
+    x = np.asarray(x, dtype=F32)
+    labels = mu_law_encode(x, to_int=True).reshape(-1)                              # :33-34
+    inputs = mu_law_encode(shift_right(x))                                          # :36-37
+    net = conv1d_v2(inputs, w["decoder/preprocess/kernel"], w["decoder/preprocess/bias"])   # :42-45
+    skip = conv1d_v2(net, w["decoder/skip/kernel"], w["decoder/skip/bias"])         # :53-55
+    G = cfg.G
+    for i, d in enumerate(cfg.dilations):
+        s = cfg.layer_scope(i)
+        a = conv1d_v2(net, w[s + "/gated/kernel"], w[s + "/gated/bias"], d)          # wavenet_ops.py:106
+        a = add_condition(a, local_condition, w[s + "/gated/local_condition/kernel"])
+        gated = (np.tanh(a[:, :, :G]) * _sigmoid(a[:, :, G:])).astype(F32)          # :112-113
+        skip = skip + conv1d_v2(gated, w[s + "/skip/kernel"], w[s + "/skip/bias"])
+        net = net + conv1d_v2(gated, w[s + "/residual/kernel"], w[s + "/residual/bias"])
+    net = np.maximum(skip, 0)
+    net = conv1d_v2(net, w["decoder/postprocess1/kernel"], w["decoder/postprocess1/bias"])
+    net = add_condition(net, local_condition, w["decoder/postprocess1/local_condition/kernel"])
+    net = np.maximum(net, 0)
+    net = conv1d_v2(net, w["decoder/postprocess2/kernel"], w["decoder/postprocess2/bias"])
+    return net.reshape(-1, cfg.q), labels
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic inputs of SURVEY 8d
+# --------------------------------------------------------------------------------------
+def synthetic_z_e(cfg, weights, B, F, seed=1235, kind="normal"):
+    rng = np.random.default_rng(seed)
+    E = weights["embedding/embedding"]
+    if kind == "normal":
+        return rng.standard_normal((B, F, cfg.D)).astype(F32)
+    if kind == "near_code":
+        j = rng.integers(0, cfg.K, size=(B, F))
+        return (E[j] + F32(0.02) * rng.standard_normal((B, F, cfg.D)).astype(F32)).astype(F32)
+    if kind == "scaled":   # N(0,1) scaled to the codebook's magnitude: many distinct codes get used
+        return (F32(0.13) * rng.standard_normal((B, F, cfg.D))).astype(F32)
+    raise ValueError(kind)
+
+
+def synthetic_audio(B, T, seed=1237):
+    """cfg 5: 0.5*sum of 3 sinusoids + 0.05*N, clipped."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(T, dtype=np.float64)[None, :]
+    f = rng.uniform(80.0, 1200.0, size=(B, 3, 1))
+    ph = rng.uniform(0, 2 * np.pi, size=(B, 3, 1))
+    x = 0.5 * np.sin(2 * np.pi * f * t[:, None, :] / 16000.0 + ph).sum(1) / 3.0
+    x = x + 0.05 * rng.standard_normal((B, T))
+    return np.clip(x, -1, 1).astype(F32)

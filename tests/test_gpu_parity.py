@@ -1,0 +1,333 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes -> libvqwn.so), against the
+NumPy oracle on the same seeded inputs and against the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star):
+  * VQ indices bit-exact except documented near-ties (distance gap < 1e-5 relative);
+  * teacher-forced logits within 1e-3 relative (max |diff| / max |logit|) in fp32 mode;
+  * greedy sequences identical (first 4096 samples on the full configuration); a mismatch is only
+    accepted where the oracle's own top-2 probability gap is a near-tie (< 1e-4 relative);
+  * sample mode identical given identical uniforms; a mismatch is only accepted where the uniform
+    lies within 1e-5 of a cdf boundary.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SMALL_WAVENET = dict(num_cycles=2, num_cycle_layers=3, dilation_rates=[1, 2, 4, 1, 2, 4])
+LOGIT_RTOL = 1e-3
+GREEDY_TIE = 1e-4
+SAMPLE_TIE = 1e-5
+
+
+def _engine(wavenet=None, max_batch=64, weights=None, **kw):
+    import vqvae_wavenet_b200 as pkg
+    eng = pkg.Engine(pkg.EngineConfig(wavenet=wavenet, **kw), device=0, max_batch=max_batch)
+    if weights is not None:
+        eng.set_weights(weights)
+    return eng
+
+
+@pytest.fixture(scope="module")
+def small():
+    cfg = O.Config(wavenet=SMALL_WAVENET)
+    w = O.make_weights(cfg, seed=1234)
+    eng = _engine(SMALL_WAVENET, 16, w)
+    yield cfg, w, eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def full():
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234, peaked=True)
+    eng = _engine(None, 64, w)
+    yield cfg, w, eng
+    eng.close()
+
+
+def _check_sequences(got, want, margin, tie, min_prefix):
+    """identical, or first divergence sits on a near-tie of the oracle's own draw"""
+    for b in range(want.shape[0]):
+        bad = np.nonzero(got[b] != want[b])[0]
+        if bad.size:
+            t = int(bad[0])
+            assert float(margin[b, t]) < tie, "stream %d diverges at step %d, margin %g" % (b, t, margin[b, t])
+            assert t >= min_prefix, "stream %d diverges too early (step %d)" % (b, t)
+
+
+# ----------------------------------------------------------------------------------------- VQ
+@pytest.mark.parametrize("kind", ["normal", "near_code", "scaled"])
+def test_vq_cfg2_bit_exact(kind, golden_dir):
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234)
+    eng = _engine(None, 1, w)
+    z = O.synthetic_z_e(cfg, w, 64, 104, seed=1235, kind=kind)
+    idx, zq = eng.vq_lookup(z)
+    g = np.load(os.path.join(golden_dir, "vq_cfg2.npz"))["idx_" + kind].astype(np.int64)
+    assert idx.dtype == np.int64 and idx.shape == (64, 104)
+    mism = np.nonzero(idx != g)
+    if mism[0].size:
+        d = O.vq_distances_f64(z[mism], w["embedding/embedding"])
+        a = d[np.arange(len(d)), idx[mism]]
+        b = d[np.arange(len(d)), g[mism]]
+        assert np.all(np.abs(a - b) <= 1e-5 * np.abs(b)), "index mismatch away from a near-tie"
+    assert mism[0].size <= 2
+    E = w["embedding/embedding"]
+    e_k = E[idx]
+    assert np.array_equal(zq, z + (e_k - z))          # model.py:73 bit-for-bit
+    eng.close()
+
+
+def test_vq_ties_ragged_and_empty():
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234)
+    E = w["embedding/embedding"].copy()
+    E[300] = E[17]
+    E[511] = E[0]
+    w2 = dict(w)
+    w2["embedding/embedding"] = E
+    eng = _engine(None, 1, w2)
+    # exact duplicates -> lowest index; midpoints between two codes -> lowest index
+    z = np.stack([E[17], E[300], E[511], E[0],
+                  (E[5] + E[9]) * np.float32(0.5), (E[9] + E[5]) * np.float32(0.5)])
+    for n in (1, 2, 3, 5, 6):
+        idx, zq = eng.vq_lookup(z[:n])
+        oidx, _, ozq = O.vq_discretise(z[:n], E)
+        assert np.array_equal(idx, oidx)
+        assert np.array_equal(zq, ozq)
+    assert list(eng.vq_lookup(z)[0][:4]) == [17, 17, 0, 0]
+    idx, zq = eng.vq_lookup(np.zeros((0, 64), dtype=np.float32))
+    assert idx.shape == (0,) and zq.shape == (0, 64)
+    eng.close()
+
+
+def test_vq_large_property():
+    """N = 2^16 vectors: the chosen code attains the float64 minimum distance up to 1e-5 relative,
+    and the lookup is idempotent (VQ of z_q's code row returns the same index)."""
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234)
+    E = w["embedding/embedding"]
+    eng = _engine(None, 1, w)
+    rng = np.random.default_rng(7)
+    z = (0.2 * rng.standard_normal((1 << 16, 64))).astype(np.float32)
+    idx, _ = eng.vq_lookup(z)
+    for s in range(0, z.shape[0], 8192):
+        d = O.vq_distances_f64(z[s:s + 8192], E)
+        chosen = d[np.arange(d.shape[0]), idx[s:s + 8192]]
+        assert np.all(chosen - d.min(1) <= 1e-5 * np.abs(d.min(1)))
+    idx2, _ = eng.vq_lookup(E[idx[:4096]])
+    assert np.array_equal(E[idx2], E[idx[:4096]])
+    eng.close()
+
+
+def test_encode_condition_matches_oracle(small):
+    cfg, w, eng = small
+    B, F = 5, 7
+    z = O.synthetic_z_e(cfg, w, B, F, seed=3, kind="scaled")
+    spk = np.array([0, 108, 3, 3, 57], dtype=np.int32)
+    idx, cond = eng.encode_condition(z, spk)
+    oidx, ocond = O.encode_condition(z, spk, w)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(cond, ocond)
+    zq = O.vq_discretise(z, w["embedding/embedding"])[2]
+    assert np.array_equal(eng.build_condition(zq, spk), ocond)
+    with pytest.raises(ValueError):
+        eng.encode_condition(z, np.array([0, 109, 0, 0, 0], dtype=np.int32))
+
+
+# ----------------------------------------------------------------------------------------- decoder, small config
+def _small_inputs(cfg, w):
+    B, T, F = 3, 256, 4
+    x = O.synthetic_audio(B, T, seed=1237)
+    ze = O.synthetic_z_e(cfg, w, B, F, seed=1235, kind="scaled")
+    return B, T, F, x, ze
+
+
+def test_small_teacher_forced_logits(small, golden_dir):
+    cfg, w, eng = small
+    B, T, F, x, ze = _small_inputs(cfg, w)
+    idx, cond = eng.encode_condition(ze, [0, 1, 2])
+    g = np.load(os.path.join(golden_dir, "small.npz"))
+    assert np.array_equal(idx, g["vq_idx"])
+    lg = eng.teacher_forced(x, cond)
+    scale = np.abs(g["logits_fast"]).max()
+    assert np.abs(lg[:, ::16] - g["logits_fast"]).max() <= LOGIT_RTOL * scale
+    assert np.abs(lg[:, ::16] - g["logits_conv"]).max() <= LOGIT_RTOL * scale   # second formulation
+    # oracle computed live on the same inputs, every step
+    _, _, olg = O.generate(cfg, w, cond, T, mode="greedy", teacher=x, return_logits=True)
+    assert np.abs(lg - olg).max() <= LOGIT_RTOL * np.abs(olg).max()
+
+
+def test_small_step_api_equals_loop(small):
+    """vqwn_step (one sess.run) chained on the host == the persistent teacher-forced loop"""
+    cfg, w, eng = small
+    B, T, F, x, ze = _small_inputs(cfg, w)
+    _, cond = eng.encode_condition(ze, [0, 1, 2])
+    T2 = 48
+    lg = eng.teacher_forced(x[:, :T2], cond[:, :1])
+    eng.reset(B)
+    audio = np.zeros(B, dtype=np.float32)
+    for t in range(T2):
+        probs, logits = eng.step(audio, cond[:, 0])
+        assert np.array_equal(logits, lg[:, t])
+        assert np.allclose(probs.sum(-1), 1.0, atol=1e-5)
+        assert np.allclose(probs, O.softmax(logits), atol=1e-6)
+        audio = x[:, t]
+
+
+def test_small_greedy_and_sample_sequences(small, golden_dir):
+    cfg, w, eng = small
+    B, T, F, x, ze = _small_inputs(cfg, w)
+    _, cond = eng.encode_condition(ze, [0, 1, 2])
+    g = np.load(os.path.join(golden_dir, "small.npz"))
+    audio, idx = eng.generate(cond, T, mode="greedy")
+    _check_sequences(idx, g["greedy_idx"], g["greedy_margin"], GREEDY_TIE, 32)
+    assert np.array_equal(audio, O.decode_lut()[idx])
+    u = np.random.default_rng(1236).random((T, B))
+    audio, idx = eng.generate(cond, T, mode="sample", uniforms=u)
+    _check_sequences(idx, g["sample_idx"], g["sample_margin"], SAMPLE_TIE, 32)
+    assert np.array_equal(audio, O.decode_lut()[idx])
+
+
+def test_receptive_field_property(small):
+    cfg, w, eng = small
+    B, T, F, x, ze = _small_inputs(cfg, w)
+    _, cond = eng.encode_condition(ze, [0, 1, 2])
+    base = eng.teacher_forced(x[:, :128], cond[:, :2])
+    x2 = x[:, :128].copy()
+    x2[:, 10] = 0.9
+    pert = eng.teacher_forced(x2, cond[:, :2])
+    diff = np.abs(base - pert).max(axis=(0, 2))
+    rf = cfg.receptive_field
+    assert diff[:11].max() == 0 and diff[11 + rf:].max() == 0 and diff[11:11 + rf].max() > 0
+
+
+def test_shard_equals_unsharded(small):
+    """multi-GPU partitioning is by contiguous stream slices with no exchange: a slice run alone
+    must reproduce the same streams bit-for-bit."""
+    cfg, w, eng = small
+    B, F, T = 6, 2, 128
+    ze = O.synthetic_z_e(cfg, w, B, F, seed=11, kind="scaled")
+    spk = np.arange(B, dtype=np.int32) % 4
+    _, cond = eng.encode_condition(ze, spk)
+    u = np.random.default_rng(5).random((T, B))
+    a_all, i_all = eng.generate(cond, T, mode="sample", uniforms=u)
+    for lo, hi in ((0, 2), (2, 6)):
+        a, i = eng.generate(cond[lo:hi], T, mode="sample", uniforms=np.ascontiguousarray(u[:, lo:hi]))
+        assert np.array_equal(i, i_all[lo:hi]) and np.array_equal(a, a_all[lo:hi])
+    g_all = eng.generate(cond, T, mode="greedy")[1]
+    assert np.array_equal(eng.generate(cond[1:2], T, mode="greedy")[1], g_all[1:2])
+
+
+def test_decode_api(small):
+    cfg, w, eng = small
+    rng = np.random.default_rng(2)
+    logits = rng.standard_normal((9, 256)).astype(np.float32) * 3
+    probs = O.softmax(logits)
+    idx, audio = eng.decode(probs, "greedy")
+    assert np.array_equal(idx, np.argmax(probs, -1))
+    assert np.array_equal(audio, O.decode(probs, "greedy"))
+    u = rng.random(9)
+    u[0] = 0.0
+    u[1] = 0.99999999999
+    idx, audio = eng.decode(probs, "sample", uniforms=u)
+    assert np.array_equal(idx, O.decode_indices(probs, "sample", u))
+    assert np.array_equal(audio, O.decode(probs, "sample", uniforms=u))
+    # index q (=256) overflow when the float32 cdf ends below the draw
+    p2 = np.zeros((1, 256), dtype=np.float32)
+    p2[0, :10] = 0.0999999
+    idx, audio = eng.decode(p2, "sample", uniforms=[0.9999999])
+    assert idx[0] == 256 and abs(float(audio[0]) - 1.0446261) < 1e-6
+    flat = np.zeros((1, 256), dtype=np.float32)
+    flat[0, [7, 9]] = 0.5
+    assert eng.decode(flat, "greedy")[0][0] == 7
+    with pytest.raises(NotImplementedError):
+        eng.decode(probs, "beam")
+
+
+def test_error_behaviour(small):
+    import vqvae_wavenet_b200 as pkg
+    cfg, w, eng = small
+    cond = np.zeros((2, 3, 128), dtype=np.float32)
+    with pytest.raises(NotImplementedError):
+        eng.generate(cond, 96, mode="beam")
+    with pytest.raises(ValueError):
+        eng.generate(cond, 100, mode="greedy")          # T % F != 0
+    with pytest.raises(ValueError):
+        eng.generate(np.zeros((17, 1, 128), dtype=np.float32), 4, mode="greedy")   # B > max_batch
+    with pytest.raises(ValueError):
+        eng.set_tensor("decoder/skip/bias", np.zeros(3, dtype=np.float32))
+    with pytest.raises(ValueError):
+        eng.set_tensor("decoder/nope", np.zeros(3, dtype=np.float32))
+    fresh = pkg.Engine(pkg.EngineConfig(wavenet=SMALL_WAVENET), 0, 2)
+    with pytest.raises(pkg.VqwnError, match="tensor not set"):
+        fresh.generate(cond, 96, mode="greedy")
+    with pytest.raises(NotImplementedError):
+        pkg.Engine(pkg.EngineConfig(wavenet=dict(SMALL_WAVENET, kernel_size=2)), 0, 2)
+    fresh.close()
+    # weights round-trip (generate.py:96-101 dumps)
+    assert np.array_equal(eng.get_tensor("embedding/embedding"), w["embedding/embedding"])
+    assert np.array_equal(eng.get_tensor("speaker_embedding"), w["speaker_embedding"])
+
+
+# ----------------------------------------------------------------------------------------- decoder, full config
+def test_full_teacher_forced_logits(full, golden_dir):
+    cfg, w, eng = full
+    g = np.load(os.path.join(golden_dir, "full.npz"))
+    B, Tt = 4, 512
+    ze = O.synthetic_z_e(cfg, w, B, 64, seed=1235, kind="scaled")
+    idx, cond = eng.encode_condition(ze, [0, 1, 2, 3])
+    assert np.array_equal(idx, g["vq_idx"])
+    x = O.synthetic_audio(B, Tt, seed=1237)
+    lg = eng.teacher_forced(x, cond[:, :Tt // 64])
+    want = g["teacher_logits"]
+    assert np.abs(lg[:, ::32] - want).max() <= LOGIT_RTOL * np.abs(want).max()
+
+
+def test_full_greedy_4096(full, golden_dir):
+    cfg, w, eng = full
+    g = np.load(os.path.join(golden_dir, "full.npz"))
+    B, T = 4, 4096
+    ze = O.synthetic_z_e(cfg, w, B, 64, seed=1235, kind="scaled")
+    _, cond = eng.encode_condition(ze, [0, 1, 2, 3])
+    audio, idx = eng.generate(cond, T, mode="greedy")
+    _check_sequences(idx, g["greedy_idx"], g["greedy_margin"].astype(np.float32), GREEDY_TIE, 256)
+    assert np.array_equal(audio, O.decode_lut()[idx])
+
+
+def test_full_sample_same_uniforms(full, golden_dir):
+    cfg, w, eng = full
+    g = np.load(os.path.join(golden_dir, "full.npz"))
+    B, T = 4, 1024
+    ze = O.synthetic_z_e(cfg, w, B, 64, seed=1235, kind="scaled")
+    _, cond = eng.encode_condition(ze, [0, 1, 2, 3])
+    u = np.random.default_rng(1236).random((T, B))
+    audio, idx = eng.generate(cond[:, :T // 64], T, mode="sample", uniforms=u)
+    _check_sequences(idx, g["sample_idx"], g["sample_margin"], SAMPLE_TIE, 128)
+
+
+def test_full_size_properties(full):
+    """BASELINE config 3 shape (B=64, 4 speakers) on a shorter run: outputs lie on the mu-law grid,
+    runs are deterministic, a stream's output does not depend on its neighbours."""
+    cfg, w, eng = full
+    B, T = 64, 1024
+    ze = O.synthetic_z_e(cfg, w, B, T // 64, seed=1235, kind="scaled")
+    spk = np.arange(B, dtype=np.int32) % 4
+    _, cond = eng.encode_condition(ze, spk)
+    a1, i1 = eng.generate(cond, T, mode="greedy")
+    a2, i2 = eng.generate(cond, T, mode="greedy")
+    assert np.array_equal(i1, i2) and np.array_equal(a1, a2)
+    assert i1.min() >= 0 and i1.max() <= 255
+    assert np.array_equal(a1, O.decode_lut()[i1])
+    sub = eng.generate(cond[16:20], T, mode="greedy")[1]
+    assert np.array_equal(sub, i1[16:20])
+    s1 = eng.generate(cond, 256, mode="sample", seed=7)[1]
+    s2 = eng.generate(cond, 256, mode="sample", seed=7)[1]
+    s3 = eng.generate(cond, 256, mode="sample", seed=8)[1]
+    assert np.array_equal(s1, s2) and not np.array_equal(s1, s3)
+    assert s1.max() <= 256

@@ -1,0 +1,796 @@
+// C-ABI implementation (include/vqwn.h) over the sm_100a kernels in this directory.
+// Host side only does bookkeeping: tensor registry by reference variable name, weight
+// packing (device-to-device copies), state allocation, launches and timing.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vqwn.h"
+#include "common.cuh"
+#include "vq.cuh"
+#include "wavenet_fp32.cuh"
+#include "sample.cuh"
+
+using namespace vqwn;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct TensorSlot {
+  std::string name;
+  std::vector<int64_t> shape;
+  size_t numel = 0;
+  float* dev = nullptr;
+  bool set = false;
+  bool required = true;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct vqwn_handle {
+  vqwn_config cfg;
+  int device = 0;
+  int max_batch = 0, Bp_max = 0;
+  int num_sms = 0;
+  int precision = VQWN_PREC_FP32;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<TensorSlot> tensors;
+  std::unordered_map<std::string, int> index;
+  // derived dims
+  int L = 0, R = 0, G = 0, S = 0, Q = 0, C = 0, PK = 0, K = 0, D = 0, SPK = 0;
+  int lda = 0;
+  size_t smem_fp32 = 0;
+  // packed fp32 weights
+  bool packed = false;
+  std::vector<float*> w1, b1, w2, b2;
+  float *post1_w = nullptr;
+  LayerDev* layers_dev = nullptr;
+  std::vector<LayerDev> layers_host;
+  float *enc_lut = nullptr, *dec_lut = nullptr;
+  // state
+  float *u_hist = nullptr, *cur = nullptr, *g = nullptr, *skip = nullptr, *n1 = nullptr, *logits = nullptr;
+  float* ring_base = nullptr;
+  size_t ring_floats = 0;
+  unsigned long long* barrier = nullptr;
+  int B = 0;            // streams of the current run (vqwn_reset)
+  long long t = 0;      // steps since reset
+  // resident / staging buffers
+  DevBuf cond_res, uni_res, audio_res, idx_res, logits_res, x_res, small_a, small_b, small_c, small_d;
+  DevBuf vq_z, vq_idx, vq_out, spk_idx;
+  int cond_B = 0, cond_F = 0;
+  long long uni_T = 0; int uni_B = 0;
+  long long out_T = 0; int out_B = 0;
+  long long vq_n = 0;
+  // instrumentation
+  std::string err;
+  double last_ms = 0.0;
+  int64_t launches = 0;
+  const char* last_kernel = "";
+};
+
+namespace {
+
+int fail(vqwn_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CK(h, call)                                                                      \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      char buf_[512];                                                                    \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+               __FILE__, __LINE__);                                                      \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? VQWN_ERR_NOMEM : VQWN_ERR_CUDA, buf_); \
+    }                                                                                    \
+  } while (0)
+
+int ensure(vqwn_handle* h, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return VQWN_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.bytes = 0;
+  if (bytes == 0) bytes = 16;
+  CK(h, cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return VQWN_OK;
+}
+
+void add_tensor(vqwn_handle* h, const std::string& name, std::vector<int64_t> shape, bool required = true) {
+  TensorSlot s;
+  s.name = name;
+  s.shape = shape;
+  s.numel = 1;
+  for (auto d : shape) s.numel *= (size_t)d;
+  s.required = required;
+  h->index[name] = (int)h->tensors.size();
+  h->tensors.push_back(s);
+}
+
+std::string layer_scope(const vqwn_config& c, int i) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "decoder/cycle_%d/layer_%d", 1 + i / c.num_cycle_layers, 1 + i % c.num_cycle_layers);
+  return buf;
+}
+
+float* TP(vqwn_handle* h, const std::string& name) { return h->tensors[h->index.at(name)].dev; }
+
+// default LUTs (mu_law_ops.py:26-31 and :5-8 in float32 libm); the Python shim overrides them
+// with NumPy-computed tables ("lut/mu_law_decode", "lut/mu_law_encode") for bit parity with
+// the reference's NumPy decode.
+void default_luts(int Q, std::vector<float>& dec, std::vector<float>& enc) {
+  const float mu = (float)(Q - 1);
+  dec.resize(Q + 1); enc.resize(Q + 1);
+  for (int k = 0; k <= Q; ++k) {
+    float y = (2.0f * (float)k / mu) - 1.0f;
+    float s = (y > 0.f) ? 1.f : ((y < 0.f) ? -1.f : 0.f);
+    float x = s * (powf(1.0f + mu, fabsf(y)) - 1.0f) / mu;
+    dec[k] = x;
+    float xc = fminf(fmaxf(x, -1.f), 1.f);
+    float sx = (xc > 0.f) ? 1.f : ((xc < 0.f) ? -1.f : 0.f);
+    enc[k] = sx * log1pf(mu * fabsf(xc)) / log1pf(mu);
+  }
+}
+
+int pack_weights(vqwn_handle* h) {
+  if (h->packed) return VQWN_OK;
+  for (auto& s : h->tensors)
+    if (s.required && !s.set) return fail(h, VQWN_ERR_STATE, "tensor not set: " + s.name);
+  const int R = h->R, G = h->G, S = h->S, C = h->C;
+  const size_t f = sizeof(float);
+  for (int l = 0; l < h->L; ++l) {
+    const std::string sc = layer_scope(h->cfg, l);
+    const float* gk = TP(h, sc + "/gated/kernel");          // [3,R,2G]
+    // rows: kernel[2] (current) ; kernel[1] (t-d) ; kernel[0] (t-2d) ; local_condition
+    for (int tap = 0; tap < 3; ++tap)
+      CK(h, cudaMemcpyAsync(h->w1[l] + (size_t)tap * R * 2 * G, gk + (size_t)(2 - tap) * R * 2 * G,
+                            (size_t)R * 2 * G * f, cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->w1[l] + (size_t)3 * R * 2 * G, TP(h, sc + "/gated/local_condition/kernel"),
+                          (size_t)C * 2 * G * f, cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->b1[l], TP(h, sc + "/gated/bias"), (size_t)2 * G * f, cudaMemcpyDeviceToDevice, h->stream));
+    // cols: residual | skip
+    CK(h, cudaMemcpy2DAsync(h->w2[l], (size_t)(R + S) * f, TP(h, sc + "/residual/kernel"), (size_t)R * f,
+                            (size_t)R * f, G, cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpy2DAsync(h->w2[l] + R, (size_t)(R + S) * f, TP(h, sc + "/skip/kernel"), (size_t)S * f,
+                            (size_t)S * f, G, cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->b2[l], TP(h, sc + "/residual/bias"), (size_t)R * f, cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->b2[l] + R, TP(h, sc + "/skip/bias"), (size_t)S * f, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CK(h, cudaMemcpyAsync(h->post1_w, TP(h, "decoder/postprocess1/kernel"), (size_t)S * S * f,
+                        cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->post1_w + (size_t)S * S, TP(h, "decoder/postprocess1/local_condition/kernel"),
+                        (size_t)C * S * f, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->enc_lut, TP(h, "lut/mu_law_encode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->dec_lut, TP(h, "lut/mu_law_decode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->packed = true;
+  return VQWN_OK;
+}
+
+int do_reset(vqwn_handle* h, int B) {
+  if (B < 1 || B > h->max_batch) return fail(h, VQWN_ERR_INVALID, "batch out of range (1..max_batch)");
+  const size_t Bp = h->Bp_max;
+  // only the part of the ring storage this padded batch uses (layout: launch_fp32)
+  const size_t Bp_run = (size_t)(B + FP32_TB - 1) / FP32_TB * FP32_TB;
+  CK(h, cudaMemsetAsync(h->ring_base, 0, h->ring_floats / Bp * Bp_run * sizeof(float), h->stream));
+  CK(h, cudaMemsetAsync(h->u_hist, 0, Bp * h->PK * sizeof(float), h->stream));
+  CK(h, cudaMemsetAsync(h->cur, 0, Bp * h->R * sizeof(float), h->stream));
+  CK(h, cudaMemsetAsync(h->g, 0, Bp * h->G * sizeof(float), h->stream));
+  CK(h, cudaMemsetAsync(h->skip, 0, Bp * h->S * sizeof(float), h->stream));
+  CK(h, cudaMemsetAsync(h->n1, 0, Bp * h->S * sizeof(float), h->stream));
+  CK(h, cudaMemsetAsync(h->logits, 0, Bp * h->Q * sizeof(float), h->stream));
+  h->B = B;
+  h->t = 0;
+  return VQWN_OK;
+}
+
+// ring layout depends on the padded batch of the run; rebuilt at every launch
+int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
+                const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
+                float* logits_out, float* probs_out) {
+  GenParams p;
+  memset(&p, 0, sizeof p);
+  p.L = h->L; p.R = h->R; p.G = h->G; p.S = h->S; p.Q = h->Q; p.C = h->C; p.PK = h->PK;
+  p.B = h->B;
+  p.Bp = (h->B + FP32_TB - 1) / FP32_TB * FP32_TB;
+  p.lda = h->lda;
+  p.pre_k = TP(h, "decoder/preprocess/kernel"); p.pre_b = TP(h, "decoder/preprocess/bias");
+  p.skip0_w = TP(h, "decoder/skip/kernel"); p.skip0_b = TP(h, "decoder/skip/bias");
+  p.post1_w = h->post1_w; p.post1_b = TP(h, "decoder/postprocess1/bias");
+  p.post2_w = TP(h, "decoder/postprocess2/kernel"); p.post2_b = TP(h, "decoder/postprocess2/bias");
+  // per-layer ring bases for this padded batch
+  size_t off = 0;
+  for (int l = 0; l < h->L; ++l) {
+    h->layers_host[l].ring = h->ring_base + off;
+    off += (size_t)2 * h->cfg.dilations[l] * p.Bp * h->R;
+  }
+  CK(h, cudaMemcpyAsync(h->layers_dev, h->layers_host.data(), sizeof(LayerDev) * h->L, cudaMemcpyHostToDevice, h->stream));
+  p.layers = h->layers_dev;
+  p.enc_lut = h->enc_lut; p.dec_lut = h->dec_lut;
+  p.u_hist = h->u_hist; p.cur = h->cur; p.g = h->g; p.skip = h->skip; p.n1 = h->n1; p.logits = h->logits;
+  p.t0 = h->t; p.T = T; p.mode = mode;
+  p.cond = cond; p.cond_bstride = cond_bstride; p.ratio = ratio;
+  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed;
+  p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
+  p.barrier = h->barrier;
+  CK(h, cudaMemsetAsync(h->barrier, 0, sizeof(unsigned long long), h->stream));
+  void* args[] = {&p};
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  CK(h, cudaLaunchCooperativeKernel((const void*)wavenet_fp32_persistent, dim3(h->num_sms), dim3(FP32_THREADS),
+                                    args, h->smem_fp32, h->stream));
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  h->last_kernel = "wavenet_fp32_persistent";
+  h->t += T;
+  return VQWN_OK;
+}
+
+int finish_timing(vqwn_handle* h) {
+  CK(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms;
+  return VQWN_OK;
+}
+
+int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float* out, int out_stride,
+              const int* spk_idx, int spk_dim, int F) {
+  const int K = h->K;
+  int threads = (K + 31) / 32 * 32;
+  const long long nblocks = (n + 3) / 4;
+  int grid = (int)((nblocks < (long long)h->num_sms * 1) ? nblocks : (long long)h->num_sms);
+  if (grid < 1) grid = 1;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  const float* E = TP(h, "embedding/embedding");
+  const float* spk = spk_dim > 0 ? TP(h, "speaker_embedding") : nullptr;
+  if (h->D == 64)
+    vq_direct_kernel<64, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F);
+  else if (h->D == 32)
+    vq_direct_kernel<32, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F);
+  else
+    return fail(h, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  h->last_kernel = "vq_direct_kernel";
+  return VQWN_OK;
+}
+
+int check_tensor_ready(vqwn_handle* h, const char* name) {
+  auto it = h->index.find(name);
+  if (it == h->index.end()) return fail(h, VQWN_ERR_INVALID, std::string("unknown tensor: ") + name);
+  if (!h->tensors[it->second].set) return fail(h, VQWN_ERR_STATE, std::string("tensor not set: ") + name);
+  return VQWN_OK;
+}
+
+}  // namespace
+
+#define ENTER(h)                                                              \
+  if (!(h)) return fail(nullptr, VQWN_ERR_INVALID, "null handle");            \
+  { cudaError_t e0_ = cudaSetDevice((h)->device);                             \
+    if (e0_ != cudaSuccess) return fail((h), VQWN_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e0_)); }
+
+extern "C" {
+
+const char* vqwn_version(void) { return "vqwn 0.1 (sm_100a)"; }
+
+const char* vqwn_last_error(const vqwn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle** out) {
+  if (!cfg || !out) return fail(nullptr, VQWN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const vqwn_config& c = *cfg;
+  if (c.num_layers < 1 || c.num_layers > VQWN_MAX_LAYERS) return fail(nullptr, VQWN_ERR_INVALID, "num_layers out of range");
+  if (c.kernel_size != 3) return fail(nullptr, VQWN_ERR_NOTIMPL, "only kernel_size 3 is implemented");
+  if (c.quantization_channels != 256)
+    return fail(nullptr, VQWN_ERR_NOTIMPL, "only quantization_channels 256 works end to end (reference utils.py:41, wavenet.py:113)");
+  if (c.pre_filters != c.residual_filters) return fail(nullptr, VQWN_ERR_INVALID, "preprocess.filters must equal residual_filters");
+  if (c.dilation_filters != c.residual_filters) return fail(nullptr, VQWN_ERR_INVALID, "dilation_filters must equal residual_filters");
+  const int Ccond = c.latent_dim + c.speaker_dim;
+  if (c.residual_filters % 32 || c.skip_filters % 32 || Ccond % 32 || c.dilation_filters % 32)
+    return fail(nullptr, VQWN_ERR_INVALID, "channel counts must be multiples of 32");
+  if (c.pre_kernel_size < 1 || c.pre_kernel_size > 64) return fail(nullptr, VQWN_ERR_INVALID, "preprocess.kernel_size out of range");
+  if (c.use_vq && (c.k < 1 || c.k > 512)) return fail(nullptr, VQWN_ERR_NOTIMPL, "k must be <= 512");
+  if (c.latent_dim != 32 && c.latent_dim != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
+  if (c.num_cycle_layers < 1) return fail(nullptr, VQWN_ERR_INVALID, "num_cycle_layers must be >= 1");
+  for (int i = 0; i < c.num_layers; ++i)
+    if (c.dilations[i] < 1) return fail(nullptr, VQWN_ERR_INVALID, "dilation must be >= 1");
+  if (max_batch < 1) return fail(nullptr, VQWN_ERR_INVALID, "max_batch must be >= 1");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, VQWN_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, VQWN_ERR_INVALID, "device index out of range");
+
+  vqwn_handle* h = new vqwn_handle();
+  h->cfg = c;
+  h->device = device;
+  h->max_batch = max_batch;
+  h->Bp_max = (max_batch + FP32_TB - 1) / FP32_TB * FP32_TB;
+  h->L = c.num_layers; h->R = c.residual_filters; h->G = c.dilation_filters; h->S = c.skip_filters;
+  h->Q = c.quantization_channels; h->C = Ccond; h->PK = c.pre_kernel_size; h->K = c.k; h->D = c.latent_dim;
+  h->SPK = c.speaker_dim;
+
+#define CKC(call)                                                                         \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      std::string m_ = std::string(#call) + " failed: " + cudaGetErrorString(e_);         \
+      vqwn_destroy(h);                                                                    \
+      return fail(nullptr, e_ == cudaErrorMemoryAllocation ? VQWN_ERR_NOMEM : VQWN_ERR_CUDA, m_); \
+    }                                                                                     \
+  } while (0)
+
+  CKC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    vqwn_destroy(h);
+    return fail(nullptr, VQWN_ERR_CUDA, "device is not sm_100 (Blackwell); this library is built for sm_100a only");
+  }
+  h->num_sms = prop.multiProcessorCount;
+  CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CKC(cudaEventCreate(&h->ev0));
+  CKC(cudaEventCreate(&h->ev1));
+
+  // tensor registry (reference variable names)
+  const int R = h->R, G = h->G, S = h->S, Q = h->Q, C = h->C;
+  add_tensor(h, "embedding/embedding", {c.k, c.latent_dim}, c.use_vq != 0);
+  add_tensor(h, "speaker_embedding", {c.num_speakers > 0 ? c.num_speakers : 1, c.speaker_dim > 0 ? c.speaker_dim : 1}, c.speaker_dim > 0);
+  add_tensor(h, "decoder/preprocess/kernel", {h->PK, 1, R});
+  add_tensor(h, "decoder/preprocess/bias", {R});
+  add_tensor(h, "decoder/skip/kernel", {1, R, S});
+  add_tensor(h, "decoder/skip/bias", {S});
+  for (int l = 0; l < h->L; ++l) {
+    const std::string sc = layer_scope(c, l);
+    add_tensor(h, sc + "/gated/kernel", {3, R, 2 * G});
+    add_tensor(h, sc + "/gated/bias", {2 * G});
+    add_tensor(h, sc + "/gated/local_condition/kernel", {1, C, 2 * G});
+    add_tensor(h, sc + "/skip/kernel", {1, G, S});
+    add_tensor(h, sc + "/skip/bias", {S});
+    add_tensor(h, sc + "/residual/kernel", {1, G, R});
+    add_tensor(h, sc + "/residual/bias", {R});
+  }
+  add_tensor(h, "decoder/postprocess1/kernel", {1, S, S});
+  add_tensor(h, "decoder/postprocess1/bias", {S});
+  add_tensor(h, "decoder/postprocess1/local_condition/kernel", {1, C, S});
+  add_tensor(h, "decoder/postprocess2/kernel", {1, S, Q});
+  add_tensor(h, "decoder/postprocess2/bias", {Q});
+  add_tensor(h, "lut/mu_law_decode", {Q + 1}, false);
+  add_tensor(h, "lut/mu_law_encode", {Q + 1}, false);
+  for (auto& s : h->tensors) CKC(cudaMalloc(&s.dev, s.numel * sizeof(float)));
+  {
+    std::vector<float> dec, enc;
+    default_luts(Q, dec, enc);
+    CKC(cudaMemcpy(TP(h, "lut/mu_law_decode"), dec.data(), dec.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(TP(h, "lut/mu_law_encode"), enc.data(), enc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->tensors[h->index["lut/mu_law_decode"]].set = true;
+    h->tensors[h->index["lut/mu_law_encode"]].set = true;
+  }
+
+  // packed weights
+  h->w1.resize(h->L); h->b1.resize(h->L); h->w2.resize(h->L); h->b2.resize(h->L);
+  h->layers_host.resize(h->L);
+  for (int l = 0; l < h->L; ++l) {
+    CKC(cudaMalloc(&h->w1[l], (size_t)(3 * R + C) * 2 * G * sizeof(float)));
+    CKC(cudaMalloc(&h->b1[l], (size_t)2 * G * sizeof(float)));
+    CKC(cudaMalloc(&h->w2[l], (size_t)G * (R + S) * sizeof(float)));
+    CKC(cudaMalloc(&h->b2[l], (size_t)(R + S) * sizeof(float)));
+    h->layers_host[l] = LayerDev{h->w1[l], h->b1[l], h->w2[l], h->b2[l], nullptr, c.dilations[l], 0};
+  }
+  CKC(cudaMalloc(&h->post1_w, (size_t)(S + C) * S * sizeof(float)));
+  CKC(cudaMalloc(&h->layers_dev, sizeof(LayerDev) * h->L));
+  CKC(cudaMalloc(&h->enc_lut, (Q + 1) * sizeof(float)));
+  CKC(cudaMalloc(&h->dec_lut, (Q + 1) * sizeof(float)));
+
+  // state
+  const size_t Bp = h->Bp_max;
+  size_t dsum = 0;
+  for (int l = 0; l < h->L; ++l) dsum += (size_t)c.dilations[l];
+  h->ring_floats = 2 * dsum * Bp * R;
+  CKC(cudaMalloc(&h->ring_base, h->ring_floats * sizeof(float)));
+  CKC(cudaMalloc(&h->u_hist, Bp * h->PK * sizeof(float)));
+  CKC(cudaMalloc(&h->cur, Bp * R * sizeof(float)));
+  CKC(cudaMalloc(&h->g, Bp * G * sizeof(float)));
+  CKC(cudaMalloc(&h->skip, Bp * S * sizeof(float)));
+  CKC(cudaMalloc(&h->n1, Bp * S * sizeof(float)));
+  CKC(cudaMalloc(&h->logits, Bp * Q * sizeof(float)));
+  CKC(cudaMalloc(&h->barrier, sizeof(unsigned long long)));
+
+  int kmax = 3 * R + C;
+  if (S + C > kmax) kmax = S + C;
+  h->lda = kmax + 4;
+  h->smem_fp32 = ((size_t)FP32_TB * h->lda + FP32_WARPS * 256 + (size_t)FP32_TB * h->PK + (size_t)FP32_WARPS * Q) * sizeof(float);
+  if (h->smem_fp32 > (size_t)prop.sharedMemPerBlockOptin) {
+    vqwn_destroy(h);
+    return fail(nullptr, VQWN_ERR_INVALID, "configuration needs more shared memory than the device offers");
+  }
+  CKC(cudaFuncSetAttribute((const void*)wavenet_fp32_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fp32));
+  int occ = 0;
+  CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)wavenet_fp32_persistent, FP32_THREADS, h->smem_fp32));
+  if (occ < 1) {
+    vqwn_destroy(h);
+    return fail(nullptr, VQWN_ERR_CUDA, "persistent kernel cannot be made co-resident");
+  }
+#undef CKC
+  *out = h;
+  return VQWN_OK;
+}
+
+int vqwn_destroy(vqwn_handle* h) {
+  if (!h) return VQWN_OK;
+  cudaSetDevice(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  for (auto& s : h->tensors) if (s.dev) cudaFree(s.dev);
+  for (auto p : h->w1) if (p) cudaFree(p);
+  for (auto p : h->b1) if (p) cudaFree(p);
+  for (auto p : h->w2) if (p) cudaFree(p);
+  for (auto p : h->b2) if (p) cudaFree(p);
+  void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
+                     h->skip, h->n1, h->logits, h->barrier};
+  for (void* p : singles) if (p) cudaFree(p);
+  DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
+                    &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx};
+  for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return VQWN_OK;
+}
+
+int vqwn_set_stream(vqwn_handle* h, void* cuda_stream) {
+  ENTER(h);
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return VQWN_OK;
+}
+
+int vqwn_set_precision(vqwn_handle* h, int precision) {
+  ENTER(h);
+  if (precision == VQWN_PREC_FP32) { h->precision = precision; return VQWN_OK; }
+  return fail(h, VQWN_ERR_NOTIMPL, "precision not implemented in this build");
+}
+
+int vqwn_set_tensor(vqwn_handle* h, const char* tf_name, const float* host, const int64_t* shape, int ndim) {
+  ENTER(h);
+  if (!tf_name || !host || !shape) return fail(h, VQWN_ERR_INVALID, "null argument");
+  auto it = h->index.find(tf_name);
+  if (it == h->index.end()) return fail(h, VQWN_ERR_INVALID, std::string("unknown tensor: ") + tf_name);
+  TensorSlot& s = h->tensors[it->second];
+  bool ok = (ndim == (int)s.shape.size());
+  for (int i = 0; ok && i < ndim; ++i) ok = (shape[i] == s.shape[i]);
+  if (!ok) {
+    std::string m = std::string("shape mismatch for ") + tf_name + ": expected [";
+    for (size_t i = 0; i < s.shape.size(); ++i) m += (i ? "," : "") + std::to_string(s.shape[i]);
+    m += "]";
+    return fail(h, VQWN_ERR_INVALID, m);
+  }
+  CK(h, cudaMemcpyAsync(s.dev, host, s.numel * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  s.set = true;
+  h->packed = false;
+  return VQWN_OK;
+}
+
+int vqwn_get_tensor(vqwn_handle* h, const char* tf_name, float* host_out, int64_t capacity) {
+  ENTER(h);
+  if (!tf_name || !host_out) return fail(h, VQWN_ERR_INVALID, "null argument");
+  int rc = check_tensor_ready(h, tf_name);
+  if (rc) return rc;
+  TensorSlot& s = h->tensors[h->index[tf_name]];
+  if ((int64_t)s.numel > capacity) return fail(h, VQWN_ERR_INVALID, "output buffer too small");
+  CK(h, cudaMemcpyAsync(host_out, s.dev, s.numel * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return VQWN_OK;
+}
+
+int vqwn_num_tensors(const vqwn_handle* h) { return h ? (int)h->tensors.size() : 0; }
+
+int vqwn_tensor_info(const vqwn_handle* h, int i, char* name_out, int name_cap, int64_t* shape_out, int* ndim_out,
+                     int* is_set) {
+  if (!h || i < 0 || i >= (int)h->tensors.size()) return VQWN_ERR_INVALID;
+  const TensorSlot& s = h->tensors[i];
+  if (name_out && name_cap > 0) { strncpy(name_out, s.name.c_str(), name_cap - 1); name_out[name_cap - 1] = 0; }
+  if (shape_out) for (size_t k = 0; k < s.shape.size() && k < 4; ++k) shape_out[k] = s.shape[k];
+  if (ndim_out) *ndim_out = (int)s.shape.size();
+  if (is_set) *is_set = s.set ? 1 : 0;
+  return VQWN_OK;
+}
+
+// ---------------------------------------------------------------------------------- VQ
+int vqwn_vq_upload(vqwn_handle* h, const float* z_e, int64_t n) {
+  ENTER(h);
+  if (!z_e || n < 0) return fail(h, VQWN_ERR_INVALID, "bad argument");
+  int rc;
+  if ((rc = ensure(h, h->vq_z, (size_t)n * h->D * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->vq_idx, (size_t)n * sizeof(long long)))) return rc;
+  if ((rc = ensure(h, h->vq_out, (size_t)n * h->D * sizeof(float)))) return rc;
+  CK(h, cudaMemcpyAsync(h->vq_z.p, z_e, (size_t)n * h->D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->vq_n = n;
+  return VQWN_OK;
+}
+
+int vqwn_vq_resident(vqwn_handle* h, int64_t n) {
+  ENTER(h);
+  if (!h->cfg.use_vq) return fail(h, VQWN_ERR_STATE, "use_vq is false");
+  if (n < 0 || n > h->vq_n) return fail(h, VQWN_ERR_STATE, "no resident z_e of that size (vqwn_vq_upload first)");
+  int rc = check_tensor_ready(h, "embedding/embedding");
+  if (rc) return rc;
+  if (n == 0) { h->last_ms = 0; return VQWN_OK; }
+  rc = launch_vq(h, (const float*)h->vq_z.p, n, (long long*)h->vq_idx.p, (float*)h->vq_out.p, h->D, nullptr, 0, 1);
+  if (rc) return rc;
+  return finish_timing(h);
+}
+
+int vqwn_vq_download(vqwn_handle* h, int64_t n, int64_t* idx_out, float* zq_out) {
+  ENTER(h);
+  if (n < 0 || n > h->vq_n) return fail(h, VQWN_ERR_STATE, "no resident result of that size");
+  if (idx_out) CK(h, cudaMemcpyAsync(idx_out, h->vq_idx.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  if (zq_out) CK(h, cudaMemcpyAsync(zq_out, h->vq_out.p, (size_t)n * h->D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return VQWN_OK;
+}
+
+int vqwn_vq_lookup(vqwn_handle* h, const float* z_e, int64_t n, int64_t* idx_out, float* zq_out) {
+  int rc;
+  if ((rc = vqwn_vq_upload(h, z_e, n))) return rc;
+  if ((rc = vqwn_vq_resident(h, n))) return rc;
+  return vqwn_vq_download(h, n, idx_out, zq_out);
+}
+
+static int upload_speakers(vqwn_handle* h, const int32_t* speaker_idx, int B) {
+  int rc;
+  if ((rc = ensure(h, h->spk_idx, (size_t)B * sizeof(int)))) return rc;
+  if (h->SPK > 0) {
+    if (!speaker_idx) return fail(h, VQWN_ERR_INVALID, "speaker_idx is required when speaker_embedding > 0");
+    for (int b = 0; b < B; ++b)
+      if (speaker_idx[b] < 0 || speaker_idx[b] >= h->cfg.num_speakers)
+        return fail(h, VQWN_ERR_INVALID, "speaker index out of range");
+    CK(h, cudaMemcpyAsync(h->spk_idx.p, speaker_idx, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
+  return VQWN_OK;
+}
+
+int vqwn_build_condition(vqwn_handle* h, const float* z_q, const int32_t* speaker_idx, int B, int F, float* cond_out) {
+  ENTER(h);
+  if (!z_q || !cond_out || B < 1 || F < 1) return fail(h, VQWN_ERR_INVALID, "bad argument");
+  int rc;
+  if (h->SPK > 0 && (rc = check_tensor_ready(h, "speaker_embedding"))) return rc;
+  if ((rc = upload_speakers(h, speaker_idx, B))) return rc;
+  const long long n = (long long)B * F;
+  if ((rc = ensure(h, h->vq_z, (size_t)n * h->D * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->cond_res, (size_t)n * h->C * sizeof(float)))) return rc;
+  CK(h, cudaMemcpyAsync(h->vq_z.p, z_q, (size_t)n * h->D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  const long long total = n * h->C;
+  int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  build_condition_kernel<<<grid, 256, 0, h->stream>>>((const float*)h->vq_z.p, h->SPK > 0 ? TP(h, "speaker_embedding") : nullptr,
+                                                      (const int*)h->spk_idx.p, h->D, h->SPK, F, n, (float*)h->cond_res.p);
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  h->last_kernel = "build_condition_kernel";
+  h->cond_B = B; h->cond_F = F;
+  CK(h, cudaMemcpyAsync(cond_out, h->cond_res.p, (size_t)n * h->C * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  return finish_timing(h);
+}
+
+int vqwn_encode_condition(vqwn_handle* h, const float* z_e, const int32_t* speaker_idx, int B, int F,
+                          int64_t* idx_out, float* cond_out) {
+  ENTER(h);
+  if (!z_e || !cond_out || B < 1 || F < 1) return fail(h, VQWN_ERR_INVALID, "bad argument");
+  if (!h->cfg.use_vq) {
+    // model.py:140-142: z_q = z_e
+    if (idx_out) return fail(h, VQWN_ERR_STATE, "use_vq is false: there are no indices");
+    return vqwn_build_condition(h, z_e, speaker_idx, B, F, cond_out);
+  }
+  int rc;
+  if ((rc = check_tensor_ready(h, "embedding/embedding"))) return rc;
+  if (h->SPK > 0 && (rc = check_tensor_ready(h, "speaker_embedding"))) return rc;
+  if ((rc = upload_speakers(h, speaker_idx, B))) return rc;
+  const long long n = (long long)B * F;
+  if ((rc = ensure(h, h->vq_z, (size_t)n * h->D * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->vq_idx, (size_t)n * sizeof(long long)))) return rc;
+  if ((rc = ensure(h, h->cond_res, (size_t)n * h->C * sizeof(float)))) return rc;
+  h->vq_n = 0;
+  CK(h, cudaMemcpyAsync(h->vq_z.p, z_e, (size_t)n * h->D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  rc = launch_vq(h, (const float*)h->vq_z.p, n, (long long*)h->vq_idx.p, (float*)h->cond_res.p, h->C,
+                 (const int*)h->spk_idx.p, h->SPK, F);
+  if (rc) return rc;
+  h->cond_B = B; h->cond_F = F;
+  if (idx_out) CK(h, cudaMemcpyAsync(idx_out, h->vq_idx.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(cond_out, h->cond_res.p, (size_t)n * h->C * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  return finish_timing(h);
+}
+
+// ---------------------------------------------------------------------------------- WaveNet
+int vqwn_reset(vqwn_handle* h, int B) {
+  ENTER(h);
+  int rc = do_reset(h, B);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return VQWN_OK;
+}
+
+int vqwn_step(vqwn_handle* h, const float* audio_t, const float* cond_t, float* logits_out, float* probs_out) {
+  ENTER(h);
+  if (!audio_t || !cond_t) return fail(h, VQWN_ERR_INVALID, "null argument");
+  if (h->B < 1) return fail(h, VQWN_ERR_STATE, "vqwn_reset must be called first (init_ops)");
+  int rc;
+  if ((rc = pack_weights(h))) return rc;
+  const int B = h->B;
+  if ((rc = ensure(h, h->small_a, (size_t)B * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->small_b, (size_t)B * h->C * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->small_c, (size_t)B * h->Q * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->small_d, (size_t)B * h->Q * sizeof(float)))) return rc;
+  CK(h, cudaMemcpyAsync(h->small_a.p, audio_t, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->small_b.p, cond_t, (size_t)B * h->C * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  rc = launch_fp32(h, GEN_STEP, 1, (const float*)h->small_b.p, h->C, 0, (const float*)h->small_a.p, nullptr, 0,
+                   nullptr, nullptr, (float*)h->small_c.p, (float*)h->small_d.p);
+  if (rc) return rc;
+  if (logits_out) CK(h, cudaMemcpyAsync(logits_out, h->small_c.p, (size_t)B * h->Q * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (probs_out) CK(h, cudaMemcpyAsync(probs_out, h->small_d.p, (size_t)B * h->Q * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  return finish_timing(h);
+}
+
+int vqwn_decode(vqwn_handle* h, const float* probs, int B, int mode, const double* uniforms, int32_t* idx_out,
+                float* audio_out) {
+  ENTER(h);
+  if (!probs || B < 1) return fail(h, VQWN_ERR_INVALID, "bad argument");
+  if (mode != VQWN_MODE_GREEDY && mode != VQWN_MODE_SAMPLE)
+    return fail(h, VQWN_ERR_NOTIMPL, "decode mode not implemented");     // utils.py:46
+  if (mode == VQWN_MODE_SAMPLE && !uniforms) return fail(h, VQWN_ERR_INVALID, "sample mode needs uniforms[B]");
+  int rc;
+  if ((rc = pack_weights(h))) return rc;
+  const int Q = h->Q;
+  if ((rc = ensure(h, h->small_c, (size_t)B * Q * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->small_a, (size_t)B * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->small_b, (size_t)B * (sizeof(double) + sizeof(int))))) return rc;
+  double* d_u = (double*)h->small_b.p;
+  int* d_idx = (int*)((char*)h->small_b.p + (size_t)B * sizeof(double));
+  CK(h, cudaMemcpyAsync(h->small_c.p, probs, (size_t)B * Q * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (mode == VQWN_MODE_SAMPLE)
+    CK(h, cudaMemcpyAsync(d_u, uniforms, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  decode_kernel<<<(B + 7) / 8, 256, 8 * Q * sizeof(float), h->stream>>>((const float*)h->small_c.p, B, Q, mode, d_u, h->dec_lut,
+                                                                       d_idx, (float*)h->small_a.p);
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  h->last_kernel = "decode_kernel";
+  if (idx_out) CK(h, cudaMemcpyAsync(idx_out, d_idx, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (audio_out) CK(h, cudaMemcpyAsync(audio_out, h->small_a.p, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  return finish_timing(h);
+}
+
+int vqwn_upload_condition(vqwn_handle* h, const float* cond, int B, int F) {
+  ENTER(h);
+  if (!cond || B < 1 || F < 1) return fail(h, VQWN_ERR_INVALID, "bad argument");
+  int rc;
+  const size_t bytes = (size_t)B * F * h->C * sizeof(float);
+  if ((rc = ensure(h, h->cond_res, bytes))) return rc;
+  CK(h, cudaMemcpyAsync(h->cond_res.p, cond, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->cond_B = B; h->cond_F = F;
+  return VQWN_OK;
+}
+
+int vqwn_upload_uniforms(vqwn_handle* h, const double* uniforms, int64_t T, int B) {
+  ENTER(h);
+  if (!uniforms || T < 1 || B < 1) return fail(h, VQWN_ERR_INVALID, "bad argument");
+  int rc;
+  const size_t bytes = (size_t)T * B * sizeof(double);
+  if ((rc = ensure(h, h->uni_res, bytes))) return rc;
+  CK(h, cudaMemcpyAsync(h->uni_res.p, uniforms, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->uni_T = T; h->uni_B = B;
+  return VQWN_OK;
+}
+
+static int generate_common(vqwn_handle* h, int B, int F, int64_t T, int mode, bool have_uniforms, uint64_t seed) {
+  if (mode != VQWN_MODE_GREEDY && mode != VQWN_MODE_SAMPLE)
+    return fail(h, VQWN_ERR_NOTIMPL, "decode mode not implemented");     // utils.py:46
+  if (B < 1 || B > h->max_batch) return fail(h, VQWN_ERR_INVALID, "batch out of range (1..max_batch)");
+  if (F < 1 || T < 1 || T % F != 0) return fail(h, VQWN_ERR_INVALID, "T must be a positive multiple of F (generate.py:107)");
+  if (h->cond_B != B || h->cond_F != F) return fail(h, VQWN_ERR_STATE, "resident condition does not match B,F");
+  if (have_uniforms && (h->uni_B != B || h->uni_T < T)) return fail(h, VQWN_ERR_STATE, "resident uniforms do not match T,B");
+  int rc;
+  if ((rc = pack_weights(h))) return rc;
+  if ((rc = ensure(h, h->audio_res, (size_t)B * T * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->idx_res, (size_t)B * T * sizeof(int)))) return rc;
+  if ((rc = do_reset(h, B))) return rc;
+  rc = launch_fp32(h, mode == VQWN_MODE_GREEDY ? GEN_GREEDY : GEN_SAMPLE, T, (const float*)h->cond_res.p,
+                   (long long)F * h->C, (int)(T / F), nullptr,
+                   (mode == VQWN_MODE_SAMPLE && have_uniforms) ? (const double*)h->uni_res.p : nullptr, seed,
+                   (float*)h->audio_res.p, (int*)h->idx_res.p, nullptr, nullptr);
+  if (rc) return rc;
+  h->out_B = B; h->out_T = T;
+  return VQWN_OK;
+}
+
+int vqwn_generate_resident(vqwn_handle* h, int B, int F, int64_t T, int mode, uint64_t seed) {
+  ENTER(h);
+  int rc = generate_common(h, B, F, T, mode, h->uni_T > 0 && mode == VQWN_MODE_SAMPLE, seed);
+  if (rc) return rc;
+  return finish_timing(h);
+}
+
+int vqwn_download_output(vqwn_handle* h, int B, int64_t T, float* audio_out, int32_t* idx_out) {
+  ENTER(h);
+  if (h->out_B != B || h->out_T != T) return fail(h, VQWN_ERR_STATE, "no resident output of that shape");
+  if (audio_out) CK(h, cudaMemcpyAsync(audio_out, h->audio_res.p, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (idx_out) CK(h, cudaMemcpyAsync(idx_out, h->idx_res.p, (size_t)B * T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return VQWN_OK;
+}
+
+int vqwn_generate(vqwn_handle* h, const float* cond, int B, int F, int64_t T, int mode, const double* uniforms,
+                  uint64_t seed, float* audio_out, int32_t* idx_out) {
+  ENTER(h);
+  if (!cond || !audio_out) return fail(h, VQWN_ERR_INVALID, "null argument");
+  if (mode != VQWN_MODE_GREEDY && mode != VQWN_MODE_SAMPLE)
+    return fail(h, VQWN_ERR_NOTIMPL, "decode mode not implemented");
+  if (B < 1 || F < 1 || T < 1) return fail(h, VQWN_ERR_INVALID, "bad argument");
+  int rc;
+  const size_t cbytes = (size_t)B * F * h->C * sizeof(float);
+  if ((rc = ensure(h, h->cond_res, cbytes))) return rc;
+  CK(h, cudaMemcpyAsync(h->cond_res.p, cond, cbytes, cudaMemcpyHostToDevice, h->stream));
+  h->cond_B = B; h->cond_F = F;
+  bool have_u = false;
+  if (mode == VQWN_MODE_SAMPLE && uniforms) {
+    const size_t ubytes = (size_t)T * B * sizeof(double);
+    if ((rc = ensure(h, h->uni_res, ubytes))) return rc;
+    CK(h, cudaMemcpyAsync(h->uni_res.p, uniforms, ubytes, cudaMemcpyHostToDevice, h->stream));
+    h->uni_T = T; h->uni_B = B;
+    have_u = true;
+  }
+  if ((rc = generate_common(h, B, F, T, mode, have_u, seed))) return rc;
+  CK(h, cudaMemcpyAsync(audio_out, h->audio_res.p, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (idx_out) CK(h, cudaMemcpyAsync(idx_out, h->idx_res.p, (size_t)B * T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return finish_timing(h);
+}
+
+int vqwn_teacher_forced(vqwn_handle* h, const float* x, const float* cond, int B, int F, int64_t T, float* logits_out) {
+  ENTER(h);
+  if (!x || !cond || !logits_out) return fail(h, VQWN_ERR_INVALID, "null argument");
+  if (B < 1 || B > h->max_batch) return fail(h, VQWN_ERR_INVALID, "batch out of range (1..max_batch)");
+  if (F < 1 || T < 1 || T % F != 0) return fail(h, VQWN_ERR_INVALID, "T must be a positive multiple of F");
+  int rc;
+  if ((rc = pack_weights(h))) return rc;
+  const size_t cbytes = (size_t)B * F * h->C * sizeof(float);
+  const size_t lbytes = (size_t)B * T * h->Q * sizeof(float);
+  if ((rc = ensure(h, h->cond_res, cbytes))) return rc;
+  if ((rc = ensure(h, h->x_res, (size_t)B * T * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->logits_res, lbytes))) return rc;
+  CK(h, cudaMemcpyAsync(h->cond_res.p, cond, cbytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->x_res.p, x, (size_t)B * T * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  h->cond_B = B; h->cond_F = F;
+  if ((rc = do_reset(h, B))) return rc;
+  rc = launch_fp32(h, GEN_TEACHER, T, (const float*)h->cond_res.p, (long long)F * h->C, (int)(T / F),
+                   (const float*)h->x_res.p, nullptr, 0, nullptr, nullptr, (float*)h->logits_res.p, nullptr);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(logits_out, h->logits_res.p, lbytes, cudaMemcpyDeviceToHost, h->stream));
+  return finish_timing(h);
+}
+
+double vqwn_last_kernel_ms(const vqwn_handle* h) { return h ? h->last_ms : 0.0; }
+int64_t vqwn_launch_count(const vqwn_handle* h) { return h ? h->launches : 0; }
+const char* vqwn_last_kernel_name(const vqwn_handle* h) { return h ? h->last_kernel : ""; }
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+"""Seeded synthetic weights and inputs for benchmarks / smoke runs: there is no
+network for checkpoints or datasets.  Weights are keyed by the reference's variable names."""
+import numpy as np
+
+
+def tensor_specs(config):
+    """(tf_variable_name, shape) in the order the reference's graph creates them."""
+    w, m = config.wavenet, config.model
+    R, G, S, q = w["residual_filters"], w["dilation_filters"], w["skip_filters"], w["quantization_channels"]
+    C = config.cond_channels
+    pk, pf = w["preprocess"]["kernel_size"], w["preprocess"]["filters"]
+    specs = [("embedding/embedding", (m["k"], m["latent_dim"])),
+             ("speaker_embedding", (config.num_speakers, m["speaker_embedding"])),
+             ("decoder/preprocess/kernel", (pk, 1, pf)), ("decoder/preprocess/bias", (pf,)),
+             ("decoder/skip/kernel", (1, pf, S)), ("decoder/skip/bias", (S,))]
+    for i in range(len(w["dilation_rates"])):
+        s = config.layer_scope(i)
+        specs += [(s + "/gated/kernel", (w["kernel_size"], R, 2 * G)), (s + "/gated/bias", (2 * G,)),
+                  (s + "/gated/local_condition/kernel", (1, C, 2 * G)),
+                  (s + "/skip/kernel", (1, G, S)), (s + "/skip/bias", (S,)),
+                  (s + "/residual/kernel", (1, G, R)), (s + "/residual/bias", (R,))]
+    specs += [("decoder/postprocess1/kernel", (1, S, S)), ("decoder/postprocess1/bias", (S,)),
+              ("decoder/postprocess1/local_condition/kernel", (1, C, S)),
+              ("decoder/postprocess2/kernel", (1, S, q)), ("decoder/postprocess2/bias", (q,))]
+    return specs
+
+
+def make_weights(config, seed=1234, peaked=False):
+    """kernels U(+-sqrt(3/fan_in)) (uniform_unit_scaling, wavenet_ops.py:69), biases U(+-0.05),
+    codebook factor 1.7 (model.py:49), speaker table factor 2 (model.py:26); peaked: postprocess2 x8."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in tensor_specs(config):
+        if name.endswith("bias"):
+            a = rng.uniform(-0.05, 0.05, size=shape)
+        else:
+            lim = np.sqrt(3.0 / int(np.prod(shape[:-1])))
+            lim *= {"embedding/embedding": 1.7, "speaker_embedding": 2.0}.get(name, 1.0)
+            a = rng.uniform(-lim, lim, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=np.float32)
+    if peaked:
+        out["decoder/postprocess2/kernel"] = (out["decoder/postprocess2/kernel"] * np.float32(8)).astype(np.float32)
+    return out
+
+
+def synthetic_z_e(config, B, F, seed=1235, scale=0.13):
+    """encoder-output stand-in: N(0,1) scaled to the codebook's magnitude"""
+    rng = np.random.default_rng(seed)
+    return (np.float32(scale) * rng.standard_normal((B, F, config.model["latent_dim"]))).astype(np.float32)
