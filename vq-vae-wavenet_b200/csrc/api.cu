@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <string>
 #include <unordered_map>
@@ -52,6 +53,7 @@ struct vqwn_handle {
   int L = 0, R = 0, G = 0, S = 0, Q = 0, C = 0, PK = 0, K = 0, D = 0, SPK = 0;
   int lda = 0;
   size_t smem_fp32 = 0;
+  int wfloats = 0;
   // packed fp32 weights
   bool packed = false;
   std::vector<float*> w1, b1, w2, b2;
@@ -64,6 +66,8 @@ struct vqwn_handle {
   float* ring_base = nullptr;
   size_t ring_floats = 0;
   unsigned long long* barrier = nullptr;
+  long long* prof = nullptr;
+  bool profile = false;
   int B = 0;            // streams of the current run (vqwn_reset)
   long long t = 0;      // steps since reset
   // resident / staging buffers
@@ -206,6 +210,7 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
   p.B = h->B;
   p.Bp = (h->B + FP32_TB - 1) / FP32_TB * FP32_TB;
   p.lda = h->lda;
+  p.wfloats = h->wfloats;
   p.pre_k = TP(h, "decoder/preprocess/kernel"); p.pre_b = TP(h, "decoder/preprocess/bias");
   p.skip0_w = TP(h, "decoder/skip/kernel"); p.skip0_b = TP(h, "decoder/skip/bias");
   p.post1_w = h->post1_w; p.post1_b = TP(h, "decoder/postprocess1/bias");
@@ -225,7 +230,8 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
   p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed;
   p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
   p.barrier = h->barrier;
-  CK(h, cudaMemsetAsync(h->barrier, 0, sizeof(unsigned long long), h->stream));
+  p.prof = h->profile ? h->prof : nullptr;
+  CK(h, cudaMemsetAsync(h->barrier, 0, 32 * sizeof(unsigned long long), h->stream));
   void* args[] = {&p};
   CK(h, cudaEventRecord(h->ev0, h->stream));
   CK(h, cudaLaunchCooperativeKernel((const void*)wavenet_fp32_persistent, dim3(h->num_sms), dim3(FP32_THREADS),
@@ -242,6 +248,12 @@ int finish_timing(vqwn_handle* h) {
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
+  if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
+    long long pf[8];
+    if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "[vqwn profile] CTA0 cycles: barrier=%lld act_wait=%lld compute=%lld epilogue=%lld draw=%lld issue=%lld (kernel %.3f ms)\n",
+              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], ms);
+  }
   return VQWN_OK;
 }
 
@@ -299,8 +311,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   if (c.pre_filters != c.residual_filters) return fail(nullptr, VQWN_ERR_INVALID, "preprocess.filters must equal residual_filters");
   if (c.dilation_filters != c.residual_filters) return fail(nullptr, VQWN_ERR_INVALID, "dilation_filters must equal residual_filters");
   const int Ccond = c.latent_dim + c.speaker_dim;
-  if (c.residual_filters % 32 || c.skip_filters % 32 || Ccond % 32 || c.dilation_filters % 32)
-    return fail(nullptr, VQWN_ERR_INVALID, "channel counts must be multiples of 32");
+  if (c.residual_filters % 128 || c.skip_filters % 128 || Ccond % 128 || c.dilation_filters % 128)
+    return fail(nullptr, VQWN_ERR_INVALID, "channel counts (residual, skip, gate, latent+speaker) must be multiples of 128");
   if (c.pre_kernel_size < 1 || c.pre_kernel_size > 64) return fail(nullptr, VQWN_ERR_INVALID, "preprocess.kernel_size out of range");
   if (c.use_vq && (c.k < 1 || c.k > 512)) return fail(nullptr, VQWN_ERR_NOTIMPL, "k must be <= 512");
   if (c.latent_dim != 32 && c.latent_dim != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
@@ -409,12 +421,19 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   CKC(cudaMalloc(&h->skip, Bp * S * sizeof(float)));
   CKC(cudaMalloc(&h->n1, Bp * S * sizeof(float)));
   CKC(cudaMalloc(&h->logits, Bp * Q * sizeof(float)));
-  CKC(cudaMalloc(&h->barrier, sizeof(unsigned long long)));
+  CKC(cudaMalloc(&h->barrier, 32 * sizeof(unsigned long long)));
+  CKC(cudaMalloc(&h->prof, 8 * sizeof(long long)));
+  CKC(cudaMemset(h->prof, 0, 8 * sizeof(long long)));
+  h->profile = getenv("VQWN_PROFILE") != nullptr;
 
   int kmax = 3 * R + C;
   if (S + C > kmax) kmax = S + C;
   h->lda = kmax + 4;
-  h->smem_fp32 = ((size_t)FP32_TB * h->lda + FP32_WARPS * 256 + (size_t)FP32_TB * h->PK + (size_t)FP32_WARPS * Q) * sizeof(float);
+  h->wfloats = (3 * R + C) * 16;
+  if ((S + C) * 16 > h->wfloats) h->wfloats = (S + C) * 16;
+  if (G * 32 > h->wfloats) h->wfloats = G * 32;
+  h->smem_fp32 = ((size_t)2 * h->wfloats + (size_t)FP32_TB * h->lda + FP32_RED_FLOATS + (size_t)FP32_TB * h->PK +
+                  (size_t)FP32_WARPS * Q) * sizeof(float);
   if (h->smem_fp32 > (size_t)prop.sharedMemPerBlockOptin) {
     vqwn_destroy(h);
     return fail(nullptr, VQWN_ERR_INVALID, "configuration needs more shared memory than the device offers");
@@ -441,7 +460,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->w2) if (p) cudaFree(p);
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
-                     h->skip, h->n1, h->logits, h->barrier};
+                     h->skip, h->n1, h->logits, h->barrier, h->prof};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx};

@@ -22,19 +22,25 @@ __device__ __forceinline__ void st_cg(float* p, float v) { __stcg(p, v); }
 // bar.sync) without the per-launch bookkeeping.
 // ---------------------------------------------------------------------------------------
 struct GridBarrier {
-  unsigned long long* counter;
-  unsigned long long epoch;   // barriers passed so far by this CTA (uniform across the grid)
+  unsigned long long* counter;   // counter[0]: arrivals (monotonic); counter[16]: released epoch (own 128 B line)
+  unsigned long long epoch;      // barriers passed so far by this CTA (uniform across the grid)
   __device__ __forceinline__ void sync() {
     __syncthreads();
     epoch += 1;
     if (threadIdx.x == 0) {
       const unsigned long long target = epoch * (unsigned long long)gridDim.x;
       __threadfence();
-      atomicAdd(counter, 1ULL);
-      unsigned long long v;
-      do {
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
-      } while (v < target);
+      const unsigned long long prev = atomicAdd(counter, 1ULL);
+      unsigned long long* flag = counter + 16;
+      if (prev + 1 == target) {
+        // last arriver releases everybody; pollers never touch the arrival counter's line
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+      } else {
+        unsigned long long v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        } while (v < epoch);
+      }
     }
     __syncthreads();
   }
