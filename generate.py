@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's generate.py (same flags: -restore -audio -speakers -mode -params),
+running VQ + WaveNet fast generation on the B200 library instead of TensorFlow.
+
+  python generate.py -restore runs/vctk/weights-110640 -audio p225_001.wav -speakers p225 p226 None -mode sample
+
+Outputs, as the reference writes them (generate.py:94-101,115-117):
+  <dir>/embedding_<gs>.npy  <dir>/speaker_embedding_<gs>.npy  <dir>/<gs>_<speaker>.wav (float32, 16 kHz)
+
+Weights: `<restore>.npz` holding arrays keyed by the reference's variable names (EMA shadows stored
+under the variable's own name).  Reading TensorFlow tensor-bundle checkpoints directly is SURVEY 8f #2.
+Encoder output: the encoders are SURVEY 8f #1; until they run on the device pass the encoder output
+with -z_e <file.npy> ([F,latent_dim] or [B,F,latent_dim]); -audio then only fixes the length.
+"""
+import os
+import sys
+from argparse import ArgumentParser
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main(argv=None):
+    import vqvae_wavenet_b200 as pkg
+    from vqvae_wavenet_b200 import utils, wavio
+
+    parser = ArgumentParser()
+    parser.add_argument('-restore', dest='restore_path', help='path to weights')
+    parser.add_argument('-audio', dest='audio_path', help='path to audio')
+    parser.add_argument('-speakers', nargs='+', dest='speakers', help='speaker id')
+    parser.add_argument('-mode', default='sample', dest='mode', help='decode mode, sample or greedy')
+    parser.add_argument('-params', default='model_parameters.json', dest='parameter_path', metavar='str',
+                        help='path to parameters file')
+    parser.add_argument('-z_e', dest='z_e_path', default=None, help='encoder output (.npy)')
+    parser.add_argument('-device', dest='device', type=int, default=0)
+    parser.add_argument('-seed', dest='seed', type=int, default=None, help='seed of the draw stream (sample mode)')
+    args = parser.parse_args(argv)
+
+    gs = int(args.restore_path.split('-')[-1])                     # generate.py:33
+    batch_size = len(args.speakers)
+    save_path = args.restore_path.split('/weights')[0]
+
+    dataset, num_speakers = utils.dataset_for_speakers(args.speakers)   # generate.py:46-57
+    table = utils.get_speaker_to_int(utils.find_speaker_table(dataset, roots=(".", ROOT)))
+    speaker = utils.speaker_onehot(args.speakers, table, num_speakers)  # [B,1,N]
+
+    params_path = args.parameter_path if os.path.exists(args.parameter_path) else os.path.join(ROOT, args.parameter_path)
+    cfg = pkg.EngineConfig.from_files(params_path, num_speakers=num_speakers)
+    if cfg.model['encoder'] not in ('Magenta', '64', '2019'):
+        raise NotImplementedError("encoder %s not implemented" % cfg.model['encoder'])   # generate.py:69 (Q15)
+
+    wav = wavio.prepare_audio(wavio.read_wav(args.audio_path, 16000), batch_size)        # generate.py:36-44
+    length = wav.shape[1]
+    if args.z_e_path is None:
+        raise NotImplementedError("encoder '%s' forward is not on the device yet (SURVEY 8f #1): pass -z_e"
+                                  % cfg.model['encoder'])
+    z_e = np.load(args.z_e_path).astype(np.float32)
+    if z_e.ndim == 2:
+        z_e = np.tile(z_e[None], (batch_size, 1, 1))
+    if length % z_e.shape[1] != 0:
+        raise ValueError("audio length %d is not a multiple of the %d encoder frames" % (length, z_e.shape[1]))
+
+    weights_file = args.restore_path + '.npz'
+    if not os.path.exists(weights_file):
+        raise NotImplementedError("expected %s (arrays keyed by reference variable name); TensorFlow "
+                                  "tensor-bundle checkpoints are SURVEY 8f #2" % weights_file)
+    engine = pkg.Engine(cfg, device=args.device, max_batch=batch_size)
+    with np.load(weights_file) as data:
+        wanted = dict((n, s) for n, s, _ in engine.tensor_table())
+        for name in data.files:
+            key = name[:-len('/ExponentialMovingAverage')] if name.endswith('/ExponentialMovingAverage') else name
+            key = key[len('optimiser/'):] if key.startswith('optimiser/') else key      # EMA shadow scope
+            if key in wanted:
+                engine.set_tensor(key, data[name])
+
+    model = pkg.VQVAE({'x': wav, 'z_e': z_e, 'speaker': speaker, 'encoder': None,
+                       'decoder': pkg.WavenetDecoder(cfg.wavenet), 'k': cfg.model['k'], 'beta': cfg.model['beta'],
+                       'verbose': cfg.model.get('verbose', False), 'use_vq': cfg.model['use_vq'],
+                       'speaker_embedding': cfg.model['speaker_embedding'], 'num_speakers': num_speakers,
+                       'engine': engine})
+    model.build_generator()
+    wavenet = model.decoder.wavenet
+    encoding = model.encoding                                                       # generate.py:92
+
+    if cfg.model['use_vq']:
+        np.save(save_path + '/embedding_%d.npy' % gs, model.embedding)              # generate.py:96-98
+    if cfg.model['speaker_embedding'] > 0:
+        np.save(save_path + '/speaker_embedding_%d.npy' % gs, model.speaker_embedding)
+
+    uniforms = None
+    if args.mode == 'sample' and args.seed is None:
+        uniforms = np.random.rand(length, batch_size)                               # utils.py:22, one draw per step
+    to_write, _ = wavenet.generate(encoding, length, mode=args.mode, uniforms=uniforms,
+                                   seed=0 if args.seed is None else args.seed)      # generate.py:103-113
+    for i, s in enumerate(args.speakers):
+        s = 'no_speaker' if s == 'None' else s
+        wavio.write_wav_float32(save_path + '/%d_%s.wav' % (gs, s), 16000, to_write[i])  # generate.py:115-117
+    engine.close()
+
+
+if __name__ == '__main__':
+    main()

@@ -41,6 +41,11 @@ extern "C" {
 #define VQWN_PREC_FP32 0   /* fp32 CUDA-core contraction; the parity anchor                 */
 #define VQWN_PREC_BF16 1   /* bf16 tcgen05 contraction, fp32 accumulate (tolerance 2e-2)    */
 
+/* VQ kernel selection (vqwn_set_vq_kernel); both give identical indices and z_q */
+#define VQWN_VQ_AUTO   0   /* tensor-core kernel when k = 512 and latent_dim = 64, else direct  */
+#define VQWN_VQ_DIRECT 1   /* float32 CUDA-core direct form                                      */
+#define VQWN_VQ_TENSOR 2   /* tcgen05 tf32 ranking + exact float32 re-evaluation of near-minima  */
+
 /* model_parameters.json + wavenet_parameters.json (generate.py:63-64, wavenet.py:10-21) */
 typedef struct vqwn_config {
   int32_t quantization_channels; /* wavenet_parameters.json "quantization_channels" (256)  */
@@ -75,6 +80,7 @@ const char* vqwn_last_error(const vqwn_handle* h);
  * caller can time them with its own CUDA events.  NULL restores the private stream. */
 int vqwn_set_stream(vqwn_handle* h, void* cuda_stream);
 int vqwn_set_precision(vqwn_handle* h, int precision);
+int vqwn_set_vq_kernel(vqwn_handle* h, int kernel);
 
 /* ---- weights: replaces tf.train.Saver(ema.variables_to_restore()).restore (generate.py:88-90)
  * Tensors are addressed by the reference's variable names, e.g.

@@ -61,11 +61,13 @@ def _check_sequences(got, want, margin, tie, min_prefix):
 
 
 # ----------------------------------------------------------------------------------------- VQ
+@pytest.mark.parametrize("kernel", ["direct", "tensor"])
 @pytest.mark.parametrize("kind", ["normal", "near_code", "scaled"])
-def test_vq_cfg2_bit_exact(kind, golden_dir):
+def test_vq_cfg2_bit_exact(kind, kernel, golden_dir):
     cfg = O.Config()
     w = O.make_weights(cfg, seed=1234)
     eng = _engine(None, 1, w)
+    eng.set_vq_kernel(kernel)
     z = O.synthetic_z_e(cfg, w, 64, 104, seed=1235, kind=kind)
     idx, zq = eng.vq_lookup(z)
     g = np.load(os.path.join(golden_dir, "vq_cfg2.npz"))["idx_" + kind].astype(np.int64)
@@ -83,7 +85,8 @@ def test_vq_cfg2_bit_exact(kind, golden_dir):
     eng.close()
 
 
-def test_vq_ties_ragged_and_empty():
+@pytest.mark.parametrize("kernel", ["direct", "tensor"])
+def test_vq_ties_ragged_and_empty(kernel):
     cfg = O.Config()
     w = O.make_weights(cfg, seed=1234)
     E = w["embedding/embedding"].copy()
@@ -92,6 +95,7 @@ def test_vq_ties_ragged_and_empty():
     w2 = dict(w)
     w2["embedding/embedding"] = E
     eng = _engine(None, 1, w2)
+    eng.set_vq_kernel(kernel)
     # exact duplicates -> lowest index; midpoints between two codes -> lowest index
     z = np.stack([E[17], E[300], E[511], E[0],
                   (E[5] + E[9]) * np.float32(0.5), (E[9] + E[5]) * np.float32(0.5)])
@@ -103,6 +107,42 @@ def test_vq_ties_ragged_and_empty():
     assert list(eng.vq_lookup(z)[0][:4]) == [17, 17, 0, 0]
     idx, zq = eng.vq_lookup(np.zeros((0, 64), dtype=np.float32))
     assert idx.shape == (0,) and zq.shape == (0, 64)
+    eng.close()
+
+
+def test_vq_tensor_equals_direct():
+    """the tcgen05 kernel only ranks: its indices and z_q must equal the float32 direct kernel's
+    bit for bit, on friendly and hostile inputs (ragged tile, zero vectors, huge / tiny norms,
+    duplicated codes, points equidistant from many codes)."""
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234)
+    E = w["embedding/embedding"].copy()
+    E[100:110] = E[7]                       # ten-fold duplicate
+    w2 = dict(w)
+    w2["embedding/embedding"] = E
+    eng = _engine(None, 1, w2)
+    rng = np.random.default_rng(3)
+    n = 128 * 37 + 5
+    parts = [rng.standard_normal((n, 64)), 0.13 * rng.standard_normal((n, 64)),
+             E[rng.integers(0, 512, n)] + 0.02 * rng.standard_normal((n, 64)),
+             100.0 * rng.standard_normal((257, 64)), 1e-6 * rng.standard_normal((257, 64)),
+             np.zeros((3, 64)), E[[7, 100, 109, 511, 0]], np.tile(E.mean(0), (4, 1))]
+    z = np.concatenate(parts).astype(np.float32)
+    eng.set_vq_kernel("direct")
+    i_d, q_d = eng.vq_lookup(z)
+    assert eng.last_kernel_name == "vq_direct_kernel"
+    eng.set_vq_kernel("tensor")
+    i_t, q_t = eng.vq_lookup(z)
+    assert eng.last_kernel_name == "vq_tc_kernel"
+    assert np.array_equal(i_d, i_t)
+    assert np.array_equal(q_d, q_t)
+    spk = np.array([1, 2], dtype=np.int32)
+    zc = z[:2 * 300].reshape(2, 300, 64)
+    eng.set_vq_kernel("direct")
+    a = eng.encode_condition(zc, spk)
+    eng.set_vq_kernel("tensor")
+    b = eng.encode_condition(zc, spk)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     eng.close()
 
 

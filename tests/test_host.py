@@ -1,0 +1,81 @@
+"""Host-side logic (no GPU): config files, speaker tables, WAV I/O, CLI argument surface."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_parameter_files_keep_reference_keys():
+    m = json.load(open(os.path.join(ROOT, "model_parameters.json")))
+    w = json.load(open(os.path.join(ROOT, m["wavenet_parameters"])))
+    assert m["encoder"] == "64" and m["use_vq"] is True and m["k"] == 512 and m["latent_dim"] == 64
+    assert m["speaker_embedding"] == 64 and m["beta"] == 0.25
+    assert w["dilation_rates"] == [2 ** i for i in range(10)] * 3
+    assert (w["kernel_size"], w["dilation_filters"], w["skip_filters"], w["residual_filters"]) == (3, 256, 512, 256)
+    assert w["preprocess"] == {"kernel_size": 32, "filters": 256} and w["quantization_channels"] == 256
+    import vqvae_wavenet_b200 as pkg
+    cfg = pkg.EngineConfig.from_files(os.path.join(ROOT, "model_parameters.json"))
+    assert cfg.receptive_field == 6170 and cfg.cond_channels == 128
+    c = cfg.to_c()
+    assert c.num_layers == 30 and c.dilations[9] == 512 and c.k == 512
+
+
+def test_wavenet_mirror_asserts_like_reference():
+    import vqvae_wavenet_b200 as pkg
+    wn = pkg.Wavenet(os.path.join(ROOT, "wavenet_parameters.json"))
+    assert wn.receptive_field == 6170
+    bad = dict(wn.args, dilation_rates=[1, 2, 4])
+    with pytest.raises(AssertionError):
+        pkg.Wavenet(bad)                                   # wavenet.py:13
+
+
+def test_speaker_tables_and_onehot():
+    from vqvae_wavenet_b200 import utils
+    assert utils.dataset_for_speakers(["p225"]) == ("vctk", 109)
+    assert utils.dataset_for_speakers(["S0002"]) == ("aishell", 340)
+    assert utils.dataset_for_speakers(["1034"]) == ("librispeech", 251)
+    path = utils.find_speaker_table("vctk", roots=(ROOT,))
+    table = utils.get_speaker_to_int(path)
+    assert table["p301"] == 0 and len(table) == 109
+    one = utils.speaker_onehot(["p301", "None", "p295"], table, 109)
+    assert one.shape == (3, 1, 109) and one[0, 0, 0] == 1 and one[1].sum() == 0 and one[2, 0, 1] == 1
+    assert list(np.argmax(one, -1).reshape(-1)) == [0, 0, 1]       # 'None' -> row 0
+    with pytest.raises(NotImplementedError):
+        utils.decode(np.zeros((1, 256), np.float32), mode="beam")
+    with pytest.raises(RuntimeError):
+        utils.decode(np.zeros((1, 256), np.float32), mode="greedy")   # needs an engine: no CPU path
+
+
+def test_wav_roundtrip_and_prepare(tmp_path):
+    from vqvae_wavenet_b200 import wavio, mu_law_ops
+    x = mu_law_ops.decode_lut()[np.random.default_rng(0).integers(0, 256, 2000)]
+    p = str(tmp_path / "a.wav")
+    wavio.write_wav_float32(p, 16000, x)
+    from scipy.io import wavfile
+    sr, y = wavfile.read(p)                                  # the reader the reference's users have
+    assert sr == 16000 and y.dtype == np.float32 and np.array_equal(y, x)
+    assert np.array_equal(wavio.read_wav(p), x)
+    wavfile.write(str(tmp_path / "b.wav"), 8000, (x[:800] * 32767).astype(np.int16))
+    z = wavio.read_wav(str(tmp_path / "b.wav"))
+    assert z.shape[0] == 1600 and abs(float(z[0]) - float(x[0])) < 1e-3
+    w = wavio.prepare_audio(x, 3)
+    assert w.shape == (3, 1536, 1) and np.array_equal(w[2, :, 0], x[:1536])
+
+
+def test_cli_surface(tmp_path, monkeypatch):
+    """flags and error paths of the reference CLI that do not need a device"""
+    import generate
+    from vqvae_wavenet_b200 import wavio
+    wav = str(tmp_path / "in.wav")
+    wavio.write_wav_float32(wav, 16000, np.zeros(1024, np.float32))
+    restore = str(tmp_path / "weights-42")
+    with pytest.raises(NotImplementedError, match="-z_e"):
+        generate.main(["-restore", restore, "-audio", wav, "-speakers", "p225", "None", "-mode", "greedy"])
+    np.save(str(tmp_path / "z.npy"), np.zeros((16, 64), np.float32))
+    with pytest.raises(NotImplementedError, match="npz"):
+        generate.main(["-restore", restore, "-audio", wav, "-speakers", "p225", "-z_e", str(tmp_path / "z.npy")])
+    with pytest.raises(ValueError):
+        generate.main(["-restore", str(tmp_path / "weights-x"), "-audio", wav, "-speakers", "p225"])   # gs = int(...)

@@ -14,6 +14,7 @@
 #include "../../include/vqwn.h"
 #include "common.cuh"
 #include "vq.cuh"
+#include "vq_tc.cuh"
 #include "wavenet_fp32.cuh"
 #include "sample.cuh"
 
@@ -45,6 +46,10 @@ struct vqwn_handle {
   int max_batch = 0, Bp_max = 0;
   int num_sms = 0;
   int precision = VQWN_PREC_FP32;
+  int vq_kernel = VQWN_VQ_AUTO;
+  float* emax_dev = nullptr;
+  int* vq_err = nullptr;
+  bool emax_valid = false;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<TensorSlot> tensors;
@@ -260,23 +265,51 @@ int finish_timing(vqwn_handle* h) {
 int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float* out, int out_stride,
               const int* spk_idx, int spk_dim, int F) {
   const int K = h->K;
-  int threads = (K + 31) / 32 * 32;
-  const long long nblocks = (n + 3) / 4;
-  int grid = (int)((nblocks < (long long)h->num_sms * 1) ? nblocks : (long long)h->num_sms);
-  if (grid < 1) grid = 1;
-  CK(h, cudaEventRecord(h->ev0, h->stream));
   const float* E = TP(h, "embedding/embedding");
   const float* spk = spk_dim > 0 ? TP(h, "speaker_embedding") : nullptr;
-  if (h->D == 64)
-    vq_direct_kernel<64, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F);
-  else if (h->D == 32)
-    vq_direct_kernel<32, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F);
-  else
-    return fail(h, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
+  const bool tensor_ok = (K == VT_K && h->D == VT_D);
+  if (h->vq_kernel == VQWN_VQ_TENSOR && !tensor_ok)
+    return fail(h, VQWN_ERR_NOTIMPL, "tensor-core VQ kernel needs k = 512 and latent_dim = 64");
+  const bool use_tensor = tensor_ok && h->vq_kernel != VQWN_VQ_DIRECT;
+  if (use_tensor && !h->emax_valid) {
+    vq_emax_kernel<<<1, (K + 31) / 32 * 32, 0, h->stream>>>(E, K, h->D, h->emax_dev);
+    CK(h, cudaGetLastError());
+    h->launches += 1;
+    h->emax_valid = true;
+  }
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  if (use_tensor) {
+    const long long ntiles = (n + VT_TILE - 1) / VT_TILE;
+    int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
+    if (grid < 1) grid = 1;
+    CK(h, cudaMemsetAsync(h->vq_err, 0, sizeof(int), h->stream));
+    vq_tc_kernel<<<grid, VT_THREADS, VT_SMEM, h->stream>>>(z, E, n, idx, out, out_stride, spk, spk_idx, spk_dim, F,
+                                                           h->emax_dev, h->vq_err);
+    h->last_kernel = "vq_tc_kernel";
+  } else {
+    int threads = (K + 31) / 32 * 32;
+    const long long nblocks = (n + 3) / 4;
+    int grid = (int)((nblocks < (long long)h->num_sms * 1) ? nblocks : (long long)h->num_sms);
+    if (grid < 1) grid = 1;
+    if (h->D == 64)
+      vq_direct_kernel<64, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F);
+    else if (h->D == 32)
+      vq_direct_kernel<32, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F);
+    else
+      return fail(h, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
+    h->last_kernel = "vq_direct_kernel";
+  }
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev1, h->stream));
   h->launches += 1;
-  h->last_kernel = "vq_direct_kernel";
+  return VQWN_OK;
+}
+
+int check_vq_error(vqwn_handle* h) {
+  if (strcmp(h->last_kernel, "vq_tc_kernel") != 0) return VQWN_OK;
+  int e = 0;
+  CK(h, cudaMemcpy(&e, h->vq_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) return fail(h, VQWN_ERR_CUDA, "vq_tc_kernel: pipeline wait timed out");
   return VQWN_OK;
 }
 
@@ -407,6 +440,9 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   CKC(cudaMalloc(&h->post1_w, (size_t)(S + C) * S * sizeof(float)));
   CKC(cudaMalloc(&h->layers_dev, sizeof(LayerDev) * h->L));
   CKC(cudaMalloc(&h->enc_lut, (Q + 1) * sizeof(float)));
+  CKC(cudaMalloc(&h->emax_dev, sizeof(float)));
+  CKC(cudaMalloc(&h->vq_err, sizeof(int)));
+  CKC(cudaFuncSetAttribute((const void*)vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
   CKC(cudaMalloc(&h->dec_lut, (Q + 1) * sizeof(float)));
 
   // state
@@ -460,7 +496,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->w2) if (p) cudaFree(p);
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
-                     h->skip, h->n1, h->logits, h->barrier, h->prof};
+                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx};
@@ -485,6 +521,13 @@ int vqwn_set_precision(vqwn_handle* h, int precision) {
   return fail(h, VQWN_ERR_NOTIMPL, "precision not implemented in this build");
 }
 
+int vqwn_set_vq_kernel(vqwn_handle* h, int kernel) {
+  ENTER(h);
+  if (kernel < VQWN_VQ_AUTO || kernel > VQWN_VQ_TENSOR) return fail(h, VQWN_ERR_INVALID, "unknown VQ kernel id");
+  h->vq_kernel = kernel;
+  return VQWN_OK;
+}
+
 int vqwn_set_tensor(vqwn_handle* h, const char* tf_name, const float* host, const int64_t* shape, int ndim) {
   ENTER(h);
   if (!tf_name || !host || !shape) return fail(h, VQWN_ERR_INVALID, "null argument");
@@ -503,6 +546,7 @@ int vqwn_set_tensor(vqwn_handle* h, const char* tf_name, const float* host, cons
   CK(h, cudaStreamSynchronize(h->stream));
   s.set = true;
   h->packed = false;
+  if (it->first == "embedding/embedding") h->emax_valid = false;
   return VQWN_OK;
 }
 
@@ -554,7 +598,8 @@ int vqwn_vq_resident(vqwn_handle* h, int64_t n) {
   if (n == 0) { h->last_ms = 0; return VQWN_OK; }
   rc = launch_vq(h, (const float*)h->vq_z.p, n, (long long*)h->vq_idx.p, (float*)h->vq_out.p, h->D, nullptr, 0, 1);
   if (rc) return rc;
-  return finish_timing(h);
+  if ((rc = finish_timing(h))) return rc;
+  return check_vq_error(h);
 }
 
 int vqwn_vq_download(vqwn_handle* h, int64_t n, int64_t* idx_out, float* zq_out) {
@@ -635,7 +680,8 @@ int vqwn_encode_condition(vqwn_handle* h, const float* z_e, const int32_t* speak
   h->cond_B = B; h->cond_F = F;
   if (idx_out) CK(h, cudaMemcpyAsync(idx_out, h->vq_idx.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemcpyAsync(cond_out, h->cond_res.p, (size_t)n * h->C * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  return finish_timing(h);
+  if ((rc = finish_timing(h))) return rc;
+  return check_vq_error(h);
 }
 
 // ---------------------------------------------------------------------------------- WaveNet

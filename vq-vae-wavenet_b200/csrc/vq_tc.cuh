@@ -1,0 +1,381 @@
+// VQ nearest-codebook lookup on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// Reference: model.py:57-74 (direct-form distance, lowest-index argmin, gather, straight-through).
+//
+// Results are IDENTICAL to vq_direct_kernel (csrc/vq.cuh): the tensor cores only rank the codes.
+//   D'[v,k] = z_v . e_k - 0.5*||e_k||^2 + c_v        (kind::tf32, fp32 accumulate in TMEM)
+// is maximal where ||z_v - e_k||^2 is minimal.  The -0.5*||e||^2 term (split hi/lo) and the
+// per-vector offset c_v (makes D' > 0 so float bits order as integers) ride in 8 extra K columns.
+// Every code whose D' lies within `thr` of the running maximum is recorded; thr is twice a
+// rigorous bound on |D' - exact| (tf32 operand truncation 2^-10 each, fp32 accumulation, the
+// direct form's own rounding), so the exact winner is always recorded.  A vector with a single
+// candidate is decided; otherwise the candidates are re-evaluated with the SAME float32
+// instruction sequence as vq_direct_kernel (sequential __fsub_rn/__fmaf_rn over d, lowest index
+// on ties), reading the untouched fp32 rows that already sit in shared memory as MMA operands.
+//
+// One persistent CTA per SM, 192 threads:
+//   warps 0-3  epilogue: thread = vector = TMEM lane; single TMEM read per accumulator half
+//   warp  4    MMA issue (one elected lane), TMEM allocation
+//   warp  5    loader: cp.async z tiles (fp32, K-major core-matrix layout), ||z||, K-augmentation
+// Shared memory: codebook [512 x 72] fp32 as the B operand (144 KB, loaded once), 2 stages of
+// z tile [128 x 72] fp32 as the A operand (36 KB each), candidate lists (6 KB).
+// TMEM: 512 columns = two 256-column accumulator halves (codes 0-255 / 256-511), double-buffered
+// against the MMA of the next tile.
+// Algorithmic bytes per vector: 256 in + 256 (z_q) or 512 (condition row) out + 8 index.
+#pragma once
+#include "common.cuh"
+
+namespace vqwn {
+
+constexpr int VT_THREADS = 192;
+constexpr int VT_TILE = 128;             // vectors per tile (MMA M)
+constexpr int VT_K = 512;                // codes
+constexpr int VT_D = 64;
+constexpr int VT_KA = 72;                // augmented K (64 + 8)
+constexpr int VT_LBO = 128;              // bytes between K chunks (4 floats) of a core matrix row group
+constexpr int VT_SBO = (VT_KA / 4) * 128;   // bytes between 8-row groups = 2304
+constexpr int VT_SE_BYTES = (VT_K / 8) * VT_SBO;       // 147456
+constexpr int VT_SZ_BYTES = (VT_TILE / 8) * VT_SBO;    // 36864
+constexpr int VT_LIST = 8;
+constexpr size_t VT_SMEM = VT_SE_BYTES + 2 * VT_SZ_BYTES + VT_LIST * VT_TILE * (2 + 4) + 2 * VT_TILE * 4 + 256;
+
+__device__ __forceinline__ uint32_t vt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of element (row, k) in a K-major no-swizzle 32-bit operand tile
+__device__ __forceinline__ uint32_t vt_off(int row, int k) {
+  return (uint32_t)((row >> 3) * VT_SBO + (k >> 2) * VT_LBO + (row & 7) * 16 + (k & 3) * 4);
+}
+
+__device__ __forceinline__ uint64_t vt_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(VT_LBO >> 4) << 16;
+  d |= (uint64_t)(VT_SBO >> 4) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+
+__device__ __forceinline__ void vt_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vt_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void vt_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(vt_smem_u32(bar)) : "memory");
+}
+// bounded spin: a broken pipeline must surface as an error, not as a hung GPU
+__device__ __forceinline__ bool vt_mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+  const uint32_t addr = vt_smem_u32(bar);
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  atomicExch(err, 1);
+  return false;
+}
+
+__device__ __forceinline__ void vt_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(VT_THREADS, 1)
+vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long N,
+             long long* __restrict__ idx_out, float* __restrict__ zq_out, int out_stride,
+             const float* __restrict__ spk_table, const int* __restrict__ spk_idx, int spk_dim, int F,
+             const float* __restrict__ emax_p, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t vt_smem_raw[];
+  uint8_t* smem = vt_smem_raw;
+  uint8_t* sE = smem;
+  uint8_t* sZ0 = smem + VT_SE_BYTES;
+  uint16_t* list_k = reinterpret_cast<uint16_t*>(sZ0 + 2 * VT_SZ_BYTES);          // [slot][thread]
+  uint32_t* list_v = reinterpret_cast<uint32_t*>(list_k + VT_LIST * VT_TILE);     // [slot][thread]
+  float* zn = reinterpret_cast<float*>(list_v + VT_LIST * VT_TILE);               // [2][128] ||z||
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zn + 2 * VT_TILE);
+  uint64_t* z_full = bars;        // [2] loader -> MMA, epilogue
+  uint64_t* z_empty = bars + 2;   // [2] epilogue + MMA -> loader
+  uint64_t* acc_full = bars + 4;  // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 6; // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float emax = __ldg(emax_p) * 1.000001f;
+  const long long ntiles = (N + VT_TILE - 1) / VT_TILE;
+
+  // ---- one-time setup: codebook -> shared memory (fp32 bits untouched) + K augmentation
+  for (int i = tid; i < VT_K * (VT_D / 4); i += VT_THREADS) {
+    const int k = i / (VT_D / 4), c = i - k * (VT_D / 4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(E + (size_t)k * VT_D) + c);
+    *reinterpret_cast<float4*>(sE + vt_off(k, 4 * c)) = v;
+  }
+  for (int k = tid; k < VT_K; k += VT_THREADS) {
+    float ne = 0.f;
+    for (int d = 0; d < VT_D; ++d) { const float e = __ldg(E + (size_t)k * VT_D + d); ne = fmaf(e, e, ne); }
+    const float hi = __uint_as_float(__float_as_uint(ne) & 0xFFFFE000u);   // exactly tf32-representable
+    const float lo = ne - hi;
+    *reinterpret_cast<float4*>(sE + vt_off(k, 64)) = make_float4(hi, lo, 1.0f, 0.f);
+    *reinterpret_cast<float4*>(sE + vt_off(k, 68)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      vt_mbar_init(&z_full[i], 1);
+      vt_mbar_init(&z_empty[i], 5);     // 4 epilogue warps + MMA commit
+      vt_mbar_init(&acc_full[i], 1);
+      vt_mbar_init(&acc_empty[i], 4);   // 4 epilogue warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(vt_smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 5) {
+    // ================================================================= loader
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      uint8_t* sZ = sZ0 + s * VT_SZ_BYTES;
+      if (it >= 2 && !vt_mbar_wait(&z_empty[s], ((it >> 1) - 1) & 1, err)) break;
+      const long long v0 = tile * VT_TILE;
+      // 128 rows x 16 chunks of 16 B; lanes walk the chunks of a row (coalesced 256 B rows)
+      for (int i = lane; i < VT_TILE * 16; i += 32) {
+        const int r = i >> 4, c = i & 15;
+        const bool valid = (v0 + r) < N;
+        const float* src = valid ? (z + (size_t)(v0 + r) * VT_D + 4 * c) : z;
+        const uint32_t dst = vt_smem_u32(sZ + vt_off(r, 4 * c));
+        const int nbytes = valid ? 16 : 0;    // zero-fill rows past the end
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+      }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      // ||z|| and the augmented K columns: [-0.5, -0.5, c_v, 0 | 0, 0, 0, 0]
+      for (int r = lane; r < VT_TILE; r += 32) {
+        float nz = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(sZ + vt_off(r, 4 * c));
+          nz = fmaf(v.x, v.x, nz); nz = fmaf(v.y, v.y, nz); nz = fmaf(v.z, v.z, nz); nz = fmaf(v.w, v.w, nz);
+        }
+        const float nrm = sqrtf(nz);
+        const float cv = 1.02f * (nrm * emax + 0.5f * emax * emax) + 1e-30f;
+        *reinterpret_cast<float4*>(sZ + vt_off(r, 64)) = make_float4(-0.5f, -0.5f, cv, 0.f);
+        *reinterpret_cast<float4*>(sZ + vt_off(r, 68)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        zn[s * VT_TILE + r] = nrm;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) vt_mbar_arrive(&z_full[s]);
+    }
+  } else if (warp == 4) {
+    // ================================================================= MMA issue
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      if (!vt_mbar_wait(&z_full[s], (it >> 1) & 1, err)) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_base = vt_smem_u32(sZ0 + s * VT_SZ_BYTES);
+      bool ok = true;
+      for (int h = 0; h < 2 && ok; ++h) {
+        if (it >= 1) ok = vt_mbar_wait(&acc_empty[h], (it - 1) & 1, err);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t b_base = vt_smem_u32(sE) + (uint32_t)h * (256 / 8) * VT_SBO;
+        const uint32_t d_addr = tmem + (uint32_t)h * 256;
+#pragma unroll
+        for (int ks = 0; ks < VT_KA / 8; ++ks) {
+          const uint64_t da = vt_desc(a_base + ks * 2 * VT_LBO);
+          const uint64_t db = vt_desc(b_base + ks * 2 * VT_LBO);
+          const uint32_t acc = ks > 0 ? 1u : 0u;
+          asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                       ::"r"(d_addr), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(elected) : "memory");
+        }
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                     "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+                     ::"r"(vt_smem_u32(&acc_full[h])), "r"(elected) : "memory");
+      }
+      if (!ok) break;
+      // the z stage is free for the loader once these MMAs have read it (and the epilogue is done)
+      asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                   "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+                   ::"r"(vt_smem_u32(&z_empty[s])), "r"(elected) : "memory");
+    }
+  } else {
+    // ================================================================= epilogue (thread = vector)
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint8_t* sZ = sZ0 + s * VT_SZ_BYTES;
+      const long long v0 = tile * VT_TILE;
+      if (!vt_mbar_wait(&z_full[s], (it >> 1) & 1, err)) break;   // zn[] and the fp32 rows are in place
+      const float nrm = zn[s * VT_TILE + tid];
+      // thr = 2 x bound on |D' - exact| (see header): tf32 operand truncation, key/accumulation slop,
+      // and the float32 direct form's own rounding
+      const float ze = nrm * emax;
+      const float bound = ze * (1.0f / 512.0f) + (2.f * ze + emax * emax) * (1.0f / 8192.0f) +
+                          (nrm + emax) * (nrm + emax) * (1.0f / 131072.0f);
+      const float thr = 2.0f * bound;
+      uint32_t run = 0;           // running maximum key (D' > 0: float bits order as unsigned ints)
+      uint32_t thr_key = 0;
+      int cnt = 0;
+      bool ok = true;
+      for (int h = 0; h < 2 && ok; ++h) {
+        ok = vt_mbar_wait(&acc_full[h], it & 1, err);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 64) {
+          uint32_t v[64];
+          vt_ld32(lane_base + (uint32_t)(h * 256 + c0), v);
+          vt_ld32(lane_base + (uint32_t)(h * 256 + c0 + 32), v + 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t g[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t m = v[8 * i];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) m = max(m, v[8 * i + j]);
+            g[i] = m;
+          }
+          uint32_t cm = g[0];
+#pragma unroll
+          for (int i = 1; i < 8; ++i) cm = max(cm, g[i]);
+          if (cm > run) {
+            run = cm;
+            const float t = __uint_as_float(run) - thr;
+            thr_key = t > 0.f ? __float_as_uint(t) : 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (g[i] >= thr_key) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (v[8 * i + j] >= thr_key) {
+                  if (cnt < VT_LIST) {
+                    list_k[cnt * VT_TILE + tid] = (uint16_t)(h * 256 + c0 + 8 * i + j);
+                    list_v[cnt * VT_TILE + tid] = v[8 * i + j];
+                  }
+                  ++cnt;
+                }
+              }
+            }
+          }
+        }
+        // this accumulator half may be overwritten by the next tile's MMA
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) vt_mbar_arrive(&acc_empty[h]);
+      }
+      if (!ok) break;
+
+      // ---- decide: single surviving candidate -> done; else exact float32 re-evaluation
+      const bool overflow = cnt > VT_LIST;
+      const int ncand = overflow ? VT_LIST : cnt;
+      int nvalid = 0, best_k = 0;
+      for (int j = 0; j < ncand; ++j)
+        if (list_v[j * VT_TILE + tid] >= thr_key) { ++nvalid; best_k = list_k[j * VT_TILE + tid]; }
+      const bool need = overflow || nvalid != 1;
+      if (__any_sync(0xffffffffu, need)) {
+        float zr[VT_D];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float4 q = *reinterpret_cast<const float4*>(sZ + vt_off(tid, 4 * c));
+          zr[4 * c] = q.x; zr[4 * c + 1] = q.y; zr[4 * c + 2] = q.z; zr[4 * c + 3] = q.w;
+        }
+        float bd = INFINITY;
+        int bk = 0x7fffffff;
+        const int nscan = overflow ? VT_K : ncand;       // overflow: exact scan of the whole codebook
+        const int wscan = __reduce_max_sync(0xffffffffu, need ? nscan : 0);
+        for (int j = 0; j < wscan; ++j) {
+          bool act = need && j < nscan;
+          int k = 0;
+          if (act) {
+            if (overflow) k = j;
+            else { k = list_k[j * VT_TILE + tid]; act = list_v[j * VT_TILE + tid] >= thr_key; }
+          }
+          if (act) {
+            float dist = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float4 e4 = *reinterpret_cast<const float4*>(sE + vt_off(k, 4 * c));
+              float t;
+              t = __fsub_rn(zr[4 * c], e4.x);     dist = __fmaf_rn(t, t, dist);
+              t = __fsub_rn(zr[4 * c + 1], e4.y); dist = __fmaf_rn(t, t, dist);
+              t = __fsub_rn(zr[4 * c + 2], e4.z); dist = __fmaf_rn(t, t, dist);
+              t = __fsub_rn(zr[4 * c + 3], e4.w); dist = __fmaf_rn(t, t, dist);
+            }
+            if (dist < bd || (dist == bd && k < bk)) { bd = dist; bk = k; }
+          }
+        }
+        if (need) best_k = bk;
+      }
+      if (idx_out != nullptr && v0 + tid < N) idx_out[v0 + tid] = (long long)best_k;
+
+      // ---- fused gather + straight-through + speaker concat, one coalesced row per iteration
+      if (zq_out != nullptr) {
+        const int width = VT_D + spk_dim;
+        for (int j = 0; j < 32; ++j) {
+          const int kb = __shfl_sync(0xffffffffu, best_k, j);
+          const int row = warp * 32 + j;
+          const long long gv = v0 + row;
+          if (gv >= N) break;                           // uniform across the warp
+          const float2 zz = *reinterpret_cast<const float2*>(sZ + vt_off(row, 2 * lane));
+          const float2 ee = *reinterpret_cast<const float2*>(sE + vt_off(kb, 2 * lane));
+          float2 o;
+          o.x = __fadd_rn(zz.x, __fsub_rn(ee.x, zz.x));                 // model.py:73
+          o.y = __fadd_rn(zz.y, __fsub_rn(ee.y, zz.y));
+          float* orow = zq_out + (size_t)gv * out_stride;
+          *reinterpret_cast<float2*>(orow + 2 * lane) = o;
+          if (spk_dim > 0) {
+            const float* srow = spk_table + (size_t)spk_idx[(int)(gv / F)] * spk_dim;
+            for (int c = lane; c < spk_dim; c += 32) orow[VT_D + c] = __ldg(srow + c);
+          }
+          (void)width;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) vt_mbar_arrive(&z_empty[s]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// max_k ||e_k|| (one block, K <= 1024 threads); feeds the candidate threshold of vq_tc_kernel
+__global__ void vq_emax_kernel(const float* __restrict__ E, int K, int D, float* __restrict__ out) {
+  __shared__ float red[32];
+  float nrm = 0.f;
+  if ((int)threadIdx.x < K) {
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) { const float e = E[(size_t)threadIdx.x * D + d]; s = fmaf(e, e, s); }
+    nrm = sqrtf(s);
+  }
+  for (int off = 16; off > 0; off >>= 1) nrm = fmaxf(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+}  // namespace vqwn

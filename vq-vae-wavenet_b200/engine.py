@@ -142,6 +142,9 @@ class Engine:
     def set_precision(self, name):
         self._ck(self.lib.vqwn_set_precision(self._h, {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[name]))
 
+    def set_vq_kernel(self, name):
+        self._ck(self.lib.vqwn_set_vq_kernel(self._h, {"auto": _lib.VQ_AUTO, "direct": _lib.VQ_DIRECT, "tensor": _lib.VQ_TENSOR}[name]))
+
     # ------------------------------------------------------------------ weights
     def set_tensor(self, name, array):
         a = _f32(array)
