@@ -101,6 +101,31 @@ def make_workload(B, T, rank):
     return cfg, w, z_e, spk, F
 
 
+def vq_bench(eng, vq_n):
+    """BASELINE config 2: VQ lookups/s at 64 x 104 vectors (launch-sized) and at vq_n (roofline-sized),
+    both kernels; algorithmic bytes per vector = 256 in + 256 out + 8 index (+131 KB codebook once)."""
+    out = {}
+    rng = np.random.default_rng(99)
+    zbig = (0.13 * rng.standard_normal((vq_n, 64))).astype(np.float32)
+    eng.vq_upload(zbig)
+    hbm = load_peaks()["hbm"]
+    for kern in ("tensor", "direct"):
+        eng.set_vq_kernel(kern)
+        for n in (6656, vq_n):
+            for _ in range(3):
+                eng.vq_resident(n)
+            ts = []
+            for _ in range(7):
+                eng.vq_resident(n)
+                ts.append(eng.last_kernel_ms)
+            ms = float(np.median(ts))
+            out["%s_n%d" % (kern, n)] = {"lookups_per_s": n / (ms * 1e-3), "ms": ms, "kernel": eng.last_kernel_name,
+                                         "hbm_gbs": (n * 520 + 131072) / (ms * 1e-3) / 1e9,
+                                         "hbm_frac": (n * 520 + 131072) / (ms * 1e-3) / 1e9 / hbm}
+    eng.set_vq_kernel("auto")
+    return out
+
+
 def cpu_baseline_window(B, steps, warm):
     """the oracle port (FastWavenet: per-step matmuls + FIFO deques + NumPy decode) on host cores"""
     import torch
@@ -163,6 +188,7 @@ def main():
     ap.add_argument("--cpu-window", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--vq-n", type=int, default=1 << 20)
+    ap.add_argument("--vq-only", action="store_true", help="only the VQ lookups/s micro-benchmark (config 2)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,6 +217,11 @@ def main():
     eng.set_precision(args.precision)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
+
+    if args.vq_only:
+        print(json.dumps({"metric": "VQ lookups/sec", "unit": "lookups/s", "vq": vq_bench(eng, args.vq_n)}), flush=True)
+        eng.close()
+        return
 
     # condition tensor = what generate.py:92 evaluates (VQ + gather + speaker concat on the device)
     _, cond = eng.encode_condition(z_e, spk)
@@ -260,21 +291,7 @@ def main():
     same = bool(np.array_equal(i_res, idx_pin.numpy()))
 
     # ---------------------------------------------------------------- VQ lookups/s (secondary metric)
-    vq = {}
-    if rank == 0:
-        rng = np.random.default_rng(99)
-        zbig = (0.13 * rng.standard_normal((args.vq_n, 64))).astype(np.float32)
-        eng.vq_upload(zbig)
-        for n in (6656, args.vq_n):
-            for _ in range(3):
-                eng.vq_resident(n)
-            ts = []
-            for _ in range(5):
-                eng.vq_resident(n)
-                ts.append(eng.last_kernel_ms)
-            ms = float(np.median(ts))
-            vq["n%d" % n] = {"lookups_per_s": n / (ms * 1e-3), "ms": ms,
-                             "hbm_frac": (n * 520 + 131072) / (ms * 1e-3) / 1e9 / load_peaks()["hbm"]}
+    vq = vq_bench(eng, args.vq_n) if rank == 0 else {}
 
     # ---------------------------------------------------------------- roofline + CPU baseline + report
     if rank == 0:

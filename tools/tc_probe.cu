@@ -344,6 +344,75 @@ void run_chain2(int ts) {
   cudaFree(dC);
 }
 
+// ---------------------------------------------------------------- TMEM load latency / throughput
+template <int X>
+__device__ __forceinline__ void ldtm(uint32_t addr, uint32_t* v);
+template <>
+__device__ __forceinline__ void ldtm<32>(uint32_t addr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr));
+}
+template <>
+__device__ __forceinline__ void ldtm<8>(uint32_t addr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr));
+}
+
+template <int X, int DEPTH>
+__global__ void __launch_bounds__(128, 1) probe_ldtm(int iters, int nwarps, long long* cycles, unsigned* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_base_s + ((uint32_t)(warp * 32) << 16);
+  unsigned acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  if (warp < nwarps) {
+    for (int it = 0; it < iters; ++it) {
+      uint32_t v[DEPTH][X];
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) ldtm<X>(tmem + (uint32_t)(((it * DEPTH + d) * X) & 511 & ~(X - 1)), v[d]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+        for (int j = 0; j < X; ++j) acc ^= v[d][j];
+    }
+  }
+  long long t1 = clock64();
+  if (tid == 0) cycles[0] = t1 - t0;
+  sink[tid] = acc;
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base_s));
+}
+
+template <int X, int DEPTH>
+void run_ldtm(int nwarps) {
+  long long* dC; unsigned* dS; CK(cudaMalloc(&dC, 64)); CK(cudaMalloc(&dS, 1024));
+  const int iters = 256;
+  probe_ldtm<X, DEPTH><<<1, 128>>>(iters, nwarps, dC, dS);
+  CK(cudaDeviceSynchronize());
+  long long c; CK(cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost));
+  double per = (double)c / (iters * DEPTH);
+  printf("ldtm 32x32b.x%d depth=%d warps=%d: %.1f cycles per load (%d B/warp) -> %.1f B/clk/SM\n", X, DEPTH, nwarps, per, X * 128,
+         nwarps * X * 128.0 / per);
+  cudaFree(dC); cudaFree(dS);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 template <int N>
@@ -418,6 +487,10 @@ int main(int argc, char** argv) {
     run_chain2<64, 1, 48>(0); run_chain2<64, 4, 48>(0);
     run_chain2<256, 1, 16>(0); run_chain2<256, 2, 16>(0);
     run_chain2<16, 1, 48>(1); run_chain2<16, 8, 48>(1); run_chain2<64, 4, 48>(1);
+  }
+  if (which == 0 || which == 7) {
+    run_ldtm<32, 1>(1); run_ldtm<32, 1>(4); run_ldtm<32, 2>(4); run_ldtm<32, 4>(4);
+    run_ldtm<8, 1>(1); run_ldtm<8, 4>(4); run_ldtm<8, 8>(4);
   }
   if (which == 0 || which == 3) {
     long long* dC; int* dE;

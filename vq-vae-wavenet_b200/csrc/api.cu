@@ -253,6 +253,13 @@ int finish_timing(vqwn_handle* h) {
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
+  if (h->profile && strcmp(h->last_kernel, "vq_tc_kernel") == 0) {
+    long long pf[32];
+    if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "[vqwn profile] vq_tc CTA0 cycles: setup=%lld | loader wait_empty=%lld load=%lld norm=%lld | mma wait_z=%lld wait_acc=%lld issue=%lld | "
+              "epi wait_z=%lld wait_acc=%lld scan=%lld decide=%lld output=%lld wscan_sum=%lld cand_lane0=%lld (kernel %.3f ms)\n",
+              pf[0], pf[1], pf[2], pf[3], pf[9], pf[10], pf[11], pf[17], pf[18], pf[19], pf[20], pf[21], pf[22], pf[23], ms);
+  }
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
     long long pf[8];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -284,7 +291,7 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
     if (grid < 1) grid = 1;
     CK(h, cudaMemsetAsync(h->vq_err, 0, sizeof(int), h->stream));
     vq_tc_kernel<<<grid, VT_THREADS, VT_SMEM, h->stream>>>(z, E, n, idx, out, out_stride, spk, spk_idx, spk_dim, F,
-                                                           h->emax_dev, h->vq_err);
+                                                           h->emax_dev, h->vq_err, h->profile ? h->prof : nullptr);
     h->last_kernel = "vq_tc_kernel";
   } else {
     int threads = (K + 31) / 32 * 32;
@@ -458,8 +465,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   CKC(cudaMalloc(&h->n1, Bp * S * sizeof(float)));
   CKC(cudaMalloc(&h->logits, Bp * Q * sizeof(float)));
   CKC(cudaMalloc(&h->barrier, 32 * sizeof(unsigned long long)));
-  CKC(cudaMalloc(&h->prof, 8 * sizeof(long long)));
-  CKC(cudaMemset(h->prof, 0, 8 * sizeof(long long)));
+  CKC(cudaMalloc(&h->prof, 32 * sizeof(long long)));
+  CKC(cudaMemset(h->prof, 0, 32 * sizeof(long long)));
   h->profile = getenv("VQWN_PROFILE") != nullptr;
 
   int kmax = 3 * R + C;

@@ -31,24 +31,34 @@ constexpr int VT_TILE = 128;             // vectors per tile (MMA M)
 constexpr int VT_K = 512;                // codes
 constexpr int VT_D = 64;
 constexpr int VT_KA = 72;                // augmented K (64 + 8)
-constexpr int VT_LBO = 128;              // bytes between K chunks (4 floats) of a core matrix row group
-constexpr int VT_SBO = (VT_KA / 4) * 128;   // bytes between 8-row groups = 2304
-constexpr int VT_SE_BYTES = (VT_K / 8) * VT_SBO;       // 147456
-constexpr int VT_SZ_BYTES = (VT_TILE / 8) * VT_SBO;    // 36864
+// K-major no-swizzle operand tiles stored as K-chunk PLANES: plane c (4 consecutive k) holds the
+// 8-row x 16-byte core matrices of all row groups back to back (SBO = 128 B); planes are
+// LBO = rows*16 + 16 bytes apart.  The 16-byte pad makes the 18 chunks of one row fall into
+// different banks (a row read is 2-way instead of 16-way conflicted) and a thread-per-row read
+// of one plane is a contiguous 512 B per warp.
+constexpr int VT_SBO = 128;
+constexpr int VT_LBO_E = VT_K * 16 + 16;                // 8208
+constexpr int VT_LBO_Z = VT_TILE * 16 + 16;             // 2064
+constexpr int VT_SE_BYTES = (VT_KA / 4) * VT_LBO_E;     // 147744
+constexpr int VT_SZ_BYTES = (VT_KA / 4) * VT_LBO_Z;     // 37152
 constexpr int VT_LIST = 8;
-constexpr size_t VT_SMEM = VT_SE_BYTES + 2 * VT_SZ_BYTES + VT_LIST * VT_TILE * (2 + 4) + 2 * VT_TILE * 4 + 256;
+constexpr size_t VT_SMEM = VT_SE_BYTES + 2 * VT_SZ_BYTES + (VT_LIST + 1) * VT_TILE * 4 + 2 * VT_TILE * 4 + 256;
 
 __device__ __forceinline__ uint32_t vt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// byte offset of element (row, k) in a K-major no-swizzle 32-bit operand tile
+// byte offset of element (row, k) in an operand tile whose planes are `lbo` bytes apart
+template <int LBO>
 __device__ __forceinline__ uint32_t vt_off(int row, int k) {
-  return (uint32_t)((row >> 3) * VT_SBO + (k >> 2) * VT_LBO + (row & 7) * 16 + (k & 3) * 4);
+  return (uint32_t)((k >> 2) * LBO + row * 16 + (k & 3) * 4);
 }
+#define VT_OFF_E(row, k) vt_off<VT_LBO_E>(row, k)
+#define VT_OFF_Z(row, k) vt_off<VT_LBO_Z>(row, k)
 
+template <int LBO>
 __device__ __forceinline__ uint64_t vt_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(VT_LBO >> 4) << 16;
+  d |= (uint64_t)(LBO >> 4) << 16;
   d |= (uint64_t)(VT_SBO >> 4) << 32;
   d |= 1ull << 46;
   return d;
@@ -85,18 +95,49 @@ __device__ __forceinline__ void vt_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+// scan 32 accumulator values (codes kbase .. kbase+31) held in registers: block max -> running max /
+// threshold, then record every value within thr of the running max (group maxima gate the rare path)
+#define VT_SCAN32(v, kbase)                                                                   \
+  do {                                                                                        \
+    uint32_t g_[4];                                                                           \
+    _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                        \
+      uint32_t m_ = v[8 * i_];                                                                \
+      _Pragma("unroll") for (int j_ = 1; j_ < 8; ++j_) m_ = max(m_, v[8 * i_ + j_]);          \
+      g_[i_] = m_;                                                                            \
+    }                                                                                         \
+    const uint32_t cm_ = max(max(g_[0], g_[1]), max(g_[2], g_[3]));                           \
+    if (cm_ > run) {                                                                          \
+      const float t_ = __uint_as_float(cm_) - thr;                                            \
+      thr_key = t_ > 0.f ? __float_as_uint(t_) : 0u;                                          \
+      if (thr_key > run) cnt = 0;   /* every earlier record is below the new threshold */     \
+      run = cm_;                                                                              \
+    }                                                                                         \
+    _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                        \
+      if (g_[i_] >= thr_key) {                                                                \
+        /* branch-free body: predicated store into slot min(cnt, VT_LIST) */                  \
+        _Pragma("unroll") for (int j_ = 0; j_ < 8; ++j_) {                                    \
+          const bool p_ = v[8 * i_ + j_] >= thr_key;                                          \
+          const int slot_ = min(cnt, VT_LIST);                                                \
+          if (p_) list_p[slot_ * VT_TILE + tid] = (v[8 * i_ + j_] & 0xFFFFFE00u) | (uint32_t)((kbase) + 8 * i_ + j_); \
+          cnt += p_ ? 1 : 0;                                                                  \
+        }                                                                                     \
+      }                                                                                       \
+    }                                                                                         \
+  } while (0)
+
 __global__ void __launch_bounds__(VT_THREADS, 1)
 vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long N,
              long long* __restrict__ idx_out, float* __restrict__ zq_out, int out_stride,
              const float* __restrict__ spk_table, const int* __restrict__ spk_idx, int spk_dim, int F,
-             const float* __restrict__ emax_p, int* __restrict__ err) {
+             const float* __restrict__ emax_p, int* __restrict__ err, long long* __restrict__ prof) {
   extern __shared__ __align__(1024) uint8_t vt_smem_raw[];
   uint8_t* smem = vt_smem_raw;
   uint8_t* sE = smem;
   uint8_t* sZ0 = smem + VT_SE_BYTES;
-  uint16_t* list_k = reinterpret_cast<uint16_t*>(sZ0 + 2 * VT_SZ_BYTES);          // [slot][thread]
-  uint32_t* list_v = reinterpret_cast<uint32_t*>(list_k + VT_LIST * VT_TILE);     // [slot][thread]
-  float* zn = reinterpret_cast<float*>(list_v + VT_LIST * VT_TILE);               // [2][128] ||z||
+  // candidate list [slot][thread]: (D' bits with the low 9 bits replaced by the code index); slot
+  // VT_LIST is a dummy that absorbs writes after an overflow
+  uint32_t* list_p = reinterpret_cast<uint32_t*>(sZ0 + 2 * VT_SZ_BYTES);
+  float* zn = reinterpret_cast<float*>(list_p + (VT_LIST + 1) * VT_TILE);         // [2][128] ||z||
   uint64_t* bars = reinterpret_cast<uint64_t*>(zn + 2 * VT_TILE);
   uint64_t* z_full = bars;        // [2] loader -> MMA, epilogue
   uint64_t* z_empty = bars + 2;   // [2] epilogue + MMA -> loader
@@ -107,20 +148,30 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float emax = __ldg(emax_p) * 1.000001f;
   const long long ntiles = (N + VT_TILE - 1) / VT_TILE;
+  const bool pf = prof != nullptr && blockIdx.x == 0 && lane == 0;
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pt = clock64();
+#define VT_PF(i) do { if (pf) { long long n_ = clock64(); pc[i] += n_ - pt; pt = n_; } } while (0)
 
   // ---- one-time setup: codebook -> shared memory (fp32 bits untouched) + K augmentation
+#pragma unroll 8
   for (int i = tid; i < VT_K * (VT_D / 4); i += VT_THREADS) {
-    const int k = i / (VT_D / 4), c = i - k * (VT_D / 4);
+    const int k = i >> 4, c = i & 15;
     const float4 v = __ldg(reinterpret_cast<const float4*>(E + (size_t)k * VT_D) + c);
-    *reinterpret_cast<float4*>(sE + vt_off(k, 4 * c)) = v;
+    *reinterpret_cast<float4*>(sE + VT_OFF_E(k, 4 * c)) = v;
   }
+  __syncthreads();
   for (int k = tid; k < VT_K; k += VT_THREADS) {
     float ne = 0.f;
-    for (int d = 0; d < VT_D; ++d) { const float e = __ldg(E + (size_t)k * VT_D + d); ne = fmaf(e, e, ne); }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 e = *reinterpret_cast<const float4*>(sE + VT_OFF_E(k, 4 * c));
+      ne = fmaf(e.x, e.x, ne); ne = fmaf(e.y, e.y, ne); ne = fmaf(e.z, e.z, ne); ne = fmaf(e.w, e.w, ne);
+    }
     const float hi = __uint_as_float(__float_as_uint(ne) & 0xFFFFE000u);   // exactly tf32-representable
     const float lo = ne - hi;
-    *reinterpret_cast<float4*>(sE + vt_off(k, 64)) = make_float4(hi, lo, 1.0f, 0.f);
-    *reinterpret_cast<float4*>(sE + vt_off(k, 68)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(sE + VT_OFF_E(k, 64)) = make_float4(hi, lo, 1.0f, 0.f);
+    *reinterpret_cast<float4*>(sE + VT_OFF_E(k, 68)) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -140,6 +191,7 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  VT_PF(0);
 
   if (warp == 5) {
     // ================================================================= loader
@@ -148,36 +200,40 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
       const int s = it & 1;
       uint8_t* sZ = sZ0 + s * VT_SZ_BYTES;
       if (it >= 2 && !vt_mbar_wait(&z_empty[s], ((it >> 1) - 1) & 1, err)) break;
+      VT_PF(1);
       const long long v0 = tile * VT_TILE;
       // 128 rows x 16 chunks of 16 B; lanes walk the chunks of a row (coalesced 256 B rows)
       for (int i = lane; i < VT_TILE * 16; i += 32) {
         const int r = i >> 4, c = i & 15;
         const bool valid = (v0 + r) < N;
         const float* src = valid ? (z + (size_t)(v0 + r) * VT_D + 4 * c) : z;
-        const uint32_t dst = vt_smem_u32(sZ + vt_off(r, 4 * c));
+        const uint32_t dst = vt_smem_u32(sZ + VT_OFF_Z(r, 4 * c));
         const int nbytes = valid ? 16 : 0;    // zero-fill rows past the end
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
       }
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
       __syncwarp();
+      VT_PF(2);
       // ||z|| and the augmented K columns: [-0.5, -0.5, c_v, 0 | 0, 0, 0, 0]
       for (int r = lane; r < VT_TILE; r += 32) {
         float nz = 0.f;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(sZ + vt_off(r, 4 * c));
+          const float4 v = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(r, 4 * c));
           nz = fmaf(v.x, v.x, nz); nz = fmaf(v.y, v.y, nz); nz = fmaf(v.z, v.z, nz); nz = fmaf(v.w, v.w, nz);
         }
         const float nrm = sqrtf(nz);
         const float cv = 1.02f * (nrm * emax + 0.5f * emax * emax) + 1e-30f;
-        *reinterpret_cast<float4*>(sZ + vt_off(r, 64)) = make_float4(-0.5f, -0.5f, cv, 0.f);
-        *reinterpret_cast<float4*>(sZ + vt_off(r, 68)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sZ + VT_OFF_Z(r, 64)) = make_float4(-0.5f, -0.5f, cv, 0.f);
+        *reinterpret_cast<float4*>(sZ + VT_OFF_Z(r, 68)) = make_float4(0.f, 0.f, 0.f, 0.f);
         zn[s * VT_TILE + r] = nrm;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) vt_mbar_arrive(&z_full[s]);
+      VT_PF(3);
     }
+    if (pf) for (int i = 0; i < 4; ++i) prof[i] = pc[i];
   } else if (warp == 4) {
     // ================================================================= MMA issue
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((128u >> 4) << 24);
@@ -187,19 +243,21 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
       if (!vt_mbar_wait(&z_full[s], (it >> 1) & 1, err)) break;
+      VT_PF(1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_base = vt_smem_u32(sZ0 + s * VT_SZ_BYTES);
       bool ok = true;
       for (int h = 0; h < 2 && ok; ++h) {
         if (it >= 1) ok = vt_mbar_wait(&acc_empty[h], (it - 1) & 1, err);
         if (!ok) break;
+        VT_PF(2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b_base = vt_smem_u32(sE) + (uint32_t)h * (256 / 8) * VT_SBO;
+        const uint32_t b_base = vt_smem_u32(sE) + (uint32_t)h * (256 / 8) * VT_SBO;   // codes 256.. start 32 row groups in
         const uint32_t d_addr = tmem + (uint32_t)h * 256;
 #pragma unroll
         for (int ks = 0; ks < VT_KA / 8; ++ks) {
-          const uint64_t da = vt_desc(a_base + ks * 2 * VT_LBO);
-          const uint64_t db = vt_desc(b_base + ks * 2 * VT_LBO);
+          const uint64_t da = vt_desc<VT_LBO_Z>(a_base + ks * 2 * VT_LBO_Z);
+          const uint64_t db = vt_desc<VT_LBO_E>(b_base + ks * 2 * VT_LBO_E);
           const uint32_t acc = ks > 0 ? 1u : 0u;
           asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
                        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
@@ -214,7 +272,9 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
       asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
                    "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
                    ::"r"(vt_smem_u32(&z_empty[s])), "r"(elected) : "memory");
+      VT_PF(3);
     }
+    if (pf) for (int i = 1; i < 4; ++i) prof[8 + i] = pc[i];
   } else {
     // ================================================================= epilogue (thread = vector)
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
@@ -224,6 +284,7 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
       const uint8_t* sZ = sZ0 + s * VT_SZ_BYTES;
       const long long v0 = tile * VT_TILE;
       if (!vt_mbar_wait(&z_full[s], (it >> 1) & 1, err)) break;   // zn[] and the fp32 rows are in place
+      VT_PF(1);
       const float nrm = zn[s * VT_TILE + tid];
       // thr = 2 x bound on |D' - exact| (see header): tf32 operand truncation, key/accumulation slop,
       // and the float32 direct form's own rounding
@@ -238,49 +299,25 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
       for (int h = 0; h < 2 && ok; ++h) {
         ok = vt_mbar_wait(&acc_full[h], it & 1, err);
         if (!ok) break;
+        VT_PF(2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // 8 blocks of 32 columns; the TMEM load of block b+1 is in flight while block b is scanned
+        uint32_t va[32], vb[32];
+        vt_ld32(lane_base + (uint32_t)(h * 256), va);
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 64) {
-          uint32_t v[64];
-          vt_ld32(lane_base + (uint32_t)(h * 256 + c0), v);
-          vt_ld32(lane_base + (uint32_t)(h * 256 + c0 + 32), v + 32);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          uint32_t g[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint32_t m = v[8 * i];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) m = max(m, v[8 * i + j]);
-            g[i] = m;
-          }
-          uint32_t cm = g[0];
-#pragma unroll
-          for (int i = 1; i < 8; ++i) cm = max(cm, g[i]);
-          if (cm > run) {
-            run = cm;
-            const float t = __uint_as_float(run) - thr;
-            thr_key = t > 0.f ? __float_as_uint(t) : 0u;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (g[i] >= thr_key) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (v[8 * i + j] >= thr_key) {
-                  if (cnt < VT_LIST) {
-                    list_k[cnt * VT_TILE + tid] = (uint16_t)(h * 256 + c0 + 8 * i + j);
-                    list_v[cnt * VT_TILE + tid] = v[8 * i + j];
-                  }
-                  ++cnt;
-                }
-              }
-            }
-          }
+          vt_ld32(lane_base + (uint32_t)(h * 256 + c0 + 32), vb);
+          VT_SCAN32(va, h * 256 + c0);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 64 < 256) vt_ld32(lane_base + (uint32_t)(h * 256 + c0 + 64), va);
+          VT_SCAN32(vb, h * 256 + c0 + 32);
         }
         // this accumulator half may be overwritten by the next tile's MMA
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) vt_mbar_arrive(&acc_empty[h]);
+        VT_PF(3);
       }
       if (!ok) break;
 
@@ -288,32 +325,33 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
       const bool overflow = cnt > VT_LIST;
       const int ncand = overflow ? VT_LIST : cnt;
       int nvalid = 0, best_k = 0;
-      for (int j = 0; j < ncand; ++j)
-        if (list_v[j * VT_TILE + tid] >= thr_key) { ++nvalid; best_k = list_k[j * VT_TILE + tid]; }
+      for (int j = 0; j < ncand; ++j) {
+        const uint32_t pk = list_p[j * VT_TILE + tid];
+        if ((pk | 0x1FFu) >= thr_key) {                        // survivors of the final threshold (the 9
+          best_k = (int)(pk & 0x1FFu);                         // dropped value bits are rounded up), compacted
+          list_p[nvalid * VT_TILE + tid] = pk;
+          ++nvalid;
+        }
+      }
       const bool need = overflow || nvalid != 1;
-      if (__any_sync(0xffffffffu, need)) {
+      const int nscan = !need ? 0 : (overflow ? VT_K : nvalid);   // overflow: exact scan of the whole codebook
+      const int wscan = __reduce_max_sync(0xffffffffu, nscan);
+      if (wscan > 0) {
         float zr[VT_D];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float4 q = *reinterpret_cast<const float4*>(sZ + vt_off(tid, 4 * c));
+          const float4 q = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(tid, 4 * c));
           zr[4 * c] = q.x; zr[4 * c + 1] = q.y; zr[4 * c + 2] = q.z; zr[4 * c + 3] = q.w;
         }
         float bd = INFINITY;
         int bk = 0x7fffffff;
-        const int nscan = overflow ? VT_K : ncand;       // overflow: exact scan of the whole codebook
-        const int wscan = __reduce_max_sync(0xffffffffu, need ? nscan : 0);
         for (int j = 0; j < wscan; ++j) {
-          bool act = need && j < nscan;
-          int k = 0;
-          if (act) {
-            if (overflow) k = j;
-            else { k = list_k[j * VT_TILE + tid]; act = list_v[j * VT_TILE + tid] >= thr_key; }
-          }
-          if (act) {
+          if (j < nscan) {
+            const int k = overflow ? j : (int)(list_p[j * VT_TILE + tid] & 0x1FFu);
             float dist = 0.f;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-              const float4 e4 = *reinterpret_cast<const float4*>(sE + vt_off(k, 4 * c));
+              const float4 e4 = *reinterpret_cast<const float4*>(sE + VT_OFF_E(k, 4 * c));
               float t;
               t = __fsub_rn(zr[4 * c], e4.x);     dist = __fmaf_rn(t, t, dist);
               t = __fsub_rn(zr[4 * c + 1], e4.y); dist = __fmaf_rn(t, t, dist);
@@ -326,32 +364,41 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
         if (need) best_k = bk;
       }
       if (idx_out != nullptr && v0 + tid < N) idx_out[v0 + tid] = (long long)best_k;
+      VT_PF(4);
+      if (pf) { pc[6] += wscan; pc[7] += cnt; }
 
-      // ---- fused gather + straight-through + speaker concat, one coalesced row per iteration
+      // ---- fused gather + straight-through + speaker concat: 2 rows per iteration, 16 lanes x 16 B each
       if (zq_out != nullptr) {
-        const int width = VT_D + spk_dim;
-        for (int j = 0; j < 32; ++j) {
-          const int kb = __shfl_sync(0xffffffffu, best_k, j);
-          const int row = warp * 32 + j;
+        const int sub = lane >> 4, ch = lane & 15;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+          const int rl = 2 * j + sub;                        // row within this warp's 32
+          const int kb = __shfl_sync(0xffffffffu, best_k, rl);
+          const int row = warp * 32 + rl;
           const long long gv = v0 + row;
-          if (gv >= N) break;                           // uniform across the warp
-          const float2 zz = *reinterpret_cast<const float2*>(sZ + vt_off(row, 2 * lane));
-          const float2 ee = *reinterpret_cast<const float2*>(sE + vt_off(kb, 2 * lane));
-          float2 o;
-          o.x = __fadd_rn(zz.x, __fsub_rn(ee.x, zz.x));                 // model.py:73
-          o.y = __fadd_rn(zz.y, __fsub_rn(ee.y, zz.y));
-          float* orow = zq_out + (size_t)gv * out_stride;
-          *reinterpret_cast<float2*>(orow + 2 * lane) = o;
-          if (spk_dim > 0) {
-            const float* srow = spk_table + (size_t)spk_idx[(int)(gv / F)] * spk_dim;
-            for (int c = lane; c < spk_dim; c += 32) orow[VT_D + c] = __ldg(srow + c);
+          if (gv < N) {
+            const float4 zz = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(row, 4 * ch));
+            const float4 ee = *reinterpret_cast<const float4*>(sE + VT_OFF_E(kb, 4 * ch));
+            float4 o;
+            o.x = __fadd_rn(zz.x, __fsub_rn(ee.x, zz.x));               // model.py:73
+            o.y = __fadd_rn(zz.y, __fsub_rn(ee.y, zz.y));
+            o.z = __fadd_rn(zz.z, __fsub_rn(ee.z, zz.z));
+            o.w = __fadd_rn(zz.w, __fsub_rn(ee.w, zz.w));
+            float* orow = zq_out + (size_t)gv * out_stride;
+            *reinterpret_cast<float4*>(orow + 4 * ch) = o;
+            if (spk_dim > 0) {
+              const float* srow = spk_table + (size_t)spk_idx[(int)(gv / F)] * spk_dim;
+              for (int c = 4 * ch; c < spk_dim; c += 64)
+                *reinterpret_cast<float4*>(orow + VT_D + c) = __ldg(reinterpret_cast<const float4*>(srow + c));
+            }
           }
-          (void)width;
         }
       }
       __syncwarp();
       if (lane == 0) vt_mbar_arrive(&z_empty[s]);
+      VT_PF(5);
     }
+    if (pf && warp == 0) for (int i = 1; i < 8; ++i) prof[16 + i] = pc[i];
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
