@@ -56,9 +56,13 @@ struct vqwn_handle {
   std::unordered_map<std::string, int> index;
   // derived dims
   int L = 0, R = 0, G = 0, S = 0, Q = 0, C = 0, PK = 0, K = 0, D = 0, SPK = 0;
-  int lda = 0;
+  int actA_floats = 0, actB_floats = 0, wfloatsA = 0, wfloatsB = 0;
   size_t smem_fp32 = 0;
-  int wfloats = 0;
+  float* wtiles = nullptr;          // all tile-major weights, one allocation (L2 persistence window)
+  size_t wtiles_floats = 0;
+  std::vector<size_t> off_w1t, off_w2t;
+  size_t off_skip0t = 0, off_post1t = 0, off_post2t = 0;
+  int* gen_err = nullptr;
   // packed fp32 weights
   bool packed = false;
   std::vector<float*> w1, b1, w2, b2;
@@ -181,6 +185,23 @@ int pack_weights(vqwn_handle* h) {
                         cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->post1_w + (size_t)S * S, TP(h, "decoder/postprocess1/local_condition/kernel"),
                         (size_t)C * S * f, cudaMemcpyDeviceToDevice, h->stream));
+  // tile-major copies for the bulk-copy engine (one contiguous block per stage tile)
+  {
+    auto pack = [&](const float* src, int ldw, int K, int NC, int ntiles, int pairedG, float* dst) {
+      const long long total = (long long)ntiles * K * NC;
+      int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+      pack_tiles_kernel<<<grid, 256, 0, h->stream>>>(src, ldw, K, NC, ntiles, pairedG, dst);
+      h->launches += 1;
+    };
+    pack(TP(h, "decoder/skip/kernel"), S, R, 16, S / 16, 0, h->wtiles + h->off_skip0t);
+    for (int l = 0; l < h->L; ++l) {
+      pack(h->w1[l], 2 * G, 3 * R + C, 16, G / 8, G, h->wtiles + h->off_w1t[l]);
+      pack(h->w2[l], R + S, G, 32, (R + S) / 32, 0, h->wtiles + h->off_w2t[l]);
+    }
+    pack(h->post1_w, S, S + C, 16, S / 16, 0, h->wtiles + h->off_post1t);
+    pack(TP(h, "decoder/postprocess2/kernel"), h->Q, S, 16, h->Q / 16, 0, h->wtiles + h->off_post2t);
+    CK(h, cudaGetLastError());
+  }
   CK(h, cudaMemcpyAsync(h->enc_lut, TP(h, "lut/mu_law_encode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->dec_lut, TP(h, "lut/mu_law_decode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
@@ -214,12 +235,11 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
   p.L = h->L; p.R = h->R; p.G = h->G; p.S = h->S; p.Q = h->Q; p.C = h->C; p.PK = h->PK;
   p.B = h->B;
   p.Bp = (h->B + FP32_TB - 1) / FP32_TB * FP32_TB;
-  p.lda = h->lda;
-  p.wfloats = h->wfloats;
+  p.actA_floats = h->actA_floats; p.actB_floats = h->actB_floats; p.wfloatsA = h->wfloatsA; p.wfloatsB = h->wfloatsB;
   p.pre_k = TP(h, "decoder/preprocess/kernel"); p.pre_b = TP(h, "decoder/preprocess/bias");
-  p.skip0_w = TP(h, "decoder/skip/kernel"); p.skip0_b = TP(h, "decoder/skip/bias");
-  p.post1_w = h->post1_w; p.post1_b = TP(h, "decoder/postprocess1/bias");
-  p.post2_w = TP(h, "decoder/postprocess2/kernel"); p.post2_b = TP(h, "decoder/postprocess2/bias");
+  p.skip0t = h->wtiles + h->off_skip0t; p.skip0_b = TP(h, "decoder/skip/bias");
+  p.post1t = h->wtiles + h->off_post1t; p.post1_b = TP(h, "decoder/postprocess1/bias");
+  p.post2t = h->wtiles + h->off_post2t; p.post2_b = TP(h, "decoder/postprocess2/bias");
   // per-layer ring bases for this padded batch
   size_t off = 0;
   for (int l = 0; l < h->L; ++l) {
@@ -236,6 +256,8 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
   p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
   p.barrier = h->barrier;
   p.prof = h->profile ? h->prof : nullptr;
+  p.err = h->gen_err;
+  CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
   CK(h, cudaMemsetAsync(h->barrier, 0, 32 * sizeof(unsigned long long), h->stream));
   void* args[] = {&p};
   CK(h, cudaEventRecord(h->ev0, h->stream));
@@ -253,6 +275,11 @@ int finish_timing(vqwn_handle* h) {
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
+  if (strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
+    int e = 0;
+    CK(h, cudaMemcpy(&e, h->gen_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) return fail(h, VQWN_ERR_CUDA, e == 2 ? "wavenet_fp32_persistent: operand wait timed out" : "wavenet_fp32_persistent: grid barrier timed out");
+  }
   if (h->profile && strcmp(h->last_kernel, "vq_tc_kernel") == 0) {
     long long pf[32];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -263,8 +290,8 @@ int finish_timing(vqwn_handle* h) {
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
     long long pf[8];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
-      fprintf(stderr, "[vqwn profile] CTA0 cycles: barrier=%lld act_wait=%lld compute=%lld epilogue=%lld draw=%lld issue=%lld (kernel %.3f ms)\n",
-              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], ms);
+      fprintf(stderr, "[vqwn profile] CTA0 cycles: barrier=%lld act_wait=%lld compute=%lld epilogue=%lld draw=%lld issue=%lld arrive=%lld (kernel %.3f ms)\n",
+              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], ms);
   }
   return VQWN_OK;
 }
@@ -353,6 +380,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   const int Ccond = c.latent_dim + c.speaker_dim;
   if (c.residual_filters % 128 || c.skip_filters % 128 || Ccond % 128 || c.dilation_filters % 128)
     return fail(nullptr, VQWN_ERR_INVALID, "channel counts (residual, skip, gate, latent+speaker) must be multiples of 128");
+  if ((c.residual_filters & (c.residual_filters - 1)) || (c.skip_filters & (c.skip_filters - 1)))
+    return fail(nullptr, VQWN_ERR_NOTIMPL, "residual_filters and skip_filters must be powers of two");
   if (c.pre_kernel_size < 1 || c.pre_kernel_size > 64) return fail(nullptr, VQWN_ERR_INVALID, "preprocess.kernel_size out of range");
   if (c.use_vq && (c.k < 1 || c.k > 512)) return fail(nullptr, VQWN_ERR_NOTIMPL, "k must be <= 512");
   if (c.latent_dim != 32 && c.latent_dim != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
@@ -442,7 +471,7 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     CKC(cudaMalloc(&h->b1[l], (size_t)2 * G * sizeof(float)));
     CKC(cudaMalloc(&h->w2[l], (size_t)G * (R + S) * sizeof(float)));
     CKC(cudaMalloc(&h->b2[l], (size_t)(R + S) * sizeof(float)));
-    h->layers_host[l] = LayerDev{h->w1[l], h->b1[l], h->w2[l], h->b2[l], nullptr, c.dilations[l], 0};
+    h->layers_host[l] = LayerDev{nullptr, h->b1[l], nullptr, h->b2[l], nullptr, c.dilations[l], 0};
   }
   CKC(cudaMalloc(&h->post1_w, (size_t)(S + C) * S * sizeof(float)));
   CKC(cudaMalloc(&h->layers_dev, sizeof(LayerDev) * h->L));
@@ -469,14 +498,37 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   CKC(cudaMemset(h->prof, 0, 32 * sizeof(long long)));
   h->profile = getenv("VQWN_PROFILE") != nullptr;
 
-  int kmax = 3 * R + C;
-  if (S + C > kmax) kmax = S + C;
-  h->lda = kmax + 4;
-  h->wfloats = (3 * R + C) * 16;
-  if ((S + C) * 16 > h->wfloats) h->wfloats = (S + C) * 16;
-  if (G * 32 > h->wfloats) h->wfloats = G * 32;
-  h->smem_fp32 = ((size_t)2 * h->wfloats + (size_t)FP32_TB * h->lda + FP32_RED_FLOATS + (size_t)FP32_TB * h->PK +
-                  (size_t)FP32_WARPS * Q) * sizeof(float);
+  // tile-major weight block
+  {
+    size_t off = 0;
+    h->off_skip0t = off; off += (size_t)R * S;
+    h->off_w1t.resize(h->L); h->off_w2t.resize(h->L);
+    for (int l = 0; l < h->L; ++l) {
+      h->off_w1t[l] = off; off += (size_t)(3 * R + C) * 2 * G;
+      h->off_w2t[l] = off; off += (size_t)G * (R + S);
+    }
+    h->off_post1t = off; off += (size_t)(S + C) * S;
+    h->off_post2t = off; off += (size_t)S * Q;
+    h->wtiles_floats = off;
+    CKC(cudaMalloc(&h->wtiles, off * sizeof(float)));
+    for (int l = 0; l < h->L; ++l) {
+      h->layers_host[l].w1t = h->wtiles + h->off_w1t[l];
+      h->layers_host[l].w2t = h->wtiles + h->off_w2t[l];
+    }
+  }
+  CKC(cudaMalloc(&h->gen_err, sizeof(int)));
+  h->actA_floats = FP32_TB * 3 * R;                       // gated conv: current | t-d | t-2d segments
+  if (FP32_TB * S > h->actA_floats) h->actA_floats = FP32_TB * S;   // post1: relu(skip)
+  h->actB_floats = FP32_TB * S;                           // post2: relu(n1)
+  if (FP32_TB * R > h->actB_floats) h->actB_floats = FP32_TB * R;
+  if (FP32_TB * G > h->actB_floats) h->actB_floats = FP32_TB * G;
+  h->wfloatsA = (3 * R + C) * 16;
+  if ((S + C) * 16 > h->wfloatsA) h->wfloatsA = (S + C) * 16;
+  h->wfloatsB = G * 32;
+  if (S * 16 > h->wfloatsB) h->wfloatsB = S * 16;
+  if (R * 16 > h->wfloatsB) h->wfloatsB = R * 16;
+  h->smem_fp32 = ((size_t)h->wfloatsA + h->wfloatsB + (size_t)h->actA_floats + h->actB_floats + (size_t)FP32_TB * C +
+                  FP32_RED_FLOATS + (size_t)FP32_TB * h->PK + (size_t)FP32_WARPS * Q) * sizeof(float) + 64;
   if (h->smem_fp32 > (size_t)prop.sharedMemPerBlockOptin) {
     vqwn_destroy(h);
     return fail(nullptr, VQWN_ERR_INVALID, "configuration needs more shared memory than the device offers");
@@ -503,7 +555,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->w2) if (p) cudaFree(p);
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
-                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err};
+                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx};

@@ -24,25 +24,42 @@ __device__ __forceinline__ void st_cg(float* p, float v) { __stcg(p, v); }
 struct GridBarrier {
   unsigned long long* counter;   // counter[0]: arrivals (monotonic); counter[16]: released epoch (own 128 B line)
   unsigned long long epoch;      // barriers passed so far by this CTA (uniform across the grid)
-  __device__ __forceinline__ void sync() {
+  int* err;                      // bounded wait: a broken launch reports an error instead of hanging the GPU
+  // split barrier: arrive() publishes this CTA's stores and counts it in; wait() blocks until every CTA
+  // has arrived.  Work that does not depend on other CTAs' data can be placed between the two.
+  __device__ __forceinline__ void arrive() {
     __syncthreads();
     epoch += 1;
     if (threadIdx.x == 0) {
       const unsigned long long target = epoch * (unsigned long long)gridDim.x;
       __threadfence();
       const unsigned long long prev = atomicAdd(counter, 1ULL);
-      unsigned long long* flag = counter + 16;
       if (prev + 1 == target) {
         // last arriver releases everybody; pollers never touch the arrival counter's line
-        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
-      } else {
-        unsigned long long v;
-        do {
-          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-        } while (v < epoch);
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(counter + 16), "l"(epoch) : "memory");
+      }
+    }
+  }
+  __device__ __forceinline__ void wait() {
+    if (threadIdx.x == 0) {
+      unsigned long long* flag = counter + 16;
+      unsigned long long v;
+      long long spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= epoch) break;
+        if (++spins > (1LL << 27)) {
+          if (err) atomicExch(err, 3);
+          break;
+        }
+        if ((spins & 0xFFFF) == 0 && err && *reinterpret_cast<volatile int*>(err) != 0) break;
       }
     }
     __syncthreads();
+  }
+  __device__ __forceinline__ void sync() {
+    arrive();
+    wait();
   }
 };
 

@@ -15,9 +15,14 @@
 // contraction cut into (16 streams x NC channels) tiles, one tile per CTA.  Inside a tile the
 // 256 threads form K-groups; a thread owns an 8-stream x 4-channel register tile (128 FMA per
 // 12 shared-memory vector loads), partial sums are reduced through shared memory.
-// The weight tile of the NEXT stage is prefetched with cp.async while the current stage
-// computes and while the CTA waits at the barrier (weights do not depend on the data);
-// activations (written by other CTAs) are fetched with cp.async.cg after the barrier.
+//
+// Data movement is bulk-asynchronous (cp.async.bulk + mbarrier complete_tx, the TMA copy
+// engine): weights are pre-packed tile-major so a stage's weight tile is ONE contiguous block;
+// it and the rows that do not depend on the previous stage (older dilation taps, condition)
+// are requested while the previous stage still computes / waits at the barrier; only the rows
+// produced by the previous stage are fetched after the barrier.  Stages alternate between two
+// shared-memory buffer classes (A: gated conv / post1, B: skip start / residual+skip / post2),
+// so the prefetch of stage s+1 never touches the buffers stage s computes from.
 // Per-layer dilation queues are ring buffers of depth 2d in HBM: slot t mod 2d holds the layer
 // input of step t-2d (read as the oldest tap, then overwritten with the step-t input), slot
 // (t-d) mod 2d holds the middle tap.
@@ -25,9 +30,11 @@
 // Layouts (all float32, stream-major like the reference's [B,C] tensors):
 //   cur [Bp,R]  g [Bp,G]  skip [Bp,S]  n1 [Bp,S]  logits [Bp,Q]  u_hist [Bp,PK]
 //   ring_l [2d, Bp, R]
-//   w1_l [3R+C, 2G] rows = [gated/kernel[2] ; kernel[1] ; kernel[0] ; local_condition/kernel[0]]
-//   w2_l [G, R+S]   cols = [residual/kernel[0] | skip/kernel[0]],  b2 = [residual/bias | skip/bias]
-//   post1_w [S+C, S] rows = [postprocess1/kernel[0] ; postprocess1/local_condition/kernel[0]]
+//   weight tiles (tile-major, [tile][K][NC]):
+//     w1t_l [G/8][3R+C][16]   K rows = gated/kernel[2] ; kernel[1] ; kernel[0] ; local_condition,
+//                             columns = 8 tanh channels | their 8 sigmoid partners
+//     w2t_l [(R+S)/32][G][32] columns of [residual/kernel[0] | skip/kernel[0]]
+//     skip0t [S/16][R][16]   post1t [S/16][S+C][16]   post2t [Q/16][S][16]
 #pragma once
 #include "common.cuh"
 
@@ -41,9 +48,9 @@ constexpr int FP32_RED_FLOATS = 8192;   // K-groups x tile outputs (32 x 256 or 
 enum GenMode { GEN_GREEDY = 0, GEN_SAMPLE = 1, GEN_STEP = 2, GEN_TEACHER = 3 };
 
 struct LayerDev {
-  const float* w1;
+  const float* w1t;
   const float* b1;
-  const float* w2;
+  const float* w2t;
   const float* b2;
   float* ring;
   int d;
@@ -53,9 +60,9 @@ struct LayerDev {
 struct GenParams {
   int L, R, G, S, Q, C, PK;
   int B, Bp;
-  int lda;      // shared-memory row stride of the activation tile (floats)
-  int wfloats;  // floats per weight-tile buffer
-  const float *pre_k, *pre_b, *skip0_w, *skip0_b, *post1_w, *post1_b, *post2_w, *post2_b;
+  int actA_floats, actB_floats;   // activation buffers: segment-major [segment][16 streams][segment length]
+  int wfloatsA, wfloatsB;
+  const float *pre_k, *pre_b, *skip0t, *skip0_b, *post1t, *post1_b, *post2t, *post2_b;
   const LayerDev* layers;
   const float *enc_lut, *dec_lut;
   float *u_hist, *cur, *g, *skip, *n1, *logits;
@@ -72,23 +79,40 @@ struct GenParams {
   float* logits_out;        // GEN_STEP: [B,Q]; GEN_TEACHER: [B,T,Q]; else null
   float* probs_out;         // GEN_STEP: [B,Q] or null
   unsigned long long* barrier;
-  long long* prof;          // optional [8] cycle counters of CTA 0 (VQWN_PROFILE=1), else null
+  long long* prof;          // optional cycle counters of CTA 0 (VQWN_PROFILE=1), else null
+  int* err;                 // set when a bounded wait expires
 };
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, 1.0f + expf(-x)); }
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ---------------------------------------------------------------------------------------
+// bulk async copies + mbarrier
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f32_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// one tile of one stage: which weight columns it needs and which streams it covers
+__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(f32_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(f32_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f32_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsigned parity, int* err) {
+  const unsigned addr = f32_smem_u32(bar);
+  for (int spin = 0; spin < (1 << 26); ++spin) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  atomicExch(err, 2);
+  return false;
+}
+
+// one tile of one stage
 struct TileInfo {
-  const float* W;   // null: no contraction for this tile (last layer's dead residual)
-  int ldw, K, NC, col0, col1, cb, sb;
+  const float* W;   // contiguous [K][NC] weight tile; null: no contraction (last layer's dead residual)
+  int K, NC, col0, col1, cb, sb, cls;
 };
 
 // stage ids inside a step: 0 preprocess+skip start | 1+2l gated (S1) | 2+2l residual/skip (S2)
@@ -101,88 +125,44 @@ __device__ __forceinline__ int stage_tiles(const GenParams& p, int s) {
   if (s == 2 * p.L + 2) return (p.Q / 16) * nsb;
   return 0;
 }
+// buffer class: A (1) for gated conv / post1, B (0) for the rest
+__device__ __forceinline__ int stage_class(const GenParams& p, int s) { return (s >= 1 && s <= 2 * p.L + 1) ? (s & 1) : 0; }
 
 __device__ __forceinline__ void stage_tile(const GenParams& p, int s, int tile, TileInfo& ti) {
   const int nsb = p.Bp / FP32_TB;
   ti.cb = tile / nsb;
   ti.sb = tile - ti.cb * nsb;
   ti.col1 = -1;
+  ti.cls = stage_class(p, s);
   if (s == 0) {
-    ti.W = p.skip0_w; ti.ldw = p.S; ti.K = p.R; ti.NC = 16; ti.col0 = ti.cb * 16;
+    ti.K = p.R; ti.NC = 16; ti.col0 = ti.cb * 16;
+    ti.W = p.skip0t + (long long)ti.cb * ti.K * 16;
   } else if (s <= 2 * p.L) {
     const int l = (s - 1) >> 1;
     if (s & 1) {
-      ti.W = p.layers[l].w1; ti.ldw = 2 * p.G; ti.K = 3 * p.R + p.C; ti.NC = 16;
+      ti.K = 3 * p.R + p.C; ti.NC = 16;
       ti.col0 = ti.cb * 8; ti.col1 = p.G + ti.cb * 8;      // 8 tanh channels + their 8 sigmoid partners
+      ti.W = p.layers[l].w1t + (long long)ti.cb * ti.K * 16;
     } else {
-      ti.W = p.layers[l].w2; ti.ldw = p.R + p.S; ti.K = p.G; ti.NC = 32; ti.col0 = ti.cb * 32;
+      ti.K = p.G; ti.NC = 32; ti.col0 = ti.cb * 32;
+      ti.W = p.layers[l].w2t + (long long)ti.cb * ti.K * 32;
       if (l == p.L - 1 && ti.col0 < p.R) ti.W = nullptr;   // wavenet.py:145: last residual is dead
     }
   } else if (s == 2 * p.L + 1) {
-    ti.W = p.post1_w; ti.ldw = p.S; ti.K = p.S + p.C; ti.NC = 16; ti.col0 = ti.cb * 16;
+    ti.K = p.S + p.C; ti.NC = 16; ti.col0 = ti.cb * 16;
+    ti.W = p.post1t + (long long)ti.cb * ti.K * 16;
   } else {
-    ti.W = p.post2_w; ti.ldw = p.Q; ti.K = p.S; ti.NC = 16; ti.col0 = ti.cb * 16;
+    ti.K = p.S; ti.NC = 16; ti.col0 = ti.cb * 16;
+    ti.W = p.post2t + (long long)ti.cb * ti.K * 16;
   }
 }
 
-// weight tile [K][NC] -> shared memory (16-byte async copies)
-__device__ __forceinline__ void issue_w_tile(float* wbuf, const TileInfo& ti) {
-  if (ti.W == nullptr) return;
-  const int sh = (ti.NC == 16) ? 2 : 3;          // log2(16-byte chunks per row)
-  const int c4 = threadIdx.x & ((1 << sh) - 1);
-  int col = ti.col0 + 4 * c4;
-  if (ti.col1 >= 0 && c4 >= 2) col = ti.col1 + 4 * (c4 - 2);
-  const float* src = ti.W + col;
-  float* dst = wbuf + 4 * c4;
-  const int kstep = FP32_THREADS >> sh;
-  for (int k = threadIdx.x >> sh; k < ti.K; k += kstep)
-    cp_async16(dst + k * ti.NC, src + (long long)k * ti.ldw);
-}
-
-__device__ __forceinline__ void issue_w_prefetch(const GenParams& p, float* wbuf, int s) {
-  if ((int)blockIdx.x < stage_tiles(p, s)) {
-    TileInfo ti;
-    stage_tile(p, s, blockIdx.x, ti);
-    issue_w_tile(wbuf, ti);
-  }
-}
-
-// 16 rows x len floats produced by other CTAs (global, L2-coherent .cg) -> activation tile
-__device__ __forceinline__ void issue_rows(float* act_s, int lda, int koff, const float* src, long long row_stride, int len) {
-  const int q4 = len >> 2;
-  const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x >> 5; i < FP32_TB; i += FP32_WARPS)        // warp w: rows w, w+8
-    for (int q = lane; q < q4; q += 32)
-      cp_async16(act_s + i * lda + koff + 4 * q, src + (long long)i * row_stride + 4 * q);
-}
-
-__device__ __forceinline__ void issue_cond_rows(float* act_s, int lda, int koff, const GenParams& p, int sb, long long t) {
-  const int q4 = p.C >> 2;
-  const long long frame = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
-  const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x >> 5; i < FP32_TB; i += FP32_WARPS) {
-    int b = sb * FP32_TB + i;
-    if (b >= p.B) b = p.B - 1;   // padded streams reuse the last real stream's condition
-    const float* src = p.cond + (long long)b * p.cond_bstride + frame * p.C;
-    for (int q = lane; q < q4; q += 32) cp_async16(act_s + i * lda + koff + 4 * q, src + 4 * q);
-  }
-}
-
-__device__ __forceinline__ void relu_rows(float* act_s, int lda, int len) {
-  const int q4 = len >> 2;
-  const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x >> 5; i < FP32_TB; i += FP32_WARPS)
-    for (int q = lane; q < q4; q += 32) {
-      float4* a = reinterpret_cast<float4*>(act_s + i * lda + 4 * q);
-      float4 v = *a;
-      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-      *a = v;
-    }
-}
-
-// partial sums of the (16 streams x NC channels) tile into red_s[kgroup][stream*NC + channel]
+// partial sums of the (16 streams x NC channels) tile into red_s[kgroup][stream*NC + channel].
+// Activations are segment-major: k < Kmain lives in act_s[(k >> sl_log)][stream][k & (SL-1)] (SL = 1 << sl_log
+// floats per row, 16 rows per segment); k >= Kmain is the condition tile cond_s[stream][k - Kmain] (C per row).
 template <int NC>
-__device__ __forceinline__ void tile_compute(const float* wbuf, const float* act_s, int lda, int K, float* red_s) {
+__device__ __forceinline__ void tile_compute(const float* wbuf, const float* act_s, int sl_log, int Kmain,
+                                             const float* cond_s, int C, int K, float* red_s) {
   constexpr int CQ = NC / 4;          // channel quads
   constexpr int TPG = 2 * CQ;         // threads per K-group (2 stream halves x channel quads)
   constexpr int KG = FP32_THREADS / TPG;
@@ -191,19 +171,23 @@ __device__ __forceinline__ void tile_compute(const float* wbuf, const float* act
   const int sh = r / CQ, q = r - sh * CQ;
   const int klen = K / KG;
   const int k0 = kg * klen;
+  const int SL = 1 << sl_log;
   float acc[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
   const float* wp = wbuf + q * 4;
-  const float* ap = act_s + sh * lda;
   for (int k = k0; k < k0 + klen; k += 4) {
     const float4 w0 = *reinterpret_cast<const float4*>(wp + (k + 0) * NC);
     const float4 w1 = *reinterpret_cast<const float4*>(wp + (k + 1) * NC);
     const float4 w2 = *reinterpret_cast<const float4*>(wp + (k + 2) * NC);
     const float4 w3 = *reinterpret_cast<const float4*>(wp + (k + 3) * NC);
+    const float* ap;
+    int astr;
+    if (k < Kmain) { ap = act_s + ((k >> sl_log) << (sl_log + 4)) + (k & (SL - 1)) + sh * SL; astr = 2 * SL; }
+    else { ap = cond_s + (k - Kmain) + sh * C; astr = 2 * C; }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 a = *reinterpret_cast<const float4*>(ap + (2 * j) * lda + k);   // stream 2j+sh
+      const float4 a = *reinterpret_cast<const float4*>(ap + j * astr);   // stream 2j+sh
       acc[j][0] = fmaf(a.x, w0.x, acc[j][0]); acc[j][1] = fmaf(a.x, w0.y, acc[j][1]);
       acc[j][2] = fmaf(a.x, w0.z, acc[j][2]); acc[j][3] = fmaf(a.x, w0.w, acc[j][3]);
       acc[j][0] = fmaf(a.y, w1.x, acc[j][0]); acc[j][1] = fmaf(a.y, w1.y, acc[j][1]);
@@ -229,35 +213,157 @@ __device__ __forceinline__ float tile_reduce(const float* red_s, int o) {
   return s;
 }
 
-__global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const GenParams p) {
-  extern __shared__ __align__(16) float smem[];
-  float* wbuf0 = smem;                              // 2 weight-tile buffers
-  float* act_s = smem + 2 * p.wfloats;              // [16][lda]
-  float* red_s = act_s + FP32_TB * p.lda;           // [kgroups][tile outputs]
+__device__ __forceinline__ void relu_block(float* act_s, int nfloats) {
+  for (int q = threadIdx.x; q < (nfloats >> 2); q += FP32_THREADS) {
+    float4* a = reinterpret_cast<float4*>(act_s) + q;
+    float4 v = *a;
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    *a = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// load plans.  Every helper is executed by all 256 threads with uniform arguments; thread 0
+// posts the expected byte count, threads 0..(n-1) issue one bulk copy each.
+// ---------------------------------------------------------------------------------------
+constexpr unsigned FP32_WCHUNK = 32768;   // bytes per weight bulk copy (at most 2 per tile)
+
+__device__ __forceinline__ void issue_weights(float* wbuf, const TileInfo& ti, unsigned long long* bar) {
+  if (ti.W == nullptr) return;
+  const unsigned bytes = (unsigned)ti.K * ti.NC * 4u;
+  const int nchunk = (int)((bytes + FP32_WCHUNK - 1) / FP32_WCHUNK);
+  if (threadIdx.x == 0) mbar_expect(bar, bytes);
+  if ((int)threadIdx.x < nchunk) {
+    const unsigned off = threadIdx.x * FP32_WCHUNK;
+    const unsigned n = (bytes - off < FP32_WCHUNK) ? (bytes - off) : FP32_WCHUNK;
+    bulk_g2s(wbuf + off / 4, ti.W + off / 4, n, bar);
+  }
+}
+
+// rows that do NOT depend on the previous stage: the two older dilation taps of a gated conv (S1).
+// 16 consecutive streams of one ring slot are contiguous in HBM -> one 16 KB copy per tap.
+__device__ __forceinline__ bool stage_has_pre(const GenParams& p, int s) { return s >= 1 && s <= 2 * p.L && (s & 1); }
+
+__device__ __forceinline__ void issue_pre_rows(const GenParams& p, int s, const TileInfo& ti, long long t, float* act,
+                                               unsigned long long* bar) {
+  const int tid = threadIdx.x;
+  if (tid < 2) {
+    const int which = tid;                                                  // 0: middle tap, 1: oldest tap
+    const LayerDev ly = p.layers[(s - 1) >> 1];
+    const int d2 = 2 * ly.d;
+    const long long ring_slot = (long long)p.Bp * p.R;
+    const unsigned bytes = (unsigned)(FP32_TB * p.R * 4);
+    if (which == 0) mbar_expect(bar, 2 * bytes);
+    const long long slot = (which == 0) ? ((t + ly.d) % d2) : (t % d2);
+    bulk_g2s(act + (1 + which) * FP32_TB * p.R, ly.ring + slot * ring_slot + (long long)ti.sb * FP32_TB * p.R, bytes, bar);
+  }
+}
+
+// rows produced by the previous stage (fetched after the grid barrier): one contiguous [16][len] block
+__device__ __forceinline__ bool issue_post_rows(const GenParams& p, int s, const TileInfo& ti, float* act,
+                                                unsigned long long* bar) {
+  const float* src;
+  int len;
+  if (s == 0) return false;                                   // computed locally (preprocess FIR)
+  if (s <= 2 * p.L) {
+    if (s & 1) { src = p.cur + (long long)ti.sb * FP32_TB * p.R; len = p.R; }
+    else {
+      if (ti.W == nullptr) return false;
+      src = p.g + (long long)ti.sb * FP32_TB * p.G; len = p.G;
+    }
+  } else if (s == 2 * p.L + 1) { src = p.skip + (long long)ti.sb * FP32_TB * p.S; len = p.S; }
+  else { src = p.n1 + (long long)ti.sb * FP32_TB * p.S; len = p.S; }
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)(FP32_TB * len * 4);
+    mbar_expect(bar, bytes);
+    bulk_g2s(act, src, bytes, bar);
+  }
+  return true;
+}
+
+// condition tile [16 streams][C] of stream block sb at `frame`; reloaded only when the frame changes
+__device__ __forceinline__ void issue_cond_tile(const GenParams& p, int sb, long long frame, float* cond_s,
+                                                unsigned long long* bar) {
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_expect(bar, (unsigned)(FP32_TB * p.C * 4));
+  if (tid < FP32_TB) {
+    int b = sb * FP32_TB + tid;
+    if (b >= p.B) b = p.B - 1;   // padded streams reuse the last real stream's condition
+    bulk_g2s(cond_s + tid * p.C, p.cond + (long long)b * p.cond_bstride + frame * p.C, (unsigned)p.C * 4u, bar);
+  }
+}
+
+__global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const GenParams p_in) {
+  extern __shared__ __align__(128) float smem[];
+  // per-layer table (pointers, dilation) cached in shared memory: with ~223 KB of dynamic shared memory the L1 is
+  // a few KB, and every table lookup from global memory would cost an L2 round trip on the critical path
+  __shared__ LayerDev layers_s[64];
+  for (int i = threadIdx.x; i < p_in.L; i += FP32_THREADS) layers_s[i] = p_in.layers[i];
+  GenParams p = p_in;
+  p.layers = layers_s;
+  __syncthreads();
+  float* const wA = smem;                            // class A weights
+  float* const wB = wA + p.wfloatsA;                 // class B weights
+  float* const actA = wB + p.wfloatsB;               // class A activations (segment-major)
+  float* const actB = actA + p.actA_floats;          // class B activations
+  float* const cond_s = actB + p.actB_floats;        // [16][C] condition tile of this CTA's stream block
+  float* red_s = cond_s + FP32_TB * p.C;             // [kgroups][tile outputs]
   float* u_s = red_s + FP32_RED_FLOATS;             // [16][PK]
   float* ps = u_s + FP32_TB * p.PK;                 // [8][Q]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ps + FP32_WARPS * p.Q);
+  unsigned long long* wbar = bars;        // [2] weight tile landed (per class)
+  unsigned long long* prebar = bars + 2;  // [1] class-A pre rows landed
+  unsigned long long* postbar = bars + 3; // [2] post rows landed (per class)
+  unsigned long long* condbar = bars + 5; // [1] condition tile landed
+  unsigned wphA = 0u, wphB = 0u, preph = 0u, postphA = 0u, postphB = 0u;
 
-  GridBarrier bar{p.barrier, 0ULL};
+  GridBarrier bar{p.barrier, 0ULL, p.err};
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int lda = p.lda;
   const float mu = (float)(p.Q - 1);
   const bool ext = (p.mode == GEN_STEP || p.mode == GEN_TEACHER);
   const int NS = 2 * p.L + 4;
   const int S_P1 = 2 * p.L + 1, S_P2 = 2 * p.L + 2, S_DRAW = 2 * p.L + 3;
   const long long ring_slot = (long long)p.Bp * p.R;
 
-  long long pf_bar = 0, pf_wait = 0, pf_comp = 0, pf_epi = 0, pf_draw = 0, pf_issue = 0, pf_t = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f32_smem_u32(&bars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  long long pf_bar = 0, pf_wait = 0, pf_comp = 0, pf_epi = 0, pf_draw = 0, pf_issue = 0, pf_arrive = 0, pf_t = 0;
   const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
 #define PF_START() do { if (prof) pf_t = clock64(); } while (0)
 #define PF_ADD(x) do { if (prof) { long long n_ = clock64(); x += n_ - pf_t; pf_t = n_; } } while (0)
-  int wb = 0;   // buffer holding the weight tile of the current stage's first tile
-  issue_w_prefetch(p, wbuf0, 0);
-  cp_async_commit();
 
-  for (long long t = p.t0; t < p.t0 + p.T; ++t) {
-    for (int s = 0; s < NS; ++s) {
+  // the first tile of stage `sn` at step `tn` for this CTA: weights + independent rows
+  auto prefetch_stage = [&](int sn, long long tn) {
+    if ((int)blockIdx.x < stage_tiles(p, sn)) {
+      TileInfo tn_i;
+      stage_tile(p, sn, blockIdx.x, tn_i);
+      issue_weights(tn_i.cls ? wA : wB, tn_i, &wbar[tn_i.cls]);
+      if (stage_has_pre(p, sn)) issue_pre_rows(p, sn, tn_i, tn, actA, prebar);
+    }
+  };
+
+  bool alive = true;
+  prefetch_stage(0, p.t0);
+  // condition tile: stages that use it (gated conv, post1) map tile -> stream block identically, so one tile
+  // per CTA serves a whole frame (ratio steps x 31 stages)
+  const int nsb_k = p.Bp / FP32_TB;
+  const int my_sb = (int)(blockIdx.x % nsb_k);
+  long long cond_frame = -1;
+  int cond_sb = -1;
+  unsigned condph = 0u;
+  const int sl_R = 31 - __clz(p.R), sl_S = 31 - __clz(p.S), sl_G = 31 - __clz(p.G);
+
+  for (long long t = p.t0; t < p.t0 + p.T && alive; ++t) {
+    for (int s = 0; s < NS && alive; ++s) {
       if (s == S_DRAW) {
+        // weights of the next step's first stage (same buffer class as post2, free by now)
+        if (t + 1 < p.t0 + p.T) prefetch_stage(0, t + 1);
         // -------------------------------------------------------------- softmax + draw + mu-law decode
         const int NQ = p.Q / 32;   // <= 8
         PF_START();
@@ -340,24 +446,35 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
 
       // ---------------------------------------------------------------- contraction stages
       const int ntiles = stage_tiles(p, s);
-      const int s_next = (s + 1 == S_DRAW) ? 0 : s + 1;   // next stage that owns weight tiles
       const int l = (s - 1) >> 1;                          // layer of S1/S2 stages
+      const int cls = stage_class(p, s);
+      float* act_s = cls ? actA : actB;
       bool first = true;
-      if ((int)blockIdx.x >= ntiles) {
-        // no tile here: still stream the next stage's weights
-        issue_w_prefetch(p, wbuf0 + (wb ^ 1) * p.wfloats, s_next);
-        cp_async_commit();
-      }
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      PF_START();
+      for (int tile = blockIdx.x; tile < ntiles && alive; tile += gridDim.x) {
         TileInfo ti;
         stage_tile(p, s, tile, ti);
-        float* wcur = wbuf0 + wb * p.wfloats;
+        float* wcur = cls ? wA : wB;
         const long long row0 = (long long)ti.sb * FP32_TB;
-        if (!first) issue_w_tile(wcur, ti);   // later rounds: this tile's weights were not prefetched
-        PF_START();
+        if (!first) {   // later rounds (more than gridDim tiles): nothing was prefetched for this tile
+          issue_weights(wcur, ti, &wbar[cls]);
+          if (stage_has_pre(p, s)) issue_pre_rows(p, s, ti, t, act_s, prebar);
+        }
+        const bool has_post = issue_post_rows(p, s, ti, act_s, &postbar[cls]);
+        const bool uses_cond = cls == 1;
+        if (uses_cond) {
+          const long long frame = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
+          if (frame != cond_frame || ti.sb != cond_sb) {          // uniform across the CTA
+            __syncthreads();                                      // nobody still reads the old tile
+            issue_cond_tile(p, ti.sb, frame, cond_s, condbar);
+            alive = alive && mbar_wait_bounded(condbar, condph, p.err);
+            condph ^= 1u;
+            cond_frame = frame; cond_sb = ti.sb;
+          }
+        }
 
-        // ---- activations
         if (s == 0) {
+          // ---- preprocess FIR computed in place (wavenet_ops.py:178,193): h0 = (u0*K[PK-1] + b) + u1*K[PK-2] + ...
           for (int idx = tid; idx < FP32_TB * p.PK; idx += FP32_THREADS) {
             const int i = idx / p.PK, j = idx - i * p.PK;
             const int b = ti.sb * FP32_TB + i;
@@ -378,47 +495,30 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
             u_s[i * p.PK + j] = u;
           }
           __syncthreads();
-          // h0[i][n] = (u0*K[PK-1] + bias) + u1*K[PK-2] + ...   (wavenet_ops.py:178,193)
           for (int idx = tid; idx < FP32_TB * p.R; idx += FP32_THREADS) {
             const int i = idx / p.R, n = idx - i * p.R;
             float acc = fmaf(u_s[i * p.PK], __ldg(p.pre_k + (p.PK - 1) * p.R + n), __ldg(p.pre_b + n));
             for (int j = 1; j < p.PK; ++j)
               acc = fmaf(u_s[i * p.PK + j], __ldg(p.pre_k + (p.PK - 1 - j) * p.R + n), acc);
-            act_s[i * lda + n] = acc;
+            act_s[i * p.R + n] = acc;
           }
-        } else if (s <= 2 * p.L) {
-          const LayerDev ly = p.layers[l];
-          if (s & 1) {
-            const int d2 = 2 * ly.d;
-            const int slot_old = (int)(t % d2);
-            const int slot_mid = (int)((t + ly.d) % d2);
-            issue_rows(act_s, lda, 0, p.cur + row0 * p.R, p.R, p.R);
-            issue_rows(act_s, lda, p.R, ly.ring + slot_mid * ring_slot + row0 * p.R, p.R, p.R);
-            issue_rows(act_s, lda, 2 * p.R, ly.ring + slot_old * ring_slot + row0 * p.R, p.R, p.R);
-            issue_cond_rows(act_s, lda, 3 * p.R, p, ti.sb, t);
-          } else if (ti.W != nullptr) {
-            issue_rows(act_s, lda, 0, p.g + row0 * p.G, p.G, p.G);
-          }
-        } else if (s == S_P1) {
-          issue_rows(act_s, lda, 0, p.skip + row0 * p.S, p.S, p.S);
-          issue_cond_rows(act_s, lda, p.S, p, ti.sb, t);
-        } else {
-          issue_rows(act_s, lda, 0, p.n1 + row0 * p.S, p.S, p.S);
         }
-        cp_async_commit();
-        if (first) {
-          issue_w_prefetch(p, wbuf0 + (wb ^ 1) * p.wfloats, s_next);
-          cp_async_commit();
-          first = false;
-        } else {
-          cp_async_commit();   // keep the group count uniform
-        }
+        first = false;
         PF_ADD(pf_issue);
-        cp_async_wait<1>();      // everything but the newest group (next stage's weights) has landed
+        // ---- wait for this tile's operands
+        if (ti.W != nullptr) {
+          alive = alive && mbar_wait_bounded(&wbar[cls], cls ? wphA : wphB, p.err);
+          if (cls) wphA ^= 1u; else wphB ^= 1u;
+        }
+        if (stage_has_pre(p, s)) { alive = alive && mbar_wait_bounded(prebar, preph, p.err); preph ^= 1u; }
+        if (has_post) {
+          alive = alive && mbar_wait_bounded(&postbar[cls], cls ? postphA : postphB, p.err);
+          if (cls) postphA ^= 1u; else postphB ^= 1u;
+        }
         __syncthreads();
         PF_ADD(pf_wait);
         if (s >= S_P1) {         // relu on the contraction input (wavenet.py:153,163)
-          relu_rows(act_s, lda, p.S);
+          relu_block(act_s, FP32_TB * p.S);
           __syncthreads();
         }
 
@@ -430,9 +530,13 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
           const float bias = __ldg(bias_p + col);            // in flight during the contraction
           if (s == 0 && ti.cb < p.R / 16) {
             const int n = ti.cb * 16 + c;
-            st_cg(p.cur + (row0 + i) * p.R + n, act_s[i * lda + n]);
+            st_cg(p.cur + (row0 + i) * p.R + n, act_s[i * p.R + n]);
           }
-          tile_compute<16>(wcur, act_s, lda, ti.K, red_s);
+          {
+            const int slg = (s == 0 || (s <= 2 * p.L)) ? sl_R : sl_S;
+            const int kmain = (s == 0) ? p.R : (s <= 2 * p.L) ? 3 * p.R : p.S;
+            tile_compute<16>(wcur, act_s, slg, kmain, cond_s, p.C, ti.K, red_s);
+          }
           __syncthreads();
           PF_ADD(pf_comp);
           float v = tile_reduce<16>(red_s, tid) + bias;
@@ -452,7 +556,6 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
           const LayerDev ly = p.layers[l];
           const int slot_old = (int)(t % (2 * ly.d));
           const bool is_res = ti.col0 < p.R;
-          // old residual / skip values and biases: loads in flight during the contraction
           float oldv[2], bias[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -463,7 +566,7 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
             bias[h] = __ldg(ly.b2 + col);
           }
           if (ti.W != nullptr) {
-            tile_compute<32>(wcur, act_s, lda, ti.K, red_s);
+            tile_compute<32>(wcur, act_s, sl_G, p.G, cond_s, p.C, ti.K, red_s);
             __syncthreads();
             PF_ADD(pf_comp);
           }
@@ -489,15 +592,36 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
         __syncthreads();
         PF_ADD(pf_epi);
       }
-      wb ^= 1;
+      // publish this stage's results, then request the NEXT stage's weights and independent rows while the
+      // barrier completes (they do not depend on other CTAs' data and this stage's buffers of that class are idle)
       PF_START();
-      bar.sync();
+      bar.arrive();
+      PF_ADD(pf_arrive);
+      if (s + 1 != S_DRAW) prefetch_stage(s + 1, t);
+      PF_ADD(pf_issue);
+      bar.wait();
       PF_ADD(pf_bar);
     }
   }
-  cp_async_wait<0>();
   if (prof) {
-    p.prof[0] = pf_bar; p.prof[1] = pf_wait; p.prof[2] = pf_comp; p.prof[3] = pf_epi; p.prof[4] = pf_draw; p.prof[5] = pf_issue;
+    p.prof[0] = pf_bar; p.prof[1] = pf_wait; p.prof[2] = pf_comp; p.prof[3] = pf_epi; p.prof[4] = pf_draw; p.prof[5] = pf_issue; p.prof[6] = pf_arrive;
+  }
+}
+
+// [K][ldw] row-major weights -> tile-major [tile][K][NC]; tile cb takes columns col0(cb)..+NC
+// (paired: 8 columns from cb*8 and 8 from G + cb*8)
+__global__ void pack_tiles_kernel(const float* __restrict__ src, int ldw, int K, int NC, int ntiles, int paired_G,
+                                  float* __restrict__ dst) {
+  const long long total = (long long)ntiles * K * NC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % NC);
+    const long long r = i / NC;
+    const int k = (int)(r % K);
+    const int cb = (int)(r / K);
+    int col;
+    if (paired_G > 0) col = (c < 8) ? (cb * 8 + c) : (paired_G + cb * 8 + (c - 8));
+    else col = cb * NC + c;
+    dst[i] = src[(long long)k * ldw + col];
   }
 }
 
