@@ -234,6 +234,33 @@ def test_small_greedy_and_sample_sequences(small, golden_dir):
     assert np.array_equal(audio, O.decode_lut()[idx])
 
 
+def test_dataflow_kernel_matches_barrier_kernel(monkeypatch):
+    """the experimental barrier-free kernel (VQWN_GEN_KERNEL=dataflow) computes the same tiles in the same
+    order: outputs must be bit-identical to the default kernel"""
+    cfg = O.Config(wavenet=SMALL_WAVENET)
+    w = O.make_weights(cfg, seed=1234)
+    B, T, F, x, ze = _small_inputs(cfg, w)
+    ref = _engine(SMALL_WAVENET, 16, w)
+    _, cond = ref.encode_condition(ze, [0, 1, 2])
+    a0, i0 = ref.generate(cond, T, mode="greedy")
+    l0 = ref.teacher_forced(x[:, :64], cond[:, :1])
+    assert ref.last_kernel_name == "wavenet_fp32_persistent"
+    ref.close()
+    monkeypatch.setenv("VQWN_GEN_KERNEL", "dataflow")
+    eng = _engine(SMALL_WAVENET, 16, w)
+    a1, i1 = eng.generate(cond, T, mode="greedy")
+    assert eng.last_kernel_name == "wavenet_fp32_dataflow"
+    l1 = eng.teacher_forced(x[:, :64], cond[:, :1])
+    eng.reset(B)
+    audio = np.zeros(B, dtype=np.float32)
+    for t in range(8):
+        _, logits = eng.step(audio, cond[:, 0])
+        assert np.array_equal(logits, l1[:, t])
+        audio = x[:, t]
+    eng.close()
+    assert np.array_equal(i0, i1) and np.array_equal(a0, a1) and np.array_equal(l0, l1)
+
+
 def test_receptive_field_property(small):
     cfg, w, eng = small
     B, T, F, x, ze = _small_inputs(cfg, w)

@@ -16,6 +16,7 @@
 #include "vq.cuh"
 #include "vq_tc.cuh"
 #include "wavenet_fp32.cuh"
+#include "wavenet_fp32_df.cuh"
 #include "sample.cuh"
 
 using namespace vqwn;
@@ -63,6 +64,9 @@ struct vqwn_handle {
   std::vector<size_t> off_w1t, off_w2t;
   size_t off_skip0t = 0, off_post1t = 0, off_post2t = 0;
   int* gen_err = nullptr;
+  unsigned long long* ll_base = nullptr;   // packet buffers of the dataflow kernel
+  size_t ll_packets = 0;
+  int gen_kernel = 0;                      // 0 auto, 1 barrier kernel, 2 dataflow kernel
   // packed fp32 weights
   bool packed = false;
   std::vector<float*> w1, b1, w2, b2;
@@ -221,6 +225,7 @@ int do_reset(vqwn_handle* h, int B) {
   CK(h, cudaMemsetAsync(h->skip, 0, Bp * h->S * sizeof(float), h->stream));
   CK(h, cudaMemsetAsync(h->n1, 0, Bp * h->S * sizeof(float), h->stream));
   CK(h, cudaMemsetAsync(h->logits, 0, Bp * h->Q * sizeof(float), h->stream));
+  CK(h, cudaMemsetAsync(h->ll_base, 0, h->ll_packets * sizeof(unsigned long long), h->stream));
   h->B = B;
   h->t = 0;
   return VQWN_OK;
@@ -259,8 +264,40 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
   p.err = h->gen_err;
   CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
   CK(h, cudaMemsetAsync(h->barrier, 0, 32 * sizeof(unsigned long long), h->stream));
-  void* args[] = {&p};
+  // dataflow kernel: every stage's tiles must fit the grid (tile index == blockIdx in every stage)
+  const int nsb = p.Bp / FP32_TB;
+  int max_tiles = (h->S / 16) * nsb;
+  if ((h->G / 8) * nsb > max_tiles) max_tiles = (h->G / 8) * nsb;
+  if (((h->R + h->S) / 32) * nsb > max_tiles) max_tiles = ((h->R + h->S) / 32) * nsb;
+  const bool df_ok = max_tiles <= h->num_sms;
+  // measured slower than the barrier kernel (packets move through the LSU path at ~19 B/clk/SM): opt-in only
+  const bool use_df = df_ok && h->gen_kernel == 2;
   CK(h, cudaEventRecord(h->ev0, h->stream));
+  if (use_df) {
+    DfParams dp;
+    dp.g = p;
+    unsigned long long* q = h->ll_base;
+    const size_t Bp_max = h->Bp_max;
+    dp.cur_ll = q; q += (size_t)h->L * Bp_max * h->R;
+    dp.g_ll = q; q += (size_t)h->L * Bp_max * h->G;
+    dp.skip0_ll = q; q += Bp_max * h->S;
+    dp.skip_ll = q; q += Bp_max * h->S;
+    dp.n1_ll = q; q += Bp_max * h->S;
+    dp.logit_ll = q; q += Bp_max * h->Q;
+    dp.u_ll = q;
+    // per-layer strides inside the kernel use the run's padded batch
+    dp.cur_ll = h->ll_base;
+    dp.g_ll = h->ll_base + (size_t)h->L * Bp_max * h->R;
+    void* dargs[] = {&dp};
+    CK(h, cudaLaunchCooperativeKernel((const void*)wavenet_fp32_dataflow, dim3(h->num_sms), dim3(FP32_THREADS), dargs,
+                                      h->smem_fp32, h->stream));
+    CK(h, cudaEventRecord(h->ev1, h->stream));
+    h->launches += 1;
+    h->last_kernel = "wavenet_fp32_dataflow";
+    h->t += T;
+    return VQWN_OK;
+  }
+  void* args[] = {&p};
   CK(h, cudaLaunchCooperativeKernel((const void*)wavenet_fp32_persistent, dim3(h->num_sms), dim3(FP32_THREADS),
                                     args, h->smem_fp32, h->stream));
   CK(h, cudaEventRecord(h->ev1, h->stream));
@@ -275,10 +312,10 @@ int finish_timing(vqwn_handle* h) {
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
-  if (strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
+  if (strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0 || strcmp(h->last_kernel, "wavenet_fp32_dataflow") == 0) {
     int e = 0;
     CK(h, cudaMemcpy(&e, h->gen_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (e) return fail(h, VQWN_ERR_CUDA, e == 2 ? "wavenet_fp32_persistent: operand wait timed out" : "wavenet_fp32_persistent: grid barrier timed out");
+    if (e) return fail(h, VQWN_ERR_CUDA, e == 2 ? "generation kernel: operand wait timed out" : (e == 4 ? "generation kernel: packet wait timed out" : "generation kernel: grid barrier timed out"));
   }
   if (h->profile && strcmp(h->last_kernel, "vq_tc_kernel") == 0) {
     long long pf[32];
@@ -290,8 +327,8 @@ int finish_timing(vqwn_handle* h) {
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
     long long pf[8];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
-      fprintf(stderr, "[vqwn profile] CTA0 cycles: barrier=%lld act_wait=%lld compute=%lld epilogue=%lld draw=%lld issue=%lld arrive=%lld (kernel %.3f ms)\n",
-              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], ms);
+      fprintf(stderr, "[vqwn profile] CTA0 cycles: barrier=%lld act_wait=%lld compute=%lld epilogue=%lld draw=%lld issue=%lld arrive=%lld prefetch=%lld (kernel %.3f ms)\n",
+              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7], ms);
   }
   return VQWN_OK;
 }
@@ -517,6 +554,9 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     }
   }
   CKC(cudaMalloc(&h->gen_err, sizeof(int)));
+  h->ll_packets = (size_t)h->L * h->Bp_max * (R + G) + (size_t)h->Bp_max * (3 * S + Q + 1);
+  CKC(cudaMalloc(&h->ll_base, h->ll_packets * sizeof(unsigned long long)));
+  if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "dataflow") == 0 ? 2 : 0);
   h->actA_floats = FP32_TB * 3 * R;                       // gated conv: current | t-d | t-2d segments
   if (FP32_TB * S > h->actA_floats) h->actA_floats = FP32_TB * S;   // post1: relu(skip)
   h->actB_floats = FP32_TB * S;                           // post2: relu(n1)
@@ -534,6 +574,7 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     return fail(nullptr, VQWN_ERR_INVALID, "configuration needs more shared memory than the device offers");
   }
   CKC(cudaFuncSetAttribute((const void*)wavenet_fp32_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fp32));
+  CKC(cudaFuncSetAttribute((const void*)wavenet_fp32_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fp32));
   int occ = 0;
   CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)wavenet_fp32_persistent, FP32_THREADS, h->smem_fp32));
   if (occ < 1) {
@@ -555,7 +596,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->w2) if (p) cudaFree(p);
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
-                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err};
+                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->ll_base};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx};

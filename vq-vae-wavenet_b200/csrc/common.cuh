@@ -32,8 +32,9 @@ struct GridBarrier {
     epoch += 1;
     if (threadIdx.x == 0) {
       const unsigned long long target = epoch * (unsigned long long)gridDim.x;
-      __threadfence();
-      const unsigned long long prev = atomicAdd(counter, 1ULL);
+      // release: this CTA's stores (ordered before by bar.sync) become visible before the arrival is counted
+      unsigned long long prev;
+      asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(prev) : "l"(counter) : "memory");
       if (prev + 1 == target) {
         // last arriver releases everybody; pollers never touch the arrival counter's line
         asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(counter + 16), "l"(epoch) : "memory");

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
   }
   __syncthreads();
 
-  long long pf_bar = 0, pf_wait = 0, pf_comp = 0, pf_epi = 0, pf_draw = 0, pf_issue = 0, pf_arrive = 0, pf_t = 0;
+  long long pf_bar = 0, pf_wait = 0, pf_comp = 0, pf_epi = 0, pf_draw = 0, pf_issue = 0, pf_arrive = 0, pf_pref = 0, pf_t = 0;
   const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
 #define PF_START() do { if (prof) pf_t = clock64(); } while (0)
 #define PF_ADD(x) do { if (prof) { long long n_ = clock64(); x += n_ - pf_t; pf_t = n_; } } while (0)
@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
   const int sl_R = 31 - __clz(p.R), sl_S = 31 - __clz(p.S), sl_G = 31 - __clz(p.G);
 
   for (long long t = p.t0; t < p.t0 + p.T && alive; ++t) {
+    const long long frame_t = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
     for (int s = 0; s < NS && alive; ++s) {
       if (s == S_DRAW) {
         // weights of the next step's first stage (same buffer class as post2, free by now)
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
         const bool has_post = issue_post_rows(p, s, ti, act_s, &postbar[cls]);
         const bool uses_cond = cls == 1;
         if (uses_cond) {
-          const long long frame = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
+          const long long frame = frame_t;
           if (frame != cond_frame || ti.sb != cond_sb) {          // uniform across the CTA
             __syncthreads();                                      // nobody still reads the old tile
             issue_cond_tile(p, ti.sb, frame, cond_s, condbar);
@@ -598,13 +599,13 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
       bar.arrive();
       PF_ADD(pf_arrive);
       if (s + 1 != S_DRAW) prefetch_stage(s + 1, t);
-      PF_ADD(pf_issue);
+      PF_ADD(pf_pref);
       bar.wait();
       PF_ADD(pf_bar);
     }
   }
   if (prof) {
-    p.prof[0] = pf_bar; p.prof[1] = pf_wait; p.prof[2] = pf_comp; p.prof[3] = pf_epi; p.prof[4] = pf_draw; p.prof[5] = pf_issue; p.prof[6] = pf_arrive;
+    p.prof[0] = pf_bar; p.prof[1] = pf_wait; p.prof[2] = pf_comp; p.prof[3] = pf_epi; p.prof[4] = pf_draw; p.prof[5] = pf_issue; p.prof[6] = pf_arrive; p.prof[7] = pf_pref;
   }
 }
 
