@@ -320,9 +320,8 @@ int finish_timing(vqwn_handle* h) {
   if (h->profile && strcmp(h->last_kernel, "vq_tc_kernel") == 0) {
     long long pf[32];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
-      fprintf(stderr, "[vqwn profile] vq_tc CTA0 cycles: setup=%lld | loader wait_empty=%lld load=%lld norm=%lld | mma wait_z=%lld wait_acc=%lld issue=%lld | "
-              "epi wait_z=%lld wait_acc=%lld scan=%lld decide=%lld output=%lld wscan_sum=%lld cand_lane0=%lld (kernel %.3f ms)\n",
-              pf[0], pf[1], pf[2], pf[3], pf[9], pf[10], pf[11], pf[17], pf[18], pf[19], pf[20], pf[21], pf[22], pf[23], ms);
+      fprintf(stderr, "[vqwn profile] vq_tc CTA0 epilogue-warp0 cycles: setup=%lld wait_z=%lld wait_acc=%lld pass1=%lld pass2=%lld decide=%lld output=%lld (kernel %.3f ms)\n",
+              pf[16], pf[17], pf[18], pf[19], pf[20], pf[21], pf[22], ms);
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
     long long pf[8];

@@ -26,7 +26,11 @@
 
 namespace vqwn {
 
-constexpr int VT_THREADS = 192;
+constexpr int VT_EPI_WARPS = 8;          // 2 warps per TMEM lane quadrant: one per accumulator half
+constexpr int VT_MMA_WARP = 8;
+constexpr int VT_LOAD_WARP0 = 9;         // 4 loader warps, 32 rows of the tile each
+constexpr int VT_LOAD_WARPS = 4;
+constexpr int VT_THREADS = 32 * (VT_EPI_WARPS + 1 + VT_LOAD_WARPS);   // 416
 constexpr int VT_TILE = 128;             // vectors per tile (MMA M)
 constexpr int VT_K = 512;                // codes
 constexpr int VT_D = 64;
@@ -41,8 +45,8 @@ constexpr int VT_LBO_E = VT_K * 16 + 16;                // 8208
 constexpr int VT_LBO_Z = VT_TILE * 16 + 16;             // 2064
 constexpr int VT_SE_BYTES = (VT_KA / 4) * VT_LBO_E;     // 147744
 constexpr int VT_SZ_BYTES = (VT_KA / 4) * VT_LBO_Z;     // 37152
-constexpr int VT_LIST = 8;
-constexpr size_t VT_SMEM = VT_SE_BYTES + 2 * VT_SZ_BYTES + (VT_LIST + 1) * VT_TILE * 4 + 2 * VT_TILE * 4 + 256;
+constexpr int VT_LIST = 4;               // candidates kept per vector per accumulator half
+constexpr size_t VT_SMEM = VT_SE_BYTES + 2 * VT_SZ_BYTES + 2 * (VT_LIST + 1) * VT_TILE * 4 + 6 * VT_TILE * 4 + 256;
 
 __device__ __forceinline__ uint32_t vt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -95,35 +99,33 @@ __device__ __forceinline__ void vt_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
-// scan 32 accumulator values (codes kbase .. kbase+31) held in registers: block max -> running max /
-// threshold, then record every value within thr of the running max (group maxima gate the rare path)
-#define VT_SCAN32(v, kbase)                                                                   \
+// running maximum of 32 accumulator values (D' > 0: float bits order as unsigned ints)
+#define VT_MAX32(v, m)                                                                        \
   do {                                                                                        \
-    uint32_t g_[4];                                                                           \
+    _Pragma("unroll") for (int i_ = 0; i_ < 32; ++i_) m = max(m, v[i_]);                      \
+  } while (0)
+
+// record every value of a 32-column block that reaches thr_key (group maxima gate the rare path; the body is
+// branch-free: predicated store into slot min(cnt, VT_LIST), the last slot being a dummy)
+#define VT_COLLECT32(v, kbase)                                                                \
+  do {                                                                                        \
     _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                        \
       uint32_t m_ = v[8 * i_];                                                                \
       _Pragma("unroll") for (int j_ = 1; j_ < 8; ++j_) m_ = max(m_, v[8 * i_ + j_]);          \
-      g_[i_] = m_;                                                                            \
-    }                                                                                         \
-    const uint32_t cm_ = max(max(g_[0], g_[1]), max(g_[2], g_[3]));                           \
-    if (cm_ > run) {                                                                          \
-      const float t_ = __uint_as_float(cm_) - thr;                                            \
-      thr_key = t_ > 0.f ? __float_as_uint(t_) : 0u;                                          \
-      if (thr_key > run) cnt = 0;   /* every earlier record is below the new threshold */     \
-      run = cm_;                                                                              \
-    }                                                                                         \
-    _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                        \
-      if (g_[i_] >= thr_key) {                                                                \
-        /* branch-free body: predicated store into slot min(cnt, VT_LIST) */                  \
-        _Pragma("unroll") for (int j_ = 0; j_ < 8; ++j_) {                                    \
-          const bool p_ = v[8 * i_ + j_] >= thr_key;                                          \
-          const int slot_ = min(cnt, VT_LIST);                                                \
-          if (p_) list_p[slot_ * VT_TILE + tid] = (v[8 * i_ + j_] & 0xFFFFFE00u) | (uint32_t)((kbase) + 8 * i_ + j_); \
-          cnt += p_ ? 1 : 0;                                                                  \
+      if (m_ >= thr_key) {                                                                    \
+        uint32_t mask_ = 0;   /* independent compares; the serial part is the rare loop below */ \
+        _Pragma("unroll") for (int j_ = 0; j_ < 8; ++j_) mask_ |= (v[8 * i_ + j_] >= thr_key ? 1u : 0u) << j_; \
+        while (mask_) {                                                                       \
+          const int j_ = __ffs(mask_) - 1;                                                    \
+          mask_ &= mask_ - 1;                                                                 \
+          mylist[min(cnt, VT_LIST) * VT_TILE] = (uint32_t)((kbase) + 8 * i_ + j_);            \
+          ++cnt;                                                                              \
         }                                                                                     \
       }                                                                                       \
     }                                                                                         \
   } while (0)
+
+__device__ __forceinline__ void vt_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(VT_THREADS, 1)
 vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long N,
@@ -134,16 +136,19 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
   uint8_t* smem = vt_smem_raw;
   uint8_t* sE = smem;
   uint8_t* sZ0 = smem + VT_SE_BYTES;
-  // candidate list [slot][thread]: (D' bits with the low 9 bits replaced by the code index); slot
-  // VT_LIST is a dummy that absorbs writes after an overflow
-  uint32_t* list_p = reinterpret_cast<uint32_t*>(sZ0 + 2 * VT_SZ_BYTES);
-  float* zn = reinterpret_cast<float*>(list_p + (VT_LIST + 1) * VT_TILE);         // [2][128] ||z||
+  uint32_t* list_p = reinterpret_cast<uint32_t*>(sZ0 + 2 * VT_SZ_BYTES);          // [half][slot][row] code indices
+  uint32_t* hmax_s = list_p + 2 * (VT_LIST + 1) * VT_TILE;                        // [half][row] maximum key of the half
+  uint32_t* cnt_s = hmax_s + 2 * VT_TILE;                                         // [half][row] candidates found
+  float* zn = reinterpret_cast<float*>(cnt_s + 2 * VT_TILE);                      // [stage][row] ||z||
   uint64_t* bars = reinterpret_cast<uint64_t*>(zn + 2 * VT_TILE);
-  uint64_t* z_full = bars;        // [2] loader -> MMA, epilogue
-  uint64_t* z_empty = bars + 2;   // [2] epilogue + MMA -> loader
+  uint64_t* z_full = bars;        // [2] loaders -> MMA, epilogue
+  uint64_t* z_empty = bars + 2;   // [2] epilogue + MMA -> loaders
   uint64_t* acc_full = bars + 4;  // [2] MMA -> epilogue
   uint64_t* acc_empty = bars + 6; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  __shared__ int bestk_s[VT_TILE];
+  __shared__ int fail_s;
+  if (threadIdx.x == 0) fail_s = 0;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float emax = __ldg(emax_p) * 1.000001f;
@@ -154,7 +159,7 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
 #define VT_PF(i) do { if (pf) { long long n_ = clock64(); pc[i] += n_ - pt; pt = n_; } } while (0)
 
   // ---- one-time setup: codebook -> shared memory (fp32 bits untouched) + K augmentation
-#pragma unroll 8
+#pragma unroll 4
   for (int i = tid; i < VT_K * (VT_D / 4); i += VT_THREADS) {
     const int k = i >> 4, c = i & 15;
     const float4 v = __ldg(reinterpret_cast<const float4*>(E + (size_t)k * VT_D) + c);
@@ -175,14 +180,14 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      vt_mbar_init(&z_full[i], 1);
-      vt_mbar_init(&z_empty[i], 5);     // 4 epilogue warps + MMA commit
+      vt_mbar_init(&z_full[i], VT_LOAD_WARPS);
+      vt_mbar_init(&z_empty[i], VT_EPI_WARPS + 1);   // epilogue warps + MMA commit
       vt_mbar_init(&acc_full[i], 1);
-      vt_mbar_init(&acc_empty[i], 4);   // 4 epilogue warps
+      vt_mbar_init(&acc_empty[i], 4);                // the 4 epilogue warps of that half
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == VT_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(vt_smem_u32(tmem_slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -193,18 +198,19 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
   const uint32_t tmem = *tmem_slot;
   VT_PF(0);
 
-  if (warp == 5) {
-    // ================================================================= loader
+  if (warp >= VT_LOAD_WARP0) {
+    // ================================================================= loaders (32 rows each)
+    const int r0 = (warp - VT_LOAD_WARP0) * 32;
     int it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
       uint8_t* sZ = sZ0 + s * VT_SZ_BYTES;
       if (it >= 2 && !vt_mbar_wait(&z_empty[s], ((it >> 1) - 1) & 1, err)) break;
-      VT_PF(1);
       const long long v0 = tile * VT_TILE;
-      // 128 rows x 16 chunks of 16 B; lanes walk the chunks of a row (coalesced 256 B rows)
-      for (int i = lane; i < VT_TILE * 16; i += 32) {
-        const int r = i >> 4, c = i & 15;
+#pragma unroll 4
+      for (int m = 0; m < 16; ++m) {
+        const int i = lane + 32 * m;
+        const int r = r0 + (i >> 4), c = i & 15;
         const bool valid = (v0 + r) < N;
         const float* src = valid ? (z + (size_t)(v0 + r) * VT_D + 4 * c) : z;
         const uint32_t dst = vt_smem_u32(sZ + VT_OFF_Z(r, 4 * c));
@@ -213,9 +219,9 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
       }
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
       __syncwarp();
-      VT_PF(2);
-      // ||z|| and the augmented K columns: [-0.5, -0.5, c_v, 0 | 0, 0, 0, 0]
-      for (int r = lane; r < VT_TILE; r += 32) {
+      {
+        // ||z|| and the augmented K columns [-0.5, -0.5, c_v, 0 | 0, 0, 0, 0]; lane = row: conflict-free plane reads
+        const int r = r0 + lane;
         float nz = 0.f;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -231,10 +237,8 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) vt_mbar_arrive(&z_full[s]);
-      VT_PF(3);
     }
-    if (pf) for (int i = 0; i < 4; ++i) prof[i] = pc[i];
-  } else if (warp == 4) {
+  } else if (warp == VT_MMA_WARP) {
     // ================================================================= MMA issue
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((128u >> 4) << 24);
     uint32_t elected;
@@ -243,14 +247,12 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
       if (!vt_mbar_wait(&z_full[s], (it >> 1) & 1, err)) break;
-      VT_PF(1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_base = vt_smem_u32(sZ0 + s * VT_SZ_BYTES);
       bool ok = true;
       for (int h = 0; h < 2 && ok; ++h) {
         if (it >= 1) ok = vt_mbar_wait(&acc_empty[h], (it - 1) & 1, err);
         if (!ok) break;
-        VT_PF(2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t b_base = vt_smem_u32(sE) + (uint32_t)h * (256 / 8) * VT_SBO;   // codes 256.. start 32 row groups in
         const uint32_t d_addr = tmem + (uint32_t)h * 256;
@@ -268,142 +270,173 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
                      ::"r"(vt_smem_u32(&acc_full[h])), "r"(elected) : "memory");
       }
       if (!ok) break;
-      // the z stage is free for the loader once these MMAs have read it (and the epilogue is done)
+      // the z stage is free for the loaders once these MMAs have read it (and the epilogue is done)
       asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
                    "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
                    ::"r"(vt_smem_u32(&z_empty[s])), "r"(elected) : "memory");
-      VT_PF(3);
     }
-    if (pf) for (int i = 1; i < 4; ++i) prof[8 + i] = pc[i];
   } else {
-    // ================================================================= epilogue (thread = vector)
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // ================================================================= epilogue
+    // warp = hsel*4 + q: TMEM lane quadrant q (vectors 32q..32q+31), accumulator half hsel (codes 256*hsel..)
+    const int q = warp & 3, hsel = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * 256);
+    uint32_t* mylist = list_p + hsel * (VT_LIST + 1) * VT_TILE + row;
     int it = 0;
+    bool ok = true;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
       const uint8_t* sZ = sZ0 + s * VT_SZ_BYTES;
       const long long v0 = tile * VT_TILE;
-      if (!vt_mbar_wait(&z_full[s], (it >> 1) & 1, err)) break;   // zn[] and the fp32 rows are in place
+      ok = ok && vt_mbar_wait(&z_full[s], (it >> 1) & 1, err);   // zn[] and the fp32 rows are in place
       VT_PF(1);
-      const float nrm = zn[s * VT_TILE + tid];
-      // thr = 2 x bound on |D' - exact| (see header): tf32 operand truncation, key/accumulation slop,
+      const float nrm = zn[s * VT_TILE + row];
+      // thr = 2 x bound on |D' - exact| (see header): tf32 operand truncation, accumulation slop,
       // and the float32 direct form's own rounding
       const float ze = nrm * emax;
       const float bound = ze * (1.0f / 512.0f) + (2.f * ze + emax * emax) * (1.0f / 8192.0f) +
                           (nrm + emax) * (nrm + emax) * (1.0f / 131072.0f);
       const float thr = 2.0f * bound;
-      uint32_t run = 0;           // running maximum key (D' > 0: float bits order as unsigned ints)
-      uint32_t thr_key = 0;
-      int cnt = 0;
-      bool ok = true;
-      for (int h = 0; h < 2 && ok; ++h) {
-        ok = vt_mbar_wait(&acc_full[h], it & 1, err);
-        if (!ok) break;
-        VT_PF(2);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // 8 blocks of 32 columns; the TMEM load of block b+1 is in flight while block b is scanned
-        uint32_t va[32], vb[32];
-        vt_ld32(lane_base + (uint32_t)(h * 256), va);
+      ok = ok && vt_mbar_wait(&acc_full[hsel], it & 1, err);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      VT_PF(2);
+      // ---- pass 1: maximum key of this half (8 blocks of 32 columns, next TMEM load in flight)
+      uint32_t va[32], vb[32];
+      uint32_t hm = 0;
+      vt_ld32(lane_base, va);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 64) {
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          vt_ld32(lane_base + (uint32_t)(h * 256 + c0 + 32), vb);
-          VT_SCAN32(va, h * 256 + c0);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (c0 + 64 < 256) vt_ld32(lane_base + (uint32_t)(h * 256 + c0 + 64), va);
-          VT_SCAN32(vb, h * 256 + c0 + 32);
-        }
-        // this accumulator half may be overwritten by the next tile's MMA
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) vt_mbar_arrive(&acc_empty[h]);
-        VT_PF(3);
+      for (int c0 = 0; c0 < 256; c0 += 64) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        vt_ld32(lane_base + (uint32_t)(c0 + 32), vb);
+        VT_MAX32(va, hm);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        vt_ld32(lane_base + (uint32_t)((c0 + 64) & 255), va);     // wraps to block 0: first block of pass 2
+        VT_MAX32(vb, hm);
       }
-      if (!ok) break;
+      hmax_s[hsel * VT_TILE + row] = hm;
+      vt_epi_sync();
+      const uint32_t gmax = max(hmax_s[row], hmax_s[VT_TILE + row]);
+      const float tthr = __uint_as_float(gmax) - thr;
+      const uint32_t thr_key = tthr > 0.f ? __float_as_uint(tthr) : 0u;
+      VT_PF(3);
+      // ---- pass 2: codes of this half within thr of the global maximum
+      int cnt = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 64) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        vt_ld32(lane_base + (uint32_t)(c0 + 32), vb);
+        VT_COLLECT32(va, hsel * 256 + c0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 64 < 256) vt_ld32(lane_base + (uint32_t)(c0 + 64), va);
+        VT_COLLECT32(vb, hsel * 256 + c0 + 32);
+      }
+      cnt_s[hsel * VT_TILE + row] = (uint32_t)cnt;
+      if (!ok) fail_s = 1;        // a timed-out wait: every epilogue warp leaves after this tile (uniform decision)
+      // this accumulator half may be overwritten by the next tile's MMA
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) vt_mbar_arrive(&acc_empty[hsel]);
+      vt_epi_sync();
+      VT_PF(4);
 
-      // ---- decide: single surviving candidate -> done; else exact float32 re-evaluation
-      const bool overflow = cnt > VT_LIST;
-      const int ncand = overflow ? VT_LIST : cnt;
-      int nvalid = 0, best_k = 0;
-      for (int j = 0; j < ncand; ++j) {
-        const uint32_t pk = list_p[j * VT_TILE + tid];
-        if ((pk | 0x1FFu) >= thr_key) {                        // survivors of the final threshold (the 9
-          best_k = (int)(pk & 0x1FFu);                         // dropped value bits are rounded up), compacted
-          list_p[nvalid * VT_TILE + tid] = pk;
-          ++nvalid;
-        }
-      }
-      const bool need = overflow || nvalid != 1;
-      const int nscan = !need ? 0 : (overflow ? VT_K : nvalid);   // overflow: exact scan of the whole codebook
-      const int wscan = __reduce_max_sync(0xffffffffu, nscan);
-      if (wscan > 0) {
-        float zr[VT_D];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float4 q = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(tid, 4 * c));
-          zr[4 * c] = q.x; zr[4 * c + 1] = q.y; zr[4 * c + 2] = q.z; zr[4 * c + 3] = q.w;
-        }
+      // ---- decide: single candidate -> done; else exact float32 re-evaluation, the two warps that share a
+      //      row (half 0 / half 1) each take every other candidate
+      {
+        const int n0 = (int)cnt_s[row], n1 = (int)cnt_s[VT_TILE + row];
+        const bool overflow = n0 > VT_LIST || n1 > VT_LIST;
+        const int total = n0 + n1;
+        const bool need = overflow || total != 1;
+        const int nall = !need ? 0 : (overflow ? VT_K : total);   // overflow: exact scan of the whole codebook
+        const int mine = (nall + 1 - hsel) >> 1;                  // candidates hsel, hsel+2, ...
+        const int wscan = __reduce_max_sync(0xffffffffu, mine);
         float bd = INFINITY;
         int bk = 0x7fffffff;
-        for (int j = 0; j < wscan; ++j) {
-          if (j < nscan) {
-            const int k = overflow ? j : (int)(list_p[j * VT_TILE + tid] & 0x1FFu);
-            float dist = 0.f;
+        if (wscan > 0) {
+          float zr[VT_D];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const float4 e4 = *reinterpret_cast<const float4*>(sE + VT_OFF_E(k, 4 * c));
-              float t;
-              t = __fsub_rn(zr[4 * c], e4.x);     dist = __fmaf_rn(t, t, dist);
-              t = __fsub_rn(zr[4 * c + 1], e4.y); dist = __fmaf_rn(t, t, dist);
-              t = __fsub_rn(zr[4 * c + 2], e4.z); dist = __fmaf_rn(t, t, dist);
-              t = __fsub_rn(zr[4 * c + 3], e4.w); dist = __fmaf_rn(t, t, dist);
+          for (int c = 0; c < 16; ++c) {
+            const float4 qv = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(row, 4 * c));
+            zr[4 * c] = qv.x; zr[4 * c + 1] = qv.y; zr[4 * c + 2] = qv.z; zr[4 * c + 3] = qv.w;
+          }
+          for (int j = 0; j < wscan; ++j) {
+            if (j < mine) {
+              const int ci = 2 * j + hsel;
+              int k;
+              if (overflow) k = ci;
+              else k = (ci < n0) ? (int)list_p[ci * VT_TILE + row] : (int)list_p[((VT_LIST + 1) + (ci - n0)) * VT_TILE + row];
+              float dist = 0.f;
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float4 e4 = *reinterpret_cast<const float4*>(sE + VT_OFF_E(k, 4 * c));
+                float t;
+                t = __fsub_rn(zr[4 * c], e4.x);     dist = __fmaf_rn(t, t, dist);
+                t = __fsub_rn(zr[4 * c + 1], e4.y); dist = __fmaf_rn(t, t, dist);
+                t = __fsub_rn(zr[4 * c + 2], e4.z); dist = __fmaf_rn(t, t, dist);
+                t = __fsub_rn(zr[4 * c + 3], e4.w); dist = __fmaf_rn(t, t, dist);
+              }
+              if (dist < bd || (dist == bd && k < bk)) { bd = dist; bk = k; }
             }
-            if (dist < bd || (dist == bd && k < bk)) { bd = dist; bk = k; }
           }
         }
-        if (need) best_k = bk;
+        // partial winners of the two warps -> shared memory (reusing hmax_s / cnt_s, no longer needed)
+        vt_epi_sync();
+        if (hsel == 1) { hmax_s[row] = __float_as_uint(bd); hmax_s[VT_TILE + row] = (uint32_t)bk; }
+        vt_epi_sync();
+        if (hsel == 0) {
+          int best_k;
+          if (!need) best_k = (n0 > 0) ? (int)list_p[row] : (int)list_p[(VT_LIST + 1) * VT_TILE + row];
+          else {
+            const float od = __uint_as_float(hmax_s[row]);
+            const int ok2 = (int)hmax_s[VT_TILE + row];
+            best_k = (od < bd || (od == bd && ok2 < bk)) ? ok2 : bk;
+          }
+          bestk_s[row] = best_k;
+          if (idx_out != nullptr && v0 + row < N) idx_out[v0 + row] = (long long)best_k;
+        }
       }
-      if (idx_out != nullptr && v0 + tid < N) idx_out[v0 + tid] = (long long)best_k;
-      VT_PF(4);
-      if (pf) { pc[6] += wscan; pc[7] += cnt; }
+      vt_epi_sync();
+      VT_PF(5);
 
-      // ---- fused gather + straight-through + speaker concat: 2 rows per iteration, 16 lanes x 16 B each
+      // ---- fused gather + straight-through + speaker concat: warp w writes rows 16w..16w+15, 2 per iteration
       if (zq_out != nullptr) {
         const int sub = lane >> 4, ch = lane & 15;
-#pragma unroll 4
-        for (int j = 0; j < 16; ++j) {
-          const int rl = 2 * j + sub;                        // row within this warp's 32
-          const int kb = __shfl_sync(0xffffffffu, best_k, rl);
-          const int row = warp * 32 + rl;
-          const long long gv = v0 + row;
-          if (gv < N) {
-            const float4 zz = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(row, 4 * ch));
-            const float4 ee = *reinterpret_cast<const float4*>(sE + VT_OFF_E(kb, 4 * ch));
-            float4 o;
-            o.x = __fadd_rn(zz.x, __fsub_rn(ee.x, zz.x));               // model.py:73
-            o.y = __fadd_rn(zz.y, __fsub_rn(ee.y, zz.y));
-            o.z = __fadd_rn(zz.z, __fsub_rn(ee.z, zz.z));
-            o.w = __fadd_rn(zz.w, __fsub_rn(ee.w, zz.w));
-            float* orow = zq_out + (size_t)gv * out_stride;
-            *reinterpret_cast<float4*>(orow + 4 * ch) = o;
-            if (spk_dim > 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int orow = warp * 16 + 2 * j + sub;
+          const int kb = bestk_s[orow];
+          const long long gv = v0 + orow;
+          const float4 zz = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(orow, 4 * ch));
+          const float4 ee = *reinterpret_cast<const float4*>(sE + VT_OFF_E(kb, 4 * ch));
+          float4 o;
+          o.x = __fadd_rn(zz.x, __fsub_rn(ee.x, zz.x));               // model.py:73
+          o.y = __fadd_rn(zz.y, __fsub_rn(ee.y, zz.y));
+          o.z = __fadd_rn(zz.z, __fsub_rn(ee.z, zz.z));
+          o.w = __fadd_rn(zz.w, __fsub_rn(ee.w, zz.w));
+          if (gv < N) *reinterpret_cast<float4*>(zq_out + (size_t)gv * out_stride + 4 * ch) = o;
+        }
+        if (spk_dim > 0) {
+          for (int j = 0; j < 8; ++j) {
+            const long long gv = v0 + warp * 16 + 2 * j + sub;
+            if (gv < N) {
               const float* srow = spk_table + (size_t)spk_idx[(int)(gv / F)] * spk_dim;
+              float* op = zq_out + (size_t)gv * out_stride + VT_D;
               for (int c = 4 * ch; c < spk_dim; c += 64)
-                *reinterpret_cast<float4*>(orow + VT_D + c) = __ldg(reinterpret_cast<const float4*>(srow + c));
+                *reinterpret_cast<float4*>(op + c) = __ldg(reinterpret_cast<const float4*>(srow + c));
             }
           }
         }
       }
       __syncwarp();
       if (lane == 0) vt_mbar_arrive(&z_empty[s]);
-      VT_PF(5);
+      VT_PF(6);
+      if (fail_s) break;
     }
-    if (pf && warp == 0) for (int i = 1; i < 8; ++i) prof[16 + i] = pc[i];
+    if (pf && warp == 0) for (int i = 0; i < 8; ++i) prof[16 + i] = pc[i];
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  if (warp == VT_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 // max_k ||e_k|| (one block, K <= 1024 threads); feeds the candidate threshold of vq_tc_kernel
