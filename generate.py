@@ -9,8 +9,8 @@ Outputs, as the reference writes them (generate.py:94-101,115-117):
 
 Weights: `<restore>.npz` holding arrays keyed by the reference's variable names (EMA shadows stored
 under the variable's own name).  Reading TensorFlow tensor-bundle checkpoints directly is SURVEY 8f #2.
-Encoder output: the encoders are SURVEY 8f #1; until they run on the device pass the encoder output
-with -z_e <file.npy> ([F,latent_dim] or [B,F,latent_dim]); -audio then only fixes the length.
+Encoder: Encoder_64 ("encoder": "64") runs on the device; for the other two pass the
+encoder output with -z_e <file.npy> ([F,latent_dim] or [B,F,latent_dim]); -audio then only fixes the length.
 """
 import os
 import sys
@@ -53,14 +53,16 @@ def main(argv=None):
 
     wav = wavio.prepare_audio(wavio.read_wav(args.audio_path, 16000), batch_size)        # generate.py:36-44
     length = wav.shape[1]
-    if args.z_e_path is None:
-        raise NotImplementedError("encoder '%s' forward is not on the device yet (SURVEY 8f #1): pass -z_e"
+    z_e = None
+    if args.z_e_path is not None:
+        z_e = np.load(args.z_e_path).astype(np.float32)
+        if z_e.ndim == 2:
+            z_e = np.tile(z_e[None], (batch_size, 1, 1))
+        if length % z_e.shape[1] != 0:
+            raise ValueError("audio length %d is not a multiple of the %d encoder frames" % (length, z_e.shape[1]))
+    elif cfg.model['encoder'] != '64':
+        raise NotImplementedError("encoder %s not implemented on the device (SURVEY 8f #1): pass -z_e"
                                   % cfg.model['encoder'])
-    z_e = np.load(args.z_e_path).astype(np.float32)
-    if z_e.ndim == 2:
-        z_e = np.tile(z_e[None], (batch_size, 1, 1))
-    if length % z_e.shape[1] != 0:
-        raise ValueError("audio length %d is not a multiple of the %d encoder frames" % (length, z_e.shape[1]))
 
     weights_file = args.restore_path + '.npz'
     if not os.path.exists(weights_file):
@@ -75,7 +77,12 @@ def main(argv=None):
             if key in wanted:
                 engine.set_tensor(key, data[name])
 
-    model = pkg.VQVAE({'x': wav, 'z_e': z_e, 'speaker': speaker, 'encoder': None,
+    encoder = None
+    if z_e is None:
+        # generate.py:40 tiles ONE utterance over the batch: encode it once, tile the result
+        encoder = pkg.Encoder_64(cfg.model['latent_dim'], engine)
+        z_e = np.tile(encoder.build(wav[:1]), (batch_size, 1, 1))
+    model = pkg.VQVAE({'x': wav, 'z_e': z_e, 'speaker': speaker, 'encoder': encoder,
                        'decoder': pkg.WavenetDecoder(cfg.wavenet), 'k': cfg.model['k'], 'beta': cfg.model['beta'],
                        'verbose': cfg.model.get('verbose', False), 'use_vq': cfg.model['use_vq'],
                        'speaker_embedding': cfg.model['speaker_embedding'], 'num_speakers': num_speakers,

@@ -63,6 +63,7 @@ typedef struct vqwn_config {
   int32_t speaker_dim;           /* "speaker_embedding" (64; 0 = no speaker condition)      */
   int32_t num_speakers;          /* 109 / 340 / 251 (generate.py:46-57)                     */
   int32_t use_vq;                /* "use_vq"                                                */
+  int32_t encoder;               /* "encoder": 64 = Encoder_64 on the device, 0 = encoder output is supplied */
 } vqwn_config;
 
 typedef struct vqwn_handle vqwn_handle;
@@ -100,6 +101,13 @@ int vqwn_num_tensors(const vqwn_handle* h);
 /* name / shape of the i-th expected tensor; is_set tells whether vqwn_set_tensor was called */
 int vqwn_tensor_info(const vqwn_handle* h, int i, char* name_out, int name_cap,
                      int64_t* shape_out /*[4]*/, int* ndim_out, int* is_set);
+
+/* ---- encoder ----------------------------------------------------------- */
+/* replaces Encoder_64.build (Encoder/encoder.py:8-26; model.py:36-42): x [B,T] float audio ->
+ * z_e_out [B, T/64, latent_dim].  T must be a multiple of 64.  Needs cfg.encoder == 64 and the
+ * keras variables "encoder/conv1d[_i]/{kernel,bias}", "encoder/batch_normalization[_i]/{gamma,
+ * beta,moving_mean,moving_variance}", i = 1..6 (no suffix for the first). */
+int vqwn_encode_audio(vqwn_handle* h, const float* x, int B, int64_t T, float* z_e_out);
 
 /* ---- VQ bottleneck + conditioning ---------------------------------------------------- */
 /* replaces VQVAE._discretise (model.py:57-74): direct-form squared distance, lowest-index

@@ -457,6 +457,78 @@ def wavenet_teacher_forced(cfg, weights, x, local_condition):
 
 
 # --------------------------------------------------------------------------------------
+# Encoder_64 (Encoder/encoder.py:8-26) -- SURVEY 8f #1: the step right before the path
+# --------------------------------------------------------------------------------------
+def encoder64_specs(cfg):
+    """keras auto-names inside variable_scope('encoder') (model.py:134-135): conv1d, conv1d_1, ...,
+    batch_normalization, batch_normalization_1, ...; kernels [k, in, out]."""
+    specs = []
+    cin = 1
+    for i in range(7):
+        sfx = "" if i == 0 else "_%d" % i
+        cout = 768 if i < 6 else cfg.D
+        k = 5 if i < 6 else 1
+        specs += [("encoder/conv1d%s/kernel" % sfx, (k, cin, cout)), ("encoder/conv1d%s/bias" % sfx, (cout,)),
+                  ("encoder/batch_normalization%s/gamma" % sfx, (cout,)), ("encoder/batch_normalization%s/beta" % sfx, (cout,)),
+                  ("encoder/batch_normalization%s/moving_mean" % sfx, (cout,)),
+                  ("encoder/batch_normalization%s/moving_variance" % sfx, (cout,))]
+        cin = cout
+    return specs
+
+
+def make_encoder64_weights(cfg, seed=4321):
+    """seeded synthetic encoder weights: glorot-uniform kernels (keras default), small biases, BN statistics
+    away from the identity so every term is exercised"""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in encoder64_specs(cfg):
+        if name.endswith("kernel"):
+            lim = np.sqrt(6.0 / (shape[0] * shape[1] + shape[0] * shape[2]))
+            a = rng.uniform(-lim, lim, size=shape)
+        elif name.endswith("moving_variance"):
+            a = rng.uniform(0.5, 1.5, size=shape)
+        elif name.endswith("gamma"):
+            a = rng.uniform(0.8, 1.2, size=shape)
+        else:
+            a = rng.uniform(-0.1, 0.1, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=F32)
+    return out
+
+
+def encoder64_forward(cfg, weights, x):
+    """Encoder/encoder.py:13-26.  x [B,T,1] -> z_e [B,T/64,latent_dim].
+    Conv1D(768, k=5, strides=2, padding='same', relu): TF 'same' with stride 2 pads
+    total = max((ceil(T/2)-1)*2 + 5 - T, 0), left = total // 2 (1 left / 2 right for even T).
+    BatchNormalization() is called without training= -> inference form with the moving statistics,
+    epsilon 1e-3 (keras default)."""
+    net = np.asarray(x, dtype=F32)
+    for i in range(7):
+        sfx = "" if i == 0 else "_%d" % i
+        K = weights["encoder/conv1d%s/kernel" % sfx]
+        b = weights["encoder/conv1d%s/bias" % sfx]
+        k = K.shape[0]
+        stride = 2 if i < 6 else 1
+        T = net.shape[1]
+        To = (T + stride - 1) // stride
+        total = max((To - 1) * stride + k - T, 0)
+        left = total // 2
+        xp = np.pad(net, [(0, 0), (left, total - left), (0, 0)])
+        out = None
+        for j in range(k):
+            term = xp[:, j: j + (To - 1) * stride + 1: stride] @ K[j]
+            out = term if out is None else out + term
+        out = out + b
+        if i < 6:
+            out = np.maximum(out, 0)
+        g = weights["encoder/batch_normalization%s/gamma" % sfx]
+        be = weights["encoder/batch_normalization%s/beta" % sfx]
+        mu = weights["encoder/batch_normalization%s/moving_mean" % sfx]
+        var = weights["encoder/batch_normalization%s/moving_variance" % sfx]
+        net = ((out - mu) * (g / np.sqrt(var + F32(1e-3))) + be).astype(F32)
+    return net
+
+
+# --------------------------------------------------------------------------------------
 # Synthetic inputs of SURVEY 8d
 # --------------------------------------------------------------------------------------
 def synthetic_z_e(cfg, weights, B, F, seed=1235, kind="normal"):

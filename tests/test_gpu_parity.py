@@ -180,6 +180,67 @@ def test_encode_condition_matches_oracle(small):
         eng.encode_condition(z, np.array([0, 109, 0, 0, 0], dtype=np.int32))
 
 
+# ----------------------------------------------------------------------------------------- encoder
+def test_encoder64_matches_oracle():
+    import vqvae_wavenet_b200 as pkg
+    cfg = O.Config()
+    w = O.make_encoder64_weights(cfg, seed=4321)
+    eng = pkg.Engine(pkg.EngineConfig(wavenet=SMALL_WAVENET), device=0, max_batch=4)
+    eng.set_weights(w)
+    for B, T in ((1, 64), (3, 2048), (2, 4096 + 64)):
+        x = O.synthetic_audio(B, T, seed=5)
+        z = eng.encode_audio(x)
+        oz = O.encoder64_forward(cfg, w, x[:, :, None])
+        assert z.shape == oz.shape == (B, T // 64, 64)
+        assert np.abs(z - oz).max() <= 1e-4 * max(1.0, np.abs(oz).max())
+    enc = pkg.Encoder_64(64, eng)
+    assert np.array_equal(enc.build(x[:, :, None]), z)
+    with pytest.raises(ValueError):
+        eng.encode_audio(x[:, :100])
+    none = pkg.Engine(pkg.EngineConfig(wavenet=SMALL_WAVENET, model=dict(encoder="2019")), device=0, max_batch=1)
+    with pytest.raises(NotImplementedError):
+        none.encode_audio(x)
+    none.close()
+    eng.close()
+
+
+def test_cli_end_to_end(tmp_path):
+    """generate.py with the reference's flags, TF-free: audio -> Encoder_64 -> VQ -> WaveNet -> WAVs"""
+    import generate
+    import vqvae_wavenet_b200 as pkg
+    from vqvae_wavenet_b200 import synthetic, wavio
+    cfg = pkg.EngineConfig.from_files(os.path.join(os.path.dirname(generate.__file__), "model_parameters.json"))
+    w = synthetic.make_weights(cfg, seed=1234, peaked=True)
+    w.update(synthetic.make_encoder64_weights(cfg))
+    run = tmp_path / "run"
+    run.mkdir()
+    np.savez(str(run / "weights-7.npz"), **{("optimiser/" + k + "/ExponentialMovingAverage" if k.startswith("decoder/cycle_1") else k): v
+                                            for k, v in w.items()})
+    x = O.synthetic_audio(1, 1100, seed=9)[0]
+    wavio.write_wav_float32(str(tmp_path / "in.wav"), 16000, x)
+    generate.main(["-restore", str(run / "weights-7"), "-audio", str(tmp_path / "in.wav"), "-speakers", "p225", "None",
+                   "-mode", "greedy"])
+    a = wavio.read_wav(str(run / "7_p225.wav"))
+    b = wavio.read_wav(str(run / "7_no_speaker.wav"))
+    assert a.shape == b.shape == (1024,)                      # trimmed to a multiple of 512 (generate.py:39)
+    assert not np.array_equal(a, b)
+    lut = O.decode_lut()
+    assert np.all(np.isin(a, lut)) and np.all(np.isin(b, lut))
+    assert np.array_equal(np.load(str(run / "embedding_7.npy")), w["embedding/embedding"])
+    assert np.load(str(run / "speaker_embedding_7.npy")).shape == (109, 64)
+    # same result as driving the pieces by hand
+    ocfg = O.Config()
+    z = O.encoder64_forward(ocfg, w, x[None, :1024, None])
+    eng = pkg.Engine(cfg, 0, 2)
+    eng.set_weights(w)
+    table = pkg.utils.get_speaker_to_int(pkg.utils.find_speaker_table("vctk", roots=(os.path.dirname(generate.__file__),)))
+    _, cond = eng.encode_condition(np.tile(eng.encode_audio(x[None, :1024]), (2, 1, 1)), [table["p225"], 0])
+    audio, _ = eng.generate(cond, 1024, mode="greedy")
+    assert np.array_equal(audio[0], a) and np.array_equal(audio[1], b)
+    assert np.abs(eng.encode_audio(x[None, :1024]) - z).max() < 1e-4
+    eng.close()
+
+
 # ----------------------------------------------------------------------------------------- decoder, small config
 def _small_inputs(cfg, w):
     B, T, F = 3, 256, 4

@@ -9,6 +9,7 @@ from .engine import Engine, EngineConfig  # noqa: F401
 from .model import VQVAE  # noqa: F401
 from .decoder import WavenetDecoder  # noqa: F401
 from .wavenet import Wavenet  # noqa: F401
+from .encoder import Encoder_64, Encoder_Magenta, Encoder_2019  # noqa: F401
 from . import mu_law_ops, utils  # noqa: F401
 
 __all__ = ["load_library", "library_path", "VqwnError", "Engine", "EngineConfig", "VQVAE",

@@ -34,6 +34,7 @@ class Config(C.Structure):
         ("speaker_dim", C.c_int32),
         ("num_speakers", C.c_int32),
         ("use_vq", C.c_int32),
+        ("encoder", C.c_int32),
     ]
 
 
@@ -62,6 +63,7 @@ PROTOTYPES = {
     "vqwn_get_tensor": (C.c_int, [_H, C.c_char_p, _f32p, C.c_int64]),
     "vqwn_num_tensors": (C.c_int, [_H]),
     "vqwn_tensor_info": (C.c_int, [_H, C.c_int, C.c_char_p, C.c_int, _i64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vqwn_encode_audio": (C.c_int, [_H, _f32p, C.c_int, C.c_int64, _f32p]),
     "vqwn_vq_lookup": (C.c_int, [_H, _f32p, C.c_int64, _i64p, _f32p]),
     "vqwn_build_condition": (C.c_int, [_H, _f32p, _i32p, C.c_int, C.c_int, _f32p]),
     "vqwn_encode_condition": (C.c_int, [_H, _f32p, _i32p, C.c_int, C.c_int, _i64p, _f32p]),

@@ -18,6 +18,7 @@
 #include "wavenet_fp32.cuh"
 #include "wavenet_fp32_df.cuh"
 #include "sample.cuh"
+#include "encoder.cuh"
 
 using namespace vqwn;
 
@@ -86,6 +87,7 @@ struct vqwn_handle {
   // resident / staging buffers
   DevBuf cond_res, uni_res, audio_res, idx_res, logits_res, x_res, small_a, small_b, small_c, small_d;
   DevBuf vq_z, vq_idx, vq_out, spk_idx;
+  DevBuf enc_x, enc_a, enc_b, enc_fold, enc_z;
   int cond_B = 0, cond_F = 0;
   long long uni_T = 0; int uni_B = 0;
   long long out_T = 0; int out_B = 0;
@@ -421,6 +423,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   if (c.pre_kernel_size < 1 || c.pre_kernel_size > 64) return fail(nullptr, VQWN_ERR_INVALID, "preprocess.kernel_size out of range");
   if (c.use_vq && (c.k < 1 || c.k > 512)) return fail(nullptr, VQWN_ERR_NOTIMPL, "k must be <= 512");
   if (c.latent_dim != 32 && c.latent_dim != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
+  if (c.encoder != 0 && c.encoder != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "only Encoder_64 runs on the device (encoder = 64) or none (0)");
+  if (c.encoder == 64 && c.latent_dim != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "Encoder_64 on the device needs latent_dim = 64");
   if (c.num_cycle_layers < 1) return fail(nullptr, VQWN_ERR_INVALID, "num_cycle_layers must be >= 1");
   for (int i = 0; i < c.num_layers; ++i)
     if (c.dilations[i] < 1) return fail(nullptr, VQWN_ERR_INVALID, "dilation must be >= 1");
@@ -487,6 +491,21 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   add_tensor(h, "decoder/postprocess1/local_condition/kernel", {1, C, S});
   add_tensor(h, "decoder/postprocess2/kernel", {1, S, Q});
   add_tensor(h, "decoder/postprocess2/bias", {Q});
+  if (c.encoder == 64) {
+    int cin = 1;
+    for (int i = 0; i < 7; ++i) {
+      const std::string sfx = i == 0 ? "" : "_" + std::to_string(i);
+      const int cout = i < 6 ? 768 : c.latent_dim;
+      const int k = i < 6 ? 5 : 1;
+      add_tensor(h, "encoder/conv1d" + sfx + "/kernel", {k, cin, cout}, false);
+      add_tensor(h, "encoder/conv1d" + sfx + "/bias", {cout}, false);
+      add_tensor(h, "encoder/batch_normalization" + sfx + "/gamma", {cout}, false);
+      add_tensor(h, "encoder/batch_normalization" + sfx + "/beta", {cout}, false);
+      add_tensor(h, "encoder/batch_normalization" + sfx + "/moving_mean", {cout}, false);
+      add_tensor(h, "encoder/batch_normalization" + sfx + "/moving_variance", {cout}, false);
+      cin = cout;
+    }
+  }
   add_tensor(h, "lut/mu_law_decode", {Q + 1}, false);
   add_tensor(h, "lut/mu_law_encode", {Q + 1}, false);
   for (auto& s : h->tensors) CKC(cudaMalloc(&s.dev, s.numel * sizeof(float)));
@@ -598,7 +617,8 @@ int vqwn_destroy(vqwn_handle* h) {
                      h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->ll_base};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
-                    &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx};
+                    &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,
+                    &h->enc_x, &h->enc_a, &h->enc_b, &h->enc_fold, &h->enc_z};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -672,6 +692,85 @@ int vqwn_tensor_info(const vqwn_handle* h, int i, char* name_out, int name_cap, 
   if (ndim_out) *ndim_out = (int)s.shape.size();
   if (is_set) *is_set = s.set ? 1 : 0;
   return VQWN_OK;
+}
+
+// ---------------------------------------------------------------------------------- encoder
+int vqwn_encode_audio(vqwn_handle* h, const float* x, int B, int64_t T, float* z_e_out) {
+  ENTER(h);
+  if (!x || !z_e_out || B < 1 || T < 64) return fail(h, VQWN_ERR_INVALID, "bad argument");
+  if (h->cfg.encoder != 64) return fail(h, VQWN_ERR_NOTIMPL, "no encoder configured on the device (vqwn_config.encoder = 64)");
+  if (T % 64 != 0) return fail(h, VQWN_ERR_INVALID, "T must be a multiple of 64 (Encoder_64 hop)");
+  int rc;
+  std::vector<std::string> sfx(7);
+  for (int i = 0; i < 7; ++i) {
+    sfx[i] = i == 0 ? "" : "_" + std::to_string(i);
+    const char* parts[] = {"/kernel", "/bias"};
+    for (const char* pt : parts)
+      if ((rc = check_tensor_ready(h, ("encoder/conv1d" + sfx[i] + pt).c_str()))) return rc;
+    const char* bparts[] = {"/gamma", "/beta", "/moving_mean", "/moving_variance"};
+    for (const char* pt : bparts)
+      if ((rc = check_tensor_ready(h, ("encoder/batch_normalization" + sfx[i] + pt).c_str()))) return rc;
+  }
+  // folded BatchNorm (scale, shift) per layer
+  const int D = h->D;
+  if ((rc = ensure(h, h->enc_fold, (size_t)7 * 2 * 768 * sizeof(float)))) return rc;
+  float* fold = (float*)h->enc_fold.p;
+  for (int i = 0; i < 7; ++i) {
+    const int cout = i < 6 ? 768 : D;
+    const std::string bn = "encoder/batch_normalization" + sfx[i];
+    bn_fold_kernel<<<(cout + 255) / 256, 256, 0, h->stream>>>(TP(h, bn + "/gamma"), TP(h, bn + "/beta"), TP(h, bn + "/moving_mean"),
+                                                              TP(h, bn + "/moving_variance"), 1e-3f, fold + (size_t)i * 1536,
+                                                              fold + (size_t)i * 1536 + 768, cout);
+    h->launches += 1;
+  }
+  // utterances are processed in groups that keep the two ping-pong activation buffers under ~1 GiB
+  const size_t per_stream = (size_t)(T / 2) * 768 * sizeof(float) + (size_t)(T / 4) * 768 * sizeof(float);
+  size_t gsz = per_stream ? (((size_t)1 << 30) / per_stream) : 1;
+  if (gsz < 1) gsz = 1;
+  int group = gsz > (size_t)B ? B : (int)gsz;
+  if (group > B) group = B;
+  if ((rc = ensure(h, h->enc_x, (size_t)group * T * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->enc_a, (size_t)group * (T / 2) * 768 * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->enc_b, (size_t)group * (T / 4) * 768 * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->enc_z, (size_t)group * (T / 64) * D * sizeof(float)))) return rc;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int g = (B - b0 < group) ? (B - b0) : group;
+    CK(h, cudaMemcpyAsync(h->enc_x.p, x + (size_t)b0 * T, (size_t)g * T * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    const float* in = (const float*)h->enc_x.p;
+    int Tin = (int)T, cin = 1;
+    for (int i = 0; i < 7; ++i) {
+      const int cout = i < 6 ? 768 : D;
+      const int k = i < 6 ? 5 : 1, stride = i < 6 ? 2 : 1;
+      const int Tout = (Tin + stride - 1) / stride;
+      int total_pad = (Tout - 1) * stride + k - Tin;
+      if (total_pad < 0) total_pad = 0;
+      const int left = total_pad / 2;                 // TF 'same': 1 left / 2 right for even T, k = 5, stride 2
+      float* out = (i == 6) ? (float*)h->enc_z.p : ((i & 1) ? (float*)h->enc_b.p : (float*)h->enc_a.p);
+      const float* Wk = TP(h, "encoder/conv1d" + sfx[i] + "/kernel");
+      const float* bk = TP(h, "encoder/conv1d" + sfx[i] + "/bias");
+      const float* sc = fold + (size_t)i * 1536;
+      const float* sh = sc + 768;
+      if (cin == 1) {
+        const long long total = (long long)g * Tout * cout;
+        int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
+        conv1d_in1_kernel<<<grid, 256, 0, h->stream>>>(in, Wk, bk, sc, sh, out, g, Tin, Tout, cout, k, stride, left);
+      } else {
+        const long long M = (long long)g * Tout;
+        dim3 grid((unsigned)((M + ENC_BM - 1) / ENC_BM), (unsigned)(cout / ENC_BN));
+        conv1d_gemm_kernel<<<grid, 256, 0, h->stream>>>(in, Wk, bk, sc, sh, out, g, Tin, cin, Tout, cout, k, stride, left,
+                                                        i < 6 ? 1 : 0);
+      }
+      CK(h, cudaGetLastError());
+      h->launches += 1;
+      in = out; Tin = Tout; cin = cout;
+    }
+    CK(h, cudaMemcpyAsync(z_e_out + (size_t)b0 * (T / 64) * D, h->enc_z.p, (size_t)g * (T / 64) * D * sizeof(float),
+                          cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->last_kernel = "conv1d_gemm_kernel";
+  return finish_timing(h);
 }
 
 // ---------------------------------------------------------------------------------- VQ

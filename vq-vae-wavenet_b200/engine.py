@@ -72,6 +72,7 @@ class EngineConfig:
         c.speaker_dim = m["speaker_embedding"]
         c.num_speakers = self.num_speakers
         c.use_vq = 1 if m["use_vq"] else 0
+        c.encoder = 64 if str(m.get("encoder")) == "64" else 0
         return c
 
 
@@ -170,6 +171,17 @@ class Engine:
         out = np.empty(shape, dtype=np.float32)
         self._ck(self.lib.vqwn_get_tensor(self._h, name.encode(), _ptr(out, C.c_float), out.size))
         return out
+
+    # ------------------------------------------------------------------ encoder
+    def encode_audio(self, x):
+        """Encoder_64.build: x [B,T] or [B,T,1] float audio -> z_e [B,T/64,latent_dim]"""
+        xx = _f32(x)
+        if xx.ndim == 3:
+            xx = np.ascontiguousarray(xx[:, :, 0])
+        B, T = xx.shape
+        z = np.empty((B, T // 64, self.D), dtype=np.float32)
+        self._ck(self.lib.vqwn_encode_audio(self._h, _ptr(xx, C.c_float), B, T, _ptr(z, C.c_float)))
+        return z
 
     # ------------------------------------------------------------------ VQ + conditioning
     def vq_lookup(self, z_e):

@@ -47,3 +47,35 @@ def synthetic_z_e(config, B, F, seed=1235, scale=0.13):
     """encoder-output stand-in: N(0,1) scaled to the codebook's magnitude"""
     rng = np.random.default_rng(seed)
     return (np.float32(scale) * rng.standard_normal((B, F, config.model["latent_dim"]))).astype(np.float32)
+
+
+def encoder64_specs(config):
+    """keras auto-names inside variable_scope('encoder'): conv1d[_i] / batch_normalization[_i]"""
+    specs, cin = [], 1
+    for i in range(7):
+        sfx = "" if i == 0 else "_%d" % i
+        cout = 768 if i < 6 else config.model["latent_dim"]
+        k = 5 if i < 6 else 1
+        specs += [("encoder/conv1d%s/kernel" % sfx, (k, cin, cout)), ("encoder/conv1d%s/bias" % sfx, (cout,)),
+                  ("encoder/batch_normalization%s/gamma" % sfx, (cout,)), ("encoder/batch_normalization%s/beta" % sfx, (cout,)),
+                  ("encoder/batch_normalization%s/moving_mean" % sfx, (cout,)),
+                  ("encoder/batch_normalization%s/moving_variance" % sfx, (cout,))]
+        cin = cout
+    return specs
+
+
+def make_encoder64_weights(config, seed=4321):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in encoder64_specs(config):
+        if name.endswith("kernel"):
+            lim = np.sqrt(6.0 / (shape[0] * shape[1] + shape[0] * shape[2]))
+            a = rng.uniform(-lim, lim, size=shape)
+        elif name.endswith("moving_variance"):
+            a = rng.uniform(0.5, 1.5, size=shape)
+        elif name.endswith("gamma"):
+            a = rng.uniform(0.8, 1.2, size=shape)
+        else:
+            a = rng.uniform(-0.1, 0.1, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return out
