@@ -296,8 +296,9 @@ def test_small_greedy_and_sample_sequences(small, golden_dir):
 
 
 def test_dataflow_kernel_matches_barrier_kernel(monkeypatch):
-    """the experimental barrier-free kernel (VQWN_GEN_KERNEL=dataflow) computes the same tiles in the same
-    order: outputs must be bit-identical to the default kernel"""
+    """the experimental barrier-free kernel (VQWN_GEN_KERNEL=dataflow: per-(stage, stream block) counters
+    instead of grid barriers) computes the same tiles in the same order as the default kernel: outputs must be
+    bit-identical"""
     cfg = O.Config(wavenet=SMALL_WAVENET)
     w = O.make_weights(cfg, seed=1234)
     B, T, F, x, ze = _small_inputs(cfg, w)
@@ -306,12 +307,15 @@ def test_dataflow_kernel_matches_barrier_kernel(monkeypatch):
     a0, i0 = ref.generate(cond, T, mode="greedy")
     l0 = ref.teacher_forced(x[:, :64], cond[:, :1])
     assert ref.last_kernel_name == "wavenet_fp32_persistent"
+    u = np.random.default_rng(3).random((T, B))
+    s0 = ref.generate(cond, T, mode="sample", uniforms=u)[1]
     ref.close()
     monkeypatch.setenv("VQWN_GEN_KERNEL", "dataflow")
     eng = _engine(SMALL_WAVENET, 16, w)
     a1, i1 = eng.generate(cond, T, mode="greedy")
     assert eng.last_kernel_name == "wavenet_fp32_dataflow"
     l1 = eng.teacher_forced(x[:, :64], cond[:, :1])
+    s1 = eng.generate(cond, T, mode="sample", uniforms=u)[1]
     eng.reset(B)
     audio = np.zeros(B, dtype=np.float32)
     for t in range(8):
@@ -319,7 +323,7 @@ def test_dataflow_kernel_matches_barrier_kernel(monkeypatch):
         assert np.array_equal(logits, l1[:, t])
         audio = x[:, t]
     eng.close()
-    assert np.array_equal(i0, i1) and np.array_equal(a0, a1) and np.array_equal(l0, l1)
+    assert np.array_equal(i0, i1) and np.array_equal(a0, a1) and np.array_equal(l0, l1) and np.array_equal(s0, s1)
 
 
 def test_receptive_field_property(small):

@@ -65,8 +65,10 @@ struct vqwn_handle {
   std::vector<size_t> off_w1t, off_w2t;
   size_t off_skip0t = 0, off_post1t = 0, off_post2t = 0;
   int* gen_err = nullptr;
-  unsigned long long* ll_base = nullptr;   // packet buffers of the dataflow kernel
-  size_t ll_packets = 0;
+  float* df_base = nullptr;                // per-layer cur / g buffers + skip start of the dataflow kernel
+  size_t df_floats = 0;
+  unsigned* df_cnt = nullptr;              // dependency counters
+  size_t df_ncnt = 0;
   int gen_kernel = 0;                      // 0 auto, 1 barrier kernel, 2 dataflow kernel
   // packed fp32 weights
   bool packed = false;
@@ -227,7 +229,6 @@ int do_reset(vqwn_handle* h, int B) {
   CK(h, cudaMemsetAsync(h->skip, 0, Bp * h->S * sizeof(float), h->stream));
   CK(h, cudaMemsetAsync(h->n1, 0, Bp * h->S * sizeof(float), h->stream));
   CK(h, cudaMemsetAsync(h->logits, 0, Bp * h->Q * sizeof(float), h->stream));
-  CK(h, cudaMemsetAsync(h->ll_base, 0, h->ll_packets * sizeof(unsigned long long), h->stream));
   h->B = B;
   h->t = 0;
   return VQWN_OK;
@@ -272,24 +273,19 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
   if ((h->G / 8) * nsb > max_tiles) max_tiles = (h->G / 8) * nsb;
   if (((h->R + h->S) / 32) * nsb > max_tiles) max_tiles = ((h->R + h->S) / 32) * nsb;
   const bool df_ok = max_tiles <= h->num_sms;
-  // measured slower than the barrier kernel (packets move through the LSU path at ~19 B/clk/SM): opt-in only
+  // measured slower than the barrier kernel (404 vs 338 us per time step at B = 64): opt-in only
   const bool use_df = df_ok && h->gen_kernel == 2;
   CK(h, cudaEventRecord(h->ev0, h->stream));
   if (use_df) {
     DfParams dp;
     dp.g = p;
-    unsigned long long* q = h->ll_base;
     const size_t Bp_max = h->Bp_max;
-    dp.cur_ll = q; q += (size_t)h->L * Bp_max * h->R;
-    dp.g_ll = q; q += (size_t)h->L * Bp_max * h->G;
-    dp.skip0_ll = q; q += Bp_max * h->S;
-    dp.skip_ll = q; q += Bp_max * h->S;
-    dp.n1_ll = q; q += Bp_max * h->S;
-    dp.logit_ll = q; q += Bp_max * h->Q;
-    dp.u_ll = q;
-    // per-layer strides inside the kernel use the run's padded batch
-    dp.cur_ll = h->ll_base;
-    dp.g_ll = h->ll_base + (size_t)h->L * Bp_max * h->R;
+    dp.cur_l = h->df_base;
+    dp.g_l = h->df_base + (size_t)h->L * Bp_max * h->R;
+    dp.skip0 = dp.g_l + (size_t)h->L * Bp_max * h->G;
+    dp.cnt = h->df_cnt;
+    dp.cnt_res = h->df_cnt + (size_t)(2 * h->L + 4) * (Bp_max / FP32_TB);
+    CK(h, cudaMemsetAsync(h->df_cnt, 0, h->df_ncnt * sizeof(unsigned), h->stream));
     void* dargs[] = {&dp};
     CK(h, cudaLaunchCooperativeKernel((const void*)wavenet_fp32_dataflow, dim3(h->num_sms), dim3(FP32_THREADS), dargs,
                                       h->smem_fp32, h->stream));
@@ -324,6 +320,12 @@ int finish_timing(vqwn_handle* h) {
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
       fprintf(stderr, "[vqwn profile] vq_tc CTA0 epilogue-warp0 cycles: setup=%lld wait_z=%lld wait_acc=%lld pass1=%lld pass2=%lld decide=%lld output=%lld (kernel %.3f ms)\n",
               pf[16], pf[17], pf[18], pf[19], pf[20], pf[21], pf[22], ms);
+  }
+  if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_dataflow") == 0) {
+    long long pf[32];
+    if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "[vqwn profile] dataflow CTA0 cycles: dep_wait=%lld operand_wait=%lld compute=%lld epilogue+signal=%lld prefetch=%lld other=%lld (kernel %.3f ms)\n",
+              pf[8], pf[9], pf[10], pf[11], pf[12], pf[13], ms);
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
     long long pf[8];
@@ -572,8 +574,10 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     }
   }
   CKC(cudaMalloc(&h->gen_err, sizeof(int)));
-  h->ll_packets = (size_t)h->L * h->Bp_max * (R + G) + (size_t)h->Bp_max * (3 * S + Q + 1);
-  CKC(cudaMalloc(&h->ll_base, h->ll_packets * sizeof(unsigned long long)));
+  h->df_floats = (size_t)h->L * h->Bp_max * (R + G) + (size_t)h->Bp_max * S;
+  CKC(cudaMalloc(&h->df_base, h->df_floats * sizeof(float)));
+  h->df_ncnt = (size_t)(3 * h->L + 4) * (h->Bp_max / FP32_TB);
+  CKC(cudaMalloc(&h->df_cnt, h->df_ncnt * sizeof(unsigned)));
   if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "dataflow") == 0 ? 2 : 0);
   h->actA_floats = FP32_TB * 3 * R;                       // gated conv: current | t-d | t-2d segments
   if (FP32_TB * S > h->actA_floats) h->actA_floats = FP32_TB * S;   // post1: relu(skip)
@@ -614,7 +618,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->w2) if (p) cudaFree(p);
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
-                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->ll_base};
+                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->df_base, h->df_cnt};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,

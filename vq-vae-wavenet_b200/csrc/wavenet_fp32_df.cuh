@@ -1,92 +1,61 @@
 // WaveNet fast generation, float32, DATAFLOW variant of the persistent kernel (wavenet_fp32.cuh).
 //
-// Same arithmetic, same tiles, same weight/tap streaming as wavenet_fp32_persistent, but there is
-// NO grid barrier: every value one CTA hands to another travels as an 8-byte packet {float, tag}
-// written with one 64-bit store and polled with 64-bit L2 loads by the consumers (tag = step+1).
-// A stage's tile starts as soon as the packets it needs carry the current tag, so the fence +
-// atomic + flag round trips of a barrier (about 3.5k cycles per stage) disappear from the
-// dependency chain of a step.  Per time step the chain is the same 63 stages:
-//   preprocess FIR + skip start -> 30 x (gated conv -> residual/skip) -> post1 -> post2 -> draw
+// Same arithmetic, same tiles, same weight/tap streaming as wavenet_fp32_persistent, but NO grid
+// barrier: dependencies are tracked per (stage, 16-stream block) with monotonic counters.  A tile
+// that has stored its outputs does bar.sync + one red.release.gpu on the counter of its stage and
+// stream block; a consumer tile polls (ld.acquire.gpu, one thread) until all producers of the stage
+// it depends on have signalled, then that same thread issues the bulk copy of the rows it needs.
+// Compared with the barrier kernel a hand-off loses the "last arriver -> release flag -> everybody"
+// round trip and only waits for the 8-32 producers it really depends on instead of all 148 CTAs.
 // Requirements: every stage's tile count <= gridDim (B <= 64 streams on 148 SMs), so tile index ==
-// blockIdx for every stage and a CTA owns the same channels of the same streams in every layer:
-//   * the residual stream slice and the skip accumulator slice of a CTA stay in REGISTERS across
-//     the 30 layers (the barrier kernel round-trips them through L2 every layer);
+// blockIdx in every stage and a CTA owns the same channels of the same streams in every layer:
+//   * the residual-stream slice and the skip-sum slice of a CTA stay in REGISTERS across the 30
+//     layers (the barrier kernel round-trips them through L2 every layer);
 //   * the preprocess FIR history of a CTA's streams stays in shared memory across steps.
-// Buffers are per layer, so a packet is overwritten one full step after it was consumed (every
-// consumer of step t has finished before the draw of step t, which precedes all writes of t+1).
+// cur and g are per-layer buffers, so a buffer is overwritten one full step after its last reader
+// (every consumer of step t has finished before the draw of step t, which precedes step t+1).
 // Reference semantics: see wavenet_fp32.cuh.
 #pragma once
 #include "wavenet_fp32.cuh"
 
 namespace vqwn {
 
-typedef unsigned long long ll_packet;   // low 32 bits: float value, high 32 bits: tag
-
 struct DfParams {
   GenParams g;
-  ll_packet* cur_ll;    // [L][Bp][R]   input of layer l
-  ll_packet* g_ll;      // [L][Bp][G]   gated output of layer l
-  ll_packet* skip0_ll;  // [Bp][S]      skip start (preprocess -> first layer's skip owners)
-  ll_packet* skip_ll;   // [Bp][S]      skip sum (last layer -> post1)
-  ll_packet* n1_ll;     // [Bp][S]
-  ll_packet* logit_ll;  // [Bp][Q]
-  ll_packet* u_ll;      // [Bp]         next network input (draw -> preprocess of the next step)
+  float* cur_l;      // [L][Bp][R]  input of layer l
+  float* g_l;        // [L][Bp][G]  gated output of layer l
+  float* skip0;      // [Bp][S]     skip start (preprocess -> first layer's skip owners)
+  unsigned* cnt;     // [2L+4][nsb] arrivals per (stage, stream block), zeroed at launch
+  unsigned* cnt_res; // [L][nsb]    arrivals of the residual tiles of S2_l only
 };
 
-__device__ __forceinline__ ll_packet ll_pack(float v, unsigned tag) {
-  return ((ll_packet)tag << 32) | (ll_packet)__float_as_uint(v);
+__device__ __forceinline__ void df_signal(unsigned* c) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
 }
-__device__ __forceinline__ void ll_store(ll_packet* p, float v, unsigned tag) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(ll_pack(v, tag)) : "memory");
-}
-__device__ __forceinline__ ll_packet ll_load(const ll_packet* p) {
-  ll_packet v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// one packet, spin until it carries `tag` (bounded by wall-clock cycles; a dead producer becomes an error)
-__device__ __forceinline__ float ll_wait_one(const ll_packet* p, unsigned tag, int* err, bool& alive) {
-  ll_packet v = ll_load(p);
-  if ((unsigned)(v >> 32) != tag) {
-    const long long t0 = clock64();
-    do {
-      v = ll_load(p);
-      if ((unsigned)(v >> 32) == tag) break;
-      if (clock64() - t0 > 2000000000LL || *reinterpret_cast<volatile int*>(err) != 0) {
-        atomicExch(err, 4);
-        alive = false;
-        break;
-      }
-    } while (true);
+// one thread: wait until *c >= target (bounded by cycles; a dead producer becomes an error)
+__device__ __forceinline__ bool df_wait(const unsigned* c, unsigned target, int* err) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+  if (v >= target) return true;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+    if (v >= target) return true;
+    if (clock64() - t0 > 2000000000LL || *reinterpret_cast<volatile int*>(err) != 0) {
+      atomicExch(err, 4);
+      return false;
+    }
   }
-  return __uint_as_float((unsigned)v);
-}
-
-// block-cooperative: n packets (multiple of 256) -> n floats in shared memory
-template <int PER_THREAD>
-__device__ __forceinline__ void ll_read_block(const ll_packet* src, unsigned tag, float* dst, int* err, bool& alive) {
-  ll_packet v[PER_THREAD];
-#pragma unroll
-  for (int j = 0; j < PER_THREAD; ++j) v[j] = ll_load(src + threadIdx.x + j * FP32_THREADS);
-#pragma unroll
-  for (int j = 0; j < PER_THREAD; ++j) {
-    float f;
-    if ((unsigned)(v[j] >> 32) == tag) f = __uint_as_float((unsigned)v[j]);
-    else f = ll_wait_one(src + threadIdx.x + j * FP32_THREADS, tag, err, alive);
-    dst[threadIdx.x + j * FP32_THREADS] = f;
-  }
-}
-__device__ __forceinline__ void ll_read_block_n(const ll_packet* src, int n, unsigned tag, float* dst, int* err, bool& alive) {
-  // n in {4096, 8192}
-  for (int base = 0; base < n; base += 8 * FP32_THREADS) ll_read_block<8>(src + base, tag, dst + base, err, alive);
 }
 
 __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const DfParams dp) {
   extern __shared__ __align__(128) float smem[];
   __shared__ LayerDev layers_s[64];
+  __shared__ int alive_s;
   for (int i = threadIdx.x; i < dp.g.L; i += FP32_THREADS) layers_s[i] = dp.g.layers[i];
   GenParams p = dp.g;
   p.layers = layers_s;
+  if (threadIdx.x == 0) alive_s = 1;
   __syncthreads();
 
   float* const wA = smem;
@@ -100,8 +69,9 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(ps + FP32_WARPS * p.Q);
   unsigned long long* wbar = bars;        // [2]
   unsigned long long* prebar = bars + 2;
+  unsigned long long* postbar = bars + 3; // [2]
   unsigned long long* condbar = bars + 5;
-  unsigned wphA = 0u, wphB = 0u, preph = 0u, condph = 0u;
+  unsigned wphA = 0u, wphB = 0u, preph = 0u, postphA = 0u, postphB = 0u, condph = 0u;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float mu = (float)(p.Q - 1);
@@ -125,10 +95,12 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
       u_s[idx] = p.u_hist[(long long)(st0_sb * FP32_TB) * p.PK + idx];
   __syncthreads();
 
+  const bool pf = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+  long long pc[6] = {0, 0, 0, 0, 0, 0};
+  long long pt = clock64();
+#define DF_PF(i) do { if (pf) { long long n_ = clock64(); pc[i] += n_ - pt; pt = n_; } } while (0)
   bool alive = true;
-  // has this CTA a tile in stage s?
   auto has_tile = [&](int s) { return s != S_DRAW && tile < stage_tiles(p, s); };
-  // next stage (same or later step) in which this CTA owns a contraction tile
   auto next_stage = [&](int s, long long t, int& sn, long long& tn) {
     sn = s; tn = t;
     for (int i = 0; i < NS; ++i) {
@@ -155,18 +127,21 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
   float own[2] = {0.f, 0.f};     // residual-stream slice or skip-sum slice owned by this CTA (2 values per thread)
 
   for (long long t = p.t0; t < p.t0 + p.T && alive; ++t) {
-    const unsigned tag = (unsigned)(t + 1);
+    const unsigned trel = (unsigned)(t - p.t0 + 1);       // counters are zeroed at launch
     const long long frame = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
     for (int s = 0; s < NS && alive; ++s) {
       if (s == S_DRAW) {
         // -------------------------------------------------------------- softmax + draw + mu-law decode
         const int NQ = p.Q / 32;
         for (int b = blockIdx.x * FP32_WARPS + warp; b < p.B; b += gridDim.x * FP32_WARPS) {
+          // all post2 tiles of this stream's block have published their logits
+          if (lane == 0) alive = df_wait(dp.cnt + (size_t)S_P2 * nsb + b / FP32_TB, (unsigned)(p.Q / 16) * trel, p.err) && alive;
+          alive = __shfl_sync(0xffffffffu, alive ? 1 : 0, 0) != 0;
           float lg[8], pr[8];
           float m = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            lg[i] = (i < NQ) ? ll_wait_one(dp.logit_ll + (long long)b * p.Q + lane + 32 * i, tag, p.err, alive) : -INFINITY;
+            lg[i] = (i < NQ) ? ld_cg(p.logits + (long long)b * p.Q + lane + 32 * i) : -INFINITY;
             m = fmaxf(m, lg[i]);
           }
 #pragma unroll
@@ -226,9 +201,8 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
           if (lane == 0) {
             p.audio_out[(long long)b * p.T + (t - p.t0)] = __ldg(p.dec_lut + k);
             if (p.idx_out) p.idx_out[(long long)b * p.T + (t - p.t0)] = k;
-            const float un = __ldg(p.enc_lut + k);
-            ll_store(dp.u_ll + b, un, tag);                       // consumed by the preprocess stage of step t+1
-            st_cg(p.u_hist + (long long)b * p.PK + (int)((t + 1) % p.PK), un);   // and kept for a later launch
+            st_cg(p.u_hist + (long long)b * p.PK + (int)((t + 1) % p.PK), __ldg(p.enc_lut + k));   // input of step t+1
+            df_signal(dp.cnt + (size_t)S_DRAW * nsb + b / FP32_TB);
           }
         }
         continue;
@@ -247,9 +221,16 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
       const bool have_next = next_stage(s, t, sn, tn);
       const bool next_same_class = have_next && stage_class(p, sn) == cls;
 
-      // ---- inputs produced by other CTAs (packets)
+      // ---- wait for the producers this tile depends on, then request the rows they produced (thread 0)
+      bool has_post = false;
+      DF_PF(5);
       if (s == 0) {
         // newest network input of this tile's 16 streams -> FIR history column t % PK
+        if (!ext && t > p.t0) {
+          if (tid == 0) alive_s = df_wait(dp.cnt + (size_t)S_DRAW * nsb + ti.sb, (unsigned)min(FP32_TB, p.B - ti.sb * FP32_TB) * (trel - 1), p.err) ? 1 : 0;
+          __syncthreads();
+          alive = alive_s != 0;
+        }
         if (tid < FP32_TB) {
           const int b = ti.sb * FP32_TB + tid;
           float u = 0.f;
@@ -260,10 +241,8 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
               else x = (t > p.t0) ? p.ext_audio[(long long)b * p.T + (t - p.t0 - 1)] : 0.f;
             }
             u = mu_law_encode_dev(x, mu, 0.f);
-          } else if (t > p.t0 && b < p.B) {
-            u = ll_wait_one(dp.u_ll + b, (unsigned)t, p.err, alive);   // tag of step t-1
-          } else if (t == p.t0 && t > 0 && b < p.B) {
-            u = p.u_hist[(long long)b * p.PK + (int)(t % p.PK)];       // continued generation: stored by the last launch
+          } else if (b < p.B && t > 0) {
+            u = ld_cg(p.u_hist + (long long)b * p.PK + (int)(t % p.PK));   // written by the draw of step t-1
           }
           u_s[tid * p.PK + (int)(t % p.PK)] = u;
         }
@@ -279,14 +258,39 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
           }
           act_s[i * p.R + n] = acc;
         }
-      } else if (s <= 2 * p.L) {
-        if (s & 1) ll_read_block_n(dp.cur_ll + ((long long)l * p.Bp + row0) * p.R, FP32_TB * p.R, tag, act_s, p.err, alive);
-        else if (ti.W != nullptr) ll_read_block_n(dp.g_ll + ((long long)l * p.Bp + row0) * p.G, FP32_TB * p.G, tag, act_s, p.err, alive);
-      } else if (s == S_P1) {
-        ll_read_block_n(dp.skip_ll + row0 * p.S, FP32_TB * p.S, tag, act_s, p.err, alive);
       } else {
-        ll_read_block_n(dp.n1_ll + row0 * p.S, FP32_TB * p.S, tag, act_s, p.err, alive);
+        const float* src = nullptr;
+        int len = 0;
+        const unsigned* c = nullptr;
+        unsigned target = 0;
+        if (s <= 2 * p.L) {
+          if (s & 1) {
+            src = dp.cur_l + ((long long)l * p.Bp + row0) * p.R; len = p.R;
+            if (l == 0) { c = dp.cnt + ti.sb; target = (unsigned)(p.S / 16) * trel; }      // all preprocess tiles
+            else { c = dp.cnt_res + (size_t)(l - 1) * nsb + ti.sb; target = (unsigned)(p.R / 32) * trel; }
+          } else {
+            c = dp.cnt + (size_t)(s - 1) * nsb + ti.sb; target = (unsigned)(p.G / 8) * trel;   // all gated tiles of this layer
+            if (ti.W != nullptr) { src = dp.g_l + ((long long)l * p.Bp + row0) * p.G; len = p.G; }
+          }
+        } else if (s == S_P1) {
+          src = p.skip + row0 * p.S; len = p.S;
+          c = dp.cnt + (size_t)(2 * p.L) * nsb + ti.sb; target = (unsigned)(p.S / 32) * trel;     // skip tiles of the last layer
+        } else {
+          src = p.n1 + row0 * p.S; len = p.S;
+          c = dp.cnt + (size_t)S_P1 * nsb + ti.sb; target = (unsigned)(p.S / 16) * trel;
+        }
+        if (tid == 0) {
+          const bool ok = df_wait(c, target, p.err);
+          alive_s = ok ? 1 : 0;
+          if (ok && src != nullptr) {
+            const unsigned bytes = (unsigned)(FP32_TB * len * 4);
+            mbar_expect(&postbar[cls], bytes);
+            bulk_g2s(act_s, src, bytes, &postbar[cls]);
+          }
+        }
+        has_post = src != nullptr;
       }
+      DF_PF(0);
       // ---- condition tile (gated conv / post1), reloaded when the frame changes
       if (cls == 1 && frame != cond_frame) {
         __syncthreads();
@@ -301,8 +305,13 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
         if (cls) wphA ^= 1u; else wphB ^= 1u;
       }
       if (stage_has_pre(p, s)) { alive = alive && mbar_wait_bounded(prebar, preph, p.err); preph ^= 1u; }
-      __syncthreads();
-      if (have_next && !next_same_class) prefetch(sn, tn);     // other buffer class: safe to stream during the math
+      __syncthreads();                                   // alive_s and (for stage 0) the FIR tile are visible
+      alive = alive && alive_s != 0;
+      if (has_post && alive) {
+        alive = mbar_wait_bounded(&postbar[cls], cls ? postphA : postphB, p.err);
+        if (cls) postphA ^= 1u; else postphB ^= 1u;
+      }
+      DF_PF(1);
       if (s >= S_P1) {
         relu_block(act_s, FP32_TB * p.S);
         __syncthreads();
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
         const long long row = row0 + i;
         if (s == 0 && ti.cb < p.R / 16) {
           const int n = ti.cb * 16 + c;
-          ll_store(dp.cur_ll + row * p.R + n, act_s[i * p.R + n], tag);          // input of layer 0
+          st_cg(dp.cur_l + row * p.R + n, act_s[i * p.R + n]);          // input of layer 0
         }
         {
           const int slg = (s <= 2 * p.L) ? sl_R : sl_S;
@@ -325,18 +334,23 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
           tile_compute<16>(wcur, act_s, slg, kmain, cond_s, p.C, ti.K, red_s);
         }
         __syncthreads();
-        if (have_next && next_same_class) prefetch(sn, tn);    // same class: only after the math has read it
+        DF_PF(2);
         float v = tile_reduce<16>(red_s, tid) + bias;
         if (s == 0) {
-          ll_store(dp.skip0_ll + row * p.S + col, v, tag);
+          st_cg(dp.skip0 + row * p.S + col, v);
         } else if (s <= 2 * p.L) {
           const float partner = __shfl_down_sync(0xffffffffu, v, 8);
-          if (c < 8) ll_store(dp.g_ll + ((long long)l * p.Bp + row) * p.G + col, tanhf(v) * sigmoid_f(partner), tag);
+          if (c < 8) st_cg(dp.g_l + ((long long)l * p.Bp + row) * p.G + col, tanhf(v) * sigmoid_f(partner));
         } else if (s == S_P1) {
-          ll_store(dp.n1_ll + row * p.S + col, v, tag);
+          st_cg(p.n1 + row * p.S + col, v);
         } else {
-          ll_store(dp.logit_ll + row * p.Q + col, v, tag);
+          st_cg(p.logits + row * p.Q + col, v);
         }
+        __syncthreads();                                       // every thread's stores precede the signal
+        if (tid == 0) df_signal(dp.cnt + (size_t)s * nsb + ti.sb);
+        DF_PF(3);
+        if (have_next) prefetch(sn, tn);   // weights + older taps of this CTA's next tile: overlaps the wait for its producers
+        DF_PF(4);
       } else {
         // residual / skip owners: 2 values per thread, kept in registers from layer to layer
         const LayerDev ly = p.layers[l];
@@ -349,16 +363,13 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
           const long long row = row0 + (o >> 5);
           const int col = ti.col0 + (o & 31);
           bias[h] = __ldg(ly.b2 + col);
-          if (l == 0) {
-            own[h] = is_res ? ll_wait_one(dp.cur_ll + row * p.R + col, tag, p.err, alive)
-                            : ll_wait_one(dp.skip0_ll + row * p.S + (col - p.R), tag, p.err, alive);
-          }
+          if (l == 0) own[h] = is_res ? ld_cg(dp.cur_l + row * p.R + col) : ld_cg(dp.skip0 + row * p.S + (col - p.R));
         }
         if (ti.W != nullptr) {
           tile_compute<32>(wcur, act_s, sl_G, p.G, cond_s, p.C, ti.K, red_s);
           __syncthreads();
         }
-        if (have_next && next_same_class) prefetch(sn, tn);
+        DF_PF(2);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int o = tid + h * FP32_THREADS;
@@ -368,17 +379,25 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
             st_cg(ly.ring + slot_old * ring_slot + row * p.R + col, own[h]);      // push_ops (layer input of step t)
             if (ti.W != nullptr) {
               own[h] = own[h] + (tile_reduce<32>(red_s, o) + bias[h]);
-              ll_store(dp.cur_ll + ((long long)(l + 1) * p.Bp + row) * p.R + col, own[h], tag);
+              st_cg(dp.cur_l + ((long long)(l + 1) * p.Bp + row) * p.R + col, own[h]);
             }
           } else {
             own[h] = own[h] + (tile_reduce<32>(red_s, o) + bias[h]);
-            if (l == p.L - 1) ll_store(dp.skip_ll + row * p.S + (col - p.R), own[h], tag);
+            if (l == p.L - 1) st_cg(p.skip + row * p.S + (col - p.R), own[h]);
           }
         }
+        __syncthreads();
+        if (tid == 0) {
+          if (is_res) df_signal(dp.cnt_res + (size_t)l * nsb + ti.sb);
+          else df_signal(dp.cnt + (size_t)s * nsb + ti.sb);
+        }
+        DF_PF(3);
+        if (have_next) prefetch(sn, tn);
+        DF_PF(4);
       }
-      __syncthreads();
     }
   }
+  if (pf) for (int i = 0; i < 6; ++i) p.prof[8 + i] = pc[i];
   // FIR history back to global for a later launch (one writer per stream block)
   if (has_st0 && st0_cb == 0) {
     const int skip_col = (int)((p.t0 + p.T) % p.PK);     // written by the draw stage (input of the next step)
