@@ -43,6 +43,7 @@ namespace vqwn {
 constexpr int FP32_TB = 16;        // streams per tile
 constexpr int FP32_THREADS = 256;  // 8 warps
 constexpr int FP32_WARPS = 8;
+constexpr int FIR_TAPS = 32;       // preprocess kernel size with a register-resident fast path
 constexpr int FP32_RED_FLOATS = 8192;   // K-groups x tile outputs (32 x 256 or 16 x 512)
 
 enum GenMode { GEN_GREEDY = 0, GEN_SAMPLE = 1, GEN_STEP = 2, GEN_TEACHER = 3 };
@@ -348,6 +349,15 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
     }
   };
 
+  // preprocess FIR taps of channel `tid`, newest sample first (fast path for the default geometry: one channel
+  // per thread, 32 taps); the generic path reads them through the L2 every step, which costs ~50k cycles per step
+  const bool fir_regs = (p.R == FP32_THREADS) && (p.PK == FIR_TAPS);
+  float fir_k[FIR_TAPS];
+  float fir_b = 0.f;
+#pragma unroll
+  for (int j = 0; j < FIR_TAPS; ++j) fir_k[j] = fir_regs ? __ldg(p.pre_k + (FIR_TAPS - 1 - j) * p.R + tid) : 0.f;
+  if (fir_regs) fir_b = __ldg(p.pre_b + tid);
+
   bool alive = true;
   prefetch_stage(0, p.t0);
   // condition tile: stages that use it (gated conv, post1) map tile -> stream block identically, so one tile
@@ -496,12 +506,28 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
             u_s[i * p.PK + j] = u;
           }
           __syncthreads();
-          for (int idx = tid; idx < FP32_TB * p.R; idx += FP32_THREADS) {
-            const int i = idx / p.R, n = idx - i * p.R;
-            float acc = fmaf(u_s[i * p.PK], __ldg(p.pre_k + (p.PK - 1) * p.R + n), __ldg(p.pre_b + n));
-            for (int j = 1; j < p.PK; ++j)
-              acc = fmaf(u_s[i * p.PK + j], __ldg(p.pre_k + (p.PK - 1 - j) * p.R + n), acc);
-            act_s[i * p.R + n] = acc;
+          if (fir_regs) {
+            // thread = channel, taps in registers, the 16 streams' histories broadcast from shared memory
+#pragma unroll 4
+            for (int i = 0; i < FP32_TB; ++i) {
+              const float4* up = reinterpret_cast<const float4*>(u_s + i * FIR_TAPS);
+              float acc = fir_b;
+#pragma unroll
+              for (int j4 = 0; j4 < FIR_TAPS / 4; ++j4) {
+                const float4 u4 = up[j4];
+                acc = fmaf(u4.x, fir_k[4 * j4 + 0], acc); acc = fmaf(u4.y, fir_k[4 * j4 + 1], acc);
+                acc = fmaf(u4.z, fir_k[4 * j4 + 2], acc); acc = fmaf(u4.w, fir_k[4 * j4 + 3], acc);
+              }
+              act_s[i * p.R + tid] = acc;
+            }
+          } else {
+            for (int idx = tid; idx < FP32_TB * p.R; idx += FP32_THREADS) {
+              const int i = idx / p.R, n = idx - i * p.R;
+              float acc = fmaf(u_s[i * p.PK], __ldg(p.pre_k + (p.PK - 1) * p.R + n), __ldg(p.pre_b + n));
+              for (int j = 1; j < p.PK; ++j)
+                acc = fmaf(u_s[i * p.PK + j], __ldg(p.pre_k + (p.PK - 1 - j) * p.R + n), acc);
+              act_s[i * p.R + n] = acc;
+            }
           }
         }
         first = false;
