@@ -302,6 +302,7 @@ def test_dataflow_kernel_matches_barrier_kernel(monkeypatch):
     cfg = O.Config(wavenet=SMALL_WAVENET)
     w = O.make_weights(cfg, seed=1234)
     B, T, F, x, ze = _small_inputs(cfg, w)
+    monkeypatch.setenv("VQWN_GEN_KERNEL", "barrier")
     ref = _engine(SMALL_WAVENET, 16, w)
     _, cond = ref.encode_condition(ze, [0, 1, 2])
     a0, i0 = ref.generate(cond, T, mode="greedy")
@@ -324,6 +325,50 @@ def test_dataflow_kernel_matches_barrier_kernel(monkeypatch):
         audio = x[:, t]
     eng.close()
     assert np.array_equal(i0, i1) and np.array_equal(a0, a1) and np.array_equal(l0, l1) and np.array_equal(s0, s1)
+
+
+@pytest.mark.parametrize("B", [3, 23, 64])
+def test_cluster_kernel_matches_barrier_kernel(monkeypatch, B):
+    """the default generation kernel (thread-block clusters of 16 CTAs, activations exchanged through distributed
+    shared memory) against the grid-barrier kernel: same float32 arithmetic with a different K split, so logits
+    agree to float32 rounding and the drawn sequences are identical away from near-ties.  B = 23 leaves the last
+    cluster partly filled, B = 64 is the benchmark shape (10 streams per cluster)."""
+    cfg = O.Config(wavenet=SMALL_WAVENET)
+    w = O.make_weights(cfg, seed=1234)
+    T, F = 96, 2
+    rng = np.random.default_rng(77)
+    x = O.synthetic_audio(B, T, seed=5)
+    ze = O.synthetic_z_e(cfg, w, B, F, seed=6, kind="scaled")
+    spk = [int(v) for v in rng.integers(0, cfg.num_speakers, size=B)]
+    u = rng.random((T, B))
+    out = {}
+    for kernel, name in (("barrier", "wavenet_fp32_persistent"), ("cluster", "wavenet_fp32_cluster")):
+        monkeypatch.setenv("VQWN_GEN_KERNEL", kernel)
+        eng = _engine(SMALL_WAVENET, B, w)
+        _, cond = eng.encode_condition(ze, spk)
+        logits = eng.teacher_forced(x, cond)
+        assert eng.last_kernel_name == name
+        gi = eng.generate(cond, T, mode="greedy")[1]
+        si = eng.generate(cond, T, mode="sample", uniforms=u)[1]
+        # step API continues the same state layout
+        eng.reset(B)
+        audio = np.zeros(B, dtype=np.float32)
+        steps = []
+        for t in range(4):
+            _, lg = eng.step(audio, cond[:, 0])
+            steps.append(lg)
+            audio = x[:, t]
+        out[kernel] = (logits, gi, si, np.stack(steps, 1))
+        eng.close()
+    l0, g0, s0, st0 = out["barrier"]
+    l1, g1, s1, st1 = out["cluster"]
+    scale = np.abs(l0).max()
+    assert np.abs(l0 - l1).max() <= 2e-5 * scale
+    assert np.abs(st0 - st1).max() <= 2e-5 * scale
+    assert np.abs(st1 - l1[:, :4]).max() <= 2e-5 * scale
+    assert (g0 == g1).mean() > 0.98 and (s0 == s1).mean() > 0.98
+    # the first steps cannot have diverged yet
+    assert np.array_equal(g0[:, :8], g1[:, :8])
 
 
 def test_receptive_field_property(small):

@@ -17,6 +17,7 @@
 #include "vq_tc.cuh"
 #include "wavenet_fp32.cuh"
 #include "wavenet_fp32_df.cuh"
+#include "wavenet_fp32_cluster.cuh"
 #include "sample.cuh"
 #include "encoder.cuh"
 
@@ -69,7 +70,14 @@ struct vqwn_handle {
   size_t df_floats = 0;
   unsigned* df_cnt = nullptr;              // dependency counters
   size_t df_ncnt = 0;
-  int gen_kernel = 0;                      // 0 auto, 1 barrier kernel, 2 dataflow kernel
+  int gen_kernel = 0;                      // 0 auto (cluster kernel when it applies), 1 barrier, 2 dataflow, 3 cluster
+  // cluster kernel (wavenet_fp32_cluster.cuh)
+  bool cl_ok = false;                      // geometry constraints hold and 16-CTA clusters can be scheduled
+  int cl_max_clusters = 0;                 // co-resident clusters of 16 CTAs (measured 7 on a B200)
+  float* wcl = nullptr;                    // cluster-tiled weights, same block order as wtiles
+  ClLayerDev* cl_layers_dev = nullptr;
+  std::vector<ClLayerDev> cl_layers_host;
+  int cl_w1_floats = 0, cl_w2_floats = 0;
   // packed fp32 weights
   bool packed = false;
   std::vector<float*> w1, b1, w2, b2;
@@ -210,6 +218,24 @@ int pack_weights(vqwn_handle* h) {
     pack(TP(h, "decoder/postprocess2/kernel"), h->Q, S, 16, h->Q / 16, 0, h->wtiles + h->off_post2t);
     CK(h, cudaGetLastError());
   }
+  if (h->cl_ok) {
+    // per-CTA column slices of the cluster kernel: [16][K][columns of CTA r]
+    auto packc = [&](const float* src, int ldw, int K, int n0, int base1, int n1, float* dst) {
+      const long long total = (long long)CL_CS * K * (n0 + n1);
+      int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+      pack_cluster_kernel<<<grid, 256, 0, h->stream>>>(src, ldw, K, n0, base1, n1, CL_CS, dst);
+      h->launches += 1;
+    };
+    const int Qn = h->Q;
+    packc(TP(h, "decoder/skip/kernel"), S, R, S / CL_CS, 0, 0, h->wcl + h->off_skip0t);
+    for (int l = 0; l < h->L; ++l) {
+      packc(h->w1[l], 2 * G, 3 * R + C, G / CL_CS, G, G / CL_CS, h->wcl + h->off_w1t[l]);
+      packc(h->w2[l], R + S, G, R / CL_CS, R, S / CL_CS, h->wcl + h->off_w2t[l]);
+    }
+    packc(h->post1_w, S, S + C, S / CL_CS, 0, 0, h->wcl + h->off_post1t);
+    packc(TP(h, "decoder/postprocess2/kernel"), Qn, S, Qn / CL_CS, 0, 0, h->wcl + h->off_post2t);
+    CK(h, cudaGetLastError());
+  }
   CK(h, cudaMemcpyAsync(h->enc_lut, TP(h, "lut/mu_law_encode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->dec_lut, TP(h, "lut/mu_law_decode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
@@ -234,10 +260,115 @@ int do_reset(vqwn_handle* h, int B) {
   return VQWN_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// cluster kernel plumbing
+// ---------------------------------------------------------------------------------------
+typedef void (*cl_kernel_t)(const ClParams);
+cl_kernel_t cl_kernel_for(int MS) {
+  switch (MS) {
+    case 2: return wavenet_fp32_cluster<2>;
+    case 4: return wavenet_fp32_cluster<4>;
+    case 6: return wavenet_fp32_cluster<6>;
+    case 8: return wavenet_fp32_cluster<8>;
+    default: return wavenet_fp32_cluster<10>;
+  }
+}
+
+// K-groups of a stage: as many as fit the 256 threads, dividing K into multiples of 4, with the partial sums
+// fitting the (aliased) weight buffer
+int cl_kgroups(int K, int NC, int MS, int buf_floats) {
+  int kg = 256 / (NC / 4);
+  if (kg > K / 4) kg = K / 4;
+  for (; kg > 1; --kg)
+    if (K % (4 * kg) == 0 && kg * MS * NC <= buf_floats) break;
+  return kg < 1 ? 1 : kg;
+}
+
+size_t cl_smem_bytes(const vqwn_handle* h, int MS) {
+  const int R = h->R, G = h->G, S = h->S, Q = h->Q, C = h->C, PK = h->PK;
+  const int NSK = S / CL_CS, NC2 = R / CL_CS + NSK;
+  int stage_cols = NC2 > 2 * G / CL_CS ? NC2 : 2 * G / CL_CS;
+  if (NSK > stage_cols) stage_cols = NSK;
+  size_t fl = (size_t)h->cl_w1_floats + h->cl_w2_floats + (size_t)MS * (G + 3 * R + C + Q + 2 * PK + NSK + stage_cols) + 1;
+  return fl * sizeof(float) + 4 * sizeof(unsigned long long) + 16;
+}
+
+// streams per cluster for a batch: the smallest supported size that covers B with the co-resident clusters
+int cl_streams_per_cluster(const vqwn_handle* h, int B) {
+  if (!h->cl_ok || h->cl_max_clusters < 1) return 0;
+  const int need = (B + h->cl_max_clusters - 1) / h->cl_max_clusters;
+  for (int ms = 2; ms <= CL_MAX_MS; ms += 2)
+    if (ms >= need) return ms;
+  return 0;
+}
+
+int launch_cluster(vqwn_handle* h, int MS, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
+                   const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
+                   float* logits_out, float* probs_out) {
+  ClParams p;
+  memset(&p, 0, sizeof p);
+  const int R = h->R, G = h->G, S = h->S, Q = h->Q, C = h->C;
+  p.L = h->L; p.R = R; p.G = G; p.S = S; p.Q = Q; p.C = C; p.PK = h->PK;
+  p.B = h->B;
+  p.Bp = (h->B + FP32_TB - 1) / FP32_TB * FP32_TB;      // ring layout shared with the barrier kernel
+  p.w1_floats = h->cl_w1_floats; p.w2_floats = h->cl_w2_floats;
+  const int NSK = S / CL_CS, NC1 = 2 * G / CL_CS, NC2 = R / CL_CS + NSK, NQ = Q / CL_CS;
+  p.kg_s0 = cl_kgroups(R, NSK, MS, h->cl_w2_floats);
+  p.kg_s1 = cl_kgroups(3 * R + C, NC1, MS, h->cl_w1_floats);
+  p.kg_s2 = cl_kgroups(G, NC2, MS, h->cl_w2_floats);
+  p.kg_p1 = cl_kgroups(S + C, NSK, MS, h->cl_w1_floats);
+  p.kg_p2 = cl_kgroups(S, NQ, MS, h->cl_w2_floats);
+  p.pre_k = TP(h, "decoder/preprocess/kernel"); p.pre_b = TP(h, "decoder/preprocess/bias");
+  p.skip0c = h->wcl + h->off_skip0t; p.skip0_b = TP(h, "decoder/skip/bias");
+  p.post1c = h->wcl + h->off_post1t; p.post1_b = TP(h, "decoder/postprocess1/bias");
+  p.post2c = h->wcl + h->off_post2t; p.post2_b = TP(h, "decoder/postprocess2/bias");
+  size_t off = 0;
+  for (int l = 0; l < h->L; ++l) {
+    h->cl_layers_host[l].ring = h->ring_base + off;
+    off += (size_t)2 * h->cfg.dilations[l] * p.Bp * R;
+  }
+  CK(h, cudaMemcpyAsync(h->cl_layers_dev, h->cl_layers_host.data(), sizeof(ClLayerDev) * h->L, cudaMemcpyHostToDevice, h->stream));
+  p.layers = h->cl_layers_dev;
+  p.enc_lut = h->enc_lut; p.dec_lut = h->dec_lut;
+  p.u_hist = h->u_hist;
+  p.t0 = h->t; p.T = T; p.mode = mode;
+  p.cond = cond; p.cond_bstride = cond_bstride; p.ratio = ratio;
+  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed;
+  p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
+  p.prof = h->profile ? h->prof : nullptr;
+  p.err = h->gen_err;
+  CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
+  const int nclusters = (h->B + MS - 1) / MS;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(nclusters * CL_CS);
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = cl_smem_bytes(h, MS);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  CK(h, cudaLaunchKernelEx(&cfg, cl_kernel_for(MS), p));
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  h->last_kernel = "wavenet_fp32_cluster";
+  h->t += T;
+  return VQWN_OK;
+}
+
 // ring layout depends on the padded batch of the run; rebuilt at every launch
 int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
                 const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
                 float* logits_out, float* probs_out) {
+  if (h->gen_kernel == 0 || h->gen_kernel == 3) {
+    const int ms = cl_streams_per_cluster(h, h->B);
+    if (ms > 0)
+      return launch_cluster(h, ms, mode, T, cond, cond_bstride, ratio, ext_audio, uniforms, seed, audio_out, idx_out,
+                            logits_out, probs_out);
+    if (h->gen_kernel == 3) return fail(h, VQWN_ERR_INVALID, "cluster kernel does not apply to this geometry / batch");
+  }
   GenParams p;
   memset(&p, 0, sizeof p);
   p.L = h->L; p.R = h->R; p.G = h->G; p.S = h->S; p.Q = h->Q; p.C = h->C; p.PK = h->PK;
@@ -310,7 +441,7 @@ int finish_timing(vqwn_handle* h) {
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
-  if (strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0 || strcmp(h->last_kernel, "wavenet_fp32_dataflow") == 0) {
+  if (strncmp(h->last_kernel, "wavenet_fp32", 12) == 0) {
     int e = 0;
     CK(h, cudaMemcpy(&e, h->gen_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (e) return fail(h, VQWN_ERR_CUDA, e == 2 ? "generation kernel: operand wait timed out" : (e == 4 ? "generation kernel: packet wait timed out" : "generation kernel: grid barrier timed out"));
@@ -326,6 +457,15 @@ int finish_timing(vqwn_handle* h) {
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
       fprintf(stderr, "[vqwn profile] dataflow CTA0 cycles: dep_wait=%lld operand_wait=%lld compute=%lld epilogue+signal=%lld prefetch=%lld other=%lld (kernel %.3f ms)\n",
               pf[8], pf[9], pf[10], pf[11], pf[12], pf[13], ms);
+  }
+  if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_cluster") == 0) {
+    long long pf[24];
+    if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      const char* cls[3] = {"S1", "S2", "other"};
+      for (int c = 0; c < 3; ++c)
+        fprintf(stderr, "[vqwn profile] cluster CTA0 %s cycles: fir=%lld operand_wait=%lld contraction=%lld epilogue+push=%lld prefetch_issue=%lld cluster_barrier=%lld draw=%lld (kernel %.3f ms)\n",
+                cls[c], pf[8 * c + 0], pf[8 * c + 1], pf[8 * c + 2], pf[8 * c + 3], pf[8 * c + 6], pf[8 * c + 4], pf[8 * c + 5], ms);
+    }
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
     long long pf[8];
@@ -573,12 +713,54 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
       h->layers_host[l].w2t = h->wtiles + h->off_w2t[l];
     }
   }
+  // cluster kernel: geometry constraints, weight block, shared-memory sizes, schedulable clusters
+  {
+    const bool pow2 = (R & (R - 1)) == 0 && (S & (S - 1)) == 0 && (G & (G - 1)) == 0;
+    const bool div = R % CL_CS == 0 && S % CL_CS == 0 && G % CL_CS == 0 && Q % CL_CS == 0 &&
+                     (G / CL_CS) % 4 == 0 && (R / CL_CS) % 4 == 0 && (S / CL_CS) % 4 == 0 && (Q / CL_CS) % 4 == 0 &&
+                     C % 4 == 0 && Q <= 256 && Q % 32 == 0;
+    h->cl_ok = pow2 && div && S <= 2 * R && S <= G + R && h->L <= 64;
+    if (h->cl_ok) {
+      const int NSK = S / CL_CS, NC1 = 2 * G / CL_CS, NC2 = R / CL_CS + NSK, NQ = Q / CL_CS;
+      h->cl_w1_floats = (3 * R + C) * NC1;
+      if ((S + C) * NSK > h->cl_w1_floats) h->cl_w1_floats = (S + C) * NSK;
+      h->cl_w2_floats = G * NC2;
+      if (S * NQ > h->cl_w2_floats) h->cl_w2_floats = S * NQ;
+      if (R * NSK > h->cl_w2_floats) h->cl_w2_floats = R * NSK;
+      if (cl_smem_bytes(h, CL_MAX_MS) + 4096 > (size_t)prop.sharedMemPerBlockOptin) h->cl_ok = false;   // + static table
+    }
+    if (h->cl_ok) {
+      CKC(cudaMalloc(&h->wcl, h->wtiles_floats * sizeof(float)));
+      CKC(cudaMalloc(&h->cl_layers_dev, sizeof(ClLayerDev) * h->L));
+      h->cl_layers_host.resize(h->L);
+      for (int l = 0; l < h->L; ++l)
+        h->cl_layers_host[l] = ClLayerDev{h->wcl + h->off_w1t[l], h->b1[l], h->wcl + h->off_w2t[l], h->b2[l], nullptr,
+                                          c.dilations[l], 0};
+      h->cl_max_clusters = 1 << 30;
+      for (int ms = 2; ms <= CL_MAX_MS; ms += 2) {
+        cl_kernel_t k = cl_kernel_for(ms);
+        CKC(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem_bytes(h, ms)));
+        CKC(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(CL_CS); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = cl_smem_bytes(h, ms);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, (const void*)k, &cfg) != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
+        if (nc < h->cl_max_clusters) h->cl_max_clusters = nc;
+      }
+      if (h->cl_max_clusters < 1) h->cl_ok = false;
+    }
+  }
   CKC(cudaMalloc(&h->gen_err, sizeof(int)));
   h->df_floats = (size_t)h->L * h->Bp_max * (R + G) + (size_t)h->Bp_max * S;
   CKC(cudaMalloc(&h->df_base, h->df_floats * sizeof(float)));
   h->df_ncnt = (size_t)(3 * h->L + 4) * (h->Bp_max / FP32_TB);
   CKC(cudaMalloc(&h->df_cnt, h->df_ncnt * sizeof(unsigned)));
-  if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "dataflow") == 0 ? 2 : 0);
+  if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "dataflow") == 0 ? 2 : (strcmp(gk, "cluster") == 0 ? 3 : 0));
   h->actA_floats = FP32_TB * 3 * R;                       // gated conv: current | t-d | t-2d segments
   if (FP32_TB * S > h->actA_floats) h->actA_floats = FP32_TB * S;   // post1: relu(skip)
   h->actB_floats = FP32_TB * S;                           // post2: relu(n1)
@@ -618,7 +800,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->w2) if (p) cudaFree(p);
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
-                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->df_base, h->df_cnt};
+                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->df_base, h->df_cnt, h->wcl, h->cl_layers_dev};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,
