@@ -718,7 +718,11 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     const bool pow2 = (R & (R - 1)) == 0 && (S & (S - 1)) == 0 && (G & (G - 1)) == 0;
     const bool div = R % CL_CS == 0 && S % CL_CS == 0 && G % CL_CS == 0 && Q % CL_CS == 0 &&
                      (G / CL_CS) % 4 == 0 && (R / CL_CS) % 4 == 0 && (S / CL_CS) % 4 == 0 && (Q / CL_CS) % 4 == 0 &&
-                     C % 4 == 0 && Q <= 256 && Q % 32 == 0;
+                     C % 4 == 0 && Q <= 256 && Q % 32 == 0 &&
+                     // power-of-two slices (index masks), tiles of at most 512 outputs, one gate output per thread
+                     ((2 * G / CL_CS) & (2 * G / CL_CS - 1)) == 0 && ((S / CL_CS) & (S / CL_CS - 1)) == 0 &&
+                     ((Q / CL_CS) & (Q / CL_CS - 1)) == 0 && CL_MAX_MS * (R / CL_CS + S / CL_CS) <= 512 &&
+                     CL_MAX_MS * (G / CL_CS) <= 256 && CL_MAX_MS * (S / CL_CS) / 4 <= 256;
     h->cl_ok = pow2 && div && S <= 2 * R && S <= G + R && h->L <= 64;
     if (h->cl_ok) {
       const int NSK = S / CL_CS, NC1 = 2 * G / CL_CS, NC2 = R / CL_CS + NSK, NQ = Q / CL_CS;

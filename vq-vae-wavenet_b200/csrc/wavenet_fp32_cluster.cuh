@@ -94,28 +94,44 @@ __device__ __forceinline__ void cl_st_async_v4(unsigned addr, float4 v, unsigned
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar) : "memory");
 }
+// weight tiles are re-read by every cluster every step: keep them in L2 ahead of the streaming queue traffic
+__device__ __forceinline__ void cl_bulk_g2s_keep(float* smem_dst, const float* gsrc, unsigned bytes, unsigned long long* bar) {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(f32_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(f32_smem_u32(bar)), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-// push a [rows][4*vec_per_row] slice (row stride src_stride floats in the local staging buffer, nvec float4 in all)
-// to the same place in `nranks` CTAs of the cluster: element (i, j) goes to dst_local + i*row_stride + col0 + 4j.
-// Thread groups of nvec threads take every (256/nvec)-th destination CTA; a thread loads its float4 once.
-__device__ __forceinline__ void cl_push_all(const float* stage, int src_stride, float* dst_local, int nvec, int vec_per_row,
-                                            int row_stride, int col0, unsigned first_rank, unsigned nranks,
-                                            unsigned long long* rx_bar = nullptr) {
+// push geometry of a thread for slices of `nvec` float4 with `vec_per_row` float4 per stream row: thread groups of nvec
+// threads take every ngroups-th destination CTA.  Packed once per kernel (no integer divisions in the step loop):
+// j | i << 8 | grp << 16 | ngroups << 24; grp = 255: thread idle.
+__device__ __forceinline__ unsigned cl_push_geo(int nvec, int vec_per_row) {
   const int tid = threadIdx.x;
   const int ngroups = CL_THREADS / nvec;          // nvec <= 256 (host-checked)
   const int grp = tid / nvec, v = tid - grp * nvec;
-  if (grp >= ngroups) return;
   const int i = v / vec_per_row, j = v - i * vec_per_row;
+  return (unsigned)j | ((unsigned)i << 8) | ((unsigned)(grp < ngroups ? grp : 255) << 16) | ((unsigned)ngroups << 24);
+}
+
+// push a [rows][4*vec_per_row] slice (row stride src_stride floats in the local staging buffer) to the same place in
+// `nranks` CTAs of the cluster: element (i, j) goes to dst_local + i*row_stride + col0 + 4j, each 16-byte store also
+// counting on the destination's receive barrier (rx_bar) when given.
+__device__ __forceinline__ void cl_push_all(unsigned geo, const float* stage, int src_stride, float* dst_local,
+                                            int row_stride, int col0, unsigned first_rank, unsigned nranks,
+                                            unsigned long long* rx_bar = nullptr) {
+  const unsigned grp = (geo >> 16) & 255u, ngroups = geo >> 24;
+  if (grp == 255u) return;
+  const int i = (int)((geo >> 8) & 255u), j = (int)(geo & 255u);
   const float4 x = *reinterpret_cast<const float4*>(stage + i * src_stride + 4 * j);
   const unsigned a = f32_smem_u32(dst_local) + (unsigned)(i * row_stride + col0 + 4 * j) * 4u;
   if (rx_bar != nullptr) {
     const unsigned mb = f32_smem_u32(rx_bar);
-    for (unsigned pr = (unsigned)grp; pr < nranks; pr += (unsigned)ngroups)
+    for (unsigned pr = grp; pr < nranks; pr += ngroups)
       cl_st_async_v4(cl_mapa(a, first_rank + pr), x, cl_mapa(mb, first_rank + pr));
   } else {
-    for (unsigned pr = (unsigned)grp; pr < nranks; pr += (unsigned)ngroups) cl_st_v4(cl_mapa(a, first_rank + pr), x);
+    for (unsigned pr = grp; pr < nranks; pr += ngroups) cl_st_v4(cl_mapa(a, first_rank + pr), x);
   }
 }
 
@@ -267,25 +283,25 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
 
   // ---- bulk-copy issue helpers (thread 0 posts the byte count; a few threads issue the copies)
   auto issue_w = [&](float* dst, const float* src, unsigned bytes, unsigned long long* bar) {
-    // the buffer was last written by generic stores (partial sums, ordered by the preceding __syncthreads): the
-    // issuing threads order them before their async-proxy writes
-    const int nchunk = (int)((bytes + FP32_WCHUNK - 1) / FP32_WCHUNK);
-    if (tid == 0) mbar_expect(bar, bytes);
-    if (tid < nchunk) {
+    // one bulk copy per weight tile (issuing a copy costs hundreds of cycles; the size only has to fit the
+    // mbarrier's 2^20-1 transaction-byte range).  The buffer was last written by generic stores (partial sums,
+    // ordered by the preceding __syncthreads): the issuing thread orders them before its async-proxy writes.
+    if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const unsigned off = (unsigned)tid * FP32_WCHUNK;
-      const unsigned n = (bytes - off < FP32_WCHUNK) ? (bytes - off) : FP32_WCHUNK;
-      bulk_g2s(dst + off / 4, src + off / 4, n, bar);
+      mbar_expect(bar, bytes);
+      cl_bulk_g2s_keep(dst, src, bytes, bar);
     }
   };
+  // older dilation taps of layer l at step t: issued by warp 1 so that they do not queue behind the weight copy
   auto issue_taps = [&](int l, long long t) {
-    if (tid < 2) {
+    if (tid == 32 || tid == 33) {
+      const int which = tid - 32;
       const ClLayerDev ly = p.layers[l];
       const int d2 = 2 * ly.d;
       const unsigned bytes = (unsigned)(nvalid * R * 4);
-      if (tid == 0) mbar_expect(tapbar, 2 * bytes);
-      const long long slot = (tid == 0) ? ((t + ly.d) % d2) : (t % d2);
-      bulk_g2s(tid == 0 ? seg1 : seg2, ly.ring + slot * ring_slot + (long long)b0 * R, bytes, tapbar);
+      if (which == 0) mbar_expect(tapbar, 2 * bytes);
+      const long long slot = (which == 0) ? ((t + ly.d) % d2) : (t % d2);
+      bulk_g2s(which == 0 ? seg1 : seg2, ly.ring + slot * ring_slot + (long long)b0 * R, bytes, tapbar);
     }
   };
   auto issue_cond = [&](long long frame) {
@@ -308,20 +324,27 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
   const unsigned rx_g = (unsigned)(CL_CS * MS * GP * 4), rx_c = (unsigned)(CL_CS * MS * NR * 4),
                  rx_s = (unsigned)(CL_CS * MS * NSK * 4);
 
+  // per-thread index decompositions, once per kernel
+  const unsigned geo_g = cl_push_geo(MS * GP / 4, GP / 4), geo_r = cl_push_geo(MS * NR / 4, NR / 4),
+                 geo_s = cl_push_geo(MS * NSK / 4, NSK / 4), geo_q = cl_push_geo(MS * NQ / 4, NQ / 4);
+  const int gate_i = tid / GP, gate_j = tid - gate_i * GP;                       // MS*GP <= 256 (host-checked)
+  const int s2_i0 = tid / NC2, s2_c0 = tid - s2_i0 * NC2;                        // outputs tid and tid + 256 of an S2 tile
+  const int s2_i1 = (tid + CL_THREADS) / NC2, s2_c1 = (tid + CL_THREADS) - s2_i1 * NC2;
+
   // one contraction stage: bias prefetch -> operand wait -> register-tile contraction -> partial sums through shared
   // memory (aliasing the weight buffer) -> stage[stream*NC + c] = sum over K + bias.  Column c of CTA `rank` is
   // global column rank*n0 + c (c < n0) or base1 + rank*n1 + (c - n0).
   float acc[MS][4];
   auto run_stage = [&](float* wbuf, int NC, int K, int KG, const float* act, int sl_log, int Kmain, const float* bias,
                        int n0, int base1, int n1, unsigned long long* barA, unsigned& phA, unsigned long long* barB,
-                       unsigned* phB) {
+                       unsigned* phB, int c0, int c1) {
     const int nout = MS * NC;                     // <= 512
     float bz[2] = {0.f, 0.f};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int o = tid + h * CL_THREADS;
       if (o < nout) {
-        const int c = o % NC;
+        const int c = h ? c1 : c0;                // o % NC, supplied by the caller (no runtime modulo here)
         bz[h] = __ldg(bias + ((c < n0) ? (rank * n0 + c) : (base1 + rank * n1 + (c - n0))));
       }
     }
@@ -421,7 +444,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
       __syncthreads();
       CL_PF_ADD(0);
       // skip start: skip = h0 . W_skip + b   (wavenet.py:117-121)
-      run_stage(wS2, NSK, R, p.kg_s0, seg0, sl_R, R, p.skip0_b, NSK, 0, 0, wbar2, ph2, nullptr, nullptr);
+      run_stage(wS2, NSK, R, p.kg_s0, seg0, sl_R, R, p.skip0_b, NSK, 0, 0, wbar2, ph2, nullptr, nullptr, tid & (NSK - 1), (tid + CL_THREADS) & (NSK - 1));
       for (int o = tid; o < MS * NSK; o += CL_THREADS) skip_acc[o] = stage[o];
       __syncthreads();
       issue_w(wS2, p.layers[0].w2c + (size_t)rank * G * NC2, (unsigned)(G * NC2 * 4), wbar2);
@@ -435,13 +458,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
       // ---------------------------------------------------------------- S1: dilated conv + condition + gate
       pf_cls = 0;
       if (l > 0) { recv_wait(cbar, phc, rx_c); CL_PF_ADD(4); }
-      run_stage(wS1, NC1, K1, p.kg_s1, seg0, sl_R, 3 * R, ly.b1, GP, G, GP, wbar1, ph1, tapbar, &phtap);
-      for (int o = tid; o < MS * GP; o += CL_THREADS) {
-        const int i = o / GP, j = o - i * GP;
-        stage[i * NC1 + j] = tanhf(stage[i * NC1 + j]) * sigmoid_f(stage[i * NC1 + GP + j]);   // wavenet_ops.py:236-240
-      }
+      run_stage(wS1, NC1, K1, p.kg_s1, seg0, sl_R, 3 * R, ly.b1, GP, G, GP, wbar1, ph1, tapbar, &phtap, tid & (NC1 - 1), (tid + CL_THREADS) & (NC1 - 1));
+      if (tid < MS * GP)
+        stage[gate_i * NC1 + gate_j] =
+            tanhf(stage[gate_i * NC1 + gate_j]) * sigmoid_f(stage[gate_i * NC1 + GP + gate_j]);   // wavenet_ops.py:236-240
       __syncthreads();
-      cl_push_all(stage, NC1, gfull, MS * GP / 4, GP / 4, G, rank * GP, 0u, CL_CS, gbar);
+      cl_push_all(geo_g, stage, NC1, gfull, G, rank * GP, 0u, CL_CS, gbar);
       CL_PF_ADD(3);
       // next S1-class weights (+ the next layer's older taps) stream in during the hand-off and S2
       if (!last) {
@@ -456,11 +478,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
       pf_cls = 1;
       recv_wait(gbar, phg, rx_g);
       CL_PF_ADD(4);
-      run_stage(wS2, NC2, G, p.kg_s2, gfull, sl_G, G, ly.b2, NR, R, NSK, wbar2, ph2, nullptr, nullptr);
+      run_stage(wS2, NC2, G, p.kg_s2, gfull, sl_G, G, ly.b2, NR, R, NSK, wbar2, ph2, nullptr, nullptr, s2_c0, s2_c1);
       {
         const int slot_old = (int)(t % (2 * ly.d));
-        for (int o = tid; o < MS * NC2; o += CL_THREADS) {
-          const int i = o / NC2, c = o - i * NC2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int o = tid + h * CL_THREADS;
+          if (o >= MS * NC2) break;
+          const int i = h ? s2_i1 : s2_i0, c = h ? s2_c1 : s2_c0;
           const float v = stage[o];
           if (c < NR) {
             const float oldv = seg0[i * R + rank * NR + c];
@@ -474,8 +499,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
         }
       }
       __syncthreads();
-      if (!last) cl_push_all(stage, NC2, seg0, MS * NR / 4, NR / 4, R, rank * NR, 0u, CL_CS, cbar);
-      else cl_push_all(stage + NR, NC2, skip_full, MS * NSK / 4, NSK / 4, S, rank * NSK, 0u, CL_CS, skbar);   // wavenet.py:145: last residual is dead
+      if (!last) cl_push_all(geo_r, stage, NC2, seg0, R, rank * NR, 0u, CL_CS, cbar);
+      else cl_push_all(geo_s, stage + NR, NC2, skip_full, S, rank * NSK, 0u, CL_CS, skbar);   // wavenet.py:145: last residual is dead
       CL_PF_ADD(3);
       if (!last) issue_w(wS2, p.layers[l + 1].w2c + (size_t)rank * G * NC2, (unsigned)(G * NC2 * 4), wbar2);
       else issue_w(wS2, p.post2c + (size_t)rank * S * NQ, (unsigned)(S * NQ * 4), wbar2);
@@ -486,10 +511,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
     pf_cls = 2;
     recv_wait(skbar, phsk, rx_s);
     CL_PF_ADD(4);
-    run_stage(wS1, NSK, S + C, p.kg_p1, skip_full, sl_S, S, p.post1_b, NSK, 0, 0, wbar1, ph1, nullptr, nullptr);
+    run_stage(wS1, NSK, S + C, p.kg_p1, skip_full, sl_S, S, p.post1_b, NSK, 0, 0, wbar1, ph1, nullptr, nullptr, tid & (NSK - 1), (tid + CL_THREADS) & (NSK - 1));
     for (int o = tid; o < MS * NSK; o += CL_THREADS) stage[o] = fmaxf(stage[o], 0.f);     // wavenet.py:163
     __syncthreads();
-    cl_push_all(stage, NSK, n1_full, MS * NSK / 4, NSK / 4, S, rank * NSK, 0u, CL_CS, n1bar);
+    cl_push_all(geo_s, stage, NSK, n1_full, S, rank * NSK, 0u, CL_CS, n1bar);
     CL_PF_ADD(3);
     if (t + 1 < p.t0 + p.T) {
       issue_w(wS1, p.layers[0].w1c + (size_t)rank * K1 * NC1, (unsigned)(K1 * NC1 * 4), wbar1);
@@ -500,8 +525,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
     // ================================================================== postprocess2 -> logits on CTA 0
     recv_wait(n1bar, phn1, rx_s);
     CL_PF_ADD(4);
-    run_stage(wS2, NQ, S, p.kg_p2, n1_full, sl_S, S, p.post2_b, NQ, 0, 0, wbar2, ph2, nullptr, nullptr);
-    cl_push_all(stage, NQ, logits_s, MS * NQ / 4, NQ / 4, Q, rank * NQ, 0u, 1u);
+    run_stage(wS2, NQ, S, p.kg_p2, n1_full, sl_S, S, p.post2_b, NQ, 0, 0, wbar2, ph2, nullptr, nullptr, tid & (NQ - 1), (tid + CL_THREADS) & (NQ - 1));
+    cl_push_all(geo_q, stage, NQ, logits_s, Q, rank * NQ, 0u, 1u);
     CL_PF_ADD(3);
     cl_arrive();
     if (t + 1 < p.t0 + p.T) issue_w(wS2, p.skip0c + (size_t)rank * R * NSK, (unsigned)(R * NSK * 4), wbar2);
