@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
       }
     }
     __syncthreads();
+    CL_PF_ADD(7);
   };
 
   // preprocess FIR taps of channel `tid` (fast path: one channel per thread, 32 taps)
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
         stage[gate_i * NC1 + gate_j] =
             tanhf(stage[gate_i * NC1 + gate_j]) * sigmoid_f(stage[gate_i * NC1 + GP + gate_j]);   // wavenet_ops.py:236-240
       __syncthreads();
+      CL_PF_ADD(5);
       cl_push_all(geo_g, stage, NC1, gfull, G, rank * GP, 0u, CL_CS, gbar);
       CL_PF_ADD(3);
       // next S1-class weights (+ the next layer's older taps) stream in during the hand-off and S2
@@ -499,6 +501,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
         }
       }
       __syncthreads();
+      CL_PF_ADD(5);
       if (!last) cl_push_all(geo_r, stage, NC2, seg0, R, rank * NR, 0u, CL_CS, cbar);
       else cl_push_all(geo_s, stage + NR, NC2, skip_full, S, rank * NSK, 0u, CL_CS, skbar);   // wavenet.py:145: last residual is dead
       CL_PF_ADD(3);
