@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_SAMPLE = 36386816          # minimal algorithmic work per generated sample per stream
 QUEUE_BYTES_PER_SAMPLE = 92160 + 512 + 4
+NCU_DRAM_BYTES_PER_STEP = 85.3e6    # dram read + write per time step, wavenet_fp32_cluster at 64 streams (profiles/)
 METRIC = "generated audio samples/sec"
 
 
@@ -301,8 +302,15 @@ def main():
         achieved_gbs = B * QUEUE_BYTES_PER_SAMPLE / step_s / 1e9
         roof_step = max(B * FLOP_PER_SAMPLE / (peaks["tensor_sustained"] * 1e12),
                         B * QUEUE_BYTES_PER_SAMPLE / (peaks["hbm"] * 1e9))
+        # DRAM bytes per launch from the committed ncu --set full capture of the same kernel and stream count
+        # (profiles/r1_cluster_full_summary.txt: 43.68 GB for a T = 512 launch = 85.3 MB per time step, almost all of it
+        # the 78.6 MB of float32 weights, which do not fit the L2 next to the queue traffic and stream from HBM once
+        # per step); other kernels / stream counts: not captured -> null
+        traffic = NCU_DRAM_BYTES_PER_STEP * T if (kernel_name == "wavenet_fp32_cluster" and B == 64) else None
         roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved_tf / peaks["tensor_sustained"], "traffic": None,
+                    "frac": achieved_tf / peaks["tensor_sustained"], "traffic": traffic,
+                    "fp32_ffma_note": "float32 CUDA-core kernel: ncu fma pipe 26.8 % of peak-active; a 3-register FFMA "
+                                      "issues every 2nd cycle per SM sub-partition, so 50 % is this pipe's ceiling",
                     "kernel": kernel_name, "kernel_ms": k_ms, "us_per_time_step": step_s * 1e6,
                     "roofline_us_per_time_step": roof_step * 1e6, "hbm_achieved_gbs": achieved_gbs,
                     "hbm_frac": achieved_gbs / peaks["hbm"], "peak_source": peaks["source"] + ", sustained bf16"}
