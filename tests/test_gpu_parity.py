@@ -508,3 +508,64 @@ def test_full_size_properties(full):
     s3 = eng.generate(cond, 256, mode="sample", seed=8)[1]
     assert np.array_equal(s1, s2) and not np.array_equal(s1, s3)
     assert s1.max() <= 256
+
+
+# ------------------------------------------------------------------------------------------------------------
+# bf16 tensor-core path (VQWN_PREC_BF16): weights and contraction inputs rounded to bfloat16, float32
+# accumulation and float32 residual / skip / softmax.  north_star tolerance for bf16: 2e-2 of max|logit|.
+# ------------------------------------------------------------------------------------------------------------
+BF16_LOGIT_RTOL = 2e-2
+
+
+def test_bf16_small_teacher_logits_and_step(golden_dir):
+    cfg = O.Config(wavenet=SMALL_WAVENET)
+    w = O.make_weights(cfg, seed=1234)
+    B, T, F, x, ze = _small_inputs(cfg, w)
+    g = np.load(os.path.join(golden_dir, "small.npz"))
+    eng = _engine(SMALL_WAVENET, 16, w)
+    eng.set_precision("bf16")
+    _, cond = eng.encode_condition(ze, [0, 1, 2])
+    lg = eng.teacher_forced(x, cond)
+    assert eng.last_kernel_name == "wavenet_bf16_cluster"
+    want = g["logits_fast"]
+    err = np.abs(lg[:, ::16] - want).max() / np.abs(want).max()
+    assert err <= BF16_LOGIT_RTOL, err
+    # the step API walks the same state
+    eng.reset(B)
+    audio = np.zeros(B, dtype=np.float32)
+    for t in range(6):
+        _, l1 = eng.step(audio, cond[:, 0])
+        assert np.abs(l1 - lg[:, t]).max() <= 1e-5 * np.abs(want).max()
+        audio = x[:, t]
+    # deterministic, on the mu-law grid, streams independent of their neighbours
+    a1, i1 = eng.generate(cond, 128, mode="greedy")
+    a2, i2 = eng.generate(cond, 128, mode="greedy")
+    assert np.array_equal(i1, i2) and np.array_equal(a1, O.decode_lut()[i1])
+    sub = eng.generate(cond[1:2], 128, mode="greedy")[1]
+    assert np.array_equal(sub[0], i1[1])
+    eng.close()
+
+
+def test_bf16_full_teacher_logits(golden_dir):
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234, peaked=True)
+    g = np.load(os.path.join(golden_dir, "full.npz"))
+    eng = _engine(None, 64, w)
+    eng.set_precision("bf16")
+    B, Tt = 4, 512
+    ze = O.synthetic_z_e(cfg, w, B, 64, seed=1235, kind="scaled")
+    _, cond = eng.encode_condition(ze, [0, 1, 2, 3])
+    x = O.synthetic_audio(B, Tt, seed=1237)
+    lg = eng.teacher_forced(x, cond[:, :Tt // 64])
+    want = g["teacher_logits"]
+    err = np.abs(lg[:, ::32] - want).max() / np.abs(want).max()
+    assert err <= BF16_LOGIT_RTOL, err
+    # 64 streams = 4 clusters; a stream's output does not depend on the batch it runs in
+    B = 64
+    ze = O.synthetic_z_e(cfg, w, B, 4, seed=1235, kind="scaled")
+    _, cond = eng.encode_condition(ze, np.arange(B, dtype=np.int32) % 4)
+    i1 = eng.generate(cond, 256, mode="greedy")[1]
+    sub = eng.generate(cond[20:23], 256, mode="greedy")[1]
+    assert np.array_equal(sub, i1[20:23])
+    assert i1.min() >= 0 and i1.max() <= 255
+    eng.close()

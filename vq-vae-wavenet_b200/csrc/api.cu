@@ -18,6 +18,7 @@
 #include "wavenet_fp32.cuh"
 #include "wavenet_fp32_df.cuh"
 #include "wavenet_fp32_cluster.cuh"
+#include "wavenet_bf16_cluster.cuh"
 #include "sample.cuh"
 #include "encoder.cuh"
 
@@ -78,6 +79,12 @@ struct vqwn_handle {
   ClLayerDev* cl_layers_dev = nullptr;
   std::vector<ClLayerDev> cl_layers_host;
   int cl_w1_floats = 0, cl_w2_floats = 0;
+  // bf16 tensor-core cluster kernel (wavenet_bf16_cluster.cuh)
+  bool bc_ok = false;                      // default geometry and 8-CTA clusters schedulable
+  int bc_max_clusters = 0;
+  __nv_bfloat16* wbc = nullptr;            // bf16 K-major plane tiles, same block order as wtiles
+  BcLayerDev* bc_layers_dev = nullptr;
+  std::vector<BcLayerDev> bc_layers_host;
   // packed fp32 weights
   bool packed = false;
   std::vector<float*> w1, b1, w2, b2;
@@ -236,6 +243,22 @@ int pack_weights(vqwn_handle* h) {
     packc(TP(h, "decoder/postprocess2/kernel"), Qn, S, Qn / CL_CS, 0, 0, h->wcl + h->off_post2t);
     CK(h, cudaGetLastError());
   }
+  if (h->bc_ok) {
+    auto packb = [&](const float* src, int ldw, int K, int rows, int mode, int n0, int base1, __nv_bfloat16* dst) {
+      const long long total = (long long)BC_CS * K * rows;
+      int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+      pack_bf16_planes_kernel<<<grid, 256, 0, h->stream>>>(src, ldw, K, rows, mode, n0, base1, BC_CS, dst);
+      h->launches += 1;
+    };
+    packb(TP(h, "decoder/skip/kernel"), S, R, BC_NSK, 0, 0, 0, h->wbc + h->off_skip0t);
+    for (int l = 0; l < h->L; ++l) {
+      packb(h->w1[l], 2 * G, 3 * R + C, BC_ROWS_S1, 1, 0, G, h->wbc + h->off_w1t[l]);
+      packb(h->w2[l], R + S, G, BC_ROWS_S2, 2, BC_NR, R, h->wbc + h->off_w2t[l]);
+    }
+    packb(h->post1_w, S, S + C, BC_NSK, 0, 0, 0, h->wbc + h->off_post1t);
+    packb(TP(h, "decoder/postprocess2/kernel"), h->Q, S, BC_NQ, 0, 0, 0, h->wbc + h->off_post2t);
+    CK(h, cudaGetLastError());
+  }
   CK(h, cudaMemcpyAsync(h->enc_lut, TP(h, "lut/mu_law_encode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->dec_lut, TP(h, "lut/mu_law_decode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
@@ -358,10 +381,64 @@ int launch_cluster(vqwn_handle* h, int MS, int mode, long long T, const float* c
   return VQWN_OK;
 }
 
+int launch_bf16(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
+                const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
+                float* logits_out, float* probs_out) {
+  const int nclusters = (h->B + BC_NS - 1) / BC_NS;
+  if (nclusters > h->bc_max_clusters)
+    return fail(h, VQWN_ERR_INVALID, "bf16 kernel: batch exceeds 16 streams x co-resident 8-CTA clusters");
+  BcParams p;
+  memset(&p, 0, sizeof p);
+  p.L = h->L; p.B = h->B; p.nclusters = nclusters;
+  p.pre_k = TP(h, "decoder/preprocess/kernel"); p.pre_b = TP(h, "decoder/preprocess/bias");
+  p.skip0 = h->wbc + h->off_skip0t; p.skip0_b = TP(h, "decoder/skip/bias");
+  p.post1 = h->wbc + h->off_post1t; p.post1_b = TP(h, "decoder/postprocess1/bias");
+  p.post2 = h->wbc + h->off_post2t; p.post2_b = TP(h, "decoder/postprocess2/bias");
+  // bf16 rings in plane layout live in the same storage as the float32 rings (half the bytes)
+  size_t off = 0;
+  __nv_bfloat16* rb = reinterpret_cast<__nv_bfloat16*>(h->ring_base);
+  for (int l = 0; l < h->L; ++l) {
+    h->bc_layers_host[l].ring = rb + off;
+    off += (size_t)2 * h->cfg.dilations[l] * nclusters * BC_R * BC_NS;
+  }
+  if (off * sizeof(__nv_bfloat16) > h->ring_floats * sizeof(float)) return fail(h, VQWN_ERR_INVALID, "bf16 kernel: ring storage too small");
+  CK(h, cudaMemcpyAsync(h->bc_layers_dev, h->bc_layers_host.data(), sizeof(BcLayerDev) * h->L, cudaMemcpyHostToDevice, h->stream));
+  p.layers = h->bc_layers_dev;
+  p.enc_lut = h->enc_lut; p.dec_lut = h->dec_lut;
+  p.u_hist = h->u_hist;
+  p.t0 = h->t; p.T = T; p.mode = mode;
+  p.cond = cond; p.cond_bstride = cond_bstride; p.ratio = ratio;
+  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed;
+  p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
+  p.prof = h->profile ? h->prof : nullptr;
+  p.err = h->gen_err;
+  CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(nclusters * BC_CS);
+  cfg.blockDim = dim3(BC_THREADS);
+  cfg.dynamicSmemBytes = BC_SMEM;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = BC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  CK(h, cudaLaunchKernelEx(&cfg, wavenet_bf16_cluster, p));
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  h->last_kernel = "wavenet_bf16_cluster";
+  h->t += T;
+  return VQWN_OK;
+}
+
 // ring layout depends on the padded batch of the run; rebuilt at every launch
 int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
                 const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
                 float* logits_out, float* probs_out) {
+  if (h->precision == VQWN_PREC_BF16)
+    return launch_bf16(h, mode, T, cond, cond_bstride, ratio, ext_audio, uniforms, seed, audio_out, idx_out, logits_out,
+                       probs_out);
   if (h->gen_kernel == 0 || h->gen_kernel == 3) {
     const int ms = cl_streams_per_cluster(h, h->B);
     if (ms > 0)
@@ -441,7 +518,7 @@ int finish_timing(vqwn_handle* h) {
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
-  if (strncmp(h->last_kernel, "wavenet_fp32", 12) == 0) {
+  if (strncmp(h->last_kernel, "wavenet_", 8) == 0) {
     int e = 0;
     CK(h, cudaMemcpy(&e, h->gen_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (e) return fail(h, VQWN_ERR_CUDA, e == 2 ? "generation kernel: operand wait timed out" : (e == 4 ? "generation kernel: packet wait timed out" : "generation kernel: grid barrier timed out"));
@@ -759,6 +836,28 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
       if (h->cl_max_clusters < 1) h->cl_ok = false;
     }
   }
+  // bf16 tensor-core cluster kernel: reference default geometry only
+  h->bc_ok = R == BC_R && G == BC_G && S == BC_S && Q == BC_Q && C == BC_C && h->PK == BC_PK && c.kernel_size == 3 && h->L <= 64;
+  if (h->bc_ok) {
+    CKC(cudaMalloc(&h->wbc, h->wtiles_floats * sizeof(__nv_bfloat16)));
+    CKC(cudaMalloc(&h->bc_layers_dev, sizeof(BcLayerDev) * h->L));
+    h->bc_layers_host.resize(h->L);
+    for (int l = 0; l < h->L; ++l)
+      h->bc_layers_host[l] = BcLayerDev{h->wbc + h->off_w1t[l], h->b1[l], h->wbc + h->off_w2t[l], h->b2[l], nullptr,
+                                        c.dilations[l], 0};
+    CKC(cudaFuncSetAttribute((const void*)wavenet_bf16_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC_SMEM));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(BC_CS); cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = BC_SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = BC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, (const void*)wavenet_bf16_cluster, &cfg) != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
+    h->bc_max_clusters = nc;
+    if (nc < 1) h->bc_ok = false;
+  }
   CKC(cudaMalloc(&h->gen_err, sizeof(int)));
   h->df_floats = (size_t)h->L * h->Bp_max * (R + G) + (size_t)h->Bp_max * S;
   CKC(cudaMalloc(&h->df_base, h->df_floats * sizeof(float)));
@@ -804,7 +903,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->w2) if (p) cudaFree(p);
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
-                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->df_base, h->df_cnt, h->wcl, h->cl_layers_dev};
+                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->df_base, h->df_cnt, h->wcl, h->cl_layers_dev, h->wbc, h->bc_layers_dev};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,
@@ -827,7 +926,13 @@ int vqwn_set_stream(vqwn_handle* h, void* cuda_stream) {
 int vqwn_set_precision(vqwn_handle* h, int precision) {
   ENTER(h);
   if (precision == VQWN_PREC_FP32) { h->precision = precision; return VQWN_OK; }
-  return fail(h, VQWN_ERR_NOTIMPL, "precision not implemented in this build");
+  if (precision == VQWN_PREC_BF16) {
+    if (!h->bc_ok)
+      return fail(h, VQWN_ERR_NOTIMPL, "bf16 tensor-core path is built for the reference's default WaveNet geometry only");
+    h->precision = precision;
+    return VQWN_OK;
+  }
+  return fail(h, VQWN_ERR_INVALID, "unknown precision id");
 }
 
 int vqwn_set_vq_kernel(vqwn_handle* h, int kernel) {

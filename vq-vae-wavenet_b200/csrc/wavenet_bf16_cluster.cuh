@@ -1,0 +1,553 @@
+// WaveNet fast generation on the 5th-generation tensor cores: bf16 operands, fp32 accumulation in TMEM
+// (VQWN_PREC_BF16).  Same reference semantics as the float32 kernels (wavenet.py:103-172,
+// wavenet_ops.py:163-267, utils.py:13-46, mu_law_ops.py:5-31); weights and the activations that feed a
+// contraction are rounded to bfloat16, everything else (biases, residual and skip chains, gate, softmax, draw)
+// stays float32.
+//
+// Structure = the float32 cluster kernel (wavenet_fp32_cluster.cuh) with the CUDA-core contraction replaced by
+// tcgen05.mma: a cluster of 8 CTAs owns 16 streams for the whole run and splits every stage by output channels;
+// the channels are the M dimension (weights = A operand, 128 rows of which 32/64/96 are real, the rest alias the
+// following shared memory and produce ignored accumulator rows), the 16 streams are N, and a stage is a chain of
+// K/16 MMAs issued by one elected thread.  Per CTA:
+//   skip start 64 ch x K 256   S1 64 rows (32 tanh/sigmoid pairs, interleaved) x K 896   S2 32 res + 64 skip x K 256
+//   post1 64 ch x K 640        post2 32 logits x K 512
+// Operands sit in shared memory as K-major no-swizzle "planes": plane p holds k = 8p..8p+7 of every row
+// (16 bytes per row, rows back to back), so LBO = plane stride and SBO = 128 in the matrix descriptors.  Weight
+// tiles arrive pre-packed in that layout with one cp.async.bulk one stage ahead; activations are pushed between
+// the CTAs of a cluster as 16-byte plane chunks with st.async + mbarrier complete_tx; the dilation queues are
+// HBM rings in the same plane layout ([2d][cluster][32 planes][16 streams][8] bf16) so a tap is one 8 KB bulk copy.
+// The accumulator (128 lanes x 16 columns of TMEM) is read with tcgen05.ld 32x32b.x16: thread = output channel.
+// The geometry is fixed to the reference's default (R = G = 256, S = 512, Q = 256, C = 128, 32-tap preprocess).
+#pragma once
+#include <cuda_bf16.h>
+#include "wavenet_fp32_cluster.cuh"
+
+namespace vqwn {
+
+constexpr int BC_CS = 8;             // CTAs per cluster
+constexpr int BC_THREADS = 256;
+constexpr int BC_NS = 16;            // streams per cluster = MMA N
+constexpr int BC_R = 256, BC_G = 256, BC_S = 512, BC_Q = 256, BC_C = 128, BC_PK = 32;
+constexpr int BC_K1 = 3 * BC_R + BC_C;                 // 896
+constexpr int BC_ROWS_S1 = 2 * BC_G / BC_CS;           // 64: tanh / sigmoid rows interleaved
+constexpr int BC_NR = BC_R / BC_CS, BC_NSK = BC_S / BC_CS, BC_NQ = BC_Q / BC_CS;   // 32, 64, 32
+constexpr int BC_ROWS_S2 = BC_NR + BC_NSK;             // 96
+constexpr int BC_PLANE_B = BC_NS * 16;                 // bytes of one activation plane (16 rows x 16 B)
+// shared memory map (bytes)
+constexpr int BC_W1_BYTES = BC_ROWS_S1 * BC_K1 * 2;    // 114688 (post1: 64 x 640 x 2 fits)
+constexpr int BC_W2_BYTES = BC_ROWS_S2 * BC_G * 2;     // 49152  (skip start 64 x 256, post2 32 x 512 fit)
+constexpr int BC_OFF_W1 = 0;
+constexpr int BC_OFF_W2 = BC_OFF_W1 + BC_W1_BYTES;
+constexpr int BC_OFF_G = BC_OFF_W2 + BC_W2_BYTES;                  // gate outputs: 32 planes
+constexpr int BC_OFF_X = BC_OFF_G + 32 * BC_PLANE_B;               // cur 32 | tap t-d 32 | tap t-2d 32 | cond 16 planes
+constexpr int BC_OFF_CUR32 = BC_OFF_X + 112 * BC_PLANE_B;          // [32 ch][16] fp32 residual chain of this CTA's channels
+constexpr int BC_OFF_SKIP32 = BC_OFF_CUR32 + BC_NR * BC_NS * 4;    // [64 ch][16] fp32 skip accumulators
+constexpr int BC_OFF_STAGE = BC_OFF_SKIP32 + BC_NSK * BC_NS * 4;   // 2 KB + 1 KB staging for pushes / ring stores
+constexpr int BC_OFF_HIST = BC_OFF_STAGE + 3072;                   // [16][32] fp32 input history ring
+constexpr int BC_OFF_US = BC_OFF_HIST + BC_NS * BC_PK * 4;         // [16][32] history in tap order
+constexpr int BC_OFF_BARS = BC_OFF_US + BC_NS * BC_PK * 4;
+constexpr int BC_SMEM = BC_OFF_BARS + 128;
+// aliases: relu(skip) for post1 = tap planes (64 planes, followed by the 16 cond planes: K = 640 contiguous);
+// post1 output for post2 = gate planes + cur planes (64 planes contiguous); logits (CTA 0) = tap planes again
+constexpr int BC_OFF_SKF = BC_OFF_X + 32 * BC_PLANE_B;
+constexpr int BC_OFF_N1F = BC_OFF_G;
+constexpr int BC_OFF_LOGITS = BC_OFF_SKF;                          // [16][256] fp32 = 16 KB = 64 planes
+
+struct BcLayerDev {
+  const __nv_bfloat16* w1;   // [8 CTAs][112 planes][64 rows][8]   row 2j = tanh channel 32r+j, row 2j+1 = its sigmoid partner
+  const float* b1;           // [2G]
+  const __nv_bfloat16* w2;   // [8][32 planes][96 rows][8]         rows 0-31 residual 32r+i, rows 32-95 skip 64r+i
+  const float* b2;           // [R+S]
+  __nv_bfloat16* ring;       // [2d][clusters][32 planes][16][8]
+  int d;
+  int pad_;
+};
+
+struct BcParams {
+  int L, B, nclusters;
+  const float *pre_k, *pre_b;
+  const __nv_bfloat16 *skip0, *post1, *post2;     // [8][32 planes][64][8], [8][80][64][8], [8][64][32][8]
+  const float *skip0_b, *post1_b, *post2_b;
+  const BcLayerDev* layers;
+  const float *enc_lut, *dec_lut;
+  float* u_hist;
+  long long t0, T;
+  int mode;
+  const float* cond;
+  long long cond_bstride;
+  int ratio;
+  const float* ext_audio;
+  const double* uniforms;
+  unsigned long long seed;
+  float* audio_out;
+  int* idx_out;
+  float* logits_out;
+  float* probs_out;
+  long long* prof;
+  int* err;
+};
+
+__device__ __forceinline__ uint64_t bc_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;     // distance between core matrices adjacent in K (= plane stride)
+  d |= (uint64_t)(128 >> 4) << 32;           // distance between 8-row groups inside a plane
+  d |= 1ull << 46;
+  return d;
+}
+__device__ __forceinline__ void bc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void bc_st_bf16(uint8_t* planes, int n, int k, float x) {
+  *reinterpret_cast<__nv_bfloat16*>(planes + (k >> 3) * BC_PLANE_B + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(x);
+}
+// push `nchunks` 16-byte chunks (contiguous in the local staging buffer and at dst_off in every destination CTA)
+__device__ __forceinline__ void bc_push(const uint8_t* stage, uint8_t* smem_base, int dst_off, int nchunks, unsigned nranks,
+                                        unsigned long long* rx_bar) {
+  const unsigned dst = f32_smem_u32(smem_base + dst_off);
+  const unsigned mb = rx_bar ? f32_smem_u32(rx_bar) : 0u;
+  for (int w = threadIdx.x; w < nchunks * (int)nranks; w += BC_THREADS) {
+    const int c = w % nchunks;
+    const unsigned pr = (unsigned)(w / nchunks);
+    const float4 x = *reinterpret_cast<const float4*>(stage + c * 16);
+    if (rx_bar) cl_st_async_v4(cl_mapa(dst + c * 16, pr), x, cl_mapa(mb, pr));
+    else cl_st_v4(cl_mapa(dst + c * 16, pr), x);
+  }
+}
+
+__global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcParams p_in) {
+  extern __shared__ __align__(1024) uint8_t bsm[];
+  __shared__ BcLayerDev layers_s[64];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < p_in.L; i += BC_THREADS) layers_s[i] = p_in.layers[i];
+  BcParams p = p_in;
+  p.layers = layers_s;
+  unsigned rank_u;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
+  const int rank = (int)rank_u;
+  const int cluster = (int)blockIdx.x / BC_CS;
+  const int b0 = cluster * BC_NS;
+  const int nvalid = min(BC_NS, p.B - b0);
+  const int L = p.L;
+
+  uint8_t* const wS1 = bsm + BC_OFF_W1;
+  uint8_t* const wS2 = bsm + BC_OFF_W2;
+  uint8_t* const gpl = bsm + BC_OFF_G;
+  uint8_t* const xpl = bsm + BC_OFF_X;
+  float* const cur32 = reinterpret_cast<float*>(bsm + BC_OFF_CUR32);
+  float* const skip32 = reinterpret_cast<float*>(bsm + BC_OFF_SKIP32);
+  uint8_t* const stage = bsm + BC_OFF_STAGE;
+  float* const hist = reinterpret_cast<float*>(bsm + BC_OFF_HIST);
+  float* const u_s = reinterpret_cast<float*>(bsm + BC_OFF_US);
+  float* const logits_s = reinterpret_cast<float*>(bsm + BC_OFF_LOGITS);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(bsm + BC_OFF_BARS);
+  unsigned long long* wbar1 = bars;       // S1-class weights landed
+  unsigned long long* wbar2 = bars + 1;   // S2-class weights landed
+  unsigned long long* tapbar = bars + 2;  // older taps landed
+  unsigned long long* accbar = bars + 3;  // MMA chain complete (tcgen05.commit)
+  unsigned long long* gbar = bars + 4;    // gate planes received from the 8 CTAs
+  unsigned long long* cbar = bars + 5;    // next layer input planes received
+  unsigned long long* skbar = bars + 6;   // relu(skip) planes received
+  unsigned long long* n1bar = bars + 7;   // post1 output planes received
+
+  for (int i = tid; i < (BC_OFF_BARS - BC_OFF_G) / 4; i += BC_THREADS) reinterpret_cast<uint32_t*>(bsm + BC_OFF_G)[i] = 0u;
+  __syncthreads();
+  constexpr unsigned RX_G = BC_CS * 4 * BC_PLANE_B, RX_C = BC_CS * 4 * BC_PLANE_B, RX_S = BC_CS * 8 * BC_PLANE_B;
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f32_smem_u32(&bars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect(gbar, RX_G);
+    mbar_expect(cbar, RX_C);
+    mbar_expect(skbar, RX_S);
+    mbar_expect(n1bar, RX_S);
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(f32_smem_u32(&tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < nvalid * BC_PK; i += BC_THREADS) hist[i] = ld_cg(p.u_hist + (long long)b0 * BC_PK + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  cl_barrier();
+
+  const float mu = (float)(BC_Q - 1);
+  const bool ext = (p.mode == GEN_STEP || p.mode == GEN_TEACHER);
+  unsigned ph1 = 0u, ph2 = 0u, phtap = 0u, phacc = 0u, phg = 0u, phc = 0u, phsk = 0u, phn1 = 0u;
+  bool alive = true;
+  uint32_t elected = 0;
+  if (warp == 4) asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BC_NS >> 3) << 17) | ((128u >> 4) << 24);
+
+  auto wait_bar = [&](unsigned long long* bar, unsigned& ph) {
+    alive = alive && mbar_wait_bounded(bar, ph, p.err);
+    ph ^= 1u;
+  };
+  auto recv_wait = [&](unsigned long long* bar, unsigned& ph, unsigned bytes) {
+    wait_bar(bar, ph);
+    if (tid == 0) mbar_expect(bar, bytes);
+  };
+  auto issue_w = [&](uint8_t* dst, const __nv_bfloat16* src, unsigned bytes, unsigned long long* bar) {
+    if (tid == 0) {
+      mbar_expect(bar, bytes);
+      cl_bulk_g2s_keep(reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(src), bytes, bar);
+    }
+  };
+  const long long ring_slot_elems = (long long)p.nclusters * BC_R * BC_NS;     // bf16 elements per ring slot
+  auto issue_taps = [&](int l, long long t) {
+    if (tid == 32 || tid == 33) {
+      const int which = tid - 32;
+      const BcLayerDev ly = p.layers[l];
+      const int d2 = 2 * ly.d;
+      const unsigned bytes = 32 * BC_PLANE_B;
+      if (which == 0) mbar_expect(tapbar, 2 * bytes);
+      const long long slot = (which == 0) ? ((t + ly.d) % d2) : (t % d2);
+      bulk_g2s(reinterpret_cast<float*>(xpl + (32 + 32 * which) * BC_PLANE_B),
+               reinterpret_cast<const float*>(ly.ring + slot * ring_slot_elems + (long long)cluster * BC_R * BC_NS), bytes, tapbar);
+    }
+  };
+  // one MMA chain: D[128 x 16] = A[128 x 16*ksteps] . B^T, A planes `a_lbo` bytes apart from a_base, B planes from b_base
+  auto mma_chain = [&](uint8_t* a_base, uint32_t a_lbo, uint8_t* b_base, int ksteps) {
+    // operands were written through the generic proxy (local stores, remote st.async) or by bulk copies: make them
+    // visible to the tensor-core (async) proxy, order against the preceding TMEM reads
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 4) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t a0 = f32_smem_u32(a_base), bb = f32_smem_u32(b_base);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t da = bc_desc(a0 + (uint32_t)ks * 2u * a_lbo, a_lbo);
+        const uint64_t db = bc_desc(bb + (uint32_t)ks * 2u * BC_PLANE_B, BC_PLANE_B);
+        const uint32_t accf = ks > 0 ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                     ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accf), "r"(elected) : "memory");
+      }
+      asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                   "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+                   ::"r"(f32_smem_u32(accbar)), "r"(elected) : "memory");
+    }
+    wait_bar(accbar, phacc);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+  const uint32_t my_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int row = (warp & 3) * 32 + lane;          // accumulator row of an epilogue thread (warps 0-3)
+
+  // preprocess FIR taps of channel `tid`
+  float fir_k[BC_PK];
+#pragma unroll
+  for (int j = 0; j < BC_PK; ++j) fir_k[j] = __ldg(p.pre_k + (BC_PK - 1 - j) * BC_R + tid);
+  const float fir_b = __ldg(p.pre_b + tid);
+
+  // ---- prologue
+  issue_w(wS2, p.skip0 + (size_t)rank * BC_NSK * BC_R, BC_NSK * BC_R * 2, wbar2);
+  issue_w(wS1, p.layers[0].w1 + (size_t)rank * BC_ROWS_S1 * BC_K1, BC_ROWS_S1 * BC_K1 * 2, wbar1);
+  long long cond_frame = -1;
+  float v[16];
+
+  for (long long t = p.t0; t < p.t0 + p.T; ++t) {
+    const long long frame_t = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
+    issue_taps(0, t);          // tap planes held the logits of the previous step until its draw finished
+    if (frame_t != cond_frame) {
+      // condition rows -> bf16 planes (16 planes behind the taps): thread = (stream, 8 channels)
+      {
+        const int n = tid >> 4, c8 = tid & 15;
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = 0.f;
+        if (n < nvalid) {
+          const float4* src = reinterpret_cast<const float4*>(p.cond + (long long)(b0 + n) * p.cond_bstride + frame_t * BC_C + c8 * 8);
+          const float4 lo = __ldg(src), hi = __ldg(src + 1);
+          x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bc_st_bf16(xpl + 96 * BC_PLANE_B, n, c8 * 8 + e, x[e]);
+      }
+      cond_frame = frame_t;
+    }
+    // ================================================================== stage 0: history -> FIR -> skip start
+    {
+      const int slot_t = (int)(t % BC_PK);
+      if (ext) {
+        if (tid < BC_NS) {
+          const int b = b0 + tid;
+          float x = 0.f;
+          if (b < p.B) {
+            if (p.mode == GEN_STEP) x = p.ext_audio[b];
+            else x = (t > p.t0) ? p.ext_audio[(long long)b * p.T + (t - p.t0 - 1)] : 0.f;
+          }
+          const float u = mu_law_encode_dev(x, mu, 0.f);
+          hist[tid * BC_PK + slot_t] = u;
+          if (rank == 0 && b < p.B) st_cg(p.u_hist + (long long)b * BC_PK + slot_t, u);
+        }
+        __syncthreads();
+      }
+      for (int idx = tid; idx < BC_NS * BC_PK; idx += BC_THREADS) {
+        const int i = idx / BC_PK, j = idx - i * BC_PK;
+        int sl = (int)((t - j) % BC_PK);
+        if (sl < 0) sl += BC_PK;
+        u_s[idx] = hist[i * BC_PK + sl];
+      }
+      __syncthreads();
+      // h0 = (u0*K[PK-1] + b) + u1*K[PK-2] + ...   (wavenet_ops.py:178,193); thread = channel
+#pragma unroll 2
+      for (int i = 0; i < BC_NS; ++i) {
+        const float4* up = reinterpret_cast<const float4*>(u_s + i * BC_PK);
+        float a = fir_b;
+#pragma unroll
+        for (int j4 = 0; j4 < BC_PK / 4; ++j4) {
+          const float4 u4 = up[j4];
+          a = fmaf(u4.x, fir_k[4 * j4 + 0], a); a = fmaf(u4.y, fir_k[4 * j4 + 1], a);
+          a = fmaf(u4.z, fir_k[4 * j4 + 2], a); a = fmaf(u4.w, fir_k[4 * j4 + 3], a);
+        }
+        bc_st_bf16(xpl, i, tid, a);
+        if ((tid >> 5) == rank) cur32[(tid & 31) * BC_NS + i] = a;     // float32 residual chain of this CTA's channels
+      }
+      // skip start (wavenet.py:117-121): 64 skip channels of this CTA
+      wait_bar(wbar2, ph2);
+      mma_chain(wS2, BC_NSK * 16, xpl, BC_R / 16);
+      issue_w(wS2, p.layers[0].w2 + (size_t)rank * BC_ROWS_S2 * BC_G, BC_ROWS_S2 * BC_G * 2, wbar2);
+      if (warp < 4) {
+        bc_ld16(my_taddr, v);
+        if (row < BC_NSK) {
+          const float bias = __ldg(p.skip0_b + rank * BC_NSK + row);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) skip32[row * BC_NS + n] = v[n] + bias;
+        }
+      }
+    }
+
+    // ================================================================== residual stacks
+    for (int l = 0; l < L; ++l) {
+      const BcLayerDev ly = p.layers[l];
+      const bool last = (l == L - 1);
+      // ---------------------------------------------------------------- S1: dilated conv + condition + gate
+      if (l > 0) recv_wait(cbar, phc, RX_C);
+      wait_bar(wbar1, ph1);
+      wait_bar(tapbar, phtap);
+      mma_chain(wS1, BC_ROWS_S1 * 16, xpl, BC_K1 / 16);
+      if (!last) {
+        issue_w(wS1, p.layers[l + 1].w1 + (size_t)rank * BC_ROWS_S1 * BC_K1, BC_ROWS_S1 * BC_K1 * 2, wbar1);
+        issue_taps(l + 1, t);
+      } else {
+        issue_w(wS1, p.post1 + (size_t)rank * BC_NSK * (BC_S + BC_C), BC_NSK * (BC_S + BC_C) * 2, wbar1);
+      }
+      if (warp < 4) {
+        bc_ld16(my_taddr, v);
+        if (row < BC_ROWS_S1) {
+          const int j = row >> 1;                      // gate channel of this CTA; even row tanh, odd row sigmoid
+          const float bias = __ldg(ly.b1 + ((row & 1) ? BC_G : 0) + rank * 32 + j);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            const float x = v[n] + bias;
+            const float partner = __shfl_xor_sync(0xffffffffu, x, 1);
+            if (!(row & 1)) bc_st_bf16(stage, n, j, tanhf(x) * sigmoid_f(partner));     // wavenet_ops.py:236-240
+          }
+        }
+      }
+      __syncthreads();
+      bc_push(stage, bsm, BC_OFF_G + rank * 4 * BC_PLANE_B, 4 * BC_PLANE_B / 16, BC_CS, gbar);
+
+      // ---------------------------------------------------------------- S2: residual + skip 1x1
+      recv_wait(gbar, phg, RX_G);
+      wait_bar(wbar2, ph2);
+      mma_chain(wS2, BC_ROWS_S2 * 16, gpl, BC_G / 16);
+      if (!last) issue_w(wS2, p.layers[l + 1].w2 + (size_t)rank * BC_ROWS_S2 * BC_G, BC_ROWS_S2 * BC_G * 2, wbar2);
+      else issue_w(wS2, p.post2 + (size_t)rank * BC_NQ * BC_S, BC_NQ * BC_S * 2, wbar2);
+      if (warp < 4) {
+        bc_ld16(my_taddr, v);
+        if (row < BC_NR) {
+          const float bias = __ldg(ly.b2 + rank * BC_NR + row);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            const float oldv = cur32[row * BC_NS + n];
+            const float nv = oldv + (v[n] + bias);
+            cur32[row * BC_NS + n] = nv;
+            if (!last) bc_st_bf16(stage, n, row, nv);      // next layer input slice (4 planes); dead after the last layer
+            bc_st_bf16(stage + 2048, n, row, oldv);        // push_ops: the layer input of this step goes to the queue
+          }
+        } else if (row < BC_ROWS_S2) {
+          const int c = row - BC_NR;
+          const float bias = __ldg(ly.b2 + BC_R + rank * BC_NSK + c);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            const float sk = skip32[c * BC_NS + n] + (v[n] + bias);
+            skip32[c * BC_NS + n] = sk;
+            if (last) bc_st_bf16(stage, n, c, fmaxf(sk, 0.f));      // wavenet.py:153 (the last residual is dead, :145)
+          }
+        }
+      }
+      __syncthreads();
+      {
+        // queue push: this CTA's 4 planes of ring slot t mod 2d
+        const int slot_old = (int)(t % (2 * ly.d));
+        if (tid < 4 * BC_PLANE_B / 16) {
+          const float4 x = *reinterpret_cast<const float4*>(stage + 2048 + tid * 16);
+          __nv_bfloat16* dst = ly.ring + slot_old * ring_slot_elems + (long long)cluster * BC_R * BC_NS + (rank * 4) * (BC_PLANE_B / 2);
+          *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + tid * 16) = x;
+        }
+      }
+      if (!last) bc_push(stage, bsm, BC_OFF_X + rank * 4 * BC_PLANE_B, 4 * BC_PLANE_B / 16, BC_CS, cbar);
+      else bc_push(stage, bsm, BC_OFF_SKF + rank * 8 * BC_PLANE_B, 8 * BC_PLANE_B / 16, BC_CS, skbar);
+    }
+
+    // ================================================================== postprocess1 (+ condition), relu
+    recv_wait(skbar, phsk, RX_S);
+    wait_bar(wbar1, ph1);
+    mma_chain(wS1, BC_NSK * 16, bsm + BC_OFF_SKF, (BC_S + BC_C) / 16);
+    if (t + 1 < p.t0 + p.T) issue_w(wS1, p.layers[0].w1 + (size_t)rank * BC_ROWS_S1 * BC_K1, BC_ROWS_S1 * BC_K1 * 2, wbar1);
+    if (warp < 4) {
+      bc_ld16(my_taddr, v);
+      if (row < BC_NSK) {
+        const float bias = __ldg(p.post1_b + rank * BC_NSK + row);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) bc_st_bf16(stage, n, row, fmaxf(v[n] + bias, 0.f));     // wavenet.py:163
+      }
+    }
+    __syncthreads();
+    bc_push(stage, bsm, BC_OFF_N1F + rank * 8 * BC_PLANE_B, 8 * BC_PLANE_B / 16, BC_CS, n1bar);
+
+    // ================================================================== postprocess2 -> logits on CTA 0
+    recv_wait(n1bar, phn1, RX_S);
+    wait_bar(wbar2, ph2);
+    mma_chain(wS2, BC_NQ * 16, bsm + BC_OFF_N1F, BC_S / 16);
+    if (t + 1 < p.t0 + p.T) issue_w(wS2, p.skip0 + (size_t)rank * BC_NSK * BC_R, BC_NSK * BC_R * 2, wbar2);
+    if (warp < 4) {
+      bc_ld16(my_taddr, v);
+      if (row < BC_NQ) {
+        const float bias = __ldg(p.post2_b + rank * BC_NQ + row);
+        float* st = reinterpret_cast<float*>(stage);          // [16 streams][32 logits] fp32
+#pragma unroll
+        for (int n = 0; n < 16; ++n) st[n * BC_NQ + row] = v[n] + bias;
+      }
+    }
+    __syncthreads();
+    {
+      // logits slice -> CTA 0: stream n, columns 32*rank .. +32 (8 chunks of 16 bytes per stream)
+      const unsigned base = f32_smem_u32(logits_s);
+      if (tid < BC_NS * 8) {
+        const int n = tid >> 3, c = tid & 7;
+        const float4 x = *reinterpret_cast<const float4*>(stage + (n * BC_NQ + c * 4) * 4);
+        cl_st_v4(cl_mapa(base + (unsigned)(n * BC_Q + rank * BC_NQ + c * 4) * 4u, 0u), x);
+      }
+    }
+    cl_barrier();
+
+    // ================================================================== softmax + draw + mu-law decode (CTA 0)
+    if (rank == 0) {
+      for (int i = warp; i < nvalid; i += BC_THREADS / 32) {
+        const int b = b0 + i;
+        float lg[8], pr[8];
+        float m = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { lg[q] = logits_s[i * BC_Q + lane + 32 * q]; m = fmaxf(m, lg[q]); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { pr[q] = expf(lg[q] - m); sum += pr[q]; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pr[q] = __fdiv_rn(pr[q], sum);
+        if (p.mode == GEN_STEP) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (p.logits_out) p.logits_out[(long long)b * BC_Q + lane + 32 * q] = lg[q];
+            if (p.probs_out) p.probs_out[(long long)b * BC_Q + lane + 32 * q] = pr[q];
+          }
+          continue;
+        }
+        if (p.mode == GEN_TEACHER) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) p.logits_out[((long long)b * p.T + (t - p.t0)) * BC_Q + lane + 32 * q] = lg[q];
+          continue;
+        }
+        int k;
+        if (p.mode == GEN_GREEDY) {
+          float bv = -1.f; int bi = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (pr[q] > bv) { bv = pr[q]; bi = lane + 32 * q; }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          k = bi;
+        } else {
+          float* pw = logits_s + i * BC_Q;
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pw[lane + 32 * q] = pr[q];
+          __syncwarp();
+          int cnt = 0;
+          if (lane == 0) {
+            const double u = p.uniforms ? p.uniforms[(t - p.t0) * p.B + b]
+                                        : counter_uniform(p.seed, (unsigned long long)t, (unsigned long long)b);
+            float c = 0.f;
+            for (int q = 0; q < BC_Q; ++q) {
+              c = __fadd_rn(c, pw[q]);
+              cnt += ((double)c < u) ? 1 : 0;
+            }
+          }
+          k = __shfl_sync(0xffffffffu, cnt, 0);
+          __syncwarp();
+        }
+        if (lane == 0) {
+          p.audio_out[(long long)b * p.T + (t - p.t0)] = __ldg(p.dec_lut + k);
+          if (p.idx_out) p.idx_out[(long long)b * p.T + (t - p.t0)] = k;
+          const float un = __ldg(p.enc_lut + k);
+          const int slot_n = (int)((t + 1) % BC_PK);
+          st_cg(p.u_hist + (long long)b * BC_PK + slot_n, un);
+          const unsigned a = f32_smem_u32(hist + i * BC_PK + slot_n);
+          for (unsigned r = 0; r < (unsigned)BC_CS; ++r) cl_st_f32(cl_mapa(a, r), un);
+        }
+      }
+    }
+    cl_barrier();
+  }
+  cl_barrier();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem));
+}
+
+// float32 [K][ldw] row-major -> bf16 K-major planes per cluster CTA: dst[cb][plane][row][8], row -> source column
+//   mode 0: column = cb*rows + row                                      (skip start, post1, post2)
+//   mode 1: row 2j -> cb*32 + j, row 2j+1 -> base1 + cb*32 + j          (S1: tanh / sigmoid partner interleaved)
+//   mode 2: row < n0 -> cb*n0 + row, else base1 + cb*(rows-n0) + row-n0 (S2: residual | skip)
+__global__ void pack_bf16_planes_kernel(const float* __restrict__ src, int ldw, int K, int rows, int mode, int n0, int base1,
+                                        int ntiles, __nv_bfloat16* __restrict__ dst) {
+  const long long total = (long long)ntiles * K * rows;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 8);
+    long long r = i / 8;
+    const int row = (int)(r % rows); r /= rows;
+    const int plane = (int)(r % (K / 8));
+    const int cb = (int)(r / (K / 8));
+    const int k = plane * 8 + e;
+    int col;
+    if (mode == 0) col = cb * rows + row;
+    else if (mode == 1) col = (row & 1) ? (base1 + cb * (rows / 2) + (row >> 1)) : (cb * (rows / 2) + (row >> 1));
+    else col = (row < n0) ? (cb * n0 + row) : (base1 + cb * (rows - n0) + (row - n0));
+    dst[i] = __float2bfloat16_rn(src[(long long)k * ldw + col]);
+  }
+}
+
+}  // namespace vqwn
