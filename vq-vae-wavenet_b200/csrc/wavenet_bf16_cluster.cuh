@@ -42,8 +42,10 @@ constexpr int BC_OFF_G = BC_OFF_W2 + BC_W2_BYTES;                  // gate outpu
 constexpr int BC_OFF_X = BC_OFF_G + 32 * BC_PLANE_B;               // cur 32 | tap t-d 32 | tap t-2d 32 | cond 16 planes
 constexpr int BC_OFF_CUR32 = BC_OFF_X + 112 * BC_PLANE_B;          // [32 ch][16] fp32 residual chain of this CTA's channels
 constexpr int BC_OFF_SKIP32 = BC_OFF_CUR32 + BC_NR * BC_NS * 4;    // [64 ch][16] fp32 skip accumulators
-constexpr int BC_OFF_STAGE = BC_OFF_SKIP32 + BC_NSK * BC_NS * 4;   // 2 KB + 1 KB staging for pushes / ring stores
-constexpr int BC_OFF_HIST = BC_OFF_STAGE + 3072;                   // [16][32] fp32 input history ring
+constexpr int BC_STAGE_PLANE = BC_PLANE_B + 16;                    // staging planes are padded by 16 B (bank spread of the 2-byte stores)
+constexpr int BC_OFF_STAGE = BC_OFF_SKIP32 + BC_NSK * BC_NS * 4;   // 8 + 4 padded planes: slice to push | queue slice
+constexpr int BC_OFF_PRE = BC_OFF_STAGE + 12 * BC_STAGE_PLANE;     // [16 streams][64 rows] fp32 pre-activations of the gate
+constexpr int BC_OFF_HIST = BC_OFF_PRE + BC_NS * BC_ROWS_S1 * 4;   // [16][32] fp32 input history ring
 constexpr int BC_OFF_US = BC_OFF_HIST + BC_NS * BC_PK * 4;         // [16][32] history in tap order
 constexpr int BC_OFF_BARS = BC_OFF_US + BC_NS * BC_PK * 4;
 constexpr int BC_SMEM = BC_OFF_BARS + 128;
@@ -109,7 +111,19 @@ __device__ __forceinline__ void bc_ld16(uint32_t taddr, float* v) {
 __device__ __forceinline__ void bc_st_bf16(uint8_t* planes, int n, int k, float x) {
   *reinterpret_cast<__nv_bfloat16*>(planes + (k >> 3) * BC_PLANE_B + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(x);
 }
-// push `nchunks` 16-byte chunks (contiguous in the local staging buffer and at dst_off in every destination CTA)
+// same element in the padded staging planes
+__device__ __forceinline__ void bc_st_stage(uint8_t* stage, int n, int k, float x) {
+  *reinterpret_cast<__nv_bfloat16*>(stage + (k >> 3) * BC_STAGE_PLANE + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(x);
+}
+// gate of the bf16 path: hardware tanh (MUFU.TANH, rel. error ~2^-11, far below the bf16 rounding of the result)
+__device__ __forceinline__ float bc_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float bc_gate(float a, float b) { return bc_tanh(a) * fmaf(0.5f, bc_tanh(0.5f * b), 0.5f); }
+// push `nchunks` 16-byte chunks (padded planes of 16 chunks in the local staging buffer, contiguous at dst_off in every
+// destination CTA)
 __device__ __forceinline__ void bc_push(const uint8_t* stage, uint8_t* smem_base, int dst_off, int nchunks, unsigned nranks,
                                         unsigned long long* rx_bar) {
   const unsigned dst = f32_smem_u32(smem_base + dst_off);
@@ -117,7 +131,7 @@ __device__ __forceinline__ void bc_push(const uint8_t* stage, uint8_t* smem_base
   for (int w = threadIdx.x; w < nchunks * (int)nranks; w += BC_THREADS) {
     const int c = w % nchunks;
     const unsigned pr = (unsigned)(w / nchunks);
-    const float4 x = *reinterpret_cast<const float4*>(stage + c * 16);
+    const float4 x = *reinterpret_cast<const float4*>(stage + c * 16 + (c >> 4) * 16);
     if (rx_bar) cl_st_async_v4(cl_mapa(dst + c * 16, pr), x, cl_mapa(mb, pr));
     else cl_st_v4(cl_mapa(dst + c * 16, pr), x);
   }
@@ -146,6 +160,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
   float* const cur32 = reinterpret_cast<float*>(bsm + BC_OFF_CUR32);
   float* const skip32 = reinterpret_cast<float*>(bsm + BC_OFF_SKIP32);
   uint8_t* const stage = bsm + BC_OFF_STAGE;
+  float* const pre = reinterpret_cast<float*>(bsm + BC_OFF_PRE);
   float* const hist = reinterpret_cast<float*>(bsm + BC_OFF_HIST);
   float* const u_s = reinterpret_cast<float*>(bsm + BC_OFF_US);
   float* const logits_s = reinterpret_cast<float*>(bsm + BC_OFF_LOGITS);
@@ -187,6 +202,13 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
   const bool ext = (p.mode == GEN_STEP || p.mode == GEN_TEACHER);
   unsigned ph1 = 0u, ph2 = 0u, phtap = 0u, phacc = 0u, phg = 0u, phc = 0u, phsk = 0u, phn1 = 0u;
   bool alive = true;
+  const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+  long long pf[24];
+  for (int i = 0; i < 24; ++i) pf[i] = 0;
+  long long pf_t = 0;
+  int pf_cls = 2;     // 0: S1, 1: S2, 2: other stages
+#define BC_PF_START() do { if (prof) pf_t = clock64(); } while (0)
+#define BC_PF_ADD(i) do { if (prof) { long long n_ = clock64(); pf[(i) + 8 * pf_cls] += n_ - pf_t; pf_t = n_; } } while (0)
   uint32_t elected = 0;
   if (warp == 4) asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BC_NS >> 3) << 17) | ((128u >> 4) << 24);
@@ -261,6 +283,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
 
   for (long long t = p.t0; t < p.t0 + p.T; ++t) {
     const long long frame_t = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
+    pf_cls = 2;
+    BC_PF_START();
     issue_taps(0, t);          // tap planes held the logits of the previous step until its draw finished
     if (frame_t != cond_frame) {
       // condition rows -> bf16 planes (16 planes behind the taps): thread = (stream, 8 channels)
@@ -315,20 +339,24 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
           a = fmaf(u4.z, fir_k[4 * j4 + 2], a); a = fmaf(u4.w, fir_k[4 * j4 + 3], a);
         }
         bc_st_bf16(xpl, i, tid, a);
-        if ((tid >> 5) == rank) cur32[(tid & 31) * BC_NS + i] = a;     // float32 residual chain of this CTA's channels
+        if ((tid >> 5) == rank) cur32[i * BC_NR + (tid & 31)] = a;     // float32 residual chain of this CTA's channels
       }
       // skip start (wavenet.py:117-121): 64 skip channels of this CTA
+      BC_PF_ADD(0);
       wait_bar(wbar2, ph2);
+      BC_PF_ADD(1);
       mma_chain(wS2, BC_NSK * 16, xpl, BC_R / 16);
+      BC_PF_ADD(2);
       issue_w(wS2, p.layers[0].w2 + (size_t)rank * BC_ROWS_S2 * BC_G, BC_ROWS_S2 * BC_G * 2, wbar2);
       if (warp < 4) {
         bc_ld16(my_taddr, v);
         if (row < BC_NSK) {
           const float bias = __ldg(p.skip0_b + rank * BC_NSK + row);
 #pragma unroll
-          for (int n = 0; n < 16; ++n) skip32[row * BC_NS + n] = v[n] + bias;
+          for (int n = 0; n < 16; ++n) skip32[n * BC_NSK + row] = v[n] + bias;
         }
       }
+      BC_PF_ADD(3);
     }
 
     // ================================================================== residual stacks
@@ -336,36 +364,50 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       const BcLayerDev ly = p.layers[l];
       const bool last = (l == L - 1);
       // ---------------------------------------------------------------- S1: dilated conv + condition + gate
+      pf_cls = 0;
       if (l > 0) recv_wait(cbar, phc, RX_C);
+      BC_PF_ADD(4);
       wait_bar(wbar1, ph1);
       wait_bar(tapbar, phtap);
+      BC_PF_ADD(1);
       mma_chain(wS1, BC_ROWS_S1 * 16, xpl, BC_K1 / 16);
+      BC_PF_ADD(2);
       if (!last) {
         issue_w(wS1, p.layers[l + 1].w1 + (size_t)rank * BC_ROWS_S1 * BC_K1, BC_ROWS_S1 * BC_K1 * 2, wbar1);
         issue_taps(l + 1, t);
       } else {
         issue_w(wS1, p.post1 + (size_t)rank * BC_NSK * (BC_S + BC_C), BC_NSK * (BC_S + BC_C) * 2, wbar1);
       }
-      if (warp < 4) {
+      if (warp < 2) {
+        // rows 0-63: pre-activation + bias -> pre[stream][row] (even row tanh input, odd row its sigmoid partner)
         bc_ld16(my_taddr, v);
-        if (row < BC_ROWS_S1) {
-          const int j = row >> 1;                      // gate channel of this CTA; even row tanh, odd row sigmoid
-          const float bias = __ldg(ly.b1 + ((row & 1) ? BC_G : 0) + rank * 32 + j);
+        const int j = row >> 1;
+        const float bias = __ldg(ly.b1 + ((row & 1) ? BC_G : 0) + rank * 32 + j);
 #pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            const float x = v[n] + bias;
-            const float partner = __shfl_xor_sync(0xffffffffu, x, 1);
-            if (!(row & 1)) bc_st_bf16(stage, n, j, tanhf(x) * sigmoid_f(partner));     // wavenet_ops.py:236-240
-          }
-        }
+        for (int n = 0; n < 16; ++n) pre[n * BC_ROWS_S1 + row] = v[n] + bias;
       }
       __syncthreads();
+      // 512 gates over all 256 threads (wavenet_ops.py:236-240)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int idx = tid + h * BC_THREADS;
+        const int n = idx >> 5, j = idx & 31;
+        const float2 ab = *reinterpret_cast<const float2*>(pre + n * BC_ROWS_S1 + 2 * j);
+        bc_st_stage(stage, n, j, bc_gate(ab.x, ab.y));
+      }
+      __syncthreads();
+      BC_PF_ADD(3);
       bc_push(stage, bsm, BC_OFF_G + rank * 4 * BC_PLANE_B, 4 * BC_PLANE_B / 16, BC_CS, gbar);
+      BC_PF_ADD(5);
 
       // ---------------------------------------------------------------- S2: residual + skip 1x1
+      pf_cls = 1;
       recv_wait(gbar, phg, RX_G);
+      BC_PF_ADD(4);
       wait_bar(wbar2, ph2);
+      BC_PF_ADD(1);
       mma_chain(wS2, BC_ROWS_S2 * 16, gpl, BC_G / 16);
+      BC_PF_ADD(2);
       if (!last) issue_w(wS2, p.layers[l + 1].w2 + (size_t)rank * BC_ROWS_S2 * BC_G, BC_ROWS_S2 * BC_G * 2, wbar2);
       else issue_w(wS2, p.post2 + (size_t)rank * BC_NQ * BC_S, BC_NQ * BC_S * 2, wbar2);
       if (warp < 4) {
@@ -374,20 +416,20 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
           const float bias = __ldg(ly.b2 + rank * BC_NR + row);
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
-            const float oldv = cur32[row * BC_NS + n];
+            const float oldv = cur32[n * BC_NR + row];
             const float nv = oldv + (v[n] + bias);
-            cur32[row * BC_NS + n] = nv;
-            if (!last) bc_st_bf16(stage, n, row, nv);      // next layer input slice (4 planes); dead after the last layer
-            bc_st_bf16(stage + 2048, n, row, oldv);        // push_ops: the layer input of this step goes to the queue
+            cur32[n * BC_NR + row] = nv;
+            if (!last) bc_st_stage(stage, n, row, nv);                       // next layer input slice (4 planes); dead after the last layer
+            bc_st_stage(stage + 8 * BC_STAGE_PLANE, n, row, oldv);           // push_ops: this step's layer input goes to the queue
           }
         } else if (row < BC_ROWS_S2) {
           const int c = row - BC_NR;
           const float bias = __ldg(ly.b2 + BC_R + rank * BC_NSK + c);
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
-            const float sk = skip32[c * BC_NS + n] + (v[n] + bias);
-            skip32[c * BC_NS + n] = sk;
-            if (last) bc_st_bf16(stage, n, c, fmaxf(sk, 0.f));      // wavenet.py:153 (the last residual is dead, :145)
+            const float sk = skip32[n * BC_NSK + c] + (v[n] + bias);
+            skip32[n * BC_NSK + c] = sk;
+            if (last) bc_st_stage(stage, n, c, fmaxf(sk, 0.f));              // wavenet.py:153 (the last residual is dead, :145)
           }
         }
       }
@@ -396,14 +438,17 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
         // queue push: this CTA's 4 planes of ring slot t mod 2d
         const int slot_old = (int)(t % (2 * ly.d));
         if (tid < 4 * BC_PLANE_B / 16) {
-          const float4 x = *reinterpret_cast<const float4*>(stage + 2048 + tid * 16);
+          const float4 x = *reinterpret_cast<const float4*>(stage + 8 * BC_STAGE_PLANE + tid * 16 + (tid >> 4) * 16);
           __nv_bfloat16* dst = ly.ring + slot_old * ring_slot_elems + (long long)cluster * BC_R * BC_NS + (rank * 4) * (BC_PLANE_B / 2);
           *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + tid * 16) = x;
         }
       }
+      BC_PF_ADD(3);
       if (!last) bc_push(stage, bsm, BC_OFF_X + rank * 4 * BC_PLANE_B, 4 * BC_PLANE_B / 16, BC_CS, cbar);
       else bc_push(stage, bsm, BC_OFF_SKF + rank * 8 * BC_PLANE_B, 8 * BC_PLANE_B / 16, BC_CS, skbar);
+      BC_PF_ADD(5);
     }
+    pf_cls = 2;
 
     // ================================================================== postprocess1 (+ condition), relu
     recv_wait(skbar, phsk, RX_S);
@@ -415,7 +460,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       if (row < BC_NSK) {
         const float bias = __ldg(p.post1_b + rank * BC_NSK + row);
 #pragma unroll
-        for (int n = 0; n < 16; ++n) bc_st_bf16(stage, n, row, fmaxf(v[n] + bias, 0.f));     // wavenet.py:163
+        for (int n = 0; n < 16; ++n) bc_st_stage(stage, n, row, fmaxf(v[n] + bias, 0.f));     // wavenet.py:163
       }
     }
     __syncthreads();
@@ -430,7 +475,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       bc_ld16(my_taddr, v);
       if (row < BC_NQ) {
         const float bias = __ldg(p.post2_b + rank * BC_NQ + row);
-        float* st = reinterpret_cast<float*>(stage);          // [16 streams][32 logits] fp32
+        float* st = pre;                                      // [16 streams][32 logits] fp32
 #pragma unroll
         for (int n = 0; n < 16; ++n) st[n * BC_NQ + row] = v[n] + bias;
       }
@@ -441,7 +486,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       const unsigned base = f32_smem_u32(logits_s);
       if (tid < BC_NS * 8) {
         const int n = tid >> 3, c = tid & 7;
-        const float4 x = *reinterpret_cast<const float4*>(stage + (n * BC_NQ + c * 4) * 4);
+        const float4 x = *reinterpret_cast<const float4*>(pre + n * BC_NQ + c * 4);
         cl_st_v4(cl_mapa(base + (unsigned)(n * BC_Q + rank * BC_NQ + c * 4) * 4u, 0u), x);
       }
     }
@@ -523,6 +568,9 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     cl_barrier();
   }
   cl_barrier();
+  if (prof) for (int i = 0; i < 24; ++i) p.prof[i] = pf[i];
+#undef BC_PF_START
+#undef BC_PF_ADD
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem));
