@@ -217,20 +217,22 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     alive = alive && mbar_wait_bounded(bar, ph, p.err);
     ph ^= 1u;
   };
+  // housekeeping runs on warps 5-7 so that the epilogue warps (0-3) and the MMA warp (4) never wait for it:
+  // weight copies on warp 5, tap copies on warp 6, receive-barrier re-arming on warp 7
   auto recv_wait = [&](unsigned long long* bar, unsigned& ph, unsigned bytes) {
     wait_bar(bar, ph);
-    if (tid == 0) mbar_expect(bar, bytes);
+    if (tid == 224) mbar_expect(bar, bytes);
   };
   auto issue_w = [&](uint8_t* dst, const __nv_bfloat16* src, unsigned bytes, unsigned long long* bar) {
-    if (tid == 0) {
+    if (tid == 160) {
       mbar_expect(bar, bytes);
       cl_bulk_g2s_keep(reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(src), bytes, bar);
     }
   };
   const long long ring_slot_elems = (long long)p.nclusters * BC_R * BC_NS;     // bf16 elements per ring slot
   auto issue_taps = [&](int l, long long t) {
-    if (tid == 32 || tid == 33) {
-      const int which = tid - 32;
+    if (tid == 192 || tid == 193) {
+      const int which = tid - 192;
       const BcLayerDev ly = p.layers[l];
       const int d2 = 2 * ly.d;
       const unsigned bytes = 32 * BC_PLANE_B;
@@ -345,15 +347,15 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       BC_PF_ADD(0);
       wait_bar(wbar2, ph2);
       BC_PF_ADD(1);
+      const float bias_s0 = (warp < 2) ? __ldg(p.skip0_b + rank * BC_NSK + row) : 0.f;
       mma_chain(wS2, BC_NSK * 16, xpl, BC_R / 16);
       BC_PF_ADD(2);
       issue_w(wS2, p.layers[0].w2 + (size_t)rank * BC_ROWS_S2 * BC_G, BC_ROWS_S2 * BC_G * 2, wbar2);
       if (warp < 4) {
         bc_ld16(my_taddr, v);
         if (row < BC_NSK) {
-          const float bias = __ldg(p.skip0_b + rank * BC_NSK + row);
 #pragma unroll
-          for (int n = 0; n < 16; ++n) skip32[n * BC_NSK + row] = v[n] + bias;
+          for (int n = 0; n < 16; ++n) skip32[n * BC_NSK + row] = v[n] + bias_s0;
         }
       }
       BC_PF_ADD(3);
@@ -370,6 +372,10 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       wait_bar(wbar1, ph1);
       wait_bar(tapbar, phtap);
       BC_PF_ADD(1);
+      // biases of this thread's accumulator rows: requested before the MMA chain so the L2 latency hides behind it
+      const float bias_s1 = (warp < 2) ? __ldg(ly.b1 + ((row & 1) ? BC_G : 0) + rank * 32 + (row >> 1)) : 0.f;
+      const float bias_s2 = (warp < 4 && row < BC_ROWS_S2)
+                                ? __ldg(ly.b2 + (row < BC_NR ? rank * BC_NR + row : BC_R + rank * BC_NSK + (row - BC_NR))) : 0.f;
       mma_chain(wS1, BC_ROWS_S1 * 16, xpl, BC_K1 / 16);
       BC_PF_ADD(2);
       if (!last) {
@@ -381,10 +387,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       if (warp < 2) {
         // rows 0-63: pre-activation + bias -> pre[stream][row] (even row tanh input, odd row its sigmoid partner)
         bc_ld16(my_taddr, v);
-        const int j = row >> 1;
-        const float bias = __ldg(ly.b1 + ((row & 1) ? BC_G : 0) + rank * 32 + j);
 #pragma unroll
-        for (int n = 0; n < 16; ++n) pre[n * BC_ROWS_S1 + row] = v[n] + bias;
+        for (int n = 0; n < 16; ++n) pre[n * BC_ROWS_S1 + row] = v[n] + bias_s1;
       }
       __syncthreads();
       // 512 gates over all 256 threads (wavenet_ops.py:236-240)
@@ -413,21 +417,19 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       if (warp < 4) {
         bc_ld16(my_taddr, v);
         if (row < BC_NR) {
-          const float bias = __ldg(ly.b2 + rank * BC_NR + row);
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
             const float oldv = cur32[n * BC_NR + row];
-            const float nv = oldv + (v[n] + bias);
+            const float nv = oldv + (v[n] + bias_s2);
             cur32[n * BC_NR + row] = nv;
             if (!last) bc_st_stage(stage, n, row, nv);                       // next layer input slice (4 planes); dead after the last layer
             bc_st_stage(stage + 8 * BC_STAGE_PLANE, n, row, oldv);           // push_ops: this step's layer input goes to the queue
           }
         } else if (row < BC_ROWS_S2) {
           const int c = row - BC_NR;
-          const float bias = __ldg(ly.b2 + BC_R + rank * BC_NSK + c);
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
-            const float sk = skip32[n * BC_NSK + c] + (v[n] + bias);
+            const float sk = skip32[n * BC_NSK + c] + (v[n] + bias_s2);
             skip32[n * BC_NSK + c] = sk;
             if (last) bc_st_stage(stage, n, c, fmaxf(sk, 0.f));              // wavenet.py:153 (the last residual is dead, :145)
           }
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       __syncthreads();
       {
         // queue push: this CTA's 4 planes of ring slot t mod 2d
-        const int slot_old = (int)(t % (2 * ly.d));
+        const int slot_old = (t < 0x7fffffffLL) ? (int)((unsigned)t % (unsigned)(2 * ly.d)) : (int)(t % (2 * ly.d));
         if (tid < 4 * BC_PLANE_B / 16) {
           const float4 x = *reinterpret_cast<const float4*>(stage + 8 * BC_STAGE_PLANE + tid * 16 + (tid >> 4) * 16);
           __nv_bfloat16* dst = ly.ring + slot_old * ring_slot_elems + (long long)cluster * BC_R * BC_NS + (rank * 4) * (BC_PLANE_B / 2);
@@ -453,14 +455,15 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     // ================================================================== postprocess1 (+ condition), relu
     recv_wait(skbar, phsk, RX_S);
     wait_bar(wbar1, ph1);
+    const float bias_p1 = (warp < 2) ? __ldg(p.post1_b + rank * BC_NSK + row) : 0.f;
+    const float bias_p2 = (warp < 1) ? __ldg(p.post2_b + rank * BC_NQ + row) : 0.f;
     mma_chain(wS1, BC_NSK * 16, bsm + BC_OFF_SKF, (BC_S + BC_C) / 16);
     if (t + 1 < p.t0 + p.T) issue_w(wS1, p.layers[0].w1 + (size_t)rank * BC_ROWS_S1 * BC_K1, BC_ROWS_S1 * BC_K1 * 2, wbar1);
     if (warp < 4) {
       bc_ld16(my_taddr, v);
       if (row < BC_NSK) {
-        const float bias = __ldg(p.post1_b + rank * BC_NSK + row);
 #pragma unroll
-        for (int n = 0; n < 16; ++n) bc_st_stage(stage, n, row, fmaxf(v[n] + bias, 0.f));     // wavenet.py:163
+        for (int n = 0; n < 16; ++n) bc_st_stage(stage, n, row, fmaxf(v[n] + bias_p1, 0.f));     // wavenet.py:163
       }
     }
     __syncthreads();
@@ -474,10 +477,9 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     if (warp < 4) {
       bc_ld16(my_taddr, v);
       if (row < BC_NQ) {
-        const float bias = __ldg(p.post2_b + rank * BC_NQ + row);
         float* st = pre;                                      // [16 streams][32 logits] fp32
 #pragma unroll
-        for (int n = 0; n < 16; ++n) st[n * BC_NQ + row] = v[n] + bias;
+        for (int n = 0; n < 16; ++n) st[n * BC_NQ + row] = v[n] + bias_p2;
       }
     }
     __syncthreads();
