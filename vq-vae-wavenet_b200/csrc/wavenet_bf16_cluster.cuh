@@ -213,16 +213,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
   if (warp == 4) asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BC_NS >> 3) << 17) | ((128u >> 4) << 24);
 
-  auto wait_bar = [&](unsigned long long* bar, unsigned& ph) {
-    alive = alive && mbar_wait_bounded(bar, ph, p.err);
-    ph ^= 1u;
-  };
-  // housekeeping runs on warps 5-7 so that the epilogue warps (0-3) and the MMA warp (4) never wait for it:
-  // weight copies on warp 5, tap copies on warp 6, receive-barrier re-arming on warp 7
-  auto recv_wait = [&](unsigned long long* bar, unsigned& ph, unsigned bytes) {
-    wait_bar(bar, ph);
-    if (tid == 224) mbar_expect(bar, bytes);
-  };
+  // housekeeping runs on warps 5-6 so that the epilogue warps (0-3) and the MMA warp (4) never wait for it:
+  // weight copies on warp 5, tap copies on warp 6
   auto issue_w = [&](uint8_t* dst, const __nv_bfloat16* src, unsigned bytes, unsigned long long* bar) {
     if (tid == 160) {
       mbar_expect(bar, bytes);
@@ -242,32 +234,54 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
                reinterpret_cast<const float*>(ly.ring + slot * ring_slot_elems + (long long)cluster * BC_R * BC_NS), bytes, tapbar);
     }
   };
-  // one MMA chain: D[128 x 16] = A[128 x 16*ksteps] . B^T, A planes `a_lbo` bytes apart from a_base, B planes from b_base
-  auto mma_chain = [&](uint8_t* a_base, uint32_t a_lbo, uint8_t* b_base, int ksteps) {
-    // operands were written through the generic proxy (local stores, remote st.async) or by bulk copies: make them
-    // visible to the tensor-core (async) proxy, order against the preceding TMEM reads
+  // every stage starts here (all threads): operands written through the generic proxy by this CTA (FIR output,
+  // condition planes) become visible to the tensor-core (async) proxy, and the TMEM reads of earlier epilogues are
+  // ordered before the MMAs that overwrite those accumulators
+  auto stage_sync = [&]() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp == 4) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const uint32_t a0 = f32_smem_u32(a_base), bb = f32_smem_u32(b_base);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t da = bc_desc(a0 + (uint32_t)ks * 2u * a_lbo, a_lbo);
-        const uint64_t db = bc_desc(bb + (uint32_t)ks * 2u * BC_PLANE_B, BC_PLANE_B);
-        const uint32_t accf = ks > 0 ? 1u : 0u;
-        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-                     "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                     ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accf), "r"(elected) : "memory");
-      }
-      asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-                   "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
-                   ::"r"(f32_smem_u32(accbar)), "r"(elected) : "memory");
+  };
+  // ---- warp 4 only: operand waits, MMA issue, commit.  Only this warp needs the operands; everybody else waits for
+  // the accumulator.
+  auto w4_wait = [&](unsigned long long* bar, unsigned& ph) {
+    alive = alive && mbar_wait_bounded(bar, ph, p.err);
+    ph ^= 1u;
+  };
+  auto w4_recv = [&](unsigned long long* bar, unsigned& ph, unsigned bytes) {
+    // pushed activation block landed; re-arm the barrier for its next use (the next block cannot be sent before
+    // every CTA has consumed this one: each sender first needs this CTA's output of the stage that reads it)
+    w4_wait(bar, ph);
+    if (lane == 0) mbar_expect(bar, bytes);
+  };
+  // K steps [ks0, ks1) of D[128 x 16] (TMEM column d_col) (+)= A . B^T; A planes a_lbo bytes apart, B planes 256 B
+  auto mma_issue = [&](uint32_t d_col, uint8_t* a_base, uint32_t a_lbo, uint8_t* b_base, int ks0, int ks1, bool fresh) {
+    // remote st.async / bulk-copy data observed through the mbarriers above -> tensor-core proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t a0 = f32_smem_u32(a_base), bb = f32_smem_u32(b_base);
+    for (int ks = ks0; ks < ks1; ++ks) {
+      const uint64_t da = bc_desc(a0 + (uint32_t)ks * 2u * a_lbo, a_lbo);
+      const uint64_t db = bc_desc(bb + (uint32_t)ks * 2u * BC_PLANE_B, BC_PLANE_B);
+      const uint32_t accf = (fresh && ks == ks0) ? 0u : 1u;
+      asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                   "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                   ::"r"(tmem + d_col), "l"(da), "l"(db), "r"(idesc), "r"(accf), "r"(elected) : "memory");
     }
-    wait_bar(accbar, phacc);
+  };
+  auto mma_commit = [&]() {     // accbar fires when every MMA issued so far has completed
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+                 ::"r"(f32_smem_u32(accbar)), "r"(elected) : "memory");
+  };
+  auto acc_wait = [&]() {
+    alive = alive && mbar_wait_bounded(accbar, phacc, p.err);
+    phacc ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
+  constexpr uint32_t D1 = 0, D2 = 16;     // TMEM accumulator columns: S1-class stages | S2-class stages
+  constexpr int KS_CUR = BC_R / 16;       // K steps of the current-input part of S1 (the rest: older taps + condition)
   const uint32_t my_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int row = (warp & 3) * 32 + lane;          // accumulator row of an epilogue thread (warps 0-3)
 
@@ -345,14 +359,22 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       }
       // skip start (wavenet.py:117-121): 64 skip channels of this CTA
       BC_PF_ADD(0);
-      wait_bar(wbar2, ph2);
-      BC_PF_ADD(1);
       const float bias_s0 = (warp < 2) ? __ldg(p.skip0_b + rank * BC_NSK + row) : 0.f;
-      mma_chain(wS2, BC_NSK * 16, xpl, BC_R / 16);
+      stage_sync();
+      if (warp == 4) {
+        w4_wait(wbar2, ph2);
+        mma_issue(D2, wS2, BC_NSK * 16, xpl, 0, BC_R / 16, true);
+        mma_commit();
+        // early part of layer 0's gated conv: older taps + condition (they do not depend on this step's chain)
+        w4_wait(wbar1, ph1);
+        w4_wait(tapbar, phtap);
+        mma_issue(D1, wS1, BC_ROWS_S1 * 16, xpl, KS_CUR, BC_K1 / 16, true);
+      }
+      acc_wait();
       BC_PF_ADD(2);
       issue_w(wS2, p.layers[0].w2 + (size_t)rank * BC_ROWS_S2 * BC_G, BC_ROWS_S2 * BC_G * 2, wbar2);
       if (warp < 4) {
-        bc_ld16(my_taddr, v);
+        bc_ld16(my_taddr + D2, v);
         if (row < BC_NSK) {
 #pragma unroll
           for (int n = 0; n < 16; ++n) skip32[n * BC_NSK + row] = v[n] + bias_s0;
@@ -367,16 +389,17 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       const bool last = (l == L - 1);
       // ---------------------------------------------------------------- S1: dilated conv + condition + gate
       pf_cls = 0;
-      if (l > 0) recv_wait(cbar, phc, RX_C);
-      BC_PF_ADD(4);
-      wait_bar(wbar1, ph1);
-      wait_bar(tapbar, phtap);
-      BC_PF_ADD(1);
       // biases of this thread's accumulator rows: requested before the MMA chain so the L2 latency hides behind it
       const float bias_s1 = (warp < 2) ? __ldg(ly.b1 + ((row & 1) ? BC_G : 0) + rank * 32 + (row >> 1)) : 0.f;
       const float bias_s2 = (warp < 4 && row < BC_ROWS_S2)
                                 ? __ldg(ly.b2 + (row < BC_NR ? rank * BC_NR + row : BC_R + rank * BC_NSK + (row - BC_NR))) : 0.f;
-      mma_chain(wS1, BC_ROWS_S1 * 16, xpl, BC_K1 / 16);
+      stage_sync();
+      if (warp == 4) {
+        if (l > 0) w4_recv(cbar, phc, RX_C);
+        mma_issue(D1, wS1, BC_ROWS_S1 * 16, xpl, 0, KS_CUR, false);     // onto the early part
+        mma_commit();
+      }
+      acc_wait();
       BC_PF_ADD(2);
       if (!last) {
         issue_w(wS1, p.layers[l + 1].w1 + (size_t)rank * BC_ROWS_S1 * BC_K1, BC_ROWS_S1 * BC_K1 * 2, wbar1);
@@ -386,7 +409,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       }
       if (warp < 2) {
         // rows 0-63: pre-activation + bias -> pre[stream][row] (even row tanh input, odd row its sigmoid partner)
-        bc_ld16(my_taddr, v);
+        bc_ld16(my_taddr + D1, v);
 #pragma unroll
         for (int n = 0; n < 16; ++n) pre[n * BC_ROWS_S1 + row] = v[n] + bias_s1;
       }
@@ -406,16 +429,26 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
 
       // ---------------------------------------------------------------- S2: residual + skip 1x1
       pf_cls = 1;
-      recv_wait(gbar, phg, RX_G);
-      BC_PF_ADD(4);
-      wait_bar(wbar2, ph2);
-      BC_PF_ADD(1);
-      mma_chain(wS2, BC_ROWS_S2 * 16, gpl, BC_G / 16);
+      stage_sync();
+      if (warp == 4) {
+        w4_recv(gbar, phg, RX_G);
+        w4_wait(wbar2, ph2);
+        mma_issue(D2, wS2, BC_ROWS_S2 * 16, gpl, 0, BC_G / 16, true);
+        mma_commit();
+        if (!last) {
+          // early part of the next layer's gated conv runs on the tensor pipe behind this chain, while the epilogue,
+          // the pushes and the wait for the next layer input proceed
+          w4_wait(wbar1, ph1);
+          w4_wait(tapbar, phtap);
+          mma_issue(D1, wS1, BC_ROWS_S1 * 16, xpl, KS_CUR, BC_K1 / 16, true);
+        }
+      }
+      acc_wait();
       BC_PF_ADD(2);
       if (!last) issue_w(wS2, p.layers[l + 1].w2 + (size_t)rank * BC_ROWS_S2 * BC_G, BC_ROWS_S2 * BC_G * 2, wbar2);
       else issue_w(wS2, p.post2 + (size_t)rank * BC_NQ * BC_S, BC_NQ * BC_S * 2, wbar2);
       if (warp < 4) {
-        bc_ld16(my_taddr, v);
+        bc_ld16(my_taddr + D2, v);
         if (row < BC_NR) {
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
@@ -453,14 +486,19 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     pf_cls = 2;
 
     // ================================================================== postprocess1 (+ condition), relu
-    recv_wait(skbar, phsk, RX_S);
-    wait_bar(wbar1, ph1);
     const float bias_p1 = (warp < 2) ? __ldg(p.post1_b + rank * BC_NSK + row) : 0.f;
     const float bias_p2 = (warp < 1) ? __ldg(p.post2_b + rank * BC_NQ + row) : 0.f;
-    mma_chain(wS1, BC_NSK * 16, bsm + BC_OFF_SKF, (BC_S + BC_C) / 16);
+    stage_sync();
+    if (warp == 4) {
+      w4_recv(skbar, phsk, RX_S);
+      w4_wait(wbar1, ph1);
+      mma_issue(D1, wS1, BC_NSK * 16, bsm + BC_OFF_SKF, 0, (BC_S + BC_C) / 16, true);
+      mma_commit();
+    }
+    acc_wait();
     if (t + 1 < p.t0 + p.T) issue_w(wS1, p.layers[0].w1 + (size_t)rank * BC_ROWS_S1 * BC_K1, BC_ROWS_S1 * BC_K1 * 2, wbar1);
     if (warp < 4) {
-      bc_ld16(my_taddr, v);
+      bc_ld16(my_taddr + D1, v);
       if (row < BC_NSK) {
 #pragma unroll
         for (int n = 0; n < 16; ++n) bc_st_stage(stage, n, row, fmaxf(v[n] + bias_p1, 0.f));     // wavenet.py:163
@@ -470,12 +508,17 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     bc_push(stage, bsm, BC_OFF_N1F + rank * 8 * BC_PLANE_B, 8 * BC_PLANE_B / 16, BC_CS, n1bar);
 
     // ================================================================== postprocess2 -> logits on CTA 0
-    recv_wait(n1bar, phn1, RX_S);
-    wait_bar(wbar2, ph2);
-    mma_chain(wS2, BC_NQ * 16, bsm + BC_OFF_N1F, BC_S / 16);
+    stage_sync();
+    if (warp == 4) {
+      w4_recv(n1bar, phn1, RX_S);
+      w4_wait(wbar2, ph2);
+      mma_issue(D2, wS2, BC_NQ * 16, bsm + BC_OFF_N1F, 0, BC_S / 16, true);
+      mma_commit();
+    }
+    acc_wait();
     if (t + 1 < p.t0 + p.T) issue_w(wS2, p.skip0 + (size_t)rank * BC_NSK * BC_R, BC_NSK * BC_R * 2, wbar2);
     if (warp < 4) {
-      bc_ld16(my_taddr, v);
+      bc_ld16(my_taddr + D2, v);
       if (row < BC_NQ) {
         float* st = pre;                                      // [16 streams][32 logits] fp32
 #pragma unroll
