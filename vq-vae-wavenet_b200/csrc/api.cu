@@ -549,8 +549,8 @@ int finish_timing(vqwn_handle* h) {
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess) {
       const char* cls[3] = {"S1", "S2", "other"};
       for (int c = 0; c < 3; ++c)
-        fprintf(stderr, "[vqwn profile] bf16 CTA0 %s cycles: fir=%lld recv_wait=%lld operand_wait=%lld mma_chain=%lld epilogue=%lld push=%lld (kernel %.3f ms)\n",
-                cls[c], pf[8 * c + 0], pf[8 * c + 4], pf[8 * c + 1], pf[8 * c + 2], pf[8 * c + 3], pf[8 * c + 5], ms);
+        fprintf(stderr, "[vqwn profile] bf16 CTA0 %s cycles: fir=%lld recv_wait=%lld operand_wait=%lld mma_chain=%lld tmem_ld=%lld ep_math=%lld ep_sync+queue=%lld push=%lld (kernel %.3f ms)\n",
+                cls[c], pf[8 * c + 0], pf[8 * c + 4], pf[8 * c + 1], pf[8 * c + 2], pf[8 * c + 7], pf[8 * c + 6], pf[8 * c + 3], pf[8 * c + 5], ms);
     }
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {

@@ -124,11 +124,14 @@ __device__ __forceinline__ float bc_tanh(float x) {
 __device__ __forceinline__ float bc_gate(float a, float b) { return bc_tanh(a) * fmaf(0.5f, bc_tanh(0.5f * b), 0.5f); }
 // push `nchunks` 16-byte chunks (padded planes of 16 chunks in the local staging buffer, contiguous at dst_off in every
 // destination CTA)
+// executed by the first `nthr` threads of the CTA
 __device__ __forceinline__ void bc_push(const uint8_t* stage, uint8_t* smem_base, int dst_off, int nchunks, unsigned nranks,
-                                        unsigned long long* rx_bar) {
+                                        unsigned long long* rx_bar, int nthr = BC_THREADS) {
   const unsigned dst = f32_smem_u32(smem_base + dst_off);
   const unsigned mb = rx_bar ? f32_smem_u32(rx_bar) : 0u;
-  for (int w = threadIdx.x; w < nchunks * (int)nranks; w += BC_THREADS) {
+  const int t0 = threadIdx.x, nt = nthr;
+  if (t0 >= nthr) return;
+  for (int w = t0; w < nchunks * (int)nranks; w += nt) {
     const int c = w % nchunks;
     const unsigned pr = (unsigned)(w / nchunks);
     const float4 x = *reinterpret_cast<const float4*>(stage + c * 16 + (c >> 4) * 16);
@@ -243,6 +246,16 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
+  // stages after the first: only the epilogue warps (0-3) and the MMA warp (4) meet; warps 5-7 (copy issue) are
+  // paced by the accumulator barrier alone, so a slow bulk-copy issue never holds a stage up
+  auto stage_sync5 = [&]() {
+    if (warp < 5) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 3, 160;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+  };
+  auto ep_sync = [&]() { if (warp < 4) asm volatile("bar.sync 2, 128;" ::: "memory"); };
   // ---- warp 4 only: operand waits, MMA issue, commit.  Only this warp needs the operands; everybody else waits for
   // the accumulator.
   auto w4_wait = [&](unsigned long long* bar, unsigned& ph) {
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       const float bias_s1 = (warp < 2) ? __ldg(ly.b1 + ((row & 1) ? BC_G : 0) + rank * 32 + (row >> 1)) : 0.f;
       const float bias_s2 = (warp < 4 && row < BC_ROWS_S2)
                                 ? __ldg(ly.b2 + (row < BC_NR ? rank * BC_NR + row : BC_R + rank * BC_NSK + (row - BC_NR))) : 0.f;
-      stage_sync();
+      stage_sync5();
       if (warp == 4) {
         if (l > 0) w4_recv(cbar, phc, RX_C);
         mma_issue(D1, wS1, BC_ROWS_S1 * 16, xpl, 0, KS_CUR, false);     // onto the early part
@@ -413,23 +426,25 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
 #pragma unroll
         for (int n = 0; n < 16; ++n) pre[n * BC_ROWS_S1 + row] = v[n] + bias_s1;
       }
-      __syncthreads();
-      // 512 gates over all 256 threads (wavenet_ops.py:236-240)
+      ep_sync();
+      // 512 gates over the 128 epilogue threads (wavenet_ops.py:236-240)
+      if (warp < 4) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int idx = tid + h * BC_THREADS;
-        const int n = idx >> 5, j = idx & 31;
-        const float2 ab = *reinterpret_cast<const float2*>(pre + n * BC_ROWS_S1 + 2 * j);
-        bc_st_stage(stage, n, j, bc_gate(ab.x, ab.y));
+        for (int h = 0; h < 4; ++h) {
+          const int idx = tid + h * 128;
+          const int n = idx >> 5, j = idx & 31;
+          const float2 ab = *reinterpret_cast<const float2*>(pre + n * BC_ROWS_S1 + 2 * j);
+          bc_st_stage(stage, n, j, bc_gate(ab.x, ab.y));
+        }
       }
-      __syncthreads();
+      ep_sync();
       BC_PF_ADD(3);
-      bc_push(stage, bsm, BC_OFF_G + rank * 4 * BC_PLANE_B, 4 * BC_PLANE_B / 16, BC_CS, gbar);
+      bc_push(stage, bsm, BC_OFF_G + rank * 4 * BC_PLANE_B, 4 * BC_PLANE_B / 16, BC_CS, gbar, 128);
       BC_PF_ADD(5);
 
       // ---------------------------------------------------------------- S2: residual + skip 1x1
       pf_cls = 1;
-      stage_sync();
+      stage_sync5();
       if (warp == 4) {
         w4_recv(gbar, phg, RX_G);
         w4_wait(wbar2, ph2);
@@ -449,26 +464,35 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
       else issue_w(wS2, p.post2 + (size_t)rank * BC_NQ * BC_S, BC_NQ * BC_S * 2, wbar2);
       if (warp < 4) {
         bc_ld16(my_taddr + D2, v);
+        BC_PF_ADD(7);
+        // (all loads first: the byte stores into the staging planes may alias anything as far as the compiler knows)
         if (row < BC_NR) {
+          float oldv[16];
+#pragma unroll
+          for (int n = 0; n < 16; ++n) oldv[n] = cur32[n * BC_NR + row];
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
-            const float oldv = cur32[n * BC_NR + row];
-            const float nv = oldv + (v[n] + bias_s2);
+            const float nv = oldv[n] + (v[n] + bias_s2);
             cur32[n * BC_NR + row] = nv;
             if (!last) bc_st_stage(stage, n, row, nv);                       // next layer input slice (4 planes); dead after the last layer
-            bc_st_stage(stage + 8 * BC_STAGE_PLANE, n, row, oldv);           // push_ops: this step's layer input goes to the queue
+            bc_st_stage(stage + 8 * BC_STAGE_PLANE, n, row, oldv[n]);        // push_ops: this step's layer input goes to the queue
           }
         } else if (row < BC_ROWS_S2) {
           const int c = row - BC_NR;
+          float sk[16];
+#pragma unroll
+          for (int n = 0; n < 16; ++n) sk[n] = skip32[n * BC_NSK + c];
 #pragma unroll
           for (int n = 0; n < 16; ++n) {
-            const float sk = skip32[n * BC_NSK + c] + (v[n] + bias_s2);
-            skip32[n * BC_NSK + c] = sk;
-            if (last) bc_st_stage(stage, n, c, fmaxf(sk, 0.f));              // wavenet.py:153 (the last residual is dead, :145)
+            sk[n] += v[n] + bias_s2;
+            skip32[n * BC_NSK + c] = sk[n];
+            if (last) bc_st_stage(stage, n, c, fmaxf(sk[n], 0.f));           // wavenet.py:153 (the last residual is dead, :145)
           }
         }
       }
-      __syncthreads();
+      BC_PF_ADD(6);
+      // (the MMA warp is still issuing the next layer's early part: only the epilogue warps meet here)
+      ep_sync();
       {
         // queue push: this CTA's 4 planes of ring slot t mod 2d
         const int slot_old = (t < 0x7fffffffLL) ? (int)((unsigned)t % (unsigned)(2 * ly.d)) : (int)(t % (2 * ly.d));
@@ -479,8 +503,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
         }
       }
       BC_PF_ADD(3);
-      if (!last) bc_push(stage, bsm, BC_OFF_X + rank * 4 * BC_PLANE_B, 4 * BC_PLANE_B / 16, BC_CS, cbar);
-      else bc_push(stage, bsm, BC_OFF_SKF + rank * 8 * BC_PLANE_B, 8 * BC_PLANE_B / 16, BC_CS, skbar);
+      if (!last) bc_push(stage, bsm, BC_OFF_X + rank * 4 * BC_PLANE_B, 4 * BC_PLANE_B / 16, BC_CS, cbar, 128);
+      else bc_push(stage, bsm, BC_OFF_SKF + rank * 8 * BC_PLANE_B, 8 * BC_PLANE_B / 16, BC_CS, skbar, 128);
       BC_PF_ADD(5);
     }
     pf_cls = 2;
@@ -488,7 +512,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     // ================================================================== postprocess1 (+ condition), relu
     const float bias_p1 = (warp < 2) ? __ldg(p.post1_b + rank * BC_NSK + row) : 0.f;
     const float bias_p2 = (warp < 1) ? __ldg(p.post2_b + rank * BC_NQ + row) : 0.f;
-    stage_sync();
+    stage_sync5();
     if (warp == 4) {
       w4_recv(skbar, phsk, RX_S);
       w4_wait(wbar1, ph1);
@@ -504,11 +528,11 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
         for (int n = 0; n < 16; ++n) bc_st_stage(stage, n, row, fmaxf(v[n] + bias_p1, 0.f));     // wavenet.py:163
       }
     }
-    __syncthreads();
-    bc_push(stage, bsm, BC_OFF_N1F + rank * 8 * BC_PLANE_B, 8 * BC_PLANE_B / 16, BC_CS, n1bar);
+    ep_sync();
+    bc_push(stage, bsm, BC_OFF_N1F + rank * 8 * BC_PLANE_B, 8 * BC_PLANE_B / 16, BC_CS, n1bar, 128);
 
     // ================================================================== postprocess2 -> logits on CTA 0
-    stage_sync();
+    stage_sync5();
     if (warp == 4) {
       w4_recv(n1bar, phn1, RX_S);
       w4_wait(wbar2, ph2);
