@@ -1,0 +1,23 @@
+import os, sys, numpy as np
+sys.path.insert(0, "/root/repo")
+from oracle import oracle as O
+import vqvae_wavenet_b200 as pkg
+g = np.load("/root/repo/tests/golden/full.npz")
+cfg = O.Config(); w = O.make_weights(cfg, seed=1234, peaked=True)
+eng = pkg.Engine(pkg.EngineConfig(), device=0, max_batch=64); eng.set_weights(w)
+B, Tt = 4, 512
+ze = O.synthetic_z_e(cfg, w, B, 64, seed=1235, kind="scaled")
+_, cond = eng.encode_condition(ze, [0, 1, 2, 3])
+x = O.synthetic_audio(B, Tt, seed=1237)
+want = g["teacher_logits"]
+for prec in ("fp32", "bf16"):
+    eng.set_precision(prec)
+    lg = eng.teacher_forced(x, cond[:, :Tt // 64])
+    print(prec, eng.last_kernel_name, "max|dlogit|/max|logit| =", np.abs(lg[:, ::32] - want).max() / np.abs(want).max())
+eng.set_precision("fp32")
+a0, i0 = eng.generate(cond, 4096, mode="greedy")
+eng.set_precision("bf16")
+a1, i1 = eng.generate(cond, 4096, mode="greedy")
+agree = (i0 == i1)
+first = [int(np.argmin(r)) if not r.all() else len(r) for r in agree]
+print("greedy bf16 vs fp32: first divergence per stream", first, "overall agreement", agree.mean())
