@@ -7,8 +7,9 @@ running VQ + WaveNet fast generation on the B200 library instead of TensorFlow.
 Outputs, as the reference writes them (generate.py:94-101,115-117):
   <dir>/embedding_<gs>.npy  <dir>/speaker_embedding_<gs>.npy  <dir>/<gs>_<speaker>.wav (float32, 16 kHz)
 
-Weights: `<restore>.npz` holding arrays keyed by the reference's variable names (EMA shadows stored
-under the variable's own name).  Reading TensorFlow tensor-bundle checkpoints directly is SURVEY 8f #2.
+Weights: the reference's own TensorFlow checkpoint `<restore>.index` / `<restore>.data-*` (read without TensorFlow,
+EMA shadows preferred as `ema.variables_to_restore()` does), or `<restore>.npz` holding arrays keyed by the
+reference's variable names.
 Encoder: Encoder_64 ("encoder": "64") runs on the device; for the other two pass the
 encoder output with -z_e <file.npy> ([F,latent_dim] or [B,F,latent_dim]); -audio then only fixes the length.
 """
@@ -64,18 +65,24 @@ def main(argv=None):
         raise NotImplementedError("encoder %s not implemented on the device (SURVEY 8f #1): pass -z_e"
                                   % cfg.model['encoder'])
 
+    from vqvae_wavenet_b200 import tf_checkpoint
     weights_file = args.restore_path + '.npz'
-    if not os.path.exists(weights_file):
-        raise NotImplementedError("expected %s (arrays keyed by reference variable name); TensorFlow "
-                                  "tensor-bundle checkpoints are SURVEY 8f #2" % weights_file)
+    if not tf_checkpoint.is_bundle(args.restore_path) and not os.path.exists(weights_file):
+        raise FileNotFoundError("neither a TensorFlow checkpoint (%s.index) nor %s (arrays keyed by reference "
+                                "variable name) exists" % (args.restore_path, weights_file))
     engine = pkg.Engine(cfg, device=args.device, max_batch=batch_size)
-    with np.load(weights_file) as data:
-        wanted = dict((n, s) for n, s, _ in engine.tensor_table())
-        for name in data.files:
-            key = name[:-len('/ExponentialMovingAverage')] if name.endswith('/ExponentialMovingAverage') else name
-            key = key[len('optimiser/'):] if key.startswith('optimiser/') else key      # EMA shadow scope
-            if key in wanted:
-                engine.set_tensor(key, data[name])
+    wanted = dict((n, s) for n, s, _ in engine.tensor_table())
+    if tf_checkpoint.is_bundle(args.restore_path):
+        # generate.py:88-90: Saver(ema.variables_to_restore()).restore(sess, restore_path), read without TensorFlow
+        for key, value in tf_checkpoint.generator_weights(args.restore_path, wanted).items():
+            engine.set_tensor(key, value)
+    else:
+        with np.load(weights_file) as data:
+            for name in data.files:
+                key = name[:-len('/ExponentialMovingAverage')] if name.endswith('/ExponentialMovingAverage') else name
+                key = key[len('optimiser/'):] if key.startswith('optimiser/') else key      # EMA shadow scope
+                if key in wanted:
+                    engine.set_tensor(key, data[name])
 
     encoder = None
     if z_e is None:

@@ -239,6 +239,24 @@ def test_cli_end_to_end(tmp_path):
     assert np.array_equal(audio[0], a) and np.array_equal(audio[1], b)
     assert np.abs(eng.encode_audio(x[None, :1024]) - z).max() < 1e-4
     eng.close()
+    # the same run restored from a TensorFlow tensor-bundle checkpoint instead of the .npz: raw
+    # variables hold garbage, the EMA shadows hold the weights - generate.py:88-90 restores the shadows
+    from vqvae_wavenet_b200 import tf_checkpoint
+    run2 = tmp_path / "run_tf"
+    run2.mkdir()
+    bundle = {}
+    for k, v in w.items():
+        if k.startswith("decoder/"):
+            bundle[k] = np.full_like(v, 123.0)
+            bundle["optimiser/" + k + "/ExponentialMovingAverage"] = v
+        else:
+            bundle[k] = v
+    bundle["global_step"] = np.array(9, dtype=np.int64)
+    tf_checkpoint.write_bundle(str(run2 / "weights-9"), bundle)
+    generate.main(["-restore", str(run2 / "weights-9"), "-audio", str(tmp_path / "in.wav"), "-speakers", "p225", "None",
+                   "-mode", "greedy"])
+    assert np.array_equal(wavio.read_wav(str(run2 / "9_p225.wav")), a)
+    assert np.array_equal(wavio.read_wav(str(run2 / "9_no_speaker.wav")), b)
 
 
 # ----------------------------------------------------------------------------------------- decoder, small config

@@ -72,10 +72,10 @@ def test_cli_surface(tmp_path, monkeypatch):
     wav = str(tmp_path / "in.wav")
     wavio.write_wav_float32(wav, 16000, np.zeros(1024, np.float32))
     restore = str(tmp_path / "weights-42")
-    with pytest.raises(NotImplementedError, match="npz"):
+    with pytest.raises(FileNotFoundError, match="npz"):      # neither <restore>.index (TF checkpoint) nor <restore>.npz
         generate.main(["-restore", restore, "-audio", wav, "-speakers", "p225", "None", "-mode", "greedy"])
     np.save(str(tmp_path / "z.npy"), np.zeros((16, 64), np.float32))
-    with pytest.raises(NotImplementedError, match="npz"):
+    with pytest.raises(FileNotFoundError, match="npz"):
         generate.main(["-restore", restore, "-audio", wav, "-speakers", "p225", "-z_e", str(tmp_path / "z.npy")])
     with pytest.raises(ValueError):
         generate.main(["-restore", str(tmp_path / "weights-x"), "-audio", wav, "-speakers", "p225"])   # gs = int(...)
