@@ -587,3 +587,31 @@ def test_bf16_full_teacher_logits(golden_dir):
     assert np.array_equal(sub, i1[20:23])
     assert i1.min() >= 0 and i1.max() <= 255
     eng.close()
+
+
+@pytest.mark.parametrize("precision,B", [("fp32", 100), ("bf16", 250)])
+def test_batches_above_cluster_capacity_run_as_several_launches(precision, B):
+    """the cluster kernels hold 7 x 10 (float32) / 15 x 16 (bf16) streams per launch; larger batches run as consecutive
+    launches over disjoint stream groups.  Streams never interact, so every stream must come out exactly as it does
+    in a small batch of its own - including the ones in the second launch."""
+    cfg = O.Config(wavenet=SMALL_WAVENET)
+    w = O.make_weights(cfg, seed=1234)
+    T, F = 48, 1
+    rng = np.random.default_rng(11)
+    ze = O.synthetic_z_e(cfg, w, B, F, seed=21, kind="scaled")
+    spk = [int(v) for v in rng.integers(0, cfg.num_speakers, size=B)]
+    eng = _engine(SMALL_WAVENET, B, w)
+    eng.set_precision(precision)
+    _, cond = eng.encode_condition(ze, spk)
+    full = eng.generate(cond, T, mode="greedy")[1]
+    launches = eng.launch_count
+    eng.generate(cond, T, mode="greedy")
+    assert eng.launch_count - launches == 2                  # two launches of the generation kernel
+    u = rng.random((T, B))
+    fulls = eng.generate(cond, T, mode="sample", uniforms=u)[1]
+    for lo, hi in ((0, 6), (B - 9, B)):
+        sub = eng.generate(cond[lo:hi], T, mode="greedy")[1]
+        assert np.array_equal(sub, full[lo:hi])
+        subs = eng.generate(cond[lo:hi], T, mode="sample", uniforms=u[:, lo:hi])[1]
+        assert np.array_equal(subs, fulls[lo:hi])
+    eng.close()

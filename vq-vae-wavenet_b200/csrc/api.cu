@@ -322,7 +322,7 @@ int cl_streams_per_cluster(const vqwn_handle* h, int B) {
   const int need = (B + h->cl_max_clusters - 1) / h->cl_max_clusters;
   for (int ms = 2; ms <= CL_MAX_MS; ms += 2)
     if (ms >= need) return ms;
-  return 0;
+  return CL_MAX_MS;      // more streams than the co-resident clusters hold: several launches of full clusters
 }
 
 int launch_cluster(vqwn_handle* h, int MS, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
@@ -364,7 +364,6 @@ int launch_cluster(vqwn_handle* h, int MS, int mode, long long T, const float* c
   const int nclusters = (h->B + MS - 1) / MS;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(nclusters * CL_CS);
   cfg.blockDim = dim3(CL_THREADS);
   cfg.dynamicSmemBytes = cl_smem_bytes(h, MS);
   cfg.stream = h->stream;
@@ -373,9 +372,16 @@ int launch_cluster(vqwn_handle* h, int MS, int mode, long long T, const float* c
   attr[0].val.clusterDim.x = CL_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   CK(h, cudaEventRecord(h->ev0, h->stream));
-  CK(h, cudaLaunchKernelEx(&cfg, cl_kernel_for(MS), p));
+  // clusters are independent (streams never interact): a batch larger than the co-resident clusters runs as
+  // consecutive launches over disjoint stream groups
+  for (int c0 = 0; c0 < nclusters; c0 += h->cl_max_clusters) {
+    const int nc = (nclusters - c0 < h->cl_max_clusters) ? (nclusters - c0) : h->cl_max_clusters;
+    p.cluster0 = c0;
+    cfg.gridDim = dim3(nc * CL_CS);
+    CK(h, cudaLaunchKernelEx(&cfg, cl_kernel_for(MS), p));
+    h->launches += 1;
+  }
   CK(h, cudaEventRecord(h->ev1, h->stream));
-  h->launches += 1;
   h->last_kernel = "wavenet_fp32_cluster";
   h->t += T;
   return VQWN_OK;
@@ -385,8 +391,6 @@ int launch_bf16(vqwn_handle* h, int mode, long long T, const float* cond, long l
                 const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
                 float* logits_out, float* probs_out) {
   const int nclusters = (h->B + BC_NS - 1) / BC_NS;
-  if (nclusters > h->bc_max_clusters)
-    return fail(h, VQWN_ERR_INVALID, "bf16 kernel: batch exceeds 16 streams x co-resident 8-CTA clusters");
   BcParams p;
   memset(&p, 0, sizeof p);
   p.L = h->L; p.B = h->B; p.nclusters = nclusters;
@@ -415,7 +419,6 @@ int launch_bf16(vqwn_handle* h, int mode, long long T, const float* cond, long l
   CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(nclusters * BC_CS);
   cfg.blockDim = dim3(BC_THREADS);
   cfg.dynamicSmemBytes = BC_SMEM;
   cfg.stream = h->stream;
@@ -424,9 +427,14 @@ int launch_bf16(vqwn_handle* h, int mode, long long T, const float* cond, long l
   attr[0].val.clusterDim.x = BC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   CK(h, cudaEventRecord(h->ev0, h->stream));
-  CK(h, cudaLaunchKernelEx(&cfg, wavenet_bf16_cluster, p));
+  for (int c0 = 0; c0 < nclusters; c0 += h->bc_max_clusters) {      // disjoint stream groups, one launch per co-resident set
+    const int nc = (nclusters - c0 < h->bc_max_clusters) ? (nclusters - c0) : h->bc_max_clusters;
+    p.cluster0 = c0;
+    cfg.gridDim = dim3(nc * BC_CS);
+    CK(h, cudaLaunchKernelEx(&cfg, wavenet_bf16_cluster, p));
+    h->launches += 1;
+  }
   CK(h, cudaEventRecord(h->ev1, h->stream));
-  h->launches += 1;
   h->last_kernel = "wavenet_bf16_cluster";
   h->t += T;
   return VQWN_OK;

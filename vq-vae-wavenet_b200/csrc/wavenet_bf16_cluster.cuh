@@ -66,7 +66,8 @@ struct BcLayerDev {
 };
 
 struct BcParams {
-  int L, B, nclusters;
+  int L, B, nclusters;      // nclusters: clusters of the whole batch (ring layout)
+  int cluster0;             // first cluster of this launch
   const float *pre_k, *pre_b;
   const __nv_bfloat16 *skip0, *post1, *post2;     // [8][32 planes][64][8], [8][80][64][8], [8][64][32][8]
   const float *skip0_b, *post1_b, *post2_b;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
   unsigned rank_u;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
   const int rank = (int)rank_u;
-  const int cluster = (int)blockIdx.x / BC_CS;
+  const int cluster = p_in.cluster0 + (int)blockIdx.x / BC_CS;
   const int b0 = cluster * BC_NS;
   const int nvalid = min(BC_NS, p.B - b0);
   const int L = p.L;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
   const bool ext = (p.mode == GEN_STEP || p.mode == GEN_TEACHER);
   unsigned ph1 = 0u, ph2 = 0u, phtap = 0u, phacc = 0u, phg = 0u, phc = 0u, phsk = 0u, phn1 = 0u;
   bool alive = true;
-  const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+  const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && p.cluster0 == 0 && tid == 0;
   long long pf[24];
   for (int i = 0; i < 24; ++i) pf[i] = 0;
   long long pf_t = 0;

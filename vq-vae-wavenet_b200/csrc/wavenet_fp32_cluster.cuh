@@ -50,6 +50,7 @@ struct ClLayerDev {
 struct ClParams {
   int L, R, G, S, Q, C, PK;
   int B, Bp;
+  int cluster0;             // first cluster of this launch (batches above the co-resident capacity run as several launches)
   int kg_s0, kg_s1, kg_s2, kg_p1, kg_p2;   // K-groups per stage (host-chosen: kg * NC/4 <= 256, K % (4 kg) == 0)
   int w1_floats, w2_floats;                // shared-memory weight buffers
   const float *pre_k, *pre_b, *skip0c, *skip0_b, *post1c, *post1_b, *post2c, *post2_b;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
   unsigned rank_u;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
   const int rank = (int)rank_u;
-  const int cluster = (int)blockIdx.x / CL_CS;
+  const int cluster = p_in.cluster0 + (int)blockIdx.x / CL_CS;
   const int b0 = cluster * MS;                                  // first stream of this cluster
   const int nvalid = min(MS, p.B - b0);                         // >= 1 (host launches only clusters with work)
 
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
   unsigned ph1 = 0u, ph2 = 0u, phtap = 0u, phcond = 0u;
   bool alive = true;
 
-  const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+  const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && p.cluster0 == 0 && tid == 0;
   long long pf[24];
   for (int i = 0; i < 24; ++i) pf[i] = 0;
   long long pf_t = 0;
