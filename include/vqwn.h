@@ -80,6 +80,11 @@ const char* vqwn_last_error(const vqwn_handle* h);
 /* run the library's kernels on a caller stream (a cudaStream_t) instead of its own, so the
  * caller can time them with its own CUDA events.  NULL restores the private stream. */
 int vqwn_set_stream(vqwn_handle* h, void* cuda_stream);
+/* arithmetic of the generation loop (wavenet.py:103-172 evaluated by vqwn_generate / vqwn_step / vqwn_teacher_forced).
+ * VQWN_PREC_FP32 (default): every contraction in float32, the parity anchor (logits 1e-6 from the restatement).
+ * VQWN_PREC_BF16: tcgen05 tensor-core kernel, weights and contraction inputs rounded to bfloat16, float32 accumulation
+ * and float32 residual / skip / softmax (logits within 2e-2); the reference's default WaveNet geometry only, otherwise
+ * VQWN_ERR_NOTIMPL.  Set it before vqwn_reset / the first generate call of a run: the dilation-queue layout differs. */
 int vqwn_set_precision(vqwn_handle* h, int precision);
 int vqwn_set_vq_kernel(vqwn_handle* h, int kernel);
 
