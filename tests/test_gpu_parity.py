@@ -615,3 +615,32 @@ def test_batches_above_cluster_capacity_run_as_several_launches(precision, B):
         subs = eng.generate(cond[lo:hi], T, mode="sample", uniforms=u[:, lo:hi])[1]
         assert np.array_equal(subs, fulls[lo:hi])
     eng.close()
+
+
+def test_cfg5_teacher_forced_full_size(monkeypatch):
+    """BASELINE config 5 at its full size (teacher-forced decoder forward, batch 8, length 6656 = 104 frames x hop 64,
+    default 30-layer WaveNet) - too long for the NumPy oracle, so checked through size-independent properties: the three
+    independent kernels (float32 cluster, float32 grid-barrier, bf16 tensor-core) must agree on every one of the
+    8 x 6656 x 256 logits within their tolerances, and a prefix of the run equals the short run the oracle pins
+    (test_full_teacher_forced_logits)."""
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234, peaked=True)
+    B, T, F = 8, 6656, 104
+    ze = O.synthetic_z_e(cfg, w, B, F, seed=1235, kind="scaled")
+    x = O.synthetic_audio(B, T, seed=1237)
+    out = {}
+    for kernel in ("cluster", "barrier"):
+        monkeypatch.setenv("VQWN_GEN_KERNEL", kernel)
+        eng = _engine(None, B, w)
+        _, cond = eng.encode_condition(ze, np.arange(B, dtype=np.int32) % 4)
+        out[kernel] = eng.teacher_forced(x, cond)
+        if kernel == "cluster":
+            short = eng.teacher_forced(x[:, :512], cond[:, :8])
+            assert np.array_equal(short, out[kernel][:, :512])           # a run is a prefix of a longer run
+            eng.set_precision("bf16")
+            out["bf16"] = eng.teacher_forced(x, cond)
+        eng.close()
+    scale = np.abs(out["barrier"]).max()
+    assert out["cluster"].shape == (B, T, 256)
+    assert np.abs(out["cluster"] - out["barrier"]).max() <= 2e-5 * scale
+    assert np.abs(out["bf16"] - out["cluster"]).max() <= BF16_LOGIT_RTOL * scale
