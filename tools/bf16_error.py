@@ -1,8 +1,10 @@
+"""bf16 tensor-core path vs the float32 path and the oracle's golden logits (run on a B200): logit error, KL, greedy divergence."""
 import os, sys, numpy as np
-sys.path.insert(0, "/root/repo")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 from oracle import oracle as O
 import vqvae_wavenet_b200 as pkg
-g = np.load("/root/repo/tests/golden/full.npz")
+g = np.load(os.path.join(ROOT, "tests", "golden", "full.npz"))
 cfg = O.Config(); w = O.make_weights(cfg, seed=1234, peaked=True)
 eng = pkg.Engine(pkg.EngineConfig(), device=0, max_batch=64); eng.set_weights(w)
 B, Tt = 4, 512
