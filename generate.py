@@ -10,8 +10,8 @@ Outputs, as the reference writes them (generate.py:94-101,115-117):
 Weights: the reference's own TensorFlow checkpoint `<restore>.index` / `<restore>.data-*` (read without TensorFlow,
 EMA shadows preferred as `ema.variables_to_restore()` does), or `<restore>.npz` holding arrays keyed by the
 reference's variable names.
-Encoder: Encoder_64 ("encoder": "64") runs on the device; for the other two pass the
-encoder output with -z_e <file.npy> ([F,latent_dim] or [B,F,latent_dim]); -audio then only fixes the length.
+Encoder: Encoder_64 ("encoder": "64") and Encoder_Magenta ("Magenta") run on the device; for Encoder_2019
+pass the encoder output with -z_e <file.npy> ([F,latent_dim] or [B,F,latent_dim]); -audio then only fixes the length.
 """
 import os
 import sys
@@ -61,7 +61,7 @@ def main(argv=None):
             z_e = np.tile(z_e[None], (batch_size, 1, 1))
         if length % z_e.shape[1] != 0:
             raise ValueError("audio length %d is not a multiple of the %d encoder frames" % (length, z_e.shape[1]))
-    elif cfg.model['encoder'] != '64':
+    elif cfg.model['encoder'] not in ('64', 'Magenta'):
         raise NotImplementedError("encoder %s not implemented on the device (SURVEY 8f #1): pass -z_e"
                                   % cfg.model['encoder'])
 
@@ -87,7 +87,8 @@ def main(argv=None):
     encoder = None
     if z_e is None:
         # generate.py:40 tiles ONE utterance over the batch: encode it once, tile the result
-        encoder = pkg.Encoder_64(cfg.model['latent_dim'], engine)
+        enc_cls = pkg.Encoder_64 if cfg.model['encoder'] == '64' else pkg.Encoder_Magenta        # generate.py:65-69
+        encoder = enc_cls(cfg.model['latent_dim'], engine)
         z_e = np.tile(encoder.build(wav[:1]), (batch_size, 1, 1))
     model = pkg.VQVAE({'x': wav, 'z_e': z_e, 'speaker': speaker, 'encoder': encoder,
                        'decoder': pkg.WavenetDecoder(cfg.wavenet), 'k': cfg.model['k'], 'beta': cfg.model['beta'],

@@ -37,6 +37,11 @@ extern "C" {
 #define VQWN_MODE_GREEDY 0
 #define VQWN_MODE_SAMPLE 1
 
+/* vqwn_config.encoder */
+#define VQWN_ENCODER_NONE 0
+#define VQWN_ENCODER_MAGENTA 1   /* Encoder_Magenta (Encoder/encoder.py:29-64) */
+#define VQWN_ENCODER_64 64       /* Encoder_64 (Encoder/encoder.py:8-26) */
+
 /* arithmetic of the decoder step (vqwn_set_precision) */
 #define VQWN_PREC_FP32 0   /* fp32 CUDA-core contraction; the parity anchor                 */
 #define VQWN_PREC_BF16 1   /* bf16 tcgen05 contraction, fp32 accumulate (tolerance 2e-2)    */
@@ -63,7 +68,7 @@ typedef struct vqwn_config {
   int32_t speaker_dim;           /* "speaker_embedding" (64; 0 = no speaker condition)      */
   int32_t num_speakers;          /* 109 / 340 / 251 (generate.py:46-57)                     */
   int32_t use_vq;                /* "use_vq"                                                */
-  int32_t encoder;               /* "encoder": 64 = Encoder_64 on the device, 0 = encoder output is supplied */
+  int32_t encoder;               /* "encoder": VQWN_ENCODER_64 / VQWN_ENCODER_MAGENTA run on the device, 0 = encoder output is supplied */
 } vqwn_config;
 
 typedef struct vqwn_handle vqwn_handle;
@@ -108,10 +113,13 @@ int vqwn_tensor_info(const vqwn_handle* h, int i, char* name_out, int name_cap,
                      int64_t* shape_out /*[4]*/, int* ndim_out, int* is_set);
 
 /* ---- encoder ----------------------------------------------------------- */
-/* replaces Encoder_64.build (Encoder/encoder.py:8-26; model.py:36-42): x [B,T] float audio ->
- * z_e_out [B, T/64, latent_dim].  T must be a multiple of 64.  Needs cfg.encoder == 64 and the
- * keras variables "encoder/conv1d[_i]/{kernel,bias}", "encoder/batch_normalization[_i]/{gamma,
- * beta,moving_mean,moving_variance}", i = 1..6 (no suffix for the first). */
+/* replaces Encoder_64.build / Encoder_Magenta.build (Encoder/encoder.py:8-26, 29-64; model.py:36-42): x [B,T] float
+ * audio -> z_e_out [B, T/64, latent_dim].  T must be a multiple of 64.
+ * cfg.encoder == VQWN_ENCODER_64: keras variables "encoder/conv1d[_i]/{kernel,bias}", "encoder/batch_normalization[_i]/
+ *   {gamma,beta,moving_mean,moving_variance}" (i = 1..6, the first without suffix; BatchNorm in inference form, eps 1e-3).
+ * cfg.encoder == VQWN_ENCODER_MAGENTA: "encoder/preprocess/{kernel,bias}", "encoder/cycle_1/layer_l/{dilated,gate,filter,
+ *   residual}/{kernel,bias}" (l = 1..6), "encoder/postprocess/{kernel,bias}"; shift_right + mu_law_encode on the input.
+ * Encoder_2019 (MFCC front end) is not built: VQWN_ERR_NOTIMPL. */
 int vqwn_encode_audio(vqwn_handle* h, const float* x, int B, int64_t T, float* z_e_out);
 
 /* ---- VQ bottleneck + conditioning ---------------------------------------------------- */

@@ -531,6 +531,61 @@ def encoder64_forward(cfg, weights, x):
 # --------------------------------------------------------------------------------------
 # Synthetic inputs of SURVEY 8d
 # --------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------
+# Encoder_Magenta (Encoder/encoder.py:29-64) - SURVEY 8f #1, second encoder
+# ---------------------------------------------------------------------------------------------
+MAGENTA_DILATIONS = [1, 2, 4, 8, 16, 16]        # encoder.py:34
+MAGENTA_FILTERS = 128                            # encoder.py:39
+MAGENTA_KERNEL = 5                               # encoder.py:40
+
+
+def encoder_magenta_specs(cfg):
+    """variables under variable_scope('encoder') (model.py:134-135): conv1d_v2 creates 'kernel' [k,in,out] and 'bias'
+    in the enclosing scope (wavenet_ops.py:66-76)"""
+    C, k = MAGENTA_FILTERS, MAGENTA_KERNEL
+    specs = [("encoder/preprocess/kernel", (k, 1, C)), ("encoder/preprocess/bias", (C,))]
+    for i in range(len(MAGENTA_DILATIONS)):
+        sc = "encoder/cycle_%d/layer_%d" % (1 + i // 6, 1 + i % 6)           # encoder.py:49-50
+        specs += [(sc + "/dilated/kernel", (1, C, C)), (sc + "/dilated/bias", (C,)),
+                  (sc + "/gate/kernel", (k, C, C)), (sc + "/gate/bias", (C,)),
+                  (sc + "/filter/kernel", (k, C, C)), (sc + "/filter/bias", (C,)),
+                  (sc + "/residual/kernel", (1, C, C)), (sc + "/residual/bias", (C,))]
+    specs += [("encoder/postprocess/kernel", (1, C, cfg.D)), ("encoder/postprocess/bias", (cfg.D,))]
+    return specs
+
+
+def make_encoder_magenta_weights(cfg, seed=4322):
+    """seeded synthetic weights: kernels U(+-sqrt(3/fan_in)) as uniform_unit_scaling_initializer(1.0)
+    (wavenet_ops.py:69), small non-zero biases"""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in encoder_magenta_specs(cfg):
+        if name.endswith("kernel"):
+            lim = np.sqrt(3.0 / (shape[0] * shape[1]))
+            a = rng.uniform(-lim, lim, size=shape)
+        else:
+            a = rng.uniform(-0.05, 0.05, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=F32)
+    return out
+
+
+def encoder_magenta_forward(cfg, weights, x):
+    """Encoder/encoder.py:37-64.  x [B,T,1] -> z_e [B,T/64,latent_dim] (T a multiple of 64).
+    shift_right + mu_law_encode (float path), causal k=5 preprocess conv, then 6 x [1x1 stride-2 conv 'dilated'
+    (wavenet_ops.py:83-86: VALID with stride 2 keeps samples 0,2,4,...), gate / filter = causal dilated k=5 convs of
+    it, tanh(gate) * sigmoid(filter), residual 1x1 added to the strided signal], then a 1x1 postprocess conv."""
+    net = mu_law_encode(shift_right(np.asarray(x, dtype=F32)))
+    en = conv1d_v2(net, weights["encoder/preprocess/kernel"], weights["encoder/preprocess/bias"])
+    for i, dil in enumerate(MAGENTA_DILATIONS):
+        sc = "encoder/cycle_%d/layer_%d" % (1 + i // 6, 1 + i % 6)
+        d = conv1d_v2(en[:, ::2], weights[sc + "/dilated/kernel"], weights[sc + "/dilated/bias"])
+        g = conv1d_v2(d, weights[sc + "/gate/kernel"], weights[sc + "/gate/bias"], dilations=dil)
+        f = conv1d_v2(d, weights[sc + "/filter/kernel"], weights[sc + "/filter/bias"], dilations=dil)
+        gated = (np.tanh(g) * (F32(1) / (F32(1) + np.exp(-f)))).astype(F32)
+        en = (d + conv1d_v2(gated, weights[sc + "/residual/kernel"], weights[sc + "/residual/bias"])).astype(F32)
+    return conv1d_v2(en, weights["encoder/postprocess/kernel"], weights["encoder/postprocess/bias"])
+
+
 def synthetic_z_e(cfg, weights, B, F, seed=1235, kind="normal"):
     rng = np.random.default_rng(seed)
     E = weights["embedding/embedding"]

@@ -204,6 +204,30 @@ def test_encoder64_matches_oracle():
     eng.close()
 
 
+def test_encoder_magenta_matches_oracle():
+    """Encoder_Magenta (Encoder/encoder.py:29-64) on the device against the NumPy restatement (itself checked against a
+    torch conv1d witness in tests/test_oracle.py): shift_right + mu-law, causal dilated convs, stride-2 subsampling"""
+    import vqvae_wavenet_b200 as pkg
+    cfg = O.Config()
+    w = O.make_encoder_magenta_weights(cfg, seed=4322)
+    eng = pkg.Engine(pkg.EngineConfig(wavenet=SMALL_WAVENET, model=dict(encoder="Magenta")), device=0, max_batch=4)
+    eng.set_weights(w)
+    for B, T in ((1, 64), (3, 2048), (2, 4096 + 64)):
+        x = O.synthetic_audio(B, T, seed=5)
+        z = eng.encode_audio(x)
+        oz = O.encoder_magenta_forward(cfg, w, x[:, :, None])
+        assert z.shape == oz.shape == (B, T // 64, 64)
+        assert np.abs(z - oz).max() <= 1e-4 * max(1.0, np.abs(oz).max())
+    enc = pkg.Encoder_Magenta(64, eng)
+    assert np.array_equal(enc.build(x[:, :, None]), z)
+    # causality: the encoder never looks ahead (every conv is left-padded) - frame f depends on samples < 64 (f+1) only
+    x2 = x.copy()
+    x2[:, 64 * 30:] = 0.0
+    z2 = eng.encode_audio(x2)
+    assert np.array_equal(z2[:, :30], z[:, :30]) and not np.array_equal(z2[:, 30:], z[:, 30:])
+    eng.close()
+
+
 def test_cli_end_to_end(tmp_path):
     """generate.py with the reference's flags, TF-free: audio -> Encoder_64 -> VQ -> WaveNet -> WAVs"""
     import generate

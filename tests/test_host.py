@@ -79,3 +79,19 @@ def test_cli_surface(tmp_path, monkeypatch):
         generate.main(["-restore", restore, "-audio", wav, "-speakers", "p225", "-z_e", str(tmp_path / "z.npy")])
     with pytest.raises(ValueError):
         generate.main(["-restore", str(tmp_path / "weights-x"), "-audio", wav, "-speakers", "p225"])   # gs = int(...)
+
+
+def test_synthetic_magenta_encoder_weights_equal_oracle():
+    """the package's seeded Encoder_Magenta weights are the oracle's (the package itself never imports oracle/)"""
+    import vqvae_wavenet_b200 as pkg
+    from vqvae_wavenet_b200 import synthetic
+    from oracle import oracle as O
+    cfg = pkg.EngineConfig(model=dict(encoder="Magenta"))
+    assert cfg.to_c().encoder == 1
+    a = synthetic.make_encoder_magenta_weights(cfg)
+    b = O.make_encoder_magenta_weights(O.Config())
+    assert sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    with pytest.raises(RuntimeError):
+        pkg.Encoder_Magenta(64).build(np.zeros((1, 64, 1), np.float32))
+    with pytest.raises(NotImplementedError):
+        pkg.Encoder_2019(64)

@@ -153,3 +153,40 @@ def test_product_synthetic_weights_equal_oracle():
     cfg = O.Config()
     z = synthetic.synthetic_z_e(pkg.EngineConfig(), 3, 5)
     assert np.array_equal(z, O.synthetic_z_e(cfg, {"embedding/embedding": None}, 3, 5, kind="scaled"))
+
+
+def test_encoder_magenta_against_torch_witness():
+    """Encoder_Magenta restatement (Encoder/encoder.py:29-64) vs an independent float64 torch.nn.functional.conv1d
+    evaluation of the same graph (causal left padding, dilation, stride-2 1x1 subsampling)"""
+    import torch
+    import torch.nn.functional as Fn
+    from oracle import oracle as O
+    cfg = O.Config()
+    w = O.make_encoder_magenta_weights(cfg)
+    assert [n for n, _ in O.encoder_magenta_specs(cfg)][:4] == ["encoder/preprocess/kernel", "encoder/preprocess/bias",
+                                                                "encoder/cycle_1/layer_1/dilated/kernel",
+                                                                "encoder/cycle_1/layer_1/dilated/bias"]
+    B, T = 2, 1024
+    x = O.synthetic_audio(B, T, seed=3)[:, :, None]
+    z = O.encoder_magenta_forward(cfg, w, x)
+    assert z.shape == (B, T // 64, 64)
+
+    def tconv(net, name, dil=1, stride=1):
+        K, b = w[name + "/kernel"], w[name + "/bias"]
+        k = K.shape[0]
+        xin = Fn.pad(torch.from_numpy(np.asarray(net, dtype=np.float64)).permute(0, 2, 1), (dil * (k - 1), 0))
+        y = Fn.conv1d(xin, torch.from_numpy(K).permute(2, 1, 0).double(), torch.from_numpy(b).double(), stride=stride, dilation=dil)
+        return y.permute(0, 2, 1).numpy()
+
+    en = tconv(O.mu_law_encode(O.shift_right(x.astype(np.float32))), "encoder/preprocess")
+    for i, dil in enumerate(O.MAGENTA_DILATIONS):
+        sc = "encoder/cycle_1/layer_%d" % (i + 1)
+        d = tconv(en, sc + "/dilated", stride=2)
+        gated = np.tanh(tconv(d, sc + "/gate", dil=dil)) / (1.0 + np.exp(-tconv(d, sc + "/filter", dil=dil)))
+        en = d + tconv(gated, sc + "/residual")
+    zt = tconv(en, "encoder/postprocess")
+    assert np.abs(zt - z).max() < 2e-5
+    # causality of the restatement
+    x2 = x.copy()
+    x2[:, 64 * 10:] = 0
+    assert np.array_equal(O.encoder_magenta_forward(cfg, w, x2)[:, :10], z[:, :10])

@@ -104,7 +104,7 @@ struct vqwn_handle {
   // resident / staging buffers
   DevBuf cond_res, uni_res, audio_res, idx_res, logits_res, x_res, small_a, small_b, small_c, small_d;
   DevBuf vq_z, vq_idx, vq_out, spk_idx;
-  DevBuf enc_x, enc_a, enc_b, enc_fold, enc_z;
+  DevBuf enc_x, enc_a, enc_b, enc_fold, enc_z, enc_c, enc_d, enc_e, enc_f;
   int cond_B = 0, cond_F = 0;
   long long uni_T = 0; int uni_B = 0;
   long long out_T = 0; int out_B = 0;
@@ -659,8 +659,10 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   if (c.pre_kernel_size < 1 || c.pre_kernel_size > 64) return fail(nullptr, VQWN_ERR_INVALID, "preprocess.kernel_size out of range");
   if (c.use_vq && (c.k < 1 || c.k > 512)) return fail(nullptr, VQWN_ERR_NOTIMPL, "k must be <= 512");
   if (c.latent_dim != 32 && c.latent_dim != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
-  if (c.encoder != 0 && c.encoder != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "only Encoder_64 runs on the device (encoder = 64) or none (0)");
-  if (c.encoder == 64 && c.latent_dim != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "Encoder_64 on the device needs latent_dim = 64");
+  if (c.encoder != VQWN_ENCODER_NONE && c.encoder != VQWN_ENCODER_64 && c.encoder != VQWN_ENCODER_MAGENTA)
+    return fail(nullptr, VQWN_ERR_NOTIMPL, "encoders on the device: Encoder_64 (64), Encoder_Magenta (1), or none (0)");
+  if (c.encoder != VQWN_ENCODER_NONE && c.latent_dim != 64)
+    return fail(nullptr, VQWN_ERR_NOTIMPL, "the device encoders need latent_dim = 64");
   if (c.num_cycle_layers < 1) return fail(nullptr, VQWN_ERR_INVALID, "num_cycle_layers must be >= 1");
   for (int i = 0; i < c.num_layers; ++i)
     if (c.dilations[i] < 1) return fail(nullptr, VQWN_ERR_INVALID, "dilation must be >= 1");
@@ -741,6 +743,25 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
       add_tensor(h, "encoder/batch_normalization" + sfx + "/moving_variance", {cout}, false);
       cin = cout;
     }
+  }
+  if (c.encoder == VQWN_ENCODER_MAGENTA) {
+    // Encoder/encoder.py:37-64: conv1d_v2 variables ("kernel" [k,in,out], "bias") in their scopes under "encoder/"
+    const int MC = 128, MK = 5;
+    add_tensor(h, "encoder/preprocess/kernel", {MK, 1, MC}, false);
+    add_tensor(h, "encoder/preprocess/bias", {MC}, false);
+    for (int i = 0; i < 6; ++i) {
+      const std::string sc = "encoder/cycle_1/layer_" + std::to_string(i + 1);
+      add_tensor(h, sc + "/dilated/kernel", {1, MC, MC}, false);
+      add_tensor(h, sc + "/dilated/bias", {MC}, false);
+      add_tensor(h, sc + "/gate/kernel", {MK, MC, MC}, false);
+      add_tensor(h, sc + "/gate/bias", {MC}, false);
+      add_tensor(h, sc + "/filter/kernel", {MK, MC, MC}, false);
+      add_tensor(h, sc + "/filter/bias", {MC}, false);
+      add_tensor(h, sc + "/residual/kernel", {1, MC, MC}, false);
+      add_tensor(h, sc + "/residual/bias", {MC}, false);
+    }
+    add_tensor(h, "encoder/postprocess/kernel", {1, MC, c.latent_dim}, false);
+    add_tensor(h, "encoder/postprocess/bias", {c.latent_dim}, false);
   }
   add_tensor(h, "lut/mu_law_decode", {Q + 1}, false);
   add_tensor(h, "lut/mu_law_encode", {Q + 1}, false);
@@ -924,7 +945,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,
-                    &h->enc_x, &h->enc_a, &h->enc_b, &h->enc_fold, &h->enc_z};
+                    &h->enc_x, &h->enc_a, &h->enc_b, &h->enc_fold, &h->enc_z, &h->enc_c, &h->enc_d, &h->enc_e, &h->enc_f};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1007,11 +1028,100 @@ int vqwn_tensor_info(const vqwn_handle* h, int i, char* name_out, int name_cap, 
 }
 
 // ---------------------------------------------------------------------------------- encoder
+// Encoder_Magenta (Encoder/encoder.py:37-64) on the device: shift_right + mu_law_encode, causal k=5 preprocess conv,
+// 6 x [1x1 stride-2 conv, causal dilated k=5 gate / filter convs, tanh*sigmoid, 1x1 residual], 1x1 postprocess.
+static int encode_magenta(vqwn_handle* h, const float* x, int B, int64_t T, float* z_e_out) {
+  int rc;
+  const int MC = 128, MK = 5, D = h->D;
+  const int dil[6] = {1, 2, 4, 8, 16, 16};
+  const char* parts[] = {"/kernel", "/bias"};
+  for (const char* pt : parts) {
+    if ((rc = check_tensor_ready(h, (std::string("encoder/preprocess") + pt).c_str()))) return rc;
+    if ((rc = check_tensor_ready(h, (std::string("encoder/postprocess") + pt).c_str()))) return rc;
+    for (int i = 0; i < 6; ++i)
+      for (const char* sub : {"/dilated", "/gate", "/filter", "/residual"})
+        if ((rc = check_tensor_ready(h, ("encoder/cycle_1/layer_" + std::to_string(i + 1) + sub + pt).c_str()))) return rc;
+  }
+  // identity scale / shift for the shared conv epilogue
+  if ((rc = ensure(h, h->enc_fold, (size_t)7 * 2 * 768 * sizeof(float)))) return rc;
+  {
+    std::vector<float> ident(2 * 768, 0.f);
+    for (int i = 0; i < 768; ++i) ident[i] = 1.f;
+    CK(h, cudaMemcpyAsync(h->enc_fold.p, ident.data(), ident.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
+  const float* one = (const float*)h->enc_fold.p;
+  const float* zero = one + 768;
+  // per stream: u [T], en [T,128] (ping), and at half rate d, g, f, gated/res [T/2,128] each
+  const size_t per_stream = (size_t)T * sizeof(float) + (size_t)T * MC * sizeof(float) + 4 * (size_t)(T / 2) * MC * sizeof(float);
+  size_t gsz = ((size_t)1 << 30) / per_stream;
+  if (gsz < 1) gsz = 1;
+  const int group = gsz > (size_t)B ? B : (int)gsz;
+  if ((rc = ensure(h, h->enc_x, (size_t)group * T * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->enc_a, (size_t)group * T * sizeof(float)))) return rc;               // u
+  if ((rc = ensure(h, h->enc_b, (size_t)group * T * MC * sizeof(float)))) return rc;          // en
+  if ((rc = ensure(h, h->enc_c, (size_t)group * (T / 2) * MC * sizeof(float)))) return rc;    // d
+  if ((rc = ensure(h, h->enc_d, (size_t)group * (T / 2) * MC * sizeof(float)))) return rc;    // gate conv
+  if ((rc = ensure(h, h->enc_e, (size_t)group * (T / 2) * MC * sizeof(float)))) return rc;    // filter conv
+  if ((rc = ensure(h, h->enc_f, (size_t)group * (T / 2) * MC * sizeof(float)))) return rc;    // gated, then residual conv
+  if ((rc = ensure(h, h->enc_z, (size_t)group * (T / 64) * D * sizeof(float)))) return rc;
+  auto ew_grid = [](long long n) { return (int)((n + 255) / 256 < 65535 ? (n + 255) / 256 : 65535); };
+  auto conv = [&](const float* in, const std::string& scope, float* out, int g, int Tin, int cin, int Tout, int cout, int k,
+                  int stride, int dl) {
+    const long long M = (long long)g * Tout;
+    dim3 grid((unsigned)((M + ENC_BM - 1) / ENC_BM), (unsigned)(cout / ENC_BN));
+    conv1d_gemm_kernel<<<grid, 256, 0, h->stream>>>(in, TP(h, scope + "/kernel"), TP(h, scope + "/bias"), one, zero, out, g, Tin,
+                                                    cin, Tout, cout, k, stride, dl * (k - 1), 0, dl);
+    h->launches += 1;
+  };
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int g = (B - b0 < group) ? (B - b0) : group;
+    CK(h, cudaMemcpyAsync(h->enc_x.p, x + (size_t)b0 * T, (size_t)g * T * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    float* u = (float*)h->enc_a.p;
+    float* en = (float*)h->enc_b.p;
+    float* d = (float*)h->enc_c.p;
+    float* gc = (float*)h->enc_d.p;
+    float* fc = (float*)h->enc_e.p;
+    float* tmp = (float*)h->enc_f.p;
+    magenta_pre_kernel<<<ew_grid((long long)g * T), 256, 0, h->stream>>>((const float*)h->enc_x.p, u, g, (int)T, 255.0f);
+    {
+      const long long total = (long long)g * T * MC;
+      conv1d_in1_kernel<<<ew_grid(total), 256, 0, h->stream>>>(u, TP(h, "encoder/preprocess/kernel"), TP(h, "encoder/preprocess/bias"),
+                                                               one, zero, en, g, (int)T, (int)T, MC, MK, 1, MK - 1, 0);
+    }
+    h->launches += 2;
+    int Tin = (int)T;
+    for (int i = 0; i < 6; ++i) {
+      const std::string sc = "encoder/cycle_1/layer_" + std::to_string(i + 1);
+      const int Tout = Tin / 2;
+      const long long n = (long long)g * Tout * MC;
+      conv(en, sc + "/dilated", d, g, Tin, MC, Tout, MC, 1, 2, 1);             // 1x1, stride 2: samples 0, 2, 4, ...
+      conv(d, sc + "/gate", gc, g, Tout, MC, Tout, MC, MK, 1, dil[i]);
+      conv(d, sc + "/filter", fc, g, Tout, MC, Tout, MC, MK, 1, dil[i]);
+      magenta_gate_kernel<<<ew_grid(n), 256, 0, h->stream>>>(gc, fc, tmp, n);
+      conv(tmp, sc + "/residual", gc, g, Tout, MC, Tout, MC, 1, 1, 1);
+      magenta_add_kernel<<<ew_grid(n), 256, 0, h->stream>>>(d, gc, en, n);
+      h->launches += 2;
+      Tin = Tout;
+    }
+    conv(en, "encoder/postprocess", (float*)h->enc_z.p, g, Tin, MC, Tin, D, 1, 1, 1);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(z_e_out + (size_t)b0 * (T / 64) * D, h->enc_z.p, (size_t)g * (T / 64) * D * sizeof(float),
+                          cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->last_kernel = "conv1d_gemm_kernel";
+  return finish_timing(h);
+}
+
 int vqwn_encode_audio(vqwn_handle* h, const float* x, int B, int64_t T, float* z_e_out) {
   ENTER(h);
   if (!x || !z_e_out || B < 1 || T < 64) return fail(h, VQWN_ERR_INVALID, "bad argument");
-  if (h->cfg.encoder != 64) return fail(h, VQWN_ERR_NOTIMPL, "no encoder configured on the device (vqwn_config.encoder = 64)");
-  if (T % 64 != 0) return fail(h, VQWN_ERR_INVALID, "T must be a multiple of 64 (Encoder_64 hop)");
+  if (h->cfg.encoder == VQWN_ENCODER_NONE)
+    return fail(h, VQWN_ERR_NOTIMPL, "no encoder configured on the device (vqwn_config.encoder = 64 or 1)");
+  if (T % 64 != 0) return fail(h, VQWN_ERR_INVALID, "T must be a multiple of 64 (encoder hop)");
+  if (h->cfg.encoder == VQWN_ENCODER_MAGENTA) return encode_magenta(h, x, B, T, z_e_out);
   int rc;
   std::vector<std::string> sfx(7);
   for (int i = 0; i < 7; ++i) {

@@ -26,7 +26,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 // first layer: one input channel (K = 5): out[b][t][co] = relu(sum_j x[b][2t+j-left] * W[j][0][co] + bias) * scale + shift
 __global__ void conv1d_in1_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
-                                  int B, int Tin, int Tout, int Cout, int ksize, int stride, int left) {
+                                  int B, int Tin, int Tout, int Cout, int ksize, int stride, int left, int relu = 1) {
   const long long total = (long long)B * Tout * Cout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
@@ -39,7 +39,8 @@ __global__ void conv1d_in1_kernel(const float* __restrict__ x, const float* __re
       const float xv = (ti >= 0 && ti < Tin) ? x[(long long)b * Tin + ti] : 0.f;
       acc = fmaf(xv, __ldg(W + j * Cout + co), acc);
     }
-    acc = fmaxf(acc + __ldg(bias + co), 0.f);
+    acc += __ldg(bias + co);
+    if (relu) acc = fmaxf(acc, 0.f);
     y[i] = fmaf(acc, __ldg(scale + co), __ldg(shift + co));
   }
 }
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256) conv1d_gemm_kernel(const float* __restric
                                                           const float* __restrict__ bias, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, float* __restrict__ y, int B,
                                                           int Tin, int Cin, int Tout, int Cout, int ksize, int stride,
-                                                          int left, int relu) {
+                                                          int left, int relu, int dil = 1) {
   __shared__ __align__(16) float As[ENC_BK][ENC_BM + 4];
   __shared__ __align__(16) float Bs[ENC_BK][ENC_BN];
   const int tid = threadIdx.x;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) conv1d_gemm_kernel(const float* __restric
   const int K = ksize * Cin;
   for (int kk = 0; kk < K; kk += ENC_BK) {
     const int j = kk / Cin, ci0 = kk - j * Cin;
-    const int ti = stride * at + j - left;
+    const int ti = stride * at + j * dil - left;
     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
     if (arow_ok && ti >= 0 && ti < Tin)
       av = __ldg(reinterpret_cast<const float4*>(x + ((long long)ab * Tin + ti) * Cin + ci0 + 4 * aq));
@@ -113,6 +114,26 @@ __global__ void __launch_bounds__(256) conv1d_gemm_kernel(const float* __restric
       *reinterpret_cast<float4*>(y + m * Cout + n0 + 4 * tx) = v;
     }
   }
+}
+
+// ---- Encoder_Magenta pieces (Encoder/encoder.py:37-64)
+// u[b][t] = mu_law_encode(x[b][t-1]), x[b][-1] = 0   (shift_right, wavenet_ops.py:9-14; float path of mu_law_ops.py:5-8)
+__global__ void magenta_pre_kernel(const float* __restrict__ x, float* __restrict__ u, int B, int T, float mu) {
+  const long long total = (long long)B * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    u[i] = mu_law_encode_dev(t > 0 ? x[i - 1] : 0.f, mu, 0.f);
+  }
+}
+// gated = tanh(gate) * sigmoid(filter)   (encoder.py:57)
+__global__ void magenta_gate_kernel(const float* __restrict__ g, const float* __restrict__ f, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = tanhf(g[i]) * __fdiv_rn(1.0f, 1.0f + expf(-f[i]));
+}
+// en = d + r   (encoder.py:59)
+__global__ void magenta_add_kernel(const float* __restrict__ d, const float* __restrict__ r, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = d[i] + r[i];
 }
 
 }  // namespace vqwn

@@ -1,5 +1,6 @@
 """Mirror of Encoder/encoder.py as generate.py uses it (generate.py:65-69): an object with .build(x) -> z_e.
-Only Encoder_64 runs on the device so far; the other two raise NotImplementedError."""
+Encoder_64 and Encoder_Magenta run on the device; Encoder_2019 (MFCC front end) raises
+NotImplementedError."""
 import numpy as np
 
 
@@ -18,8 +19,19 @@ class Encoder_64:
 
 
 class Encoder_Magenta:
+    """shift_right + mu_law_encode, causal k=5 preprocess conv (128 filters), 6 x [1x1 stride-2 conv, causal dilated k=5
+    gate / filter convs (dilations 1,2,4,8,16,16), tanh*sigmoid, 1x1 residual], 1x1 postprocess to latent_dim; hop 64
+    (Encoder/encoder.py:29-64), executed by vqwn_encode_audio with vqwn_config.encoder = VQWN_ENCODER_MAGENTA."""
+
     def __init__(self, latent_dim, engine=None):
-        raise NotImplementedError("encoder Magenta not implemented")     # SURVEY 8f #1 (after Encoder_64)
+        self.latent_dim = latent_dim
+        self.engine = engine
+        self.args = {'dilation_rates': [1, 2, 4, 8, 16, 16], 'num_cycles': 1, 'num_cycle_layers': 6}    # encoder.py:33-36
+
+    def build(self, net):
+        if self.engine is None:
+            raise RuntimeError("Encoder_Magenta needs the Engine that holds its weights (no CPU fallback)")
+        return self.engine.encode_audio(np.asarray(net, dtype=np.float32))
 
 
 class Encoder_2019:

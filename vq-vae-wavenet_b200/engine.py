@@ -72,7 +72,7 @@ class EngineConfig:
         c.speaker_dim = m["speaker_embedding"]
         c.num_speakers = self.num_speakers
         c.use_vq = 1 if m["use_vq"] else 0
-        c.encoder = 64 if str(m.get("encoder")) == "64" else 0
+        c.encoder = {"64": 64, "Magenta": 1}.get(str(m.get("encoder")), 0)      # VQWN_ENCODER_64 / _MAGENTA / _NONE
         return c
 
 

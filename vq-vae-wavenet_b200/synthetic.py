@@ -79,3 +79,34 @@ def make_encoder64_weights(config, seed=4321):
             a = rng.uniform(-0.1, 0.1, size=shape)
         out[name] = np.ascontiguousarray(a, dtype=np.float32)
     return out
+
+
+MAGENTA_DILATIONS = [1, 2, 4, 8, 16, 16]        # Encoder/encoder.py:34
+
+
+def encoder_magenta_specs(config):
+    """conv1d_v2 variables of Encoder_Magenta under variable_scope('encoder') (Encoder/encoder.py:37-64)"""
+    C, k = 128, 5
+    specs = [("encoder/preprocess/kernel", (k, 1, C)), ("encoder/preprocess/bias", (C,))]
+    for i in range(len(MAGENTA_DILATIONS)):
+        sc = "encoder/cycle_%d/layer_%d" % (1 + i // 6, 1 + i % 6)
+        specs += [(sc + "/dilated/kernel", (1, C, C)), (sc + "/dilated/bias", (C,)),
+                  (sc + "/gate/kernel", (k, C, C)), (sc + "/gate/bias", (C,)),
+                  (sc + "/filter/kernel", (k, C, C)), (sc + "/filter/bias", (C,)),
+                  (sc + "/residual/kernel", (1, C, C)), (sc + "/residual/bias", (C,))]
+    specs += [("encoder/postprocess/kernel", (1, C, config.model["latent_dim"])),
+              ("encoder/postprocess/bias", (config.model["latent_dim"],))]
+    return specs
+
+
+def make_encoder_magenta_weights(config, seed=4322):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in encoder_magenta_specs(config):
+        if name.endswith("kernel"):
+            lim = np.sqrt(3.0 / (shape[0] * shape[1]))
+            a = rng.uniform(-lim, lim, size=shape)
+        else:
+            a = rng.uniform(-0.05, 0.05, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return out
