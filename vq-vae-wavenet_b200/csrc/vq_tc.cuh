@@ -148,7 +148,9 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   __shared__ int bestk_s[VT_TILE];
   __shared__ int fail_s;
-  if (threadIdx.x == 0) fail_s = 0;
+  __shared__ int rq_n, ov_n;                          // rows queued for exact re-evaluation / for a full exact scan
+  __shared__ unsigned char rq_rows[VT_TILE];          // queued rows from the front, full-scan rows from the back
+  if (threadIdx.x == 0) { fail_s = 0; rq_n = 0; ov_n = 0; }
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float emax = __ldg(emax_p) * 1.000001f;
@@ -339,60 +341,61 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
       vt_epi_sync();
       VT_PF(4);
 
-      // ---- decide: single candidate -> done; else exact float32 re-evaluation, the two warps that share a
-      //      row (half 0 / half 1) each take every other candidate
+      // ---- decide: single candidate -> done.  Rows with several candidates (about one in five) are queued and their
+      //      (row, candidate) pairs are re-evaluated exactly, ONE PAIR PER THREAD over all 256 epilogue threads: the
+      //      divergent per-row loops this replaces made every warp pay for its worst row.  Winner per row through a
+      //      64-bit shared-memory atomicMin on (distance bits << 32 | code): smallest distance, lowest code on ties.
       {
         const int n0 = (int)cnt_s[row], n1 = (int)cnt_s[VT_TILE + row];
-        const bool overflow = n0 > VT_LIST || n1 > VT_LIST;
         const int total = n0 + n1;
+        const bool overflow = n0 > VT_LIST || n1 > VT_LIST || total == 0;   // overflow: exact scan of the whole codebook
         const bool need = overflow || total != 1;
-        const int nall = !need ? 0 : (overflow ? VT_K : total);   // overflow: exact scan of the whole codebook
-        const int mine = (nall + 1 - hsel) >> 1;                  // candidates hsel, hsel+2, ...
-        const int wscan = __reduce_max_sync(0xffffffffu, mine);
-        float bd = INFINITY;
-        int bk = 0x7fffffff;
-        if (wscan > 0) {
-          float zr[VT_D];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float4 qv = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(row, 4 * c));
-            zr[4 * c] = qv.x; zr[4 * c + 1] = qv.y; zr[4 * c + 2] = qv.z; zr[4 * c + 3] = qv.w;
-          }
-          for (int j = 0; j < wscan; ++j) {
-            if (j < mine) {
-              const int ci = 2 * j + hsel;
-              int k;
-              if (overflow) k = ci;
-              else k = (ci < n0) ? (int)list_p[ci * VT_TILE + row] : (int)list_p[((VT_LIST + 1) + (ci - n0)) * VT_TILE + row];
-              float dist = 0.f;
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const float4 e4 = *reinterpret_cast<const float4*>(sE + VT_OFF_E(k, 4 * c));
-                float t;
-                t = __fsub_rn(zr[4 * c], e4.x);     dist = __fmaf_rn(t, t, dist);
-                t = __fsub_rn(zr[4 * c + 1], e4.y); dist = __fmaf_rn(t, t, dist);
-                t = __fsub_rn(zr[4 * c + 2], e4.z); dist = __fmaf_rn(t, t, dist);
-                t = __fsub_rn(zr[4 * c + 3], e4.w); dist = __fmaf_rn(t, t, dist);
-              }
-              if (dist < bd || (dist == bd && k < bk)) { bd = dist; bk = k; }
-            }
+        unsigned long long* rowbest = reinterpret_cast<unsigned long long*>(hmax_s);     // [row], hmax_s is free now
+        if (hsel == 0) {
+          if (!need) {
+            const int best_k = (n0 > 0) ? (int)list_p[row] : (int)list_p[(VT_LIST + 1) * VT_TILE + row];
+            bestk_s[row] = best_k;
+            if (idx_out != nullptr && v0 + row < N) idx_out[v0 + row] = (long long)best_k;
+          } else {
+            rowbest[row] = ~0ULL;
+            if (overflow) rq_rows[VT_TILE - 1 - atomicAdd(&ov_n, 1)] = (unsigned char)row;
+            else rq_rows[atomicAdd(&rq_n, 1)] = (unsigned char)row;
           }
         }
-        // partial winners of the two warps -> shared memory (reusing hmax_s / cnt_s, no longer needed)
         vt_epi_sync();
-        if (hsel == 1) { hmax_s[row] = __float_as_uint(bd); hmax_s[VT_TILE + row] = (uint32_t)bk; }
-        vt_epi_sync();
-        if (hsel == 0) {
-          int best_k;
-          if (!need) best_k = (n0 > 0) ? (int)list_p[row] : (int)list_p[(VT_LIST + 1) * VT_TILE + row];
-          else {
-            const float od = __uint_as_float(hmax_s[row]);
-            const int ok2 = (int)hmax_s[VT_TILE + row];
-            best_k = (od < bd || (od == bd && ok2 < bk)) ? ok2 : bk;
+        auto exact = [&](int r, int k) {
+          // the float32 instruction sequence of vq_direct_kernel (sequential over d)
+          float dist = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float4 z4 = *reinterpret_cast<const float4*>(sZ + VT_OFF_Z(r, 4 * c));
+            const float4 e4 = *reinterpret_cast<const float4*>(sE + VT_OFF_E(k, 4 * c));
+            float t;
+            t = __fsub_rn(z4.x, e4.x); dist = __fmaf_rn(t, t, dist);
+            t = __fsub_rn(z4.y, e4.y); dist = __fmaf_rn(t, t, dist);
+            t = __fsub_rn(z4.z, e4.z); dist = __fmaf_rn(t, t, dist);
+            t = __fsub_rn(z4.w, e4.w); dist = __fmaf_rn(t, t, dist);
           }
+          atomicMin(&rowbest[r], ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(unsigned)k);
+        };
+        const int nq = rq_n, no = ov_n;
+        for (int pidx = tid; pidx < nq * 2 * VT_LIST; pidx += 32 * VT_EPI_WARPS) {
+          const int r = (int)rq_rows[pidx / (2 * VT_LIST)], j = pidx % (2 * VT_LIST);
+          const int m0 = (int)cnt_s[r], m1 = (int)cnt_s[VT_TILE + r];
+          if (j < m0 + m1)
+            exact(r, (j < m0) ? (int)list_p[j * VT_TILE + r] : (int)list_p[((VT_LIST + 1) + (j - m0)) * VT_TILE + r]);
+        }
+        for (int q2 = 0; q2 < no; ++q2) {
+          const int r = (int)rq_rows[VT_TILE - 1 - q2];
+          for (int k = tid; k < VT_K; k += 32 * VT_EPI_WARPS) exact(r, k);
+        }
+        vt_epi_sync();
+        if (hsel == 0 && need) {
+          const int best_k = (int)(unsigned)(rowbest[row] & 0xffffffffULL);
           bestk_s[row] = best_k;
           if (idx_out != nullptr && v0 + row < N) idx_out[v0 + row] = (long long)best_k;
         }
+        if (tid == 0) { rq_n = 0; ov_n = 0; }      // for the next tile (two barriers away from the next use)
       }
       vt_epi_sync();
       VT_PF(5);
