@@ -228,9 +228,12 @@ def test_encoder_magenta_matches_oracle():
     eng.close()
 
 
-def test_cli_end_to_end(tmp_path):
+def test_cli_end_to_end(tmp_path, monkeypatch):
     """generate.py with the reference's flags, TF-free: audio -> Encoder_64 -> VQ -> WaveNet -> WAVs"""
     import generate
+    from conftest import write_speaker_table
+    write_speaker_table(tmp_path)                      # synthetic table in the reference's format
+    monkeypatch.setenv("VQWN_SPEAKER_TABLES", str(tmp_path))
     import vqvae_wavenet_b200 as pkg
     from vqvae_wavenet_b200 import synthetic, wavio
     cfg = pkg.EngineConfig.from_files(os.path.join(os.path.dirname(generate.__file__), "model_parameters.json"))
@@ -257,7 +260,7 @@ def test_cli_end_to_end(tmp_path):
     z = O.encoder64_forward(ocfg, w, x[None, :1024, None])
     eng = pkg.Engine(cfg, 0, 2)
     eng.set_weights(w)
-    table = pkg.utils.get_speaker_to_int(pkg.utils.find_speaker_table("vctk", roots=(os.path.dirname(generate.__file__),)))
+    table = pkg.utils.get_speaker_to_int(pkg.utils.find_speaker_table("vctk", roots=()))
     _, cond = eng.encode_condition(np.tile(eng.encode_audio(x[None, :1024]), (2, 1, 1)), [table["p225"], 0])
     audio, _ = eng.generate(cond, 1024, mode="greedy")
     assert np.array_equal(audio[0], a) and np.array_equal(audio[1], b)

@@ -32,12 +32,20 @@ def test_wavenet_mirror_asserts_like_reference():
         pkg.Wavenet(bad)                                   # wavenet.py:13
 
 
-def test_speaker_tables_and_onehot():
+def test_speaker_tables_and_onehot(tmp_path, monkeypatch):
+    from conftest import write_speaker_table
     from vqvae_wavenet_b200 import utils
     assert utils.dataset_for_speakers(["p225"]) == ("vctk", 109)
     assert utils.dataset_for_speakers(["S0002"]) == ("aishell", 340)
     assert utils.dataset_for_speakers(["1034"]) == ("librispeech", 251)
-    path = utils.find_speaker_table("vctk", roots=(ROOT,))
+    monkeypatch.delenv("VQWN_SPEAKER_TABLES", raising=False)
+    with pytest.raises(FileNotFoundError):
+        utils.find_speaker_table("vctk", roots=(str(tmp_path),))
+    names = ["p301", "p295"] + ["p%d" % (400 + i) for i in range(107)]
+    write_speaker_table(tmp_path, "vctk", names)
+    path = utils.find_speaker_table("vctk", roots=(str(tmp_path),))
+    monkeypatch.setenv("VQWN_SPEAKER_TABLES", str(tmp_path))
+    assert utils.find_speaker_table("vctk", roots=()) == path
     table = utils.get_speaker_to_int(path)
     assert table["p301"] == 0 and len(table) == 109
     one = utils.speaker_onehot(["p301", "None", "p295"], table, 109)
@@ -69,6 +77,9 @@ def test_cli_surface(tmp_path, monkeypatch):
     """flags and error paths of the reference CLI that do not need a device"""
     import generate
     from vqvae_wavenet_b200 import wavio
+    from conftest import write_speaker_table
+    write_speaker_table(tmp_path)
+    monkeypatch.setenv("VQWN_SPEAKER_TABLES", str(tmp_path))
     wav = str(tmp_path / "in.wav")
     wavio.write_wav_float32(wav, 16000, np.zeros(1024, np.float32))
     restore = str(tmp_path / "weights-42")

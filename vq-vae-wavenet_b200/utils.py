@@ -40,14 +40,19 @@ def dataset_for_speakers(speakers):
 
 
 def find_speaker_table(dataset, roots=(".",)):
-    """generate.py reads data/<ds>_speakers.txt while the repo ships data/<ds>_info/<ds>_speakers.txt
-    (SURVEY Q14): try both."""
-    for r in roots:
+    """generate.py:46-57 reads data/<ds>_speakers.txt while the reference ships data/<ds>_info/<ds>_speakers.txt
+    (SURVEY Q14): try both, under $VQWN_SPEAKER_TABLES first, then under the given roots (the working directory of a
+    reference checkout).  The tables ("<speaker>, <index>" per line, in the order the checkpoint was trained with) are
+    the reference's data and are not redistributed with this package."""
+    env = os.environ.get("VQWN_SPEAKER_TABLES")
+    for r in ((env,) if env else ()) + tuple(roots):
         for rel in ("data/%s_speakers.txt" % dataset, "data/%s_info/%s_speakers.txt" % (dataset, dataset)):
             p = os.path.join(r, rel)
             if os.path.exists(p):
                 return p
-    raise FileNotFoundError("speaker table for %s not found under %s" % (dataset, list(roots)))
+    raise FileNotFoundError("speaker table for %s not found under %s: run from the reference checkout (it holds data/%s_info/"
+                            "%s_speakers.txt) or point VQWN_SPEAKER_TABLES at a directory that contains data/"
+                            % (dataset, list(roots), dataset, dataset))
 
 
 def speaker_onehot(speakers, speaker_to_int, num_speakers):
