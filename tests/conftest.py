@@ -24,7 +24,7 @@ def write_speaker_table(root, dataset="vctk", names=None):
     reference's own tables are its data and are not shipped with this repo"""
     import os
     if names is None:
-        names = ["p%d" % (225 + i) for i in range(109)]
+        names = ["p%d" % (224 + i) for i in range(109)]      # p225 -> 1 (index 0 is what "None" maps to, model.py:22)
     d = os.path.join(str(root), "data", "%s_info" % dataset)
     os.makedirs(d, exist_ok=True)
     path = os.path.join(d, "%s_speakers.txt" % dataset)
