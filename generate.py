@@ -37,6 +37,8 @@ def main(argv=None):
     parser.add_argument('-z_e', dest='z_e_path', default=None, help='encoder output (.npy)')
     parser.add_argument('-device', dest='device', type=int, default=0)
     parser.add_argument('-seed', dest='seed', type=int, default=None, help='seed of the draw stream (sample mode)')
+    parser.add_argument('-precision', dest='precision', default='fp32', choices=('fp32', 'bf16'),
+                        help='fp32: float32 contractions (the reference arithmetic); bf16: tcgen05 tensor-core kernel')
     args = parser.parse_args(argv)
 
     gs = int(args.restore_path.split('-')[-1])                     # generate.py:33
@@ -71,6 +73,7 @@ def main(argv=None):
         raise FileNotFoundError("neither a TensorFlow checkpoint (%s.index) nor %s (arrays keyed by reference "
                                 "variable name) exists" % (args.restore_path, weights_file))
     engine = pkg.Engine(cfg, device=args.device, max_batch=batch_size)
+    engine.set_precision(args.precision)
     wanted = dict((n, s) for n, s, _ in engine.tensor_table())
     if tf_checkpoint.is_bundle(args.restore_path):
         # generate.py:88-90: Saver(ema.variables_to_restore()).restore(sess, restore_path), read without TensorFlow
