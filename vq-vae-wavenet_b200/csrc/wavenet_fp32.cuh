@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
   const float mu = (float)(p.Q - 1);
   const bool ext = (p.mode == GEN_STEP || p.mode == GEN_TEACHER);
   const int NS = 2 * p.L + 4;
-  const int S_P1 = 2 * p.L + 1, S_P2 = 2 * p.L + 2, S_DRAW = 2 * p.L + 3;
+  const int S_P1 = 2 * p.L + 1, S_DRAW = 2 * p.L + 3;
   const long long ring_slot = (long long)p.Bp * p.R;
 
   if (tid == 0) {
@@ -362,8 +362,6 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
   prefetch_stage(0, p.t0);
   // condition tile: stages that use it (gated conv, post1) map tile -> stream block identically, so one tile
   // per CTA serves a whole frame (ratio steps x 31 stages)
-  const int nsb_k = p.Bp / FP32_TB;
-  const int my_sb = (int)(blockIdx.x % nsb_k);
   long long cond_frame = -1;
   int cond_sb = -1;
   unsigned condph = 0u;

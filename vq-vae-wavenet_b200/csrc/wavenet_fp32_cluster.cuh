@@ -189,13 +189,6 @@ __device__ __forceinline__ void cl_store_partials(float* red, int NC, int KG, co
     *reinterpret_cast<float4*>(rp + j * NC) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
 }
 
-__device__ __forceinline__ float cl_reduce(const float* red, int tile_outputs, int KG, int o) {
-  float s = 0.f;
-#pragma unroll 8
-  for (int kg = 0; kg < KG; ++kg) s += red[kg * tile_outputs + o];
-  return s;
-}
-
 template <int MS>
 __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClParams p_in) {
   extern __shared__ __align__(128) float smem[];
