@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--mode", default="greedy", choices=["greedy", "sample"])
     ap.add_argument("--precision", default=os.environ.get("VQWN_PRECISION", "fp32"))
     ap.add_argument("--no-bf16", action="store_true", help="skip the secondary bf16 tensor-core measurement")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-stream latency measurement")
     ap.add_argument("--ref-window", type=int, default=192)
     ap.add_argument("--cpu-window", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -317,6 +318,27 @@ def main():
             bf16 = None
         eng.set_precision("fp32")
 
+    # ---------------------------------------------------------------- single-stream per-step latency (BASELINE config 1)
+    # one stream, 1 s of audio (16 384 samples), greedy: the reference's own CPU-runnable case, latency-bound
+    latency = None
+    if rank == 0 and B > 1 and args.mode == "greedy" and not args.no_latency:
+        T1 = 16384
+        z1 = z_e[:1, :min(F, T1 // 64)]
+        if z1.shape[1] == T1 // 64:
+            _, c1 = eng.encode_condition(z1, spk[:1])
+            eng.upload_condition(c1)
+            eng.generate_resident(1, T1 // 64, 2048, args.mode, seed=1)            # warm
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            h0.record(stream)
+            eng.generate_resident(1, T1 // 64, T1, args.mode, seed=1)
+            h1.record(stream)
+            torch.cuda.synchronize()
+            lms = h0.elapsed_time(h1)
+            latency = {"streams": 1, "time_steps": T1, "us_per_time_step": lms * 1e3 / T1, "samples_per_s": T1 / (lms * 1e-3),
+                       "kernel": eng.last_kernel_name}
+            eng.upload_condition(cond)
+
     # ---------------------------------------------------------------- VQ lookups/s (secondary metric)
     vq = vq_bench(eng, args.vq_n) if rank == 0 else {}
 
@@ -364,6 +386,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "bf16_tensor_core": bf16,
+            "single_stream_latency": latency,
             "vq": vq,
         }
         print(json.dumps(line), flush=True)
