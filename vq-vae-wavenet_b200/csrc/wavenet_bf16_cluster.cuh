@@ -566,67 +566,11 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
     if (rank == 0) {
       for (int i = warp; i < nvalid; i += BC_THREADS / 32) {
         const int b = b0 + i;
-        float lg[8], pr[8];
-        float m = -INFINITY;
+        float lg[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { lg[q] = logits_s[i * BC_Q + lane + 32 * q]; m = fmaxf(m, lg[q]); }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-        float sum = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { pr[q] = expf(lg[q] - m); sum += pr[q]; }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) pr[q] = __fdiv_rn(pr[q], sum);
-        if (p.mode == GEN_STEP) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (p.logits_out) p.logits_out[(long long)b * BC_Q + lane + 32 * q] = lg[q];
-            if (p.probs_out) p.probs_out[(long long)b * BC_Q + lane + 32 * q] = pr[q];
-          }
-          continue;
-        }
-        if (p.mode == GEN_TEACHER) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) p.logits_out[((long long)b * p.T + (t - p.t0)) * BC_Q + lane + 32 * q] = lg[q];
-          continue;
-        }
-        int k;
-        if (p.mode == GEN_GREEDY) {
-          float bv = -1.f; int bi = 0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (pr[q] > bv) { bv = pr[q]; bi = lane + 32 * q; }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-          }
-          k = bi;
-        } else {
-          float* pw = logits_s + i * BC_Q;
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) pw[lane + 32 * q] = pr[q];
-          __syncwarp();
-          int cnt = 0;
-          if (lane == 0) {
-            const double u = p.uniforms ? p.uniforms[(t - p.t0) * p.B + b]
-                                        : counter_uniform(p.seed, (unsigned long long)t, (unsigned long long)b);
-            float c = 0.f;
-            for (int q = 0; q < BC_Q; ++q) {
-              c = __fadd_rn(c, pw[q]);
-              cnt += ((double)c < u) ? 1 : 0;
-            }
-          }
-          k = __shfl_sync(0xffffffffu, cnt, 0);
-          __syncwarp();
-        }
-        if (lane == 0) {
-          p.audio_out[(long long)b * p.T + (t - p.t0)] = __ldg(p.dec_lut + k);
-          if (p.idx_out) p.idx_out[(long long)b * p.T + (t - p.t0)] = k;
+        for (int q = 0; q < 8; ++q) lg[q] = logits_s[i * BC_Q + lane + 32 * q];
+        const int k = warp_softmax_draw(p, BC_Q, lg, b, t, lane, logits_s + i * BC_Q);
+        if (k >= 0 && lane == 0) {
           const float un = __ldg(p.enc_lut + k);
           const int slot_n = (int)((t + 1) % BC_PK);
           st_cg(p.u_hist + (long long)b * BC_PK + slot_n, un);

@@ -86,6 +86,82 @@ struct GenParams {
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, 1.0f + expf(-x)); }
 
+// One warp, one stream: softmax over the Q <= 256 logits held as lg[i] = logit[lane + 32 i] (i < Q/32, else -inf), then
+// what the mode asks for (utils.py:13-46).  GEN_STEP / GEN_TEACHER only report (logits, probs) and return -1; greedy
+// returns np.argmax(probs) (first maximum, utils.py:43); sample reproduces utils.py:20-25 - sequential float32 cumsum,
+// float64 compare, searchsorted 'left' (the result can be Q).  The drawn class is also written to audio_out (mu-law
+// decode LUT) and idx_out.  `scratch`: Q floats of shared memory private to the warp (sample mode).
+// Shared by every generation kernel (P = GenParams / ClParams / BcParams).
+template <typename P>
+__device__ __forceinline__ int warp_softmax_draw(const P& p, int Q, const float (&lg)[8], int b, long long t, int lane,
+                                                 float* scratch) {
+  const int NQ = Q >> 5;
+  float pr[8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m = fmaxf(m, lg[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { pr[i] = (i < NQ) ? expf(lg[i] - m) : 0.f; sum += pr[i]; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pr[i] = __fdiv_rn(pr[i], sum);
+
+  if (p.mode == GEN_STEP) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < NQ && p.logits_out) p.logits_out[(long long)b * Q + lane + 32 * i] = lg[i];
+      if (i < NQ && p.probs_out) p.probs_out[(long long)b * Q + lane + 32 * i] = pr[i];
+    }
+    return -1;
+  }
+  if (p.mode == GEN_TEACHER) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < NQ) p.logits_out[((long long)b * p.T + (t - p.t0)) * Q + lane + 32 * i] = lg[i];
+    return -1;
+  }
+  int k;
+  if (p.mode == GEN_GREEDY) {
+    float bv = -1.f; int bi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < NQ && pr[i] > bv) { bv = pr[i]; bi = lane + 32 * i; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    k = bi;
+  } else {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < NQ) scratch[lane + 32 * i] = pr[i];
+    __syncwarp();
+    int cnt = 0;
+    if (lane == 0) {
+      const double u = p.uniforms ? p.uniforms[(t - p.t0) * p.B + b]
+                                  : counter_uniform(p.seed, (unsigned long long)t, (unsigned long long)b);
+      float c = 0.f;
+      for (int i = 0; i < Q; ++i) {
+        c = __fadd_rn(c, scratch[i]);
+        cnt += ((double)c < u) ? 1 : 0;
+      }
+    }
+    k = __shfl_sync(0xffffffffu, cnt, 0);
+    __syncwarp();
+  }
+  if (lane == 0) {
+    p.audio_out[(long long)b * p.T + (t - p.t0)] = __ldg(p.dec_lut + k);
+    if (p.idx_out) p.idx_out[(long long)b * p.T + (t - p.t0)] = k;
+  }
+  return k;
+}
+
 // ---------------------------------------------------------------------------------------
 // bulk async copies + mbarrier
 // ---------------------------------------------------------------------------------------
@@ -377,75 +453,12 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_persistent(const
         const int NQ = p.Q / 32;   // <= 8
         PF_START();
         for (int b = blockIdx.x * FP32_WARPS + warp; b < p.B; b += gridDim.x * FP32_WARPS) {
-          float lg[8], pr[8];
-          float m = -INFINITY;
+          float lg[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            lg[i] = (i < NQ) ? ld_cg(p.logits + (long long)b * p.Q + lane + 32 * i) : -INFINITY;
-            m = fmaxf(m, lg[i]);
-          }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-          float sum = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { pr[i] = (i < NQ) ? expf(lg[i] - m) : 0.f; sum += pr[i]; }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pr[i] = __fdiv_rn(pr[i], sum);
-
-          if (p.mode == GEN_STEP) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < NQ && p.logits_out) p.logits_out[(long long)b * p.Q + lane + 32 * i] = lg[i];
-              if (i < NQ && p.probs_out) p.probs_out[(long long)b * p.Q + lane + 32 * i] = pr[i];
-            }
-            continue;
-          }
-          if (p.mode == GEN_TEACHER) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i < NQ) p.logits_out[((long long)b * p.T + (t - p.t0)) * p.Q + lane + 32 * i] = lg[i];
-            continue;
-          }
-          int k;
-          if (p.mode == GEN_GREEDY) {
-            // np.argmax(probs): first maximum (utils.py:43)
-            float bv = -1.f; int bi = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i < NQ && pr[i] > bv) { bv = pr[i]; bi = lane + 32 * i; }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            k = bi;
-          } else {
-            // utils.py:20-25: sequential float32 cumsum, float64 compare, searchsorted 'left'
-            float* pw = ps + warp * p.Q;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) if (i < NQ) pw[lane + 32 * i] = pr[i];
-            __syncwarp();
-            int cnt = 0;
-            if (lane == 0) {
-              const double u = p.uniforms ? p.uniforms[(t - p.t0) * p.B + b]
-                                          : counter_uniform(p.seed, (unsigned long long)t, (unsigned long long)b);
-              float c = 0.f;
-              for (int i = 0; i < p.Q; ++i) {
-                c = __fadd_rn(c, pw[i]);
-                cnt += ((double)c < u) ? 1 : 0;
-              }
-            }
-            k = __shfl_sync(0xffffffffu, cnt, 0);
-            __syncwarp();
-          }
-          if (lane == 0) {
-            p.audio_out[(long long)b * p.T + (t - p.t0)] = __ldg(p.dec_lut + k);
-            if (p.idx_out) p.idx_out[(long long)b * p.T + (t - p.t0)] = k;
-            st_cg(p.u_hist + (long long)b * p.PK + (int)((t + 1) % p.PK), __ldg(p.enc_lut + k));
-          }
+          for (int i = 0; i < 8; ++i) lg[i] = (i < NQ) ? ld_cg(p.logits + (long long)b * p.Q + lane + 32 * i) : -INFINITY;
+          const int k = warp_softmax_draw(p, p.Q, lg, b, t, lane, ps + warp * p.Q);
+          if (k >= 0 && lane == 0)
+            st_cg(p.u_hist + (long long)b * p.PK + (int)((t + 1) % p.PK), __ldg(p.enc_lut + k));   // input of step t+1
         }
         PF_ADD(pf_draw);
         bar.sync();

@@ -537,74 +537,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
       const int NQW = Q / 32;   // <= 8
       for (int i = warp; i < nvalid; i += CL_THREADS / 32) {
         const int b = b0 + i;
-        float lg[8], pr[8];
-        float m = -INFINITY;
+        float lg[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          lg[q] = (q < NQW) ? logits_s[i * Q + lane + 32 * q] : -INFINITY;
-          m = fmaxf(m, lg[q]);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-        float sum = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { pr[q] = (q < NQW) ? expf(lg[q] - m) : 0.f; sum += pr[q]; }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) pr[q] = __fdiv_rn(pr[q], sum);
-
-        if (p.mode == GEN_STEP) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (q < NQW && p.logits_out) p.logits_out[(long long)b * Q + lane + 32 * q] = lg[q];
-            if (q < NQW && p.probs_out) p.probs_out[(long long)b * Q + lane + 32 * q] = pr[q];
-          }
-          continue;
-        }
-        if (p.mode == GEN_TEACHER) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q < NQW) p.logits_out[((long long)b * p.T + (t - p.t0)) * Q + lane + 32 * q] = lg[q];
-          continue;
-        }
-        int k;
-        if (p.mode == GEN_GREEDY) {
-          // np.argmax(probs): first maximum (utils.py:43)
-          float bv = -1.f; int bi = 0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q < NQW && pr[q] > bv) { bv = pr[q]; bi = lane + 32 * q; }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-          }
-          k = bi;
-        } else {
-          // utils.py:20-25: sequential float32 cumsum, float64 compare, searchsorted 'left'
-          float* pw = logits_s + i * Q;      // the logits of this stream are in registers: reuse the row
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) if (q < NQW) pw[lane + 32 * q] = pr[q];
-          __syncwarp();
-          int cnt = 0;
-          if (lane == 0) {
-            const double u = p.uniforms ? p.uniforms[(t - p.t0) * p.B + b]
-                                        : counter_uniform(p.seed, (unsigned long long)t, (unsigned long long)b);
-            float c = 0.f;
-            for (int q = 0; q < Q; ++q) {
-              c = __fadd_rn(c, pw[q]);
-              cnt += ((double)c < u) ? 1 : 0;
-            }
-          }
-          k = __shfl_sync(0xffffffffu, cnt, 0);
-          __syncwarp();
-        }
-        if (lane == 0) {
-          p.audio_out[(long long)b * p.T + (t - p.t0)] = __ldg(p.dec_lut + k);
-          if (p.idx_out) p.idx_out[(long long)b * p.T + (t - p.t0)] = k;
+        for (int q = 0; q < 8; ++q) lg[q] = (q < NQW) ? logits_s[i * Q + lane + 32 * q] : -INFINITY;
+        // (sample mode reuses the stream's logits row as scratch: the logits are in registers by then)
+        const int k = warp_softmax_draw(p, Q, lg, b, t, lane, logits_s + i * Q);
+        if (k >= 0 && lane == 0) {
           const float un = __ldg(p.enc_lut + k);
           const int slot_n = (int)((t + 1) % PK);
           st_cg(p.u_hist + (long long)b * PK + slot_n, un);

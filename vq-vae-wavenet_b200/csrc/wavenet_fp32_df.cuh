@@ -137,70 +137,11 @@ __global__ void __launch_bounds__(FP32_THREADS, 1) wavenet_fp32_dataflow(const D
           // all post2 tiles of this stream's block have published their logits
           if (lane == 0) alive = df_wait(dp.cnt + (size_t)S_P2 * nsb + b / FP32_TB, (unsigned)(p.Q / 16) * trel, p.err) && alive;
           alive = __shfl_sync(0xffffffffu, alive ? 1 : 0, 0) != 0;
-          float lg[8], pr[8];
-          float m = -INFINITY;
+          float lg[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            lg[i] = (i < NQ) ? ld_cg(p.logits + (long long)b * p.Q + lane + 32 * i) : -INFINITY;
-            m = fmaxf(m, lg[i]);
-          }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-          float sum = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { pr[i] = (i < NQ) ? expf(lg[i] - m) : 0.f; sum += pr[i]; }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pr[i] = __fdiv_rn(pr[i], sum);
-          if (p.mode == GEN_STEP) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < NQ && p.logits_out) p.logits_out[(long long)b * p.Q + lane + 32 * i] = lg[i];
-              if (i < NQ && p.probs_out) p.probs_out[(long long)b * p.Q + lane + 32 * i] = pr[i];
-            }
-            continue;
-          }
-          if (p.mode == GEN_TEACHER) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i < NQ) p.logits_out[((long long)b * p.T + (t - p.t0)) * p.Q + lane + 32 * i] = lg[i];
-            continue;
-          }
-          int k;
-          if (p.mode == GEN_GREEDY) {
-            float bv = -1.f; int bi = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i < NQ && pr[i] > bv) { bv = pr[i]; bi = lane + 32 * i; }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            k = bi;
-          } else {
-            float* pw = ps + warp * p.Q;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) if (i < NQ) pw[lane + 32 * i] = pr[i];
-            __syncwarp();
-            int cnt = 0;
-            if (lane == 0) {
-              const double u = p.uniforms ? p.uniforms[(t - p.t0) * p.B + b]
-                                          : counter_uniform(p.seed, (unsigned long long)t, (unsigned long long)b);
-              float c = 0.f;
-              for (int i = 0; i < p.Q; ++i) {
-                c = __fadd_rn(c, pw[i]);
-                cnt += ((double)c < u) ? 1 : 0;
-              }
-            }
-            k = __shfl_sync(0xffffffffu, cnt, 0);
-            __syncwarp();
-          }
-          if (lane == 0) {
-            p.audio_out[(long long)b * p.T + (t - p.t0)] = __ldg(p.dec_lut + k);
-            if (p.idx_out) p.idx_out[(long long)b * p.T + (t - p.t0)] = k;
+          for (int i = 0; i < 8; ++i) lg[i] = (i < NQ) ? ld_cg(p.logits + (long long)b * p.Q + lane + 32 * i) : -INFINITY;
+          const int k = warp_softmax_draw(p, p.Q, lg, b, t, lane, ps + warp * p.Q);
+          if (k >= 0 && lane == 0) {
             st_cg(p.u_hist + (long long)b * p.PK + (int)((t + 1) % p.PK), __ldg(p.enc_lut + k));   // input of step t+1
             df_signal(dp.cnt + (size_t)S_DRAW * nsb + b / FP32_TB);
           }
