@@ -311,8 +311,10 @@ def main():
             if world > 1:
                 dist.all_reduce(tb, op=dist.ReduceOp.MAX)
             bms = float(tb.item())
+            btf = B * FLOP_PER_SAMPLE / (bms * 1e-3 / T) / 1e12
             bf16 = {"value": world * B * T / (bms * 1e-3), "unit": "samples/s", "ms_per_step": bms,
                     "us_per_time_step": bms * 1e3 / T, "kernel": eng.last_kernel_name,
+                    "achieved_tflops_per_gpu": btf, "tensor_frac": btf / load_peaks()["tensor_sustained"],
                     "tolerance": "teacher-forced logits within 2e-2 of max|logit| (tests/test_gpu_parity.py::test_bf16_*)"}
         except NotImplementedError:
             bf16 = None
