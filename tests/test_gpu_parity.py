@@ -671,3 +671,25 @@ def test_cfg5_teacher_forced_full_size(monkeypatch):
     assert out["cluster"].shape == (B, T, 256)
     assert np.abs(out["cluster"] - out["barrier"]).max() <= 2e-5 * scale
     assert np.abs(out["bf16"] - out["cluster"]).max() <= BF16_LOGIT_RTOL * scale
+
+
+def test_precision_change_invalidates_step_state(small):
+    """the dilation-queue layout differs between the float32 and the bf16 path: after vqwn_set_precision the step API
+    asks for a reset instead of walking queues of the other layout"""
+    import vqvae_wavenet_b200 as pkg
+    cfg, w, eng = small
+    B, T, F, x, ze = _small_inputs(cfg, w)
+    _, cond = eng.encode_condition(ze, [0, 1, 2])
+    eng.reset(B)
+    eng.step(np.zeros(B, np.float32), cond[:, 0])
+    eng.set_precision("bf16")
+    with pytest.raises(pkg.VqwnError):
+        eng.step(np.zeros(B, np.float32), cond[:, 0])
+    eng.reset(B)
+    eng.step(np.zeros(B, np.float32), cond[:, 0])
+    eng.set_precision("fp32")
+    with pytest.raises(pkg.VqwnError):
+        eng.step(np.zeros(B, np.float32), cond[:, 0])
+    eng.reset(B)
+    _, lg = eng.step(np.zeros(B, np.float32), cond[:, 0])
+    assert np.isfinite(lg).all()

@@ -963,10 +963,17 @@ int vqwn_set_stream(vqwn_handle* h, void* cuda_stream) {
 
 int vqwn_set_precision(vqwn_handle* h, int precision) {
   ENTER(h);
-  if (precision == VQWN_PREC_FP32) { h->precision = precision; return VQWN_OK; }
+  // the dilation-queue layout differs between the two paths: a change of precision invalidates the queue state, the
+  // step API then asks for vqwn_reset (vqwn_generate / vqwn_teacher_forced reset by themselves)
+  if (precision == VQWN_PREC_FP32) {
+    if (h->precision != precision) h->B = 0;
+    h->precision = precision;
+    return VQWN_OK;
+  }
   if (precision == VQWN_PREC_BF16) {
     if (!h->bc_ok)
       return fail(h, VQWN_ERR_NOTIMPL, "bf16 tensor-core path is built for the reference's default WaveNet geometry only");
+    if (h->precision != precision) h->B = 0;
     h->precision = precision;
     return VQWN_OK;
   }
