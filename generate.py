@@ -4,7 +4,8 @@ running VQ + WaveNet fast generation on the B200 library instead of TensorFlow.
 
   python generate.py -restore runs/vctk/weights-110640 -audio p225_001.wav -speakers p225 p226 None -mode sample
 
-Outputs, as the reference writes them (generate.py:94-101,115-117):
+Under torchrun (RANK / WORLD_SIZE / LOCAL_RANK set) every rank generates a contiguous slice of the -speakers list on its
+own GPU.  Outputs, as the reference writes them (generate.py:94-101,115-117):
   <dir>/embedding_<gs>.npy  <dir>/speaker_embedding_<gs>.npy  <dir>/<gs>_<speaker>.wav (float32, 16 kHz)
 
 Weights: the reference's own TensorFlow checkpoint `<restore>.index` / `<restore>.data-*` (read without TensorFlow,
@@ -42,10 +43,22 @@ def main(argv=None):
     args = parser.parse_args(argv)
 
     gs = int(args.restore_path.split('-')[-1])                     # generate.py:33
-    batch_size = len(args.speakers)
     save_path = args.restore_path.split('/weights')[0]
+    dataset, num_speakers = utils.dataset_for_speakers(args.speakers)   # generate.py:46-57 (decided on the full list)
 
-    dataset, num_speakers = utils.dataset_for_speakers(args.speakers)   # generate.py:46-57
+    # one process per GPU (torchrun / any launcher that sets RANK, WORLD_SIZE, LOCAL_RANK): every rank takes a contiguous
+    # slice of the requested speakers and writes that slice's WAVs - streams never interact, nothing is exchanged
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:
+        from vqvae_wavenet_b200 import sharding
+        lo, hi = sharding.stream_slice(len(args.speakers), rank, world)
+        args.speakers = args.speakers[lo:hi]
+        if args.device == 0:
+            args.device = int(os.environ.get('LOCAL_RANK', '0'))
+        if not args.speakers:
+            return
+    batch_size = len(args.speakers)
+
     table = utils.get_speaker_to_int(utils.find_speaker_table(dataset, roots=(".", ROOT)))
     speaker = utils.speaker_onehot(args.speakers, table, num_speakers)  # [B,1,N]
 
@@ -102,9 +115,9 @@ def main(argv=None):
     wavenet = model.decoder.wavenet
     encoding = model.encoding                                                       # generate.py:92
 
-    if cfg.model['use_vq']:
+    if cfg.model['use_vq'] and rank == 0:
         np.save(save_path + '/embedding_%d.npy' % gs, model.embedding)              # generate.py:96-98
-    if cfg.model['speaker_embedding'] > 0:
+    if cfg.model['speaker_embedding'] > 0 and rank == 0:
         np.save(save_path + '/speaker_embedding_%d.npy' % gs, model.speaker_embedding)
 
     uniforms = None
