@@ -6,15 +6,21 @@ mu-law softmax draw).  It is imported only by tests/, __graft_entry__.smoke() an
 bench.py's cpu_baseline / --impl reference legs.  The product path (the CUDA library
 behind include/vqwn.h) never routes through it.
 
-PARITY UNPINNED: the reference is TensorFlow-1.x graph code, TensorFlow is not installed
-in this image (nor in /opt/wheelhouse), the reference ships no tests, golden vectors or
-checkpoint, so this restatement cannot be checked against reference outputs.  What pins it
-instead (tests/test_oracle.py):
+PARITY PINNED against the reference's own code: TensorFlow 1.x cannot be installed in this image, so
+tests/golden/make_ref_golden.py executes the UNMODIFIED reference files (model.py, Decoder/decoder.py,
+Decoder/decoder_ops.py, Decoder/WaveNet/wavenet.py, Decoder/WaveNet/wavenet_ops.py, mu_law_ops.py, utils.py,
+Encoder/encoder.py) on a NumPy stand-in for the TF leaf operators (tests/golden/tf_shim.py: matmul, FIFOQueue,
+conv2d via torch, get_variable/variable_scope, ...), and writes tests/golden/ref_*.npz.  tests/test_ref_golden.py
+proves this restatement equals those outputs: variable names/shapes and receptive field, VQ indices / z_q /
+condition on BASELINE config 2 (bit-exact), queue-form logits and softmax (bit-exact), greedy and seeded-sample
+sequences incl. 16 streams x 4096 steps on the full configuration (identical), conv-form logits incl. BASELINE
+config 5 at 8 x 6656 (<= 2e-5, the shim's conv2d is torch), decode/sample known answers incl. index 256, both
+encoders.  What stays unverifiable without TensorFlow: TF's own kernels' rounding (MatMul summation order) and
+the EMA shadow-variable names inside checkpoints.
+Further pins (tests/test_oracle.py):
   * the five shipped WAVs (results/VCTK/p225_001/*.wav) lie on the mu-law decode grid
     (fixture tests/golden/wav_grid.npz) -> pins mu_law_decode_np and the float32 WAV format;
-  * the reference holds two independent formulations of the decoder (queue form
-    wavenet.py:103-172 and padded dilated-conv form wavenet.py:24-100): both are restated
-    here and must agree;
+  * queue form (wavenet.py:103-172) == padded dilated-conv form (wavenet.py:24-100);
   * two VQ distance formulations (model.py:60-65 direct, Magenta/sonnet.py:91-95 expanded);
   * an independent torch.nn.functional.conv1d witness of the conv form.
 

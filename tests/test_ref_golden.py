@@ -1,0 +1,161 @@
+"""The oracle against golden vectors produced by the reference's OWN code (CPU, no GPU).
+
+tests/golden/ref_*.npz were written by tests/golden/make_ref_golden.py, which executes the unmodified
+reference files (model.py, Decoder/*, Decoder/WaveNet/*, mu_law_ops.py, utils.py, Encoder/encoder.py) on top
+of a NumPy stand-in for the TensorFlow leaf operators (tests/golden/tf_shim.py).  These tests pin
+oracle/oracle.py to those outputs: bit-exact for indices / queue-form arithmetic, 1e-5 for the conv form
+(the shim evaluates conv2d with torch, the oracle with NumPy matmuls).
+
+Long runs are sampled so the CPU suite stays within minutes; VQWN_LONG=1 checks every step.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+SMALL_WAVENET = dict(num_cycles=2, num_cycle_layers=3, dilation_rates=[1, 2, 4, 1, 2, 4])
+LONG = os.environ.get("VQWN_LONG", "0") == "1"
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _uniforms(seed, T, B):
+    """what utils.py:22 consumed: np.random.rand(B) per step from the seeded global RNG"""
+    rs = np.random.RandomState(int(seed))
+    return np.stack([rs.rand(B) for _ in range(T)])
+
+
+def test_variable_names_and_shapes(golden_dir):
+    """the weight list the oracle (and vqwn_set_tensor) uses == what the reference's graph creates"""
+    g = _load(golden_dir, "ref_vars.npz")
+    ref = {n: tuple(int(x) for x in s.split(",")) for n, s in zip(g["variable_names"], g["variable_shapes"])}
+    mine = {n: tuple(s) for n, s in O.tensor_specs(O.Config())}
+    assert ref == mine
+    assert int(g["receptive_field"]) == O.Config().receptive_field == 6170
+
+
+@pytest.mark.parametrize("kind", ["normal", "near_code", "scaled"])
+def test_vq_matches_reference(kind, golden_dir):
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234)
+    g = _load(golden_dir, "ref_vq.npz")
+    ze = O.synthetic_z_e(cfg, w, 64, 104, seed=1235, kind=kind)
+    idx, _, zq = O.vq_discretise(ze, w["embedding/embedding"])
+    assert np.array_equal(idx, g["vq_idx_" + kind])
+    assert np.array_equal(zq.astype(np.float64).sum((1, 2)), g["vq_zq_sum_" + kind])
+    # the older oracle-made fixture holds the same indices
+    assert np.array_equal(_load(golden_dir, "vq_cfg2.npz")["idx_" + kind], g["vq_idx_" + kind])
+
+
+def test_condition_and_ties_match_reference(golden_dir):
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234)
+    g = _load(golden_dir, "ref_vq.npz")
+    ze = O.synthetic_z_e(cfg, w, 64, 104, seed=1235, kind="scaled")[:8]
+    spk = [0, 0, 1, 2, 3, 108, 5, 7]                       # the reference's 'None' row is index 0
+    _, cond = O.encode_condition(ze, spk, w)
+    assert np.array_equal(cond[:, ::8], g["vq_encoding_first8"])
+    E = w["embedding/embedding"].copy()
+    for dup, src in g["vq_tie_rows"]:
+        E[dup] = E[src]
+    idx, _, _ = O.vq_discretise(g["vq_tie_z"], E)
+    assert np.array_equal(idx, g["vq_tie_idx"])
+    assert list(idx[0][:4]) == [7, 7, 12, 12]               # duplicated rows: lowest index
+
+
+def test_codec_and_decode_kats(golden_dir):
+    g = _load(golden_dir, "ref_kat.npz")
+    assert np.array_equal(O.decode_lut(), g["kat_decode_lut"])
+    assert np.array_equal(O.mu_law_encode(g["kat_encode_x"]), g["kat_encode_float"])
+    assert np.array_equal(O.mu_law_encode(g["kat_encode_x"], to_int=True), g["kat_encode_int"])
+    pdf = g["kat_pdf"]
+    assert np.array_equal(O.decode(pdf, mode="greedy"), g["kat_greedy"])
+    for seed, want in zip(g["kat_sample_seeds"], g["kat_sample"]):
+        u = np.random.RandomState(int(seed)).rand(pdf.shape[0])
+        assert np.array_equal(O.decode(pdf, mode="sample", uniforms=u), want)
+    hi = O.decode(pdf, mode="sample", uniforms=np.full(pdf.shape[0], 0.99999999))
+    assert np.array_equal(hi, g["kat_sample_u_high"])
+    assert hi[3] == O.decode_lut()[256]                      # index 256 overflow
+
+
+def _run_config(golden_dir, tag, wav, peaked, steps_greedy, steps_sample, steps_teacher):
+    g = _load(golden_dir, "ref_%s.npz" % tag)
+    cfg = O.Config(wavenet=wav)
+    w = O.make_weights(cfg, seed=1234, peaked=peaked)
+    B, T = g[tag + "_greedy_idx"].shape
+    spk = [max(int(s), 0) for s in g[tag + "_speakers"]]
+    ze = O.synthetic_z_e(cfg, w, B, T // 64, seed=1235, kind="scaled")
+    idx, cond = O.encode_condition(ze, spk, w)
+    assert np.array_equal(idx, g[tag + "_vq_idx"])
+    stride = int(g[tag + "_logit_stride"])
+    Tt = min(steps_teacher, g[tag + "_teacher_logits"].shape[1] * stride)
+    x = O.synthetic_audio(B, g[tag + "_teacher_logits"].shape[1] * stride, seed=1237)
+    _, _, lg = O.generate(cfg, w, cond[:, :max(Tt // 64, 1)], Tt, mode="greedy", teacher=x, return_logits=True)
+    want = g[tag + "_teacher_logits"][:, : (Tt + stride - 1) // stride]
+    assert np.array_equal(lg[:, ::stride], want), "queue-form logits differ from the reference's"
+    assert np.array_equal(O.softmax(lg[:, ::stride]), g[tag + "_teacher_probs"][:, : want.shape[1]])
+    Tg = min(steps_greedy, T)
+    _, gidx = O.generate(cfg, w, cond[:, :max(Tg // 64, 1)], Tg, mode="greedy")
+    assert np.array_equal(gidx, g[tag + "_greedy_idx"][:, :Tg])
+    Ts = min(steps_sample, g[tag + "_sample_idx"].shape[1])
+    u = _uniforms(g[tag + "_sample_seed"], g[tag + "_sample_idx"].shape[1], B)
+    _, sidx = O.generate(cfg, w, cond[:, :max(Ts // 64, 1)], Ts, mode="sample", uniforms=u[:Ts])
+    assert np.array_equal(sidx, g[tag + "_sample_idx"][:, :Ts])
+
+
+def test_small_config_matches_reference(golden_dir):
+    _run_config(golden_dir, "small", SMALL_WAVENET, False, 256, 256, 256)
+
+
+def test_full_config_matches_reference(golden_dir):
+    n = 10 ** 9 if LONG else 128
+    _run_config(golden_dir, "full", None, True, n, n, 64 if not LONG else n)
+
+
+def test_small_conv_form_matches_reference(golden_dir):
+    g = _load(golden_dir, "ref_small.npz")
+    cfg = O.Config(wavenet=SMALL_WAVENET)
+    w = O.make_weights(cfg, seed=1234)
+    B, T = 3, 256
+    ze = O.synthetic_z_e(cfg, w, B, T // 64, seed=1235, kind="scaled")
+    _, cond = O.encode_condition(ze, [0, 1, 2], w)
+    x = O.synthetic_audio(B, T, seed=1237)
+    lg, labels = O.wavenet_teacher_forced(cfg, w, x[:, :, None], cond)
+    lg = lg.reshape(B, T, -1)
+    s = int(g["small_conv_stride"])
+    assert np.array_equal(labels, g["small_conv_labels"])
+    assert np.abs(lg[:, s - 1::s] - g["small_conv_logits"]).max() < 1e-5
+
+
+def test_cfg5_conv_form_matches_reference(golden_dir):
+    """BASELINE config 5 (teacher-forced, length 6656): one of the 8 streams through the oracle's conv form
+    (all 8 with VQWN_LONG=1)"""
+    g = _load(golden_dir, "ref_cfg5.npz")
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234)
+    B, T = 8, 6656
+    ze = O.synthetic_z_e(cfg, w, B, T // 64, seed=1235, kind="scaled")
+    _, cond = O.encode_condition(ze, [b % 4 for b in range(B)], w)
+    x = O.synthetic_audio(B, T, seed=1237)
+    sel = list(range(B)) if LONG else [5]
+    lg, labels = O.wavenet_teacher_forced(cfg, w, x[sel][:, :, None], cond[sel])
+    lg = lg.reshape(len(sel), T, -1)
+    s = int(g["cfg5_conv_stride"])
+    scale = np.abs(g["cfg5_conv_logits"]).max()
+    assert np.abs(lg[:, s - 1::s] - g["cfg5_conv_logits"][sel]).max() < 2e-5 * max(scale, 1.0)
+    assert np.abs(lg[:, -8:] - g["cfg5_conv_last_logits"][sel]).max() < 2e-5 * max(scale, 1.0)
+    assert np.array_equal(labels.reshape(len(sel), T), g["cfg5_conv_labels"].reshape(B, T)[sel])
+
+
+def test_encoders_match_reference(golden_dir):
+    g = _load(golden_dir, "ref_encoders.npz")
+    cfg = O.Config()
+    x = O.synthetic_audio(2, 2048, seed=1237)[:, :, None]
+    z = O.encoder64_forward(cfg, O.make_encoder64_weights(cfg), x)
+    assert np.abs(z - g["enc64_z_e"]).max() < 1e-5
+    z = O.encoder_magenta_forward(cfg, O.make_encoder_magenta_weights(cfg), x)
+    assert np.abs(z - g["encmag_z_e"]).max() < 2e-5
