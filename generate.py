@@ -38,7 +38,7 @@ def main(argv=None):
     parser.add_argument('-z_e', dest='z_e_path', default=None, help='encoder output (.npy)')
     parser.add_argument('-device', dest='device', type=int, default=0)
     parser.add_argument('-seed', dest='seed', type=int, default=None, help='seed of the draw stream (sample mode)')
-    parser.add_argument('-precision', dest='precision', default='fp32', choices=('fp32', 'bf16'),
+    parser.add_argument('-precision', dest='precision', default='fp32', choices=('fp32', 'tc', 'bf16'),
                         help='fp32: float32 contractions (the reference arithmetic); bf16: tcgen05 tensor-core kernel')
     args = parser.parse_args(argv)
 
@@ -49,6 +49,7 @@ def main(argv=None):
     # one process per GPU (torchrun / any launcher that sets RANK, WORLD_SIZE, LOCAL_RANK): every rank takes a contiguous
     # slice of the requested speakers and writes that slice's WAVs - streams never interact, nothing is exchanged
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    lo = 0
     if world > 1:
         from vqvae_wavenet_b200 import sharding
         lo, hi = sharding.stream_slice(len(args.speakers), rank, world)
@@ -123,6 +124,7 @@ def main(argv=None):
     uniforms = None
     if args.mode == 'sample' and args.seed is None:
         uniforms = np.random.rand(length, batch_size)                               # utils.py:22, one draw per step
+    engine.set_stream_offset(lo)          # -seed draws are keyed on the position in the full -speakers list
     to_write, _ = wavenet.generate(encoding, length, mode=args.mode, uniforms=uniforms,
                                    seed=0 if args.seed is None else args.seed)      # generate.py:103-113
     for i, s in enumerate(args.speakers):

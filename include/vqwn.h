@@ -45,6 +45,7 @@ extern "C" {
 /* arithmetic of the decoder step (vqwn_set_precision) */
 #define VQWN_PREC_FP32 0   /* fp32 CUDA-core contraction; the parity anchor                 */
 #define VQWN_PREC_BF16 1   /* bf16 tcgen05 contraction, fp32 accumulate (tolerance 2e-2)    */
+#define VQWN_PREC_TC   2   /* split-bf16 (hi + lo) tcgen05 contraction, fp32 accumulate: float32-grade (logits ~1e-5) */
 
 /* VQ kernel selection (vqwn_set_vq_kernel); both give identical indices and z_q */
 #define VQWN_VQ_AUTO   0   /* tensor-core kernel when k = 512 and latent_dim = 64, else direct  */
@@ -87,11 +88,18 @@ const char* vqwn_last_error(const vqwn_handle* h);
 int vqwn_set_stream(vqwn_handle* h, void* cuda_stream);
 /* arithmetic of the generation loop (wavenet.py:103-172 evaluated by vqwn_generate / vqwn_step / vqwn_teacher_forced).
  * VQWN_PREC_FP32 (default): every contraction in float32, the parity anchor (logits 1e-6 from the restatement).
+ * VQWN_PREC_TC: tcgen05 tensor-core kernel at float32-grade accuracy: every contraction operand is split into two
+ * bfloat16 numbers (hi + lo) and all four partial products are accumulated in float32 (logits ~1e-5 from the
+ * restatement; greedy / same-uniform sequences as the float32 path); default WaveNet geometry only.
  * VQWN_PREC_BF16: tcgen05 tensor-core kernel, weights and contraction inputs rounded to bfloat16, float32 accumulation
  * and float32 residual / skip / softmax (logits within 2e-2); the reference's default WaveNet geometry only, otherwise
  * VQWN_ERR_NOTIMPL.  Set it before vqwn_reset / the first generate call of a run: the dilation-queue layout differs. */
 int vqwn_set_precision(vqwn_handle* h, int precision);
 int vqwn_set_vq_kernel(vqwn_handle* h, int kernel);
+/* sharded runs (generate.py:34: the batch is the list of -speakers, cut into contiguous slices per GPU): global index of
+ * this handle's stream 0.  It keys the counter-based generator that stands in for np.random.rand (utils.py:22) when
+ * vqwn_generate gets no uniforms, so that a slice draws exactly what the unsharded run draws for the same streams. */
+int vqwn_set_stream_offset(vqwn_handle* h, int64_t offset);
 
 /* ---- weights: replaces tf.train.Saver(ema.variables_to_restore()).restore (generate.py:88-90)
  * Tensors are addressed by the reference's variable names, e.g.

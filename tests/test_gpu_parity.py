@@ -22,6 +22,9 @@ SMALL_WAVENET = dict(num_cycles=2, num_cycle_layers=3, dilation_rates=[1, 2, 4, 
 LOGIT_RTOL = 1e-3
 GREEDY_TIE = 1e-4
 SAMPLE_TIE = 1e-5
+# the two parity-grade arithmetic paths: float32 CUDA cores, and split-bf16 (hi + lo) tcgen05 tensor cores
+PRECISIONS = ["fp32", "tc"]
+KERNEL_OF = {"fp32": "wavenet_fp32_cluster", "tc": "wavenet_tc_cluster"}
 
 
 def _engine(wavenet=None, max_batch=64, weights=None, **kw):
@@ -32,32 +35,69 @@ def _engine(wavenet=None, max_batch=64, weights=None, **kw):
     return eng
 
 
-@pytest.fixture(scope="module")
-def small():
+@pytest.fixture(scope="module", params=PRECISIONS)
+def small(request):
     cfg = O.Config(wavenet=SMALL_WAVENET)
     w = O.make_weights(cfg, seed=1234)
     eng = _engine(SMALL_WAVENET, 16, w)
+    eng.set_precision(request.param)
+    eng.precision_name = request.param
     yield cfg, w, eng
     eng.close()
 
 
-@pytest.fixture(scope="module")
-def full():
+@pytest.fixture(scope="module", params=PRECISIONS)
+def full(request):
     cfg = O.Config()
     w = O.make_weights(cfg, seed=1234, peaked=True)
     eng = _engine(None, 64, w)
+    eng.set_precision(request.param)
+    eng.precision_name = request.param
     yield cfg, w, eng
     eng.close()
 
 
-def _check_sequences(got, want, margin, tie, min_prefix):
-    """identical, or first divergence sits on a near-tie of the oracle's own draw"""
+def _ref_uniforms(seed, T, B):
+    """the np.random.rand(B) per step that the reference's sample() drew (utils.py:22) from its seeded global RNG"""
+    rs = np.random.RandomState(int(seed))
+    return np.stack([rs.rand(B) for _ in range(T)])
+
+
+def _check_sequences(got, want, margin, tie, min_prefix, label=""):
+    """free-running sequences: identical, or the FIRST divergence of a stream sits on a near-tie of the reference's own
+    draw (after which the histories differ and nothing more can be compared - _check_teacher_forced_draws covers the
+    rest of the run).  Returns / prints how many streams match end to end."""
+    exact = 0
     for b in range(want.shape[0]):
         bad = np.nonzero(got[b] != want[b])[0]
         if bad.size:
             t = int(bad[0])
-            assert float(margin[b, t]) < tie, "stream %d diverges at step %d, margin %g" % (b, t, margin[b, t])
-            assert t >= min_prefix, "stream %d diverges too early (step %d)" % (b, t)
+            assert float(margin[b, t]) < tie, "%s stream %d diverges at step %d, margin %g" % (label, b, t, margin[b, t])
+            assert t >= min_prefix, "%s stream %d diverges too early (step %d)" % (label, b, t)
+        else:
+            exact += 1
+    print("%s: %d of %d streams identical over all %d steps" % (label, exact, want.shape[0], want.shape[1]))
+    return exact
+
+
+def _check_teacher_forced_draws(eng, cond, want_idx, margin, mode, tie, uniforms=None, label=""):
+    """every step of every stream, independent of earlier near-ties: feed the REFERENCE's own sequence back
+    (teacher-forced, so each step sees the reference's history) and redo the draw from the device logits; the draw must
+    equal the reference's at every step whose reference margin is not a near-tie."""
+    B, T = want_idx.shape
+    x = O.decode_lut()[want_idx]                                  # what generate.py:112-113 fed back
+    lg = eng.teacher_forced(x, cond)
+    probs = O.softmax(lg.reshape(B * T, -1)).reshape(B, T, -1)
+    if mode == "greedy":
+        got = np.argmax(probs, -1)
+    else:
+        got = np.stack([O.sample_indices(probs[:, t], uniforms[t]) for t in range(T)], 1).astype(np.int64)
+    bad = got != want_idx
+    assert np.all(margin[bad] < tie), "%s: %d draws differ away from a near-tie (worst margin %g)" % (
+        label, int((bad & (margin >= tie)).sum()), float(margin[bad].max()))
+    assert bad.mean() < 2e-3, "%s: too many near-tie flips (%d)" % (label, int(bad.sum()))
+    print("%s: teacher-forced redraw equals the reference at %d of %d steps (%d near-tie flips)"
+          % (label, int((~bad).sum()), bad.size, int(bad.sum())))
 
 
 # ----------------------------------------------------------------------------------------- VQ
@@ -318,9 +358,16 @@ def test_small_teacher_forced_logits(small, golden_dir):
     g = np.load(os.path.join(golden_dir, "small.npz"))
     assert np.array_equal(idx, g["vq_idx"])
     lg = eng.teacher_forced(x, cond)
+    assert eng.last_kernel_name == KERNEL_OF[eng.precision_name]
     scale = np.abs(g["logits_fast"]).max()
     assert np.abs(lg[:, ::16] - g["logits_fast"]).max() <= LOGIT_RTOL * scale
     assert np.abs(lg[:, ::16] - g["logits_conv"]).max() <= LOGIT_RTOL * scale   # second formulation
+    # the reference's own code (tests/golden/make_ref_golden.py): queue form and conv form; speaker row None == 0
+    r = np.load(os.path.join(golden_dir, "ref_small.npz"))
+    err = np.abs(lg[:, ::4] - r["small_teacher_logits"]).max() / scale
+    print("small teacher-forced logits vs reference (%s): %.3g of max |logit|" % (eng.precision_name, err))
+    assert err <= LOGIT_RTOL
+    assert np.abs(lg[:, 3::4] - r["small_conv_logits"]).max() <= LOGIT_RTOL * scale
     # oracle computed live on the same inputs, every step
     _, _, olg = O.generate(cfg, w, cond, T, mode="greedy", teacher=x, return_logits=True)
     assert np.abs(lg - olg).max() <= LOGIT_RTOL * np.abs(olg).max()
@@ -355,38 +402,18 @@ def test_small_greedy_and_sample_sequences(small, golden_dir):
     audio, idx = eng.generate(cond, T, mode="sample", uniforms=u)
     _check_sequences(idx, g["sample_idx"], g["sample_margin"], SAMPLE_TIE, 32)
     assert np.array_equal(audio, O.decode_lut()[idx])
-
-
-def test_dataflow_kernel_matches_barrier_kernel(monkeypatch):
-    """the experimental barrier-free kernel (VQWN_GEN_KERNEL=dataflow: per-(stage, stream block) counters
-    instead of grid barriers) computes the same tiles in the same order as the default kernel: outputs must be
-    bit-identical"""
-    cfg = O.Config(wavenet=SMALL_WAVENET)
-    w = O.make_weights(cfg, seed=1234)
-    B, T, F, x, ze = _small_inputs(cfg, w)
-    monkeypatch.setenv("VQWN_GEN_KERNEL", "barrier")
-    ref = _engine(SMALL_WAVENET, 16, w)
-    _, cond = ref.encode_condition(ze, [0, 1, 2])
-    a0, i0 = ref.generate(cond, T, mode="greedy")
-    l0 = ref.teacher_forced(x[:, :64], cond[:, :1])
-    assert ref.last_kernel_name == "wavenet_fp32_persistent"
-    u = np.random.default_rng(3).random((T, B))
-    s0 = ref.generate(cond, T, mode="sample", uniforms=u)[1]
-    ref.close()
-    monkeypatch.setenv("VQWN_GEN_KERNEL", "dataflow")
-    eng = _engine(SMALL_WAVENET, 16, w)
-    a1, i1 = eng.generate(cond, T, mode="greedy")
-    assert eng.last_kernel_name == "wavenet_fp32_dataflow"
-    l1 = eng.teacher_forced(x[:, :64], cond[:, :1])
-    s1 = eng.generate(cond, T, mode="sample", uniforms=u)[1]
-    eng.reset(B)
-    audio = np.zeros(B, dtype=np.float32)
-    for t in range(8):
-        _, logits = eng.step(audio, cond[:, 0])
-        assert np.array_equal(logits, l1[:, t])
-        audio = x[:, t]
-    eng.close()
-    assert np.array_equal(i0, i1) and np.array_equal(a0, a1) and np.array_equal(l0, l1) and np.array_equal(s0, s1)
+    # sequences produced by the reference's own loop (generate.py:103-113 + utils.decode), greedy and seeded sample
+    r = np.load(os.path.join(golden_dir, "ref_small.npz"))
+    tag = "small/%s" % eng.precision_name
+    gi = eng.generate(cond, T, mode="greedy")[1]
+    _check_sequences(gi, r["small_greedy_idx"], r["small_greedy_margin"].astype(np.float32), GREEDY_TIE, 32, tag + " greedy")
+    _check_teacher_forced_draws(eng, cond, r["small_greedy_idx"].astype(np.int64), r["small_greedy_margin"].astype(np.float32),
+                                "greedy", GREEDY_TIE, label=tag + " greedy")
+    ur = _ref_uniforms(r["small_sample_seed"], T, B)
+    si = eng.generate(cond, T, mode="sample", uniforms=ur)[1]
+    _check_sequences(si, r["small_sample_idx"], r["small_sample_margin"], SAMPLE_TIE, 32, tag + " sample")
+    _check_teacher_forced_draws(eng, cond, r["small_sample_idx"].astype(np.int64), r["small_sample_margin"], "sample",
+                                SAMPLE_TIE, uniforms=ur, label=tag + " sample")
 
 
 @pytest.mark.parametrize("B", [3, 23, 64])
@@ -461,6 +488,13 @@ def test_shard_equals_unsharded(small):
         assert np.array_equal(i, i_all[lo:hi]) and np.array_equal(a, a_all[lo:hi])
     g_all = eng.generate(cond, T, mode="greedy")[1]
     assert np.array_equal(eng.generate(cond[1:2], T, mode="greedy")[1], g_all[1:2])
+    # no uniforms supplied: the seeded generator is keyed on the GLOBAL stream index (vqwn_set_stream_offset)
+    s_all = eng.generate(cond, T, mode="sample", seed=9)[1]
+    eng.set_stream_offset(2)
+    s_slice = eng.generate(cond[2:6], T, mode="sample", seed=9)[1]
+    eng.set_stream_offset(0)
+    assert np.array_equal(s_slice, s_all[2:6])
+    assert not np.array_equal(eng.generate(cond[2:6], T, mode="sample", seed=9)[1], s_all[2:6])
 
 
 def test_decode_api(small):
@@ -515,6 +549,15 @@ def test_error_behaviour(small):
 
 
 # ----------------------------------------------------------------------------------------- decoder, full config
+def _full_ref_inputs(cfg, w, eng, golden_dir):
+    r = np.load(os.path.join(golden_dir, "ref_full.npz"))
+    B, T = r["full_greedy_idx"].shape
+    ze = O.synthetic_z_e(cfg, w, B, T // 64, seed=1235, kind="scaled")
+    idx, cond = eng.encode_condition(ze, [int(s) for s in r["full_speakers"]])
+    assert np.array_equal(idx, r["full_vq_idx"])
+    return r, B, T, cond
+
+
 def test_full_teacher_forced_logits(full, golden_dir):
     cfg, w, eng = full
     g = np.load(os.path.join(golden_dir, "full.npz"))
@@ -524,30 +567,53 @@ def test_full_teacher_forced_logits(full, golden_dir):
     assert np.array_equal(idx, g["vq_idx"])
     x = O.synthetic_audio(B, Tt, seed=1237)
     lg = eng.teacher_forced(x, cond[:, :Tt // 64])
+    assert eng.last_kernel_name == KERNEL_OF[eng.precision_name]
     want = g["teacher_logits"]
     assert np.abs(lg[:, ::32] - want).max() <= LOGIT_RTOL * np.abs(want).max()
+    # 16 streams against the logits the reference's own graph produced
+    r, B, T, cond = _full_ref_inputs(cfg, w, eng, golden_dir)
+    want = r["full_teacher_logits"]
+    Tt = want.shape[1] * int(r["full_logit_stride"])
+    x = O.synthetic_audio(B, Tt, seed=1237)
+    lg = eng.teacher_forced(x, cond[:, :Tt // 64])
+    err = np.abs(lg[:, ::32] - want).max() / np.abs(want).max()
+    print("full teacher-forced logits vs reference (%s): %.3g of max |logit|" % (eng.precision_name, err))
+    assert err <= LOGIT_RTOL
 
 
 def test_full_greedy_4096(full, golden_dir):
+    """north_star: greedy sequences match for the first 4096 samples - 16 streams, the sequences are the ones the
+    reference's own code produced; every step is also re-drawn teacher-forced so nothing stops being checked after a
+    near-tie"""
     cfg, w, eng = full
-    g = np.load(os.path.join(golden_dir, "full.npz"))
-    B, T = 4, 4096
-    ze = O.synthetic_z_e(cfg, w, B, 64, seed=1235, kind="scaled")
-    _, cond = eng.encode_condition(ze, [0, 1, 2, 3])
+    r, B, T, cond = _full_ref_inputs(cfg, w, eng, golden_dir)
+    assert (B, T) == (16, 4096)
     audio, idx = eng.generate(cond, T, mode="greedy")
-    _check_sequences(idx, g["greedy_idx"], g["greedy_margin"].astype(np.float32), GREEDY_TIE, 256)
+    margin = r["full_greedy_margin"].astype(np.float32)
+    tag = "full/%s greedy" % eng.precision_name
+    _check_sequences(idx, r["full_greedy_idx"], margin, GREEDY_TIE, 256, tag)
     assert np.array_equal(audio, O.decode_lut()[idx])
+    _check_teacher_forced_draws(eng, cond, r["full_greedy_idx"].astype(np.int64), margin, "greedy", GREEDY_TIE, label=tag)
+    # the older oracle-made fixture (4 streams) still holds
+    g = np.load(os.path.join(golden_dir, "full.npz"))
+    ze = O.synthetic_z_e(cfg, w, 4, 64, seed=1235, kind="scaled")
+    _, cond4 = eng.encode_condition(ze, [0, 1, 2, 3])
+    _check_sequences(eng.generate(cond4, T, mode="greedy")[1], g["greedy_idx"], g["greedy_margin"].astype(np.float32),
+                     GREEDY_TIE, 256, tag + " (4 streams)")
 
 
 def test_full_sample_same_uniforms(full, golden_dir):
+    """north_star: sample mode matches when fed identical uniform draws - the reference's sample() drew them from the
+    seeded global NumPy RNG (utils.py:22)"""
     cfg, w, eng = full
-    g = np.load(os.path.join(golden_dir, "full.npz"))
-    B, T = 4, 1024
-    ze = O.synthetic_z_e(cfg, w, B, 64, seed=1235, kind="scaled")
-    _, cond = eng.encode_condition(ze, [0, 1, 2, 3])
-    u = np.random.default_rng(1236).random((T, B))
+    r, B, _, cond = _full_ref_inputs(cfg, w, eng, golden_dir)
+    T = r["full_sample_idx"].shape[1]
+    u = _ref_uniforms(r["full_sample_seed"], T, B)
+    tag = "full/%s sample" % eng.precision_name
     audio, idx = eng.generate(cond[:, :T // 64], T, mode="sample", uniforms=u)
-    _check_sequences(idx, g["sample_idx"], g["sample_margin"], SAMPLE_TIE, 128)
+    _check_sequences(idx, r["full_sample_idx"], r["full_sample_margin"], SAMPLE_TIE, 128, tag)
+    _check_teacher_forced_draws(eng, cond[:, :T // 64], r["full_sample_idx"].astype(np.int64), r["full_sample_margin"],
+                                "sample", SAMPLE_TIE, uniforms=u, label=tag)
 
 
 def test_full_size_properties(full):
@@ -633,9 +699,9 @@ def test_bf16_full_teacher_logits(golden_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("precision,B", [("fp32", 100), ("bf16", 250)])
+@pytest.mark.parametrize("precision,B", [("fp32", 100), ("bf16", 250), ("tc", 130)])
 def test_batches_above_cluster_capacity_run_as_several_launches(precision, B):
-    """the cluster kernels hold 7 x 10 (float32) / 15 x 16 (bf16) streams per launch; larger batches run as consecutive
+    """the cluster kernels hold 7 x 10 (float32) / 15 x 16 (bf16) / 7 x 16 (split-bf16) streams per launch; larger batches run as consecutive
     launches over disjoint stream groups.  Streams never interact, so every stream must come out exactly as it does
     in a small batch of its own - including the ones in the second launch."""
     cfg = O.Config(wavenet=SMALL_WAVENET)
@@ -661,52 +727,71 @@ def test_batches_above_cluster_capacity_run_as_several_launches(precision, B):
     eng.close()
 
 
-def test_cfg5_teacher_forced_full_size(monkeypatch):
+def test_cfg5_teacher_forced_full_size(monkeypatch, golden_dir):
     """BASELINE config 5 at its full size (teacher-forced decoder forward, batch 8, length 6656 = 104 frames x hop 64,
-    default 30-layer WaveNet) - too long for the NumPy oracle, so checked through size-independent properties: the three
-    independent kernels (float32 cluster, float32 grid-barrier, bf16 tensor-core) must agree on every one of the
-    8 x 6656 x 256 logits within their tolerances, and a prefix of the run equals the short run the oracle pins
-    (test_full_teacher_forced_logits)."""
+    default 30-layer WaveNet; the '64' and 'Magenta' encoder variants share this decoder shape, hop 64).  The target is
+    the reference's own conv-form graph (wavenet.py:24-100 via model.py / decoder.py, run by make_ref_golden.py): its
+    logits at every 64th step + the last 8 steps + a checksum of every 16th step, and the int labels.  Then the
+    kernels must agree with each other on every one of the 8 x 6656 x 256 logits."""
+    r = np.load(os.path.join(golden_dir, "ref_cfg5.npz"))
     cfg = O.Config()
-    w = O.make_weights(cfg, seed=1234, peaked=True)
+    w = O.make_weights(cfg, seed=1234)
     B, T, F = 8, 6656, 104
     ze = O.synthetic_z_e(cfg, w, B, F, seed=1235, kind="scaled")
     x = O.synthetic_audio(B, T, seed=1237)
+    assert np.array_equal(O.mu_law_encode(x, to_int=True).reshape(-1), r["cfg5_conv_labels"])
     out = {}
-    for kernel in ("cluster", "barrier"):
-        monkeypatch.setenv("VQWN_GEN_KERNEL", kernel)
-        eng = _engine(None, B, w)
-        _, cond = eng.encode_condition(ze, np.arange(B, dtype=np.int32) % 4)
-        out[kernel] = eng.teacher_forced(x, cond)
-        if kernel == "cluster":
+    monkeypatch.setenv("VQWN_GEN_KERNEL", "cluster")
+    eng = _engine(None, B, w)
+    _, cond = eng.encode_condition(ze, np.arange(B, dtype=np.int32) % 4)
+    for prec in ("fp32", "tc", "bf16"):
+        eng.set_precision(prec)
+        out[prec] = eng.teacher_forced(x, cond)
+        if prec == "fp32":
             short = eng.teacher_forced(x[:, :512], cond[:, :8])
-            assert np.array_equal(short, out[kernel][:, :512])           # a run is a prefix of a longer run
-            eng.set_precision("bf16")
-            out["bf16"] = eng.teacher_forced(x, cond)
-        eng.close()
-    scale = np.abs(out["barrier"]).max()
-    assert out["cluster"].shape == (B, T, 256)
-    assert np.abs(out["cluster"] - out["barrier"]).max() <= 2e-5 * scale
-    assert np.abs(out["bf16"] - out["cluster"]).max() <= BF16_LOGIT_RTOL * scale
+            assert np.array_equal(short, out[prec][:, :512])           # a run is a prefix of a longer run
+    eng.close()
+    monkeypatch.setenv("VQWN_GEN_KERNEL", "barrier")
+    eng = _engine(None, B, w)
+    out["barrier"] = eng.teacher_forced(x, cond)
+    eng.close()
+    s_ = int(r["cfg5_conv_stride"])
+    scale = np.abs(r["cfg5_conv_logits"]).max()
+    for prec, tol in (("fp32", LOGIT_RTOL), ("tc", LOGIT_RTOL), ("barrier", LOGIT_RTOL), ("bf16", BF16_LOGIT_RTOL)):
+        lg = out[prec]
+        assert lg.shape == (B, T, 256)
+        e1 = np.abs(lg[:, s_ - 1::s_] - r["cfg5_conv_logits"]).max() / scale
+        e2 = np.abs(lg[:, -8:] - r["cfg5_conv_last_logits"]).max() / scale
+        e3 = np.abs(lg[:, ::16].astype(np.float64).sum(-1) - r["cfg5_conv_logit_sum"]).max() / (256 * scale)
+        print("cfg5 %s vs reference conv form: %.3g / %.3g / checksum %.3g of max |logit|" % (prec, e1, e2, e3))
+        assert max(e1, e2, e3) <= tol
+    assert np.abs(out["fp32"] - out["barrier"]).max() <= 2e-5 * scale
+    assert np.abs(out["tc"] - out["fp32"]).max() <= LOGIT_RTOL * scale
+    assert np.abs(out["bf16"] - out["fp32"]).max() <= BF16_LOGIT_RTOL * scale
 
 
-def test_precision_change_invalidates_step_state(small):
-    """the dilation-queue layout differs between the float32 and the bf16 path: after vqwn_set_precision the step API
-    asks for a reset instead of walking queues of the other layout"""
+def test_precision_change_invalidates_step_state():
+    """the dilation-queue layout differs between the float32, the split-bf16 and the bf16 path: after
+    vqwn_set_precision the step API asks for a reset instead of walking queues of another layout"""
     import vqvae_wavenet_b200 as pkg
-    cfg, w, eng = small
+    cfg = O.Config(wavenet=SMALL_WAVENET)
+    w = O.make_weights(cfg, seed=1234)
+    eng = _engine(SMALL_WAVENET, 16, w)
     B, T, F, x, ze = _small_inputs(cfg, w)
     _, cond = eng.encode_condition(ze, [0, 1, 2])
     eng.reset(B)
     eng.step(np.zeros(B, np.float32), cond[:, 0])
-    eng.set_precision("bf16")
-    with pytest.raises(pkg.VqwnError):
-        eng.step(np.zeros(B, np.float32), cond[:, 0])
-    eng.reset(B)
-    eng.step(np.zeros(B, np.float32), cond[:, 0])
-    eng.set_precision("fp32")
-    with pytest.raises(pkg.VqwnError):
-        eng.step(np.zeros(B, np.float32), cond[:, 0])
-    eng.reset(B)
-    _, lg = eng.step(np.zeros(B, np.float32), cond[:, 0])
-    assert np.isfinite(lg).all()
+    for prec in ("bf16", "tc", "fp32"):
+        eng.set_precision(prec)
+        with pytest.raises(pkg.VqwnError):
+            eng.step(np.zeros(B, np.float32), cond[:, 0])
+        eng.reset(B)
+        _, lg = eng.step(np.zeros(B, np.float32), cond[:, 0])
+        assert np.isfinite(lg).all()
+    with pytest.raises(ValueError):
+        eng.step(np.zeros(B + 1, np.float32), np.zeros((B + 1, 128), np.float32))     # batch differs from reset()
+    with pytest.raises(ValueError):
+        eng.generate(cond, 256, mode="greedy", out_audio=np.zeros((B, 255), np.float32))
+    with pytest.raises(ValueError):
+        eng.encode_condition(ze, [0, 1])
+    eng.close()

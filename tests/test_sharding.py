@@ -13,6 +13,11 @@ import torch.multiprocessing as mp
 class _PerStreamEngine:
     """deterministic per-stream function of (condition, uniforms): what independence means"""
 
+    offset = 0
+
+    def set_stream_offset(self, offset):
+        self.offset = int(offset)
+
     def generate(self, cond, length, mode="greedy", uniforms=None, seed=0):
         B = cond.shape[0]
         base = (np.abs(cond).sum(axis=(1, 2))[:, None] * 1000).astype(np.int64)

@@ -7,7 +7,7 @@ MAX_LAYERS = 64
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOTIMPL, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MODE_GREEDY, MODE_SAMPLE = 0, 1
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TC = 0, 1, 2
 VQ_AUTO, VQ_DIRECT, VQ_TENSOR = 0, 1, 2
 
 
@@ -59,6 +59,7 @@ PROTOTYPES = {
     "vqwn_set_stream": (C.c_int, [_H, C.c_void_p]),
     "vqwn_set_precision": (C.c_int, [_H, C.c_int]),
     "vqwn_set_vq_kernel": (C.c_int, [_H, C.c_int]),
+    "vqwn_set_stream_offset": (C.c_int, [_H, C.c_int64]),
     "vqwn_set_tensor": (C.c_int, [_H, C.c_char_p, _f32p, _i64p, C.c_int]),
     "vqwn_get_tensor": (C.c_int, [_H, C.c_char_p, _f32p, C.c_int64]),
     "vqwn_num_tensors": (C.c_int, [_H]),

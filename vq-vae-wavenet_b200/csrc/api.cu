@@ -16,9 +16,9 @@
 #include "vq.cuh"
 #include "vq_tc.cuh"
 #include "wavenet_fp32.cuh"
-#include "wavenet_fp32_df.cuh"
 #include "wavenet_fp32_cluster.cuh"
 #include "wavenet_bf16_cluster.cuh"
+#include "wavenet_tc_cluster.cuh"
 #include "sample.cuh"
 #include "encoder.cuh"
 
@@ -67,11 +67,7 @@ struct vqwn_handle {
   std::vector<size_t> off_w1t, off_w2t;
   size_t off_skip0t = 0, off_post1t = 0, off_post2t = 0;
   int* gen_err = nullptr;
-  float* df_base = nullptr;                // per-layer cur / g buffers + skip start of the dataflow kernel
-  size_t df_floats = 0;
-  unsigned* df_cnt = nullptr;              // dependency counters
-  size_t df_ncnt = 0;
-  int gen_kernel = 0;                      // 0 auto (cluster kernel when it applies), 1 barrier, 2 dataflow, 3 cluster
+  int gen_kernel = 0;                      // 0 auto (cluster kernel when it applies), 1 barrier, 3 cluster
   // cluster kernel (wavenet_fp32_cluster.cuh)
   bool cl_ok = false;                      // geometry constraints hold and 16-CTA clusters can be scheduled
   int cl_max_clusters = 0;                 // co-resident clusters of 16 CTAs (measured 7 on a B200)
@@ -85,6 +81,16 @@ struct vqwn_handle {
   __nv_bfloat16* wbc = nullptr;            // bf16 K-major plane tiles, same block order as wtiles
   BcLayerDev* bc_layers_dev = nullptr;
   std::vector<BcLayerDev> bc_layers_host;
+  // split-bf16 (float32-grade) tensor-core cluster kernel (wavenet_tc_cluster.cuh)
+  bool tc_ok = false;                      // default geometry and 16-CTA clusters schedulable
+  int tc_max_clusters = 0;
+  __nv_bfloat16* wtc = nullptr;            // [L][16][144 KB] hi/lo tiles, then postprocess1 [16][64 KB], postprocess2 [16][32 KB]
+  size_t wtc_bytes = 0;
+  float *tc_skf_k = nullptr, *tc_skf_b = nullptr, *tc_ctab = nullptr;
+  const float** tc_b2_ptrs = nullptr;
+  TcLayerDev* tc_layers_dev = nullptr;
+  std::vector<TcLayerDev> tc_layers_host;
+  int stream_offset = 0;                   // global index of stream 0 (vqwn_set_stream_offset)
   // packed fp32 weights
   bool packed = false;
   std::vector<float*> w1, b1, w2, b2;
@@ -259,6 +265,37 @@ int pack_weights(vqwn_handle* h) {
     packb(TP(h, "decoder/postprocess2/kernel"), h->Q, S, BC_NQ, 0, 0, 0, h->wbc + h->off_post2t);
     CK(h, cudaGetLastError());
   }
+  if (h->tc_ok) {
+    auto packt = [&](const float* src, int ldw, int k0, int K, int rows, int kind, size_t cta_stride_bytes, uint8_t* dst) {
+      const long long total = (long long)TC_CS * K * rows;
+      int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+      pack_tc_tiles_kernel<<<grid, 256, 0, h->stream>>>(src, ldw, k0, K, rows, kind, cta_stride_bytes / 2,
+                                                       reinterpret_cast<__nv_bfloat16*>(dst));
+      h->launches += 1;
+    };
+    uint8_t* base = reinterpret_cast<uint8_t*>(h->wtc);
+    for (int l = 0; l < h->L; ++l) {
+      uint8_t* lb = base + (size_t)l * TC_CS * TC_LAYER_BYTES;
+      // w1 rows: [0,R) current tap (kernel[2]) | [R,2R) tap t-d (kernel[1]) | [2R,3R) tap t-2d (kernel[0]) | condition
+      packt(h->w1[l], 2 * G, 0, R, TC_ROWS1, 0, TC_LAYER_BYTES, lb);
+      packt(h->w1[l], 2 * G, R, R, TC_ROWS1, 0, TC_LAYER_BYTES, lb + TC_W1);
+      packt(h->w1[l], 2 * G, 2 * R, R, TC_ROWS1, 0, TC_LAYER_BYTES, lb + 2 * TC_W1);
+      packt(h->w2[l], R + S, 0, G, TC_ROWS2, 1, TC_LAYER_BYTES, lb + 3 * TC_W1);
+    }
+    uint8_t* p1 = base + (size_t)h->L * TC_CS * TC_LAYER_BYTES;
+    uint8_t* p2 = p1 + (size_t)TC_CS * TC_WP1;
+    packt(h->post1_w, S, 0, S, TC_ROWSP1, 2, TC_WP1, p1);
+    packt(TP(h, "decoder/postprocess2/kernel"), h->Q, 0, S, TC_ROWSP2, 3, TC_WP2, p2);
+    std::vector<const float*> b2p(h->L);
+    for (int l = 0; l < h->L; ++l) b2p[l] = h->b2[l];
+    CK(h, cudaMemcpyAsync(h->tc_b2_ptrs, b2p.data(), sizeof(const float*) * h->L, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    fold_skip_start_kernel<<<(TC_S + 127) / 128, 128, 0, h->stream>>>(
+        TP(h, "decoder/preprocess/kernel"), TP(h, "decoder/preprocess/bias"), TP(h, "decoder/skip/kernel"),
+        TP(h, "decoder/skip/bias"), h->tc_b2_ptrs, h->L, h->tc_skf_k, h->tc_skf_b);
+    h->launches += 1;
+    CK(h, cudaGetLastError());
+  }
   CK(h, cudaMemcpyAsync(h->enc_lut, TP(h, "lut/mu_law_encode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->dec_lut, TP(h, "lut/mu_law_decode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
@@ -266,12 +303,17 @@ int pack_weights(vqwn_handle* h) {
   return VQWN_OK;
 }
 
+size_t tc_ring_bytes(const vqwn_handle* h, int B);
+
 int do_reset(vqwn_handle* h, int B) {
   if (B < 1 || B > h->max_batch) return fail(h, VQWN_ERR_INVALID, "batch out of range (1..max_batch)");
   const size_t Bp = h->Bp_max;
   // only the part of the ring storage this padded batch uses (layout: launch_fp32)
   const size_t Bp_run = (size_t)(B + FP32_TB - 1) / FP32_TB * FP32_TB;
-  CK(h, cudaMemsetAsync(h->ring_base, 0, h->ring_floats / Bp * Bp_run * sizeof(float), h->stream));
+  size_t ring_clear = h->ring_floats / Bp * Bp_run * sizeof(float);
+  if (h->tc_ok && tc_ring_bytes(h, B) > ring_clear) ring_clear = tc_ring_bytes(h, B);
+  if (ring_clear > h->ring_floats * sizeof(float)) ring_clear = h->ring_floats * sizeof(float);
+  CK(h, cudaMemsetAsync(h->ring_base, 0, ring_clear, h->stream));
   CK(h, cudaMemsetAsync(h->u_hist, 0, Bp * h->PK * sizeof(float), h->stream));
   CK(h, cudaMemsetAsync(h->cur, 0, Bp * h->R * sizeof(float), h->stream));
   CK(h, cudaMemsetAsync(h->g, 0, Bp * h->G * sizeof(float), h->stream));
@@ -356,7 +398,7 @@ int launch_cluster(vqwn_handle* h, int MS, int mode, long long T, const float* c
   p.u_hist = h->u_hist;
   p.t0 = h->t; p.T = T; p.mode = mode;
   p.cond = cond; p.cond_bstride = cond_bstride; p.ratio = ratio;
-  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed;
+  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed; p.b_offset = h->stream_offset;
   p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
   p.prof = h->profile ? h->prof : nullptr;
   p.err = h->gen_err;
@@ -412,7 +454,7 @@ int launch_bf16(vqwn_handle* h, int mode, long long T, const float* cond, long l
   p.u_hist = h->u_hist;
   p.t0 = h->t; p.T = T; p.mode = mode;
   p.cond = cond; p.cond_bstride = cond_bstride; p.ratio = ratio;
-  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed;
+  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed; p.b_offset = h->stream_offset;
   p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
   p.prof = h->profile ? h->prof : nullptr;
   p.err = h->gen_err;
@@ -440,10 +482,87 @@ int launch_bf16(vqwn_handle* h, int mode, long long T, const float* cond, long l
   return VQWN_OK;
 }
 
+// streams per cluster / clusters of a batch for the split-bf16 kernel: spread the streams over the co-resident
+// clusters (fewer streams per cluster = less hand-off traffic), at most 16 per cluster
+int tc_spc(const vqwn_handle* h, int B) {
+  int spc = (B + h->tc_max_clusters - 1) / h->tc_max_clusters;
+  if (spc > TC_NS) spc = TC_NS;
+  if (spc < 1) spc = 1;
+  return spc;
+}
+size_t tc_ring_bytes(const vqwn_handle* h, int B) {
+  const int spc = tc_spc(h, B);
+  const size_t ncl = (size_t)(B + spc - 1) / spc;
+  size_t dsum = 0;
+  for (int l = 0; l < h->L; ++l) dsum += (size_t)h->cfg.dilations[l];
+  return 2 * dsum * ncl * TC_XB;
+}
+
+int launch_tc(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
+              const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
+              float* logits_out, float* probs_out) {
+  const int spc = tc_spc(h, h->B);
+  const int nclusters = (h->B + spc - 1) / spc;
+  TcParams p;
+  memset(&p, 0, sizeof p);
+  p.L = h->L; p.B = h->B; p.nclusters = nclusters; p.spc = spc;
+  p.pre_k = TP(h, "decoder/preprocess/kernel"); p.pre_b = TP(h, "decoder/preprocess/bias");
+  p.skf_k = h->tc_skf_k; p.skf_b = h->tc_skf_b;
+  uint8_t* base = reinterpret_cast<uint8_t*>(h->wtc);
+  p.post1 = reinterpret_cast<const __nv_bfloat16*>(base + (size_t)h->L * TC_CS * TC_LAYER_BYTES);
+  p.post2 = reinterpret_cast<const __nv_bfloat16*>(base + (size_t)h->L * TC_CS * TC_LAYER_BYTES + (size_t)TC_CS * TC_WP1);
+  p.post1_lc = h->post1_w + (size_t)h->S * h->S;
+  p.post1_b = TP(h, "decoder/postprocess1/bias"); p.post2_b = TP(h, "decoder/postprocess2/bias");
+  size_t off = 0;
+  uint8_t* rb = reinterpret_cast<uint8_t*>(h->ring_base);
+  for (int l = 0; l < h->L; ++l) {
+    h->tc_layers_host[l].ring = reinterpret_cast<__nv_bfloat16*>(rb + off);
+    off += (size_t)2 * h->cfg.dilations[l] * nclusters * TC_XB;
+  }
+  if (off > h->ring_floats * sizeof(float)) return fail(h, VQWN_ERR_INVALID, "tensor-core kernel: ring storage too small");
+  CK(h, cudaMemcpyAsync(h->tc_layers_dev, h->tc_layers_host.data(), sizeof(TcLayerDev) * h->L, cudaMemcpyHostToDevice, h->stream));
+  p.layers = h->tc_layers_dev;
+  p.ctab = h->tc_ctab;
+  p.enc_lut = h->enc_lut; p.dec_lut = h->dec_lut;
+  p.u_hist = h->u_hist;
+  p.t0 = h->t; p.T = T; p.mode = mode;
+  p.cond = cond; p.cond_bstride = cond_bstride; p.ratio = ratio;
+  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed; p.b_offset = h->stream_offset;
+  p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
+  p.prof = h->profile ? h->prof : nullptr;
+  p.err = h->gen_err;
+  if (const char* fl = getenv("VQWN_TC_FLAGS")) p.flags = atoi(fl);
+  CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  for (int c0 = 0; c0 < nclusters; c0 += h->tc_max_clusters) {      // disjoint stream groups, one launch per co-resident set
+    const int nc = (nclusters - c0 < h->tc_max_clusters) ? (nclusters - c0) : h->tc_max_clusters;
+    p.cluster0 = c0;
+    cfg.gridDim = dim3(nc * TC_CS);
+    CK(h, cudaLaunchKernelEx(&cfg, wavenet_tc_cluster, p));
+    h->launches += 1;
+  }
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->last_kernel = "wavenet_tc_cluster";
+  h->t += T;
+  return VQWN_OK;
+}
+
 // ring layout depends on the padded batch of the run; rebuilt at every launch
 int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
                 const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
                 float* logits_out, float* probs_out) {
+  if (h->precision == VQWN_PREC_TC)
+    return launch_tc(h, mode, T, cond, cond_bstride, ratio, ext_audio, uniforms, seed, audio_out, idx_out, logits_out,
+                     probs_out);
   if (h->precision == VQWN_PREC_BF16)
     return launch_bf16(h, mode, T, cond, cond_bstride, ratio, ext_audio, uniforms, seed, audio_out, idx_out, logits_out,
                        probs_out);
@@ -476,41 +595,14 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
   p.u_hist = h->u_hist; p.cur = h->cur; p.g = h->g; p.skip = h->skip; p.n1 = h->n1; p.logits = h->logits;
   p.t0 = h->t; p.T = T; p.mode = mode;
   p.cond = cond; p.cond_bstride = cond_bstride; p.ratio = ratio;
-  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed;
+  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed; p.b_offset = h->stream_offset;
   p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
   p.barrier = h->barrier;
   p.prof = h->profile ? h->prof : nullptr;
   p.err = h->gen_err;
   CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
   CK(h, cudaMemsetAsync(h->barrier, 0, 32 * sizeof(unsigned long long), h->stream));
-  // dataflow kernel: every stage's tiles must fit the grid (tile index == blockIdx in every stage)
-  const int nsb = p.Bp / FP32_TB;
-  int max_tiles = (h->S / 16) * nsb;
-  if ((h->G / 8) * nsb > max_tiles) max_tiles = (h->G / 8) * nsb;
-  if (((h->R + h->S) / 32) * nsb > max_tiles) max_tiles = ((h->R + h->S) / 32) * nsb;
-  const bool df_ok = max_tiles <= h->num_sms;
-  // measured slower than the barrier kernel (404 vs 338 us per time step at B = 64): opt-in only
-  const bool use_df = df_ok && h->gen_kernel == 2;
   CK(h, cudaEventRecord(h->ev0, h->stream));
-  if (use_df) {
-    DfParams dp;
-    dp.g = p;
-    const size_t Bp_max = h->Bp_max;
-    dp.cur_l = h->df_base;
-    dp.g_l = h->df_base + (size_t)h->L * Bp_max * h->R;
-    dp.skip0 = dp.g_l + (size_t)h->L * Bp_max * h->G;
-    dp.cnt = h->df_cnt;
-    dp.cnt_res = h->df_cnt + (size_t)(2 * h->L + 4) * (Bp_max / FP32_TB);
-    CK(h, cudaMemsetAsync(h->df_cnt, 0, h->df_ncnt * sizeof(unsigned), h->stream));
-    void* dargs[] = {&dp};
-    CK(h, cudaLaunchCooperativeKernel((const void*)wavenet_fp32_dataflow, dim3(h->num_sms), dim3(FP32_THREADS), dargs,
-                                      h->smem_fp32, h->stream));
-    CK(h, cudaEventRecord(h->ev1, h->stream));
-    h->launches += 1;
-    h->last_kernel = "wavenet_fp32_dataflow";
-    h->t += T;
-    return VQWN_OK;
-  }
   void* args[] = {&p};
   CK(h, cudaLaunchCooperativeKernel((const void*)wavenet_fp32_persistent, dim3(h->num_sms), dim3(FP32_THREADS),
                                     args, h->smem_fp32, h->stream));
@@ -537,12 +629,6 @@ int finish_timing(vqwn_handle* h) {
       fprintf(stderr, "[vqwn profile] vq_tc CTA0 epilogue-warp0 cycles: setup=%lld wait_z=%lld wait_acc=%lld pass1=%lld pass2=%lld decide=%lld output=%lld (kernel %.3f ms)\n",
               pf[16], pf[17], pf[18], pf[19], pf[20], pf[21], pf[22], ms);
   }
-  if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_dataflow") == 0) {
-    long long pf[32];
-    if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
-      fprintf(stderr, "[vqwn profile] dataflow CTA0 cycles: dep_wait=%lld operand_wait=%lld compute=%lld epilogue+signal=%lld prefetch=%lld other=%lld (kernel %.3f ms)\n",
-              pf[8], pf[9], pf[10], pf[11], pf[12], pf[13], ms);
-  }
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_cluster") == 0) {
     long long pf[24];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess) {
@@ -559,6 +645,46 @@ int finish_timing(vqwn_handle* h) {
       for (int c = 0; c < 3; ++c)
         fprintf(stderr, "[vqwn profile] bf16 CTA0 %s cycles: fir=%lld recv_wait=%lld operand_wait=%lld mma_chain=%lld tmem_ld=%lld ep_math=%lld ep_sync+queue=%lld push=%lld (kernel %.3f ms)\n",
                 cls[c], pf[8 * c + 0], pf[8 * c + 4], pf[8 * c + 1], pf[8 * c + 2], pf[8 * c + 7], pf[8 * c + 6], pf[8 * c + 3], pf[8 * c + 5], ms);
+    }
+  }
+  if (h->profile && strcmp(h->last_kernel, "wavenet_tc_cluster") == 0) {
+    long long pf[256];
+    if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (getenv("VQWN_TC_TIMELINE")) {
+        // one (step, layer 7 | layer 8) of cluster 0: clock64 relative to "S1 accumulator ready" of layer 7, per CTA
+        for (int c = 0; c < 2; ++c) {
+          const long long* tl = pf + 64 + 32 * c;
+          const long long z = tl[0];
+          fprintf(stderr, "[vqwn timeline] CTA %d:", c ? 5 : 0);
+          for (int l = 0; l < 2; ++l) {
+            const long long* q = tl + 16 * l;
+            fprintf(stderr, " | L%d epi: acc1=%lld epi1=%lld push1=%lld acc2=%lld epi2=%lld push2=%lld  mma: S1enter=%lld S1slices=%lld S1commit=%lld tap1done=%lld S2enter=%lld S2slices=%lld S2commit=%lld tap2done=%lld",
+                    7 + l, q[0] - z, q[1] - z, q[2] - z, q[3] - z, q[4] - z, q[5] - z, q[8] - z, q[14] - z, q[9] - z, q[10] - z,
+                    q[11] - z, q[15] - z, q[12] - z, q[13] - z);
+          }
+          fprintf(stderr, "\n");
+        }
+        const char* nm[5] = {"slice_wait", "fence", "mma_issue", "tap_wait", "tap_issue"};
+        for (int i = 0; i < 5; ++i) {
+          fprintf(stderr, "[vqwn timeline] MMA thread %s per CTA (Mcycles):", nm[i]);
+          for (int r = 0; r < 16; ++r) fprintf(stderr, " %.1f", pf[160 + r * 5 + i] * 1e-6);
+          fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "[vqwn timeline] layer 7 gate slices seen complete at CTA 0 (clock64 relative to S1 acc ready; waited in order rank+c):");
+        for (int r = 0; r < 16; ++r) fprintf(stderr, " %lld", pf[240 + r] - pf[64]);
+        fprintf(stderr, "\n");
+        fprintf(stderr, "[vqwn timeline] W_A bulk copy (32 KB from L2), CTA 0 layer 7: issue took %lld cycles, landed %lld cycles after issue\n",
+                pf[151] - pf[150], pf[152] - pf[150]);
+        fprintf(stderr, "[vqwn timeline] globaltimer (ns) at S1 acc ready of layer 7, CTAs 0..15 relative to CTA 0:");
+        for (int r = 0; r < 16; ++r) fprintf(stderr, " %lld", pf[128 + r] - pf[128]);
+        fprintf(stderr, "\n");
+      }
+      const char* who[2] = {"epilogue thread 0", "MMA thread"};
+      for (int c = 0; c < 2; ++c)
+        fprintf(stderr, "[vqwn profile] tc CTA0 %s cycles: fir+cond=%lld S1_wait=%lld S1_epi=%lld S1_push=%lld S2_wait=%lld S2_epi=%lld S2_queue+push=%lld post1=%lld post2=%lld draw=%lld sample_wait=%lld | chain: slice_wait=%lld fence=%lld mma_issue=%lld tap_wait=%lld tap_issue=%lld (kernel %.3f ms)\n",
+                who[c], pf[16 * c + 0], pf[16 * c + 1], pf[16 * c + 2], pf[16 * c + 3], pf[16 * c + 4], pf[16 * c + 5],
+                pf[16 * c + 6], pf[16 * c + 7], pf[16 * c + 8], pf[16 * c + 9], pf[16 * c + 10], pf[16 * c + 11],
+                pf[16 * c + 12], pf[16 * c + 13], pf[16 * c + 14], pf[16 * c + 15], ms);
     }
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
@@ -595,7 +721,10 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
                                                            h->emax_dev, h->vq_err, h->profile ? h->prof : nullptr);
     h->last_kernel = "vq_tc_kernel";
   } else {
+    // at least 128 threads: the kernel stages 4 vectors with VB*D/4 <= 64 threads and reduces with one warp per vector
+    // (VB = 4 warps); threads beyond k hold no code (has_code guards)
     int threads = (K + 31) / 32 * 32;
+    if (threads < 128) threads = 128;
     const long long nblocks = (n + 3) / 4;
     int grid = (int)((nblocks < (long long)h->num_sms * 1) ? nblocks : (long long)h->num_sms);
     if (grid < 1) grid = 1;
@@ -798,6 +927,40 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   size_t dsum = 0;
   for (int l = 0; l < h->L; ++l) dsum += (size_t)c.dilations[l];
   h->ring_floats = 2 * dsum * Bp * R;
+  // the split-bf16 kernel spreads a batch over up to 7 clusters of 16 ring rows each
+  h->tc_ok = R == TC_R && G == TC_G && S == TC_S && Q == TC_Q && C == TC_C && h->PK == TC_PK && c.kernel_size == 3 &&
+             h->L >= 2 && h->L <= TC_MAXL;
+  if (h->tc_ok) {
+    CKC(cudaFuncSetAttribute((const void*)wavenet_tc_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    CKC(cudaFuncSetAttribute((const void*)wavenet_tc_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(TC_CS); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = TC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, (const void*)wavenet_tc_cluster, &cfg) != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
+    h->tc_max_clusters = nc;
+    if (nc < 1) h->tc_ok = false;
+  }
+  if (h->tc_ok) {
+    size_t worst = 0;
+    for (int b = 1; b <= max_batch; ++b) { const size_t x = tc_ring_bytes(h, b); if (x > worst) worst = x; }
+    if (worst > h->ring_floats * sizeof(float)) h->ring_floats = (worst + 3) / 4;
+    h->wtc_bytes = (size_t)h->L * TC_CS * TC_LAYER_BYTES + (size_t)TC_CS * (TC_WP1 + TC_WP2);
+    CKC(cudaMalloc(&h->wtc, h->wtc_bytes));
+    CKC(cudaMalloc(&h->tc_skf_k, (size_t)TC_PK * TC_S * sizeof(float)));
+    CKC(cudaMalloc(&h->tc_skf_b, (size_t)TC_S * sizeof(float)));
+    CKC(cudaMalloc(&h->tc_ctab, (size_t)h->tc_max_clusters * TC_CS * (h->L + 1) * 512 * sizeof(float)));
+    CKC(cudaMalloc(&h->tc_b2_ptrs, sizeof(const float*) * h->L));
+    CKC(cudaMalloc(&h->tc_layers_dev, sizeof(TcLayerDev) * h->L));
+    h->tc_layers_host.resize(h->L);
+    for (int l = 0; l < h->L; ++l)
+      h->tc_layers_host[l] = TcLayerDev{reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<uint8_t*>(h->wtc) + (size_t)l * TC_CS * TC_LAYER_BYTES),
+                                        h->w1[l] + (size_t)3 * R * 2 * G, h->b1[l], h->b2[l], nullptr, c.dilations[l], 0};
+  }
   CKC(cudaMalloc(&h->ring_base, h->ring_floats * sizeof(float)));
   CKC(cudaMalloc(&h->u_hist, Bp * h->PK * sizeof(float)));
   CKC(cudaMalloc(&h->cur, Bp * R * sizeof(float)));
@@ -806,8 +969,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   CKC(cudaMalloc(&h->n1, Bp * S * sizeof(float)));
   CKC(cudaMalloc(&h->logits, Bp * Q * sizeof(float)));
   CKC(cudaMalloc(&h->barrier, 32 * sizeof(unsigned long long)));
-  CKC(cudaMalloc(&h->prof, 32 * sizeof(long long)));
-  CKC(cudaMemset(h->prof, 0, 32 * sizeof(long long)));
+  CKC(cudaMalloc(&h->prof, 256 * sizeof(long long)));
+  CKC(cudaMemset(h->prof, 0, 256 * sizeof(long long)));
   h->profile = getenv("VQWN_PROFILE") != nullptr;
 
   // tile-major weight block
@@ -897,11 +1060,7 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     if (nc < 1) h->bc_ok = false;
   }
   CKC(cudaMalloc(&h->gen_err, sizeof(int)));
-  h->df_floats = (size_t)h->L * h->Bp_max * (R + G) + (size_t)h->Bp_max * S;
-  CKC(cudaMalloc(&h->df_base, h->df_floats * sizeof(float)));
-  h->df_ncnt = (size_t)(3 * h->L + 4) * (h->Bp_max / FP32_TB);
-  CKC(cudaMalloc(&h->df_cnt, h->df_ncnt * sizeof(unsigned)));
-  if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "dataflow") == 0 ? 2 : (strcmp(gk, "cluster") == 0 ? 3 : 0));
+  if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "cluster") == 0 ? 3 : 0);
   h->actA_floats = FP32_TB * 3 * R;                       // gated conv: current | t-d | t-2d segments
   if (FP32_TB * S > h->actA_floats) h->actA_floats = FP32_TB * S;   // post1: relu(skip)
   h->actB_floats = FP32_TB * S;                           // post2: relu(n1)
@@ -919,7 +1078,6 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     return fail(nullptr, VQWN_ERR_INVALID, "configuration needs more shared memory than the device offers");
   }
   CKC(cudaFuncSetAttribute((const void*)wavenet_fp32_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fp32));
-  CKC(cudaFuncSetAttribute((const void*)wavenet_fp32_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fp32));
   int occ = 0;
   CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)wavenet_fp32_persistent, FP32_THREADS, h->smem_fp32));
   if (occ < 1) {
@@ -941,7 +1099,8 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->w2) if (p) cudaFree(p);
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
-                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->df_base, h->df_cnt, h->wcl, h->cl_layers_dev, h->wbc, h->bc_layers_dev};
+                     h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->wcl, h->cl_layers_dev, h->wbc, h->bc_layers_dev,
+                     h->wtc, h->tc_skf_k, h->tc_skf_b, h->tc_ctab, (void*)h->tc_b2_ptrs, h->tc_layers_dev};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,
@@ -977,7 +1136,21 @@ int vqwn_set_precision(vqwn_handle* h, int precision) {
     h->precision = precision;
     return VQWN_OK;
   }
+  if (precision == VQWN_PREC_TC) {
+    if (!h->tc_ok)
+      return fail(h, VQWN_ERR_NOTIMPL, "split-bf16 tensor-core path is built for the reference's default WaveNet geometry only");
+    if (h->precision != precision) h->B = 0;
+    h->precision = precision;
+    return VQWN_OK;
+  }
   return fail(h, VQWN_ERR_INVALID, "unknown precision id");
+}
+
+int vqwn_set_stream_offset(vqwn_handle* h, int64_t offset) {
+  ENTER(h);
+  if (offset < 0 || offset > 0x7fffffff) return fail(h, VQWN_ERR_INVALID, "stream offset out of range");
+  h->stream_offset = (int)offset;
+  return VQWN_OK;
 }
 
 int vqwn_set_vq_kernel(vqwn_handle* h, int kernel) {

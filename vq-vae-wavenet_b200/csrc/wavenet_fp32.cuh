@@ -75,6 +75,7 @@ struct GenParams {
   const float* ext_audio;   // GEN_STEP: [B]; GEN_TEACHER: x [B,T]
   const double* uniforms;   // [T,B] or null
   unsigned long long seed;
+  int b_offset;             // global index of stream 0 (vqwn_set_stream_offset): keys the seeded generator
   float* audio_out;         // [B,T]
   int* idx_out;             // [B,T] or null
   float* logits_out;        // GEN_STEP: [B,Q]; GEN_TEACHER: [B,T,Q]; else null
@@ -145,7 +146,7 @@ __device__ __forceinline__ int warp_softmax_draw(const P& p, int Q, const float 
     int cnt = 0;
     if (lane == 0) {
       const double u = p.uniforms ? p.uniforms[(t - p.t0) * p.B + b]
-                                  : counter_uniform(p.seed, (unsigned long long)t, (unsigned long long)b);
+                                  : counter_uniform(p.seed, (unsigned long long)t, (unsigned long long)(b + p.b_offset));
       float c = 0.f;
       for (int i = 0; i < Q; ++i) {
         c = __fadd_rn(c, scratch[i]);
@@ -176,6 +177,7 @@ __device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned by
 }
 __device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsigned parity, int* err) {
   const unsigned addr = f32_smem_u32(bar);
+#pragma unroll 1
   for (int spin = 0; spin < (1 << 26); ++spin) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"

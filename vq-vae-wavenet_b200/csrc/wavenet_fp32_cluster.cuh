@@ -65,6 +65,7 @@ struct ClParams {
   const float* ext_audio;
   const double* uniforms;
   unsigned long long seed;
+  int b_offset;
   float* audio_out;
   int* idx_out;
   float* logits_out;

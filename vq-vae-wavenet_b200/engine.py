@@ -98,6 +98,7 @@ class Engine:
             self._h = None
             self._raise(rc, msg)
         self.device, self.max_batch = device, max_batch
+        self._B = None          # batch the library's queues are sized for (vqwn_reset); None: no run in progress
         self.q = self.config.wavenet["quantization_channels"]
         self.C = self.config.cond_channels
         self.D = self.config.model["latent_dim"]
@@ -141,7 +142,14 @@ class Engine:
         self._ck(self.lib.vqwn_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
 
     def set_precision(self, name):
-        self._ck(self.lib.vqwn_set_precision(self._h, {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[name]))
+        """"fp32": CUDA-core float32; "tc": split-bf16 tensor cores, float32-grade; "bf16": plain bf16 tensor cores.
+        The dilation-queue layout differs between them: the step API needs reset() afterwards."""
+        self._ck(self.lib.vqwn_set_precision(self._h, {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "tc": _lib.PREC_TC}[name]))
+        self._B = None
+
+    def set_stream_offset(self, offset):
+        """global index of this engine's stream 0 in a sharded run (keys the seeded sample-mode generator)"""
+        self._ck(self.lib.vqwn_set_stream_offset(self._h, int(offset)))
 
     def set_vq_kernel(self, name):
         self._ck(self.lib.vqwn_set_vq_kernel(self._h, {"auto": _lib.VQ_AUTO, "direct": _lib.VQ_DIRECT, "tensor": _lib.VQ_TENSOR}[name]))
@@ -196,7 +204,9 @@ class Engine:
     def build_condition(self, z_q, speaker_idx):
         z = _f32(z_q)
         B, F, _ = z.shape
-        s = np.ascontiguousarray(speaker_idx, dtype=np.int32)
+        s = np.ascontiguousarray(speaker_idx, dtype=np.int32).reshape(-1)
+        if s.shape[0] != B:
+            raise ValueError("speaker_idx must hold one index per stream (%d), got %d" % (B, s.shape[0]))
         cond = np.empty((B, F, self.C), dtype=np.float32)
         self._ck(self.lib.vqwn_build_condition(self._h, _ptr(z, C.c_float), _ptr(s, C.c_int32), B, F, _ptr(cond, C.c_float)))
         return cond
@@ -204,7 +214,9 @@ class Engine:
     def encode_condition(self, z_e, speaker_idx, want_indices=True):
         z = _f32(z_e)
         B, F, _ = z.shape
-        s = np.ascontiguousarray(speaker_idx, dtype=np.int32)
+        s = np.ascontiguousarray(speaker_idx, dtype=np.int32).reshape(-1)
+        if s.shape[0] != B:
+            raise ValueError("speaker_idx must hold one index per stream (%d), got %d" % (B, s.shape[0]))
         cond = np.empty((B, F, self.C), dtype=np.float32)
         idx = np.empty((B, F), dtype=np.int64) if (want_indices and self.config.model["use_vq"]) else None
         self._ck(self.lib.vqwn_encode_condition(self._h, _ptr(z, C.c_float), _ptr(s, C.c_int32), B, F,
@@ -221,7 +233,12 @@ class Engine:
         a = _f32(audio_t).reshape(-1)
         c = _f32(cond_t)
         B = a.shape[0]
-        assert c.shape == (B, self.C)
+        # the library reads and writes the batch of the last reset(), not the batch of these arrays
+        if self._B is None:
+            raise VqwnError(_lib.ERR_STATE, "step() needs reset(batch) first (no run in progress)")
+        if B != self._B or c.shape != (B, self.C):
+            raise ValueError("step(): audio_t must be [%d] and cond_t [%d,%d] (the batch given to reset), got %s and %s"
+                             % (self._B, self._B, self.C, a.shape, c.shape))
         logits = np.empty((B, self.q), dtype=np.float32)
         probs = np.empty((B, self.q), dtype=np.float32)
         self._ck(self.lib.vqwn_step(self._h, _ptr(a, C.c_float), _ptr(c, C.c_float), _ptr(logits, C.c_float), _ptr(probs, C.c_float)))
@@ -252,6 +269,13 @@ class Engine:
             assert u.shape == (length, B), "uniforms must be [T,B]"
         audio = out_audio if out_audio is not None else np.empty((B, length), dtype=np.float32)
         idx = out_idx if out_idx is not None else np.empty((B, length), dtype=np.int32)
+        for name, arr, dt in (("out_audio", audio, np.float32), ("out_idx", idx, np.int32)):
+            if not (isinstance(arr, np.ndarray) and arr.dtype == dt and arr.shape == (B, length) and arr.flags.c_contiguous
+                    and arr.flags.writeable):
+                raise ValueError("%s must be a writeable C-contiguous %s array of shape (%d, %d)" % (name, np.dtype(dt).name, B, length))
+        if c.shape[2] != self.C:
+            raise ValueError("cond must be [B,F,%d]" % self.C)
+        self._B = B             # vqwn_generate resets the queues to this batch
         self._ck(self.lib.vqwn_generate(self._h, _ptr(c, C.c_float), B, F, int(length), _MODES[mode],
                                         _ptr(u, C.c_double) if u is not None else None, C.c_uint64(seed),
                                         _ptr(audio, C.c_float), _ptr(idx, C.c_int32)))
@@ -262,6 +286,9 @@ class Engine:
         c = _f32(cond)
         B, T = xx.shape
         F = c.shape[1]
+        if c.shape[0] != B or c.shape[2] != self.C:
+            raise ValueError("cond must be [%d,F,%d], got %s" % (B, self.C, c.shape))
+        self._B = B
         logits = np.empty((B, T, self.q), dtype=np.float32)
         self._ck(self.lib.vqwn_teacher_forced(self._h, _ptr(xx, C.c_float), _ptr(c, C.c_float), B, F, T, _ptr(logits, C.c_float)))
         return logits
@@ -276,6 +303,7 @@ class Engine:
         self._ck(self.lib.vqwn_upload_uniforms(self._h, _ptr(u, C.c_double), u.shape[0], u.shape[1]))
 
     def generate_resident(self, B, F, T, mode="greedy", seed=0):
+        self._B = int(B)
         self._ck(self.lib.vqwn_generate_resident(self._h, B, F, int(T), _MODES[mode], C.c_uint64(seed)))
 
     def download_output(self, B, T):

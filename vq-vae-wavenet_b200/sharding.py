@@ -29,7 +29,9 @@ def generate_sharded(engine, cond, length, mode="greedy", uniforms=None, seed=0,
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     c, u, (lo, hi) = shard_inputs(cond, uniforms, rank, world)
     if hi > lo:
+        engine.set_stream_offset(lo)      # seeded draws (uniforms=None) are keyed on the global stream index
         audio, idx = engine.generate(c, length, mode=mode, uniforms=u, seed=seed)
+        engine.set_stream_offset(0)
     else:
         audio = np.zeros((0, length), np.float32)
         idx = np.zeros((0, length), np.int32)
