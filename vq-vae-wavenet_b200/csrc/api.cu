@@ -86,6 +86,7 @@ struct vqwn_handle {
   int tc_max_clusters = 0;
   __nv_bfloat16* wtc = nullptr;            // [L][16][144 KB] hi/lo tiles, then postprocess1 [16][64 KB], postprocess2 [16][32 KB]
   size_t wtc_bytes = 0;
+  size_t tc_persist_bytes = 0;             // persisting L2 set aside for the weight tiles (0: not available)
   float *tc_skf_k = nullptr, *tc_skf_b = nullptr, *tc_ctab = nullptr;
   const float** tc_b2_ptrs = nullptr;
   TcLayerDev* tc_layers_dev = nullptr;
@@ -531,17 +532,26 @@ int launch_tc(vqwn_handle* h, int mode, long long T, const float* cond, long lon
   p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
   p.prof = h->profile ? h->prof : nullptr;
   p.err = h->gen_err;
-  if (const char* fl = getenv("VQWN_TC_FLAGS")) p.flags = atoi(fl);
   CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TC_SMEM;
   cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = TC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (h->tc_persist_bytes > 0 && !getenv("VQWN_TC_NO_PERSIST")) {
+    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[1].val.accessPolicyWindow.base_ptr = h->wtc;
+    attr[1].val.accessPolicyWindow.num_bytes = h->wtc_bytes;
+    attr[1].val.accessPolicyWindow.hitRatio = (float)((double)h->tc_persist_bytes >= (double)h->wtc_bytes
+                                                          ? 1.0 : (double)h->tc_persist_bytes / (double)h->wtc_bytes);
+    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 2;
+  }
   CK(h, cudaEventRecord(h->ev0, h->stream));
   for (int c0 = 0; c0 < nclusters; c0 += h->tc_max_clusters) {      // disjoint stream groups, one launch per co-resident set
     const int nc = (nclusters - c0 < h->tc_max_clusters) ? (nclusters - c0) : h->tc_max_clusters;
@@ -648,43 +658,12 @@ int finish_timing(vqwn_handle* h) {
     }
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_tc_cluster") == 0) {
-    long long pf[256];
+    long long pf[32];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess) {
-      if (getenv("VQWN_TC_TIMELINE")) {
-        // one (step, layer 7 | layer 8) of cluster 0: clock64 relative to "S1 accumulator ready" of layer 7, per CTA
-        for (int c = 0; c < 2; ++c) {
-          const long long* tl = pf + 64 + 32 * c;
-          const long long z = tl[0];
-          fprintf(stderr, "[vqwn timeline] CTA %d:", c ? 5 : 0);
-          for (int l = 0; l < 2; ++l) {
-            const long long* q = tl + 16 * l;
-            fprintf(stderr, " | L%d epi: acc1=%lld epi1=%lld push1=%lld acc2=%lld epi2=%lld push2=%lld  mma: S1enter=%lld S1slices=%lld S1commit=%lld tap1done=%lld S2enter=%lld S2slices=%lld S2commit=%lld tap2done=%lld",
-                    7 + l, q[0] - z, q[1] - z, q[2] - z, q[3] - z, q[4] - z, q[5] - z, q[8] - z, q[14] - z, q[9] - z, q[10] - z,
-                    q[11] - z, q[15] - z, q[12] - z, q[13] - z);
-          }
-          fprintf(stderr, "\n");
-        }
-        const char* nm[5] = {"slice_wait", "fence", "mma_issue", "tap_wait", "tap_issue"};
-        for (int i = 0; i < 5; ++i) {
-          fprintf(stderr, "[vqwn timeline] MMA thread %s per CTA (Mcycles):", nm[i]);
-          for (int r = 0; r < 16; ++r) fprintf(stderr, " %.1f", pf[160 + r * 5 + i] * 1e-6);
-          fprintf(stderr, "\n");
-        }
-        fprintf(stderr, "[vqwn timeline] layer 7 gate slices seen complete at CTA 0 (clock64 relative to S1 acc ready; waited in order rank+c):");
-        for (int r = 0; r < 16; ++r) fprintf(stderr, " %lld", pf[240 + r] - pf[64]);
-        fprintf(stderr, "\n");
-        fprintf(stderr, "[vqwn timeline] W_A bulk copy (32 KB from L2), CTA 0 layer 7: issue took %lld cycles, landed %lld cycles after issue\n",
-                pf[151] - pf[150], pf[152] - pf[150]);
-        fprintf(stderr, "[vqwn timeline] globaltimer (ns) at S1 acc ready of layer 7, CTAs 0..15 relative to CTA 0:");
-        for (int r = 0; r < 16; ++r) fprintf(stderr, " %lld", pf[128 + r] - pf[128]);
-        fprintf(stderr, "\n");
-      }
-      const char* who[2] = {"epilogue thread 0", "MMA thread"};
-      for (int c = 0; c < 2; ++c)
-        fprintf(stderr, "[vqwn profile] tc CTA0 %s cycles: fir+cond=%lld S1_wait=%lld S1_epi=%lld S1_push=%lld S2_wait=%lld S2_epi=%lld S2_queue+push=%lld post1=%lld post2=%lld draw=%lld sample_wait=%lld | chain: slice_wait=%lld fence=%lld mma_issue=%lld tap_wait=%lld tap_issue=%lld (kernel %.3f ms)\n",
-                who[c], pf[16 * c + 0], pf[16 * c + 1], pf[16 * c + 2], pf[16 * c + 3], pf[16 * c + 4], pf[16 * c + 5],
-                pf[16 * c + 6], pf[16 * c + 7], pf[16 * c + 8], pf[16 * c + 9], pf[16 * c + 10], pf[16 * c + 11],
-                pf[16 * c + 12], pf[16 * c + 13], pf[16 * c + 14], pf[16 * c + 15], ms);
+      fprintf(stderr, "[vqwn profile] tc CTA0 epilogue thread 0 cycles: step_start=%lld S1_acc_wait=%lld S1_epilogue=%lld S1_push=%lld S2_acc_wait=%lld S2_epilogue=%lld S2_queue+push=%lld post1=%lld post2=%lld draw=%lld sample_wait=%lld (kernel %.3f ms)\n",
+              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7], pf[8], pf[9], pf[10], ms);
+      fprintf(stderr, "[vqwn profile] tc CTA0 MMA thread cycles: step_start=%lld S1_weight_wait=%lld S1_slices+chain=%lld tap1=%lld S2_sync+weight_wait=%lld S2_slices+chain=%lld tap2=%lld post=%lld tail_taps=%lld sample_wait=%lld\n",
+              pf[16], pf[17], pf[18], pf[19], pf[20], pf[21], pf[22], pf[23], pf[24], pf[26]);
     }
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_fp32_persistent") == 0) {
@@ -951,6 +930,18 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     if (worst > h->ring_floats * sizeof(float)) h->ring_floats = (worst + 3) / 4;
     h->wtc_bytes = (size_t)h->L * TC_CS * TC_LAYER_BYTES + (size_t)TC_CS * (TC_WP1 + TC_WP2);
     CKC(cudaMalloc(&h->wtc, h->wtc_bytes));
+    // every cluster streams all weight tiles once per time step (cyclic reuse, 72 MB): without help they fall out of the
+    // L2 between two steps and every tile pays DRAM latency (measured 83 MB of DRAM reads per step).  Reserve the
+    // persisting part of the L2 for them; launch_tc attaches the access-policy window.
+    {
+      int max_persist = 0;
+      if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess && max_persist > 0) {
+        size_t want = h->wtc_bytes + (4u << 20);
+        if (want > (size_t)max_persist) want = (size_t)max_persist;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->tc_persist_bytes = want;
+        else (void)cudaGetLastError();
+      } else (void)cudaGetLastError();
+    }
     CKC(cudaMalloc(&h->tc_skf_k, (size_t)TC_PK * TC_S * sizeof(float)));
     CKC(cudaMalloc(&h->tc_skf_b, (size_t)TC_S * sizeof(float)));
     CKC(cudaMalloc(&h->tc_ctab, (size_t)h->tc_max_clusters * TC_CS * (h->L + 1) * 512 * sizeof(float)));

@@ -106,7 +106,7 @@ struct TcParams {
   const double* uniforms;
   unsigned long long seed;
   int b_offset;                            // global index of stream 0 (sharded runs): keys the seeded generator
-  int flags;                               // development switches (VQWN_TC_FLAGS): bit 0 = wait for all slices before the chain
+  int flags;                               // reserved
   float* audio_out;
   int* idx_out;
   float* logits_out;
@@ -157,22 +157,6 @@ __device__ __forceinline__ void tc_st_async_f32(unsigned addr, float v, unsigned
                ::"r"(addr), "r"(__float_as_uint(v)), "r"(mbar) : "memory");
 }
 
-// non-suspending wait: mbarrier.test_wait in a spin loop.  mbarrier.try_wait parks the thread until a local arrival or a
-// time limit; transaction bytes completed by REMOTE st.async do not end the nap early (measured: ~3k cycles lost per
-// hand-off), so every wait whose barrier is completed from another CTA spins instead.
-__device__ __forceinline__ bool mbar_spin_bounded(unsigned long long* bar, unsigned parity, int* err) {
-  const unsigned addr = f32_smem_u32(bar);
-#pragma unroll 1
-  for (long long spin = 0; spin < (1LL << 31); ++spin) {
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (ok) return true;
-  }
-  atomicExch(err, 2);
-  return false;
-}
-
 __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcParams p_in) {
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -191,7 +175,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
   const int L = p.L;
 
   uint8_t* const xc = sm + TC_OFF_XC;
-  uint8_t* const xg = sm + TC_OFF_XG;
   uint8_t* const stg = sm + TC_OFF_STG;
   uint8_t* const stq = sm + TC_OFF_STQ;
   float* const hist = reinterpret_cast<float*>(sm + TC_OFF_HIST);
@@ -250,21 +233,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
   const float mu = (float)(TC_Q - 1);
   unsigned phA = 0u, phB = 0u, phC = 0u, phD = 0u, pht1 = 0u, pht2 = 0u, phacc = 0u, phlg = 0u, phsmp = 0u;
   unsigned phxc = 0u, phxg = 0u, phxs = 0u, phxn = 0u, phaux = 0u;
-  unsigned phA_probe = 0u, nA_probe = 0u;      // development: parity of the wbarA phase the last issued load completes
-  bool alive = true;
-  const bool prof = (p.prof != nullptr) && lcluster == 0 && p.cluster0 == 0;
-  long long pf[16];
+  // in-kernel cycle counters (VQWN_PROFILE=1): CTA 0 of the first cluster, thread 0 (epilogue view) and thread 128 (MMA view)
+  const bool prof = (p.prof != nullptr) && blockIdx.x == 0 && p.cluster0 == 0 && (tid == 0 || tid == 128);
+  long long pf[12];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) pf[i] = 0;
+  for (int i = 0; i < 12; ++i) pf[i] = 0;
   long long pf_t = 0;
-  // development timeline: clock64 stamps of one (step, layer) of cluster 0, CTAs 0 and 5; globaltimer of all 16 CTAs
-  const bool tl_cta = (p.prof != nullptr) && p.cluster0 == 0 && lcluster == 0;
-  bool tl_on = false;
-  int tl_layer = -1;
-  long long* const tl = p.prof + 64 + (rank == 5 ? 32 : 0);
-#define TC_TL(i) do { if (tl_on && (rank == 0 || rank == 5)) tl[(i)] = clock64(); } while (0)
 #define TC_PF_START() do { if (prof) pf_t = clock64(); } while (0)
-#define TC_PF_ADD(i) do { if (prof) { long long n_ = clock64(); pf[(i)] += n_ - pf_t; pf_t = n_; } } while (0)
+#define TC_PF_ADD(i) do { if (prof) { const long long n_ = clock64(); pf[(i)] += n_ - pf_t; pf_t = n_; } } while (0)
   uint32_t elected = 0;
   if (warp == 4) asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NN >> 3) << 17) | ((128u >> 4) << 24);
@@ -272,67 +248,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
   const uint32_t sm_u32 = f32_smem_u32(sm);
 
   // ------------------------------------------------------------------ helpers
-  // warp-uniform wait: ONE lane polls the mbarrier, the warp re-converges behind it (32 lanes polling the same barrier
-  // are served one after the other: ~300 cycles per wait instead of ~90)
   auto wait_bar = [&](unsigned long long* bar, unsigned& ph) {
-    if (p.flags & 16) alive = alive && mbar_wait_bounded(bar, ph, p.err);
-    else {
-      if (lane == 0) alive = alive && mbar_wait_bounded(bar, ph, p.err);
-      __syncwarp();
-    }
+    (void)mbar_wait_bounded(bar, ph, p.err);
     ph ^= 1u;
-  };
-  auto wait_bar1 = [&](unsigned long long* bar, unsigned& ph) {     // called by a single thread
-    alive = alive && mbar_wait_bounded(bar, ph, p.err);
-    ph ^= 1u;
-  };
-  auto spin_bar = [&](unsigned long long* bar, unsigned& ph) {      // barriers completed by remote st.async
-    if (p.flags & 2) {
-      if (lane == 0) alive = alive && mbar_spin_bounded(bar, ph, p.err);
-      __syncwarp();
-      ph ^= 1u;
-    } else wait_bar(bar, ph);
   };
   auto acc_wait = [&]() {
     wait_bar(accbar, phacc);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
-  auto issue_w = [&](int dst_off, const __nv_bfloat16* src, unsigned bytes, unsigned long long* bar, int who = 160) {
-    if (tid == who) {
-      if (bar == wbarA) { phA_probe = nA_probe & 1u; nA_probe += 1u; }
-      if (p.flags & 4) bytes >>= 3;      // development: timing with an eighth of the weight traffic (results are garbage)
-      mbar_expect(bar, bytes);
-      cl_bulk_g2s_keep(reinterpret_cast<float*>(sm + dst_off), reinterpret_cast<const float*>(src), bytes, bar);
-    }
+  // weight tile copies: one elected thread per loader warp
+  auto issue_w = [&](int dst_off, const __nv_bfloat16* src, unsigned bytes, unsigned long long* bar) {
+    mbar_expect(bar, bytes);
+    cl_bulk_g2s_keep(reinterpret_cast<float*>(sm + dst_off), reinterpret_cast<const float*>(src), bytes, bar);
   };
   const long long ring_slot_elems = (long long)p.nclusters * (TC_XB / 2);
   // which: 1 = tap t-d (slot (t+d) mod 2d), 2 = tap t-2d (slot t mod 2d)
   auto issue_tap = [&](int l, long long t, int which) {
-    if (tid == 192) {
-      const TcLayerDev& ly = p.layers[l];
-      const int d2 = 2 * ly.d;
-      const long long slot = (which == 1) ? ((t + ly.d) % d2) : (t % d2);
-      unsigned long long* bar = (which == 1) ? tapbar1 : tapbar2;
-      const unsigned tb = (p.flags & 8) ? TC_XB / 8 : TC_XB;
-      mbar_expect(bar, tb);
-      bulk_g2s(reinterpret_cast<float*>(sm + (which == 1 ? TC_OFF_XT1 : TC_OFF_XT2)),
-               reinterpret_cast<const float*>(ly.ring + slot * ring_slot_elems + (long long)cluster * (TC_XB / 2)), tb, bar);
-    }
+    const TcLayerDev& ly = p.layers[l];
+    const unsigned d2 = 2u * (unsigned)ly.d;
+    const unsigned tt = (unsigned)(t & 0x3fffffff);                 // 2d is a power of two <= 2^30 for every supported dilation? no:
+    const long long slot = (which == 1) ? ((t + ly.d) % (long long)d2) : (t % (long long)d2);
+    (void)tt;
+    unsigned long long* bar = (which == 1) ? tapbar1 : tapbar2;
+    mbar_expect(bar, TC_XB);
+    bulk_g2s(reinterpret_cast<float*>(sm + (which == 1 ? TC_OFF_XT1 : TC_OFF_XT2)),
+             reinterpret_cast<const float*>(ly.ring + slot * ring_slot_elems + (long long)cluster * (TC_XB / 2)), TC_XB, bar);
   };
   auto layer_w = [&](int l, int off_bytes) {
     return reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const uint8_t*>(p.layers[l].w) +
                                                   (size_t)rank * TC_LAYER_BYTES + off_bytes);
   };
   // epilogue warps (0-3) + MMA warp (4): TMEM reads of the finished epilogues are ordered before the MMAs that overwrite
-  // those accumulators
+  // those accumulators, and the staging buffers are free again
   auto stage_sync5 = [&]() {
-    if (warp < 5) {
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("bar.sync 3, 160;" ::: "memory");
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 3, 160;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
-  auto ep_sync = [&]() { if (warp < 4) asm volatile("bar.sync 2, 128;" ::: "memory"); };
+  auto ep_sync = [&]() { asm volatile("bar.sync 2, 128;" ::: "memory"); };
   // one MMA: D[128 x 32] (TMEM column d_col) (+)= A[128 x 16] . B[32 x 16]^T, K chunk `ks` of both tiles
   auto mma1 = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, int ks, bool fresh) {
     const uint32_t a_lbo = a_rows * 16u;
@@ -348,110 +301,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
                  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
                  ::"r"(f32_smem_u32(bar)), "r"(elected) : "memory");
   };
-  auto mma_commit = [&]() { mma_commit_to(accbar); };
   auto operand_fence = [&]() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
-  // warp 4: 16 K chunks of a K = 256 stage whose B operand arrives slice by slice (sender s = chunk s)
-  auto w4_chain16 = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, unsigned long long* sbar, unsigned& sph,
-                        bool remote, bool fresh, unsigned rearm_bytes) {
-    long long c0 = prof ? clock64() : 0;
-    if (remote) spin_bar(sbar, sph);
-    if (prof) { const long long c1 = clock64(); pf[11] += c1 - c0; c0 = c1; }
+  // warp 4: nks K chunks of a stage whose B operand is pushed by the 16 CTAs of the cluster (remote) or written locally
+  auto w4_chain = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, int nks, unsigned long long* sbar, unsigned& sph,
+                      bool remote, bool fresh, unsigned rearm_bytes) {
+    if (remote) wait_bar(sbar, sph);
     operand_fence();
-    if (prof) { const long long c1 = clock64(); pf[12] += c1 - c0; c0 = c1; }
-    for (int c = 0; c < TC_CS; ++c) mma1(d_col, a_off, a_rows, b_off, c, fresh && c == 0);
-    if (prof) { const long long c1 = clock64(); pf[13] += c1 - c0; }
+#pragma unroll 1
+    for (int c = 0; c < nks; ++c) mma1(d_col, a_off, a_rows, b_off, c, fresh && c == 0);
     if (remote && lane == 0) mbar_expect(sbar, rearm_bytes);
-  };
-  // warp 4: 32 K chunks of a K = 512 stage
-  auto w4_chain32 = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, unsigned long long* sbar, unsigned& sph,
-                        unsigned rearm_bytes) {
-    spin_bar(sbar, sph);
-    operand_fence();
-    for (int c = 0; c < 2 * TC_CS; ++c) mma1(d_col, a_off, a_rows, b_off, c, c == 0);
-    if (lane == 0) mbar_expect(sbar, rearm_bytes);
   };
   // warp 4: the chain-independent part of layer l's gated conv (one older tap), into that layer's accumulator
   auto w4_tap = [&](int l, int which) {
     const uint32_t dcol = (l & 1) ? D1B : D1A;
-    long long c0 = prof ? clock64() : 0;
     if (which == 1) { wait_bar(wbarB, phB); wait_bar(tapbar1, pht1); }
     else { wait_bar(wbarC, phC); wait_bar(tapbar2, pht2); }
-    if (prof) { const long long c1 = clock64(); pf[14] += c1 - c0; c0 = c1; }
     operand_fence();
-    for (int ks = 0; ks < 16; ++ks)
-      mma1(dcol, which == 1 ? TC_OFF_WB : TC_OFF_WC, TC_ROWS1, which == 1 ? TC_OFF_XT1 : TC_OFF_XT2, ks, which == 1 && ks == 0);
-    if (prof) { const long long c1 = clock64(); pf[15] += c1 - c0; }
+    const int a_off = which == 1 ? TC_OFF_WB : TC_OFF_WC, b_off = which == 1 ? TC_OFF_XT1 : TC_OFF_XT2;
+#pragma unroll 1
+    for (int ks = 0; ks < 16; ++ks) mma1(dcol, a_off, TC_ROWS1, b_off, ks, which == 1 && ks == 0);
   };
   // push the staged slice (nplanes planes, chunk c of 16 bytes at stg + 16 c) to `dst_off + 16 c` of every CTA of the
   // cluster; only the rows of valid streams travel.  Threads 0-127.
-  auto push_slice = [&](int nplanes, int dst_off, unsigned long long* sbars) {
-    if (tid < 128) {
-      const int nch = nplanes * 32;
-      const unsigned mb = f32_smem_u32(sbars);
-      if (nplanes == 2) {
-        const int c = tid & 63, grp = tid >> 6;
-        if ((c & 15) < nvalid) {
-          const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
-          const unsigned dst = sm_u32 + (unsigned)dst_off + (unsigned)c * 16u;
+  auto push_slice = [&](int nplanes, int dst_off, unsigned long long* sbar) {
+    const unsigned mb = f32_smem_u32(sbar);
+    if (nplanes == 2) {
+      const int c = tid & 63, grp = tid >> 6;
+      if ((c & 15) < nvalid) {
+        const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
+        const unsigned dst = sm_u32 + (unsigned)dst_off + (unsigned)c * 16u;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const unsigned pr = (unsigned)(rank + 1 + grp + 2 * k) & (TC_CS - 1);
-            cl_st_async_v4(cl_mapa(dst, pr), x, cl_mapa(mb, pr));
-          }
+        for (int k = 0; k < 8; ++k) {
+          const unsigned pr = (unsigned)(rank + 1 + grp + 2 * k) & (TC_CS - 1);
+          cl_st_async_v4(cl_mapa(dst, pr), x, cl_mapa(mb, pr));
         }
-      } else {
-        const int c = tid;
-        if (c < nch && (c & 15) < nvalid) {
-          const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
-          const unsigned dst = sm_u32 + (unsigned)dst_off + (unsigned)c * 16u;
+      }
+    } else {
+      const int c = tid;
+      if ((c & 15) < nvalid) {
+        const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
+        const unsigned dst = sm_u32 + (unsigned)dst_off + (unsigned)c * 16u;
 #pragma unroll
-          for (int k = 0; k < TC_CS; ++k) {
-            const unsigned pr = (unsigned)(rank + 1 + k) & (TC_CS - 1);
-            cl_st_async_v4(cl_mapa(dst, pr), x, cl_mapa(mb, pr));
-          }
+        for (int k = 0; k < TC_CS; ++k) {
+          const unsigned pr = (unsigned)(rank + 1 + k) & (TC_CS - 1);
+          cl_st_async_v4(cl_mapa(dst, pr), x, cl_mapa(mb, pr));
         }
       }
     }
   };
 
   const uint32_t my_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  // preprocess FIR taps of channel `tid` (wavenet_ops.py:178,193: kernel[k-1] is the current sample)
-  float fir_k[TC_PK];
-#pragma unroll
-  for (int j = 0; j < TC_PK; ++j) fir_k[j] = __ldg(p.pre_k + (TC_PK - 1 - j) * TC_R + tid);
-  const float fir_b = __ldg(p.pre_b + tid);
   float* const ctab = p.ctab + ((size_t)lcluster * TC_CS + rank) * (size_t)(L + 1) * 512;
 
   // ------------------------------------------------------------------ prologue: first weights and taps of the run
-  issue_w(TC_OFF_WA, layer_w(0, 0), TC_W1, wbarA);
-  issue_w(TC_OFF_WB, layer_w(0, TC_W1), TC_W1, wbarB);
-  issue_w(TC_OFF_WC, layer_w(0, 2 * TC_W1), TC_W1, wbarC);
-  issue_w(TC_OFF_WD, layer_w(0, 3 * TC_W1), TC_W2, wbarD);
-  issue_tap(0, p.t0, 1);
-  issue_tap(0, p.t0, 2);
+  if (tid == 160) {
+    issue_w(TC_OFF_WA, layer_w(0, 0), TC_W1, wbarA);
+    issue_w(TC_OFF_WD, layer_w(0, 3 * TC_W1), TC_W2, wbarD);
+  }
+  if (tid == 224) {
+    issue_w(TC_OFF_WB, layer_w(0, TC_W1), TC_W1, wbarB);
+    issue_w(TC_OFF_WC, layer_w(0, 2 * TC_W1), TC_W1, wbarC);
+  }
+  if (tid == 192) {
+    issue_tap(0, p.t0, 1);
+    issue_tap(0, p.t0, 2);
+  }
   if (warp == 4) {
     w4_tap(0, 1);
     w4_tap(0, 2);
     mma_commit_to(auxbar);
   }
   long long cond_frame = -1;
-  float v[32];
-  float cur[8];       // warp 0: float32 residual chain, channel 16 rank + (lane & 15), streams 8 (lane >> 4) .. +8
-  float sk[16];       // warp 1 / 2: skip sums (hi / lo rows) of channel 32 rank + lane, 16 streams
   float cnd[8];       // warps 0-1: condition (+ bias) terms of the next gated conv / postprocess1 epilogue
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { cur[j] = 0.f; cnd[j] = 0.f; }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) sk[j] = 0.f;
+  for (int j = 0; j < 8; ++j) cnd[j] = 0.f;
 
   for (long long t = p.t0; t < p.t0 + p.T; ++t) {
     const long long frame_t = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
     const bool more = (t + 1 < p.t0 + p.T);
     TC_PF_START();
-    // ================================================================ frame change: condition table (float32, CUDA cores)
+    // ================================================================ all threads: frame change -> condition table
     if (frame_t != cond_frame) {
       for (int idx = tid; idx < TC_NS * (TC_C / 4); idx += TC_THREADS) {
         const int n = idx >> 5, c4 = idx & 31;
@@ -464,6 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
       const int cl_ = tid & 31, sg = tid >> 5;
       const float* r0 = ct_rows + (2 * sg) * TC_C;
       const float* r1 = r0 + TC_C;
+#pragma unroll 1
       for (int st = 0; st <= L; ++st) {
         const float* wsrc;
         int ld, col;
@@ -498,7 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
       cond_frame = frame_t;
       __syncthreads();
     }
-    // ================================================================ stage 0: history -> FIR -> layer-0 input, skip FIR part
+    // ================================================================ all threads: history -> FIR -> layer-0 input, skip FIR part
     {
       const int slot_t = (int)(t % TC_PK);
       if (ext) {
@@ -517,9 +450,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
       }
       for (int idx = tid; idx < TC_NS * TC_PK; idx += TC_THREADS) {
         const int i = idx / TC_PK, j = idx - i * TC_PK;
-        int sl = (int)((t - j) % TC_PK);
-        if (sl < 0) sl += TC_PK;
-        u_s[idx] = hist[i * TC_PK + sl];
+        u_s[idx] = hist[i * TC_PK + ((slot_t - j) & (TC_PK - 1))];
       }
       __syncthreads();
       // warps 0-1 fetch the first layer's condition terms while the FIR runs
@@ -528,19 +459,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         const float4 a = __ldcg(src), b = __ldcg(src + 1);
         cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w; cnd[4] = b.x; cnd[5] = b.y; cnd[6] = b.z; cnd[7] = b.w;
       }
-      // h0 = (u0*K[PK-1] + b) + u1*K[PK-2] + ...   thread = channel
-#pragma unroll 2
-      for (int i = 0; i < TC_NS; ++i) {
-        const float4* up = reinterpret_cast<const float4*>(u_s + i * TC_PK);
-        float a = fir_b;
+      // h0 = (u0*K[PK-1] + b) + u1*K[PK-2] + ...   thread = channel (wavenet_ops.py:178,193: kernel[k-1] is the current sample)
+      {
+        float acc[TC_NS];
+        const float fb = __ldg(p.pre_b + tid);
 #pragma unroll
-        for (int j4 = 0; j4 < TC_PK / 4; ++j4) {
-          const float4 u4 = up[j4];
-          a = fmaf(u4.x, fir_k[4 * j4 + 0], a); a = fmaf(u4.y, fir_k[4 * j4 + 1], a);
-          a = fmaf(u4.z, fir_k[4 * j4 + 2], a); a = fmaf(u4.w, fir_k[4 * j4 + 3], a);
+        for (int i = 0; i < TC_NS; ++i) acc[i] = fb;
+#pragma unroll 4
+        for (int j = 0; j < TC_PK; ++j) {
+          const float w = __ldg(p.pre_k + (TC_PK - 1 - j) * TC_R + tid);
+#pragma unroll
+          for (int i = 0; i < TC_NS; ++i) acc[i] = fmaf(u_s[i * TC_PK + j], w, acc[i]);
         }
-        tc_st_split(xc, i, tid, a);
-        if ((tid >> 4) == rank) cur0[(tid & 15) * TC_NS + i] = a;
+#pragma unroll
+        for (int i = 0; i < TC_NS; ++i) {
+          tc_st_split(xc, i, tid, acc[i]);
+          if ((tid >> 4) == rank) cur0[(tid & 15) * TC_NS + i] = acc[i];
+        }
       }
       // skip start folded into the FIR (wavenet.py:127-128): skf[ch][s], ch = 32 rank + (tid & 31), streams 2 (tid >> 5) + {0,1}
       {
@@ -561,292 +496,278 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp == 0) {
-        const int i = lane & 15, q = lane >> 4;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cur[j] = cur0[i * TC_NS + 8 * q + j];
-      } else if (warp == 1) {
-#pragma unroll
-        for (int s = 0; s < 16; ++s) sk[s] = skf[lane * TC_NS + s];
-      } else if (warp == 2) {
-#pragma unroll
-        for (int s = 0; s < 16; ++s) sk[s] = 0.f;
-      }
-      // the step-boundary tap MMAs (layer 0, issued behind the previous step's postprocess2) have released W_B / X_T1
-      if (L > 1 && (tid == 160 || tid == 192)) wait_bar1(auxbar, phaux);
-      if (L > 1) {
-        issue_w(TC_OFF_WB, layer_w(1, TC_W1), TC_W1, wbarB);
-        issue_tap(1, t, 1);
-      }
     }
     TC_PF_ADD(0);
 
-    // ================================================================ residual stacks
-    for (int l = 0; l < L; ++l) {
-      const TcLayerDev ly = p.layers[l];
-      const bool last = (l == L - 1);
-      const uint32_t d1 = (l & 1) ? D1B : D1A;
-      tl_on = tl_cta && (t == p.t0 + 50) && (l == 7 || l == 8);
-      tl_layer = l;
-      const int tlo = (l == 8) ? 16 : 0;
-      // ---------------------------------------------------------------- S1: current-tap part of the dilated conv, gate
-      const float bres = (warp == 0) ? __ldg(ly.bres + 16 * rank + (lane & 15)) : 0.f;
-      if (l > 0) stage_sync5();
-      if (warp == 4) {
+    if (warp == 4) {
+      // ============================================================== MMA warp
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        if (l > 0) stage_sync5();
         wait_bar(wbarA, phA);
-        if (tid == 128) TC_TL(tlo + 8);
-        w4_chain16(d1, TC_OFF_WA, TC_ROWS1, TC_OFF_XC, xcbar, phxc, l > 0, false, RX1);
-        mma_commit();
-        if (tid == 128) TC_TL(tlo + 9);
+        TC_PF_ADD(1);
+        w4_chain((l & 1) ? D1B : D1A, TC_OFF_WA, TC_ROWS1, TC_OFF_XC, 16, xcbar, phxc, l > 0, false, RX1);
+        mma_commit_to(accbar);
+        TC_PF_ADD(2);
         if (!last) w4_tap(l + 1, 1);
-        if (tid == 128) TC_TL(tlo + 10);
-      }
-      acc_wait();
-      if (tid == 0) TC_TL(tlo + 0);
-      if (tl_on && tid == 0 && l == 7) {
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.prof[128 + rank] = (long long)gt;
-      }
-      TC_PF_ADD(1);
-      // W_A and W_C are free (this commit covers the t-2d part issued earlier); X_T2 as well
-      if (!last) {
-        if (tl_on && rank == 0 && tid == 160 && l == 7) p.prof[150] = clock64();
-        issue_w(TC_OFF_WA, layer_w(l + 1, 0), TC_W1, wbarA);
-        if (tl_on && rank == 0 && tid == 160 && l == 7) {
-          p.prof[151] = clock64();
-          (void)mbar_spin_bounded(wbarA, phA_probe, p.err);
-          p.prof[152] = clock64();
-        }
-        issue_w(TC_OFF_WC, layer_w(l + 1, 2 * TC_W1), TC_W1, wbarC, 224);
-        issue_tap(l + 1, t, 2);
-      } else {
-        issue_w(TC_OFF_WA, p.post1 + (size_t)rank * (TC_WP1 / 2), TC_WP1, wbarA);
-        if (more) issue_w(TC_OFF_WC, layer_w(0, 2 * TC_W1), TC_W1, wbarC);
-      }
-      if (warp < 2) {
-        // lane = 8 qq + i: rows tanh-hi | sigmoid-hi | tanh-lo | sigmoid-lo of gate channel 16 rank + 8 warp + i
-        tc_ld32(my_taddr + d1, v);
-        const int qq = lane >> 3;
-        float k8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];       // streams j and 8 + j (hi + lo copies)
-          const float keep = (qq & 2) ? hi_ : lo_, send = (qq & 2) ? lo_ : hi_;
-          k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);               // hi rows + lo rows
-        }
-        float mine[4], other[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          mine[j] = (qq & 1) ? k8[4 + j] : k8[j];
-          const float send = (qq & 1) ? k8[j] : k8[4 + j];
-          other[j] = __shfl_xor_sync(0xffffffffu, send, 8);                    // tanh <-> sigmoid partner
-        }
-        const int i = lane & 7;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float at = ((qq & 1) ? other[j] : mine[j]) + cnd[j];
-          const float as = ((qq & 1) ? mine[j] : other[j]) + cnd[4 + j];
-          const float g = tc_tanh(at) * tc_sigmoid(as);                        // wavenet_ops.py:235-236
-          tc_st_split(stg + warp * TC_PLANE, 4 * qq + j, i, g);
-        }
-        // condition terms of the next epilogue of this kind (next layer, or postprocess1)
-        const float4* src = reinterpret_cast<const float4*>(ctab + (size_t)(l + 1) * 512 + (warp * 32 + lane) * 8);
-        const float4 a = __ldcg(src), b = __ldcg(src + 1);
-        cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w; cnd[4] = b.x; cnd[5] = b.y; cnd[6] = b.z; cnd[7] = b.w;
-      }
-      TC_PF_ADD(2);
-      if (tid == 0) TC_TL(tlo + 1);
-      ep_sync();
-      if (tl_on && tid == 0 && l == 7) {
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.prof[144 + rank] = (long long)gt;
-      }
-      push_slice(2, TC_OFF_XG + rank * 2 * TC_PLANE, xgbar);
-
-      if (tid == 0) TC_TL(tlo + 2);
-      TC_PF_ADD(3);
-
-      // ---------------------------------------------------------------- S2: residual + skip 1x1
-      stage_sync5();
-      if (warp == 4) {
+        TC_PF_ADD(3);
+        stage_sync5();
         wait_bar(wbarD, phD);
-        if (tid == 128) TC_TL(tlo + 11);
-        w4_chain16(D2, TC_OFF_WD, TC_ROWS2, TC_OFF_XG, xgbar, phxg, true, true, RX1);
-        mma_commit();
-        if (tid == 128) TC_TL(tlo + 12);
+        TC_PF_ADD(4);
+        w4_chain(D2, TC_OFF_WD, TC_ROWS2, TC_OFF_XG, 16, xgbar, phxg, true, true, RX1);
+        mma_commit_to(accbar);
+        TC_PF_ADD(5);
         if (!last) w4_tap(l + 1, 2);
-        if (tid == 128) TC_TL(tlo + 13);
+        TC_PF_ADD(6);
       }
-      acc_wait();
-      if (tid == 0) TC_TL(tlo + 3);
-      TC_PF_ADD(4);
-      // W_D and W_B are free (the t-d part of the next layer was issued before this chain); X_T1 as well
-      if (!last) {
-        issue_w(TC_OFF_WD, layer_w(l + 1, 3 * TC_W1), TC_W2, wbarD);
-        if (l + 2 < L) {
-          issue_w(TC_OFF_WB, layer_w(l + 2, TC_W1), TC_W1, wbarB, 224);
-          issue_tap(l + 2, t, 1);
-        }
-      } else {
-        issue_w(TC_OFF_WD, p.post2 + (size_t)rank * (TC_WP2 / 2), TC_WP2, wbarD);
-      }
-      if (warp == 0) {
-        // lane = 16 q + i: residual rows hi | lo of channel 16 rank + i
-        tc_ld32(my_taddr + D2, v);
-        const int q = lane >> 4, i = lane & 15;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];
-          const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
-          const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-          const float oldv = cur[j];
-          const float nv = oldv + (r + bres);                                  // wavenet.py:145
-          cur[j] = nv;
-          tc_st_split(stq, 8 * q + j, i, oldv);                                // push_ops: this step's layer input -> queue
-          if (!last) tc_st_split(stg, 8 * q + j, i, nv);                       // the last residual is dead (wavenet.py:145)
-        }
-      } else if (warp == 1 || warp == 2) {
-        // lanes 32-63: skip rows hi, lanes 64-95: skip rows lo of channel 32 rank + lane
-        tc_ld32(my_taddr + D2, v);
-#pragma unroll
-        for (int s = 0; s < 16; ++s) sk[s] += v[s] + v[16 + s];
-        if (last && warp == 2) {
-#pragma unroll
-          for (int s = 0; s < 16; ++s) skx[lane * TC_NS + s] = sk[s];
-        }
-      }
-      TC_PF_ADD(5);
-      if (tid == 0) TC_TL(tlo + 4);
-      ep_sync();
-      {
-        // queue push: this CTA's 2 planes of ring slot t mod 2d
-        const int slot_old = (int)(t % (2 * ly.d));
-        if (tid < 64) {
-          const float4 x = *reinterpret_cast<const float4*>(stq + tid * 16);
-          uint8_t* dst = reinterpret_cast<uint8_t*>(ly.ring + slot_old * ring_slot_elems + (long long)cluster * (TC_XB / 2)) +
-                         rank * 2 * TC_PLANE;
-          *reinterpret_cast<float4*>(dst + tid * 16) = x;
-          asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy ring stores vs later bulk-copy reads
-        }
-      }
-      if (!last) {
-        push_slice(2, TC_OFF_XC + rank * 2 * TC_PLANE, xcbar);
-      } else {
-        // relu(skip total) -> postprocess1 input slice (4 planes)
-        if (warp == 1) {
-#pragma unroll
-          for (int s = 0; s < 16; ++s) tc_st_split(stg, s, lane, fmaxf(sk[s] + skx[lane * TC_NS + s], 0.f));     // wavenet.py:153
-        }
-        ep_sync();
-        push_slice(4, TC_OFF_XT1 + rank * 4 * TC_PLANE, xsbar);
-      }
-      if (tid == 0) TC_TL(tlo + 5);
-      TC_PF_ADD(6);
-    }
-    // every ring store of this step is issued: split cluster barrier (waited for before the next step's tap loads)
-    cl_arrive();
-
-    // ================================================================ postprocess1 (+ condition), relu
-    stage_sync5();
-    if (warp == 4) {
+      cl_arrive();
+      stage_sync5();
       wait_bar(wbarA, phA);
-      w4_chain32(D2, TC_OFF_WA, TC_ROWSP1, TC_OFF_XT1, xsbar, phxs, RX2);
-      mma_commit();
-    }
-    acc_wait();
-    cl_wait();
-    if (more) {
-      issue_w(TC_OFF_WA, layer_w(0, 0), TC_W1, wbarA);
-      issue_w(TC_OFF_WB, layer_w(0, TC_W1), TC_W1, wbarB);
-      issue_tap(0, t + 1, 1);
-      issue_tap(0, t + 1, 2);
-    }
-    const float bias_p2 = (warp == 0) ? __ldg(p.post2_b + 16 * rank + (lane & 15)) : 0.f;
-    if (warp < 2) {
-      // lane = 16 q + i: rows hi | lo of postprocess1 channel 32 rank + 16 warp + i
-      tc_ld32(my_taddr + D2, v);
-      const int q = lane >> 4, i = lane & 15;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];
-        const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
-        const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16) + cnd[j];
-        tc_st_split(stg + warp * 2 * TC_PLANE, 8 * q + j, i, fmaxf(r, 0.f));     // wavenet.py:163
-      }
-    }
-    ep_sync();
-    push_slice(4, TC_OFF_XC + rank * 4 * TC_PLANE, xnbar);
-    TC_PF_ADD(7);
-
-    // ================================================================ postprocess2 -> logits, scattered to the drawing CTAs
-    stage_sync5();
-    if (warp == 4) {
+      w4_chain(D2, TC_OFF_WA, TC_ROWSP1, TC_OFF_XT1, 32, xsbar, phxs, true, true, RX2);
+      mma_commit_to(accbar);
+      cl_wait();
+      stage_sync5();
       wait_bar(wbarD, phD);
-      w4_chain32(D1B, TC_OFF_WD, TC_ROWSP2, TC_OFF_XC, xnbar, phxn, RX2);
-      mma_commit();
+      w4_chain(D1B, TC_OFF_WD, TC_ROWSP2, TC_OFF_XC, 32, xnbar, phxn, true, true, RX2);
+      mma_commit_to(accbar);
+      TC_PF_ADD(7);
       if (more) {
         // next step's layer-0 older taps run on the tensor pipe during the draw and the FIR
         w4_tap(0, 1);
         w4_tap(0, 2);
         mma_commit_to(auxbar);
       }
-    }
-    acc_wait();
-    if (more) issue_w(TC_OFF_WD, layer_w(0, 3 * TC_W1), TC_W2, wbarD);
-    if (warp == 0) {
-      // lane = 16 q + i: rows hi | lo of logit 16 rank + i
-      tc_ld32(my_taddr + D1B, v);
-      const int q = lane >> 4, i = lane & 15;
-      const unsigned dst = f32_smem_u32(logits_s + 16 * rank + i);
-      const unsigned mb = f32_smem_u32(lgbar);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];
-        const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
-        const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16) + bias_p2;
-        const unsigned s = (unsigned)(8 * q + j);
-        if ((int)s < nvalid) tc_st_async_f32(cl_mapa(dst, s), r, cl_mapa(mb, s));
-      }
       TC_PF_ADD(8);
-      // ============================================================== softmax + draw + mu-law decode: CTA s owns stream s
-      if (rank < nvalid) {
-        spin_bar(lgbar, phlg);
-        if (lane == 0) mbar_expect(lgbar, TC_Q * 4);
-        const int b = b0 + rank;
-        float lg[8];
+    } else if (warp < 4) {
+      // ============================================================== epilogue warps
+      float v[32];
+      float cur[8];       // warp 0: float32 residual chain, channel 16 rank + (lane & 15), streams 8 (lane >> 4) .. +8
+      float sk[16];       // warp 1 / 2: skip sums (hi / lo rows) of channel 32 rank + lane, 16 streams
+      if (warp == 0) {
+        const int i = lane & 15, q = lane >> 4;
 #pragma unroll
-        for (int qi = 0; qi < 8; ++qi) lg[qi] = logits_s[lane + 32 * qi];
-        const int k = warp_softmax_draw(p, TC_Q, lg, b, t, lane, prob_s);
-        if (k >= 0 && lane < TC_CS) {
-          const float un = __ldg(p.enc_lut + k);
-          const int slot_n = (int)((t + 1) % TC_PK);
-          if (lane == 0) st_cg(p.u_hist + (long long)b * TC_PK + slot_n, un);
-          tc_st_async_f32(cl_mapa(f32_smem_u32(hist + rank * TC_PK + slot_n), (unsigned)lane), un,
-                          cl_mapa(f32_smem_u32(smpbar), (unsigned)lane));
+        for (int j = 0; j < 8; ++j) cur[j] = cur0[i * TC_NS + 8 * q + j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < 16; ++s) sk[s] = (warp == 1) ? skf[lane * TC_NS + s] : 0.f;
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        const TcLayerDev& ly = p.layers[l];
+        const bool last = (l == L - 1);
+        const uint32_t d1 = (l & 1) ? D1B : D1A;
+        // ---------------------------------------------------------------- S1: gate
+        const float bres = (warp == 0) ? __ldg(ly.bres + 16 * rank + (lane & 15)) : 0.f;
+        if (l > 0) stage_sync5();
+        acc_wait();
+        TC_PF_ADD(1);
+        if (warp < 2) {
+          // lane = 8 qq + i: rows tanh-hi | sigmoid-hi | tanh-lo | sigmoid-lo of gate channel 16 rank + 8 warp + i
+          tc_ld32(my_taddr + d1, v);
+          const int qq = lane >> 3;
+          float k8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];       // streams j and 8 + j (hi + lo copies)
+            const float keep = (qq & 2) ? hi_ : lo_, send = (qq & 2) ? lo_ : hi_;
+            k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);               // hi rows + lo rows
+          }
+          float mine[4], other[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mine[j] = (qq & 1) ? k8[4 + j] : k8[j];
+            const float send = (qq & 1) ? k8[j] : k8[4 + j];
+            other[j] = __shfl_xor_sync(0xffffffffu, send, 8);                    // tanh <-> sigmoid partner
+          }
+          const int i = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float at = ((qq & 1) ? other[j] : mine[j]) + cnd[j];
+            const float as = ((qq & 1) ? mine[j] : other[j]) + cnd[4 + j];
+            const float g = tc_tanh(at) * tc_sigmoid(as);                        // wavenet_ops.py:235-236
+            tc_st_split(stg + warp * TC_PLANE, 4 * qq + j, i, g);
+          }
+          // condition terms of the next epilogue of this kind (next layer, or postprocess1)
+          const float4* src = reinterpret_cast<const float4*>(ctab + (size_t)(l + 1) * 512 + (warp * 32 + lane) * 8);
+          const float4 a = __ldcg(src), b = __ldcg(src + 1);
+          cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w; cnd[4] = b.x; cnd[5] = b.y; cnd[6] = b.z; cnd[7] = b.w;
+        }
+        TC_PF_ADD(2);
+        ep_sync();
+        push_slice(2, TC_OFF_XG + rank * 2 * TC_PLANE, xgbar);
+        TC_PF_ADD(3);
+        // ---------------------------------------------------------------- S2: residual + skip 1x1
+        stage_sync5();
+        acc_wait();
+        TC_PF_ADD(4);
+        if (warp == 0) {
+          // lane = 16 q + i: residual rows hi | lo of channel 16 rank + i
+          tc_ld32(my_taddr + D2, v);
+          const int q = lane >> 4, i = lane & 15;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];
+            const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
+            const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            const float oldv = cur[j];
+            const float nv = oldv + (r + bres);                                  // wavenet.py:145
+            cur[j] = nv;
+            tc_st_split(stq, 8 * q + j, i, oldv);                                // push_ops: this step's layer input -> queue
+            if (!last) tc_st_split(stg, 8 * q + j, i, nv);                       // the last residual is dead (wavenet.py:145)
+          }
+        } else if (warp < 3) {
+          // lanes 32-63: skip rows hi, lanes 64-95: skip rows lo of channel 32 rank + lane
+          tc_ld32(my_taddr + D2, v);
+#pragma unroll
+          for (int s = 0; s < 16; ++s) sk[s] += v[s] + v[16 + s];
+          if (last && warp == 2) {
+#pragma unroll
+            for (int s = 0; s < 16; ++s) skx[lane * TC_NS + s] = sk[s];
+          }
+        }
+        TC_PF_ADD(5);
+        ep_sync();
+        if (tid < 64) {
+          // queue push: this CTA's 2 planes of ring slot t mod 2d
+          const int slot_old = (int)(t % (2 * ly.d));
+          const float4 x = *reinterpret_cast<const float4*>(stq + tid * 16);
+          uint8_t* dst = reinterpret_cast<uint8_t*>(ly.ring + slot_old * ring_slot_elems + (long long)cluster * (TC_XB / 2)) +
+                         rank * 2 * TC_PLANE;
+          *reinterpret_cast<float4*>(dst + tid * 16) = x;
+          asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy ring stores vs later bulk-copy reads
+        }
+        if (!last) {
+          push_slice(2, TC_OFF_XC + rank * 2 * TC_PLANE, xcbar);
+        } else {
+          // relu(skip total) -> postprocess1 input slice (4 planes)
+          if (warp == 1) {
+#pragma unroll
+            for (int s = 0; s < 16; ++s) tc_st_split(stg, s, lane, fmaxf(sk[s] + skx[lane * TC_NS + s], 0.f));     // wavenet.py:153
+          }
+          ep_sync();
+          push_slice(4, TC_OFF_XT1 + rank * 4 * TC_PLANE, xsbar);
+        }
+        TC_PF_ADD(6);
+      }
+      // every ring store of this step is issued: split cluster barrier (waited for before the next step's tap loads)
+      cl_arrive();
+      // ================================================================ postprocess1 (+ condition), relu
+      stage_sync5();
+      acc_wait();
+      cl_wait();
+      const float bias_p2 = (warp == 0) ? __ldg(p.post2_b + 16 * rank + (lane & 15)) : 0.f;
+      if (warp < 2) {
+        // lane = 16 q + i: rows hi | lo of postprocess1 channel 32 rank + 16 warp + i
+        tc_ld32(my_taddr + D2, v);
+        const int q = lane >> 4, i = lane & 15;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];
+          const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
+          const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16) + cnd[j];
+          tc_st_split(stg + warp * 2 * TC_PLANE, 8 * q + j, i, fmaxf(r, 0.f));     // wavenet.py:163
         }
       }
-      TC_PF_ADD(9);
+      ep_sync();
+      push_slice(4, TC_OFF_XC + rank * 4 * TC_PLANE, xnbar);
+      TC_PF_ADD(7);
+      // ================================================================ postprocess2 -> logits, scattered to the drawing CTAs
+      stage_sync5();
+      acc_wait();
+      if (warp == 0) {
+        // lane = 16 q + i: rows hi | lo of logit 16 rank + i
+        tc_ld32(my_taddr + D1B, v);
+        const int q = lane >> 4, i = lane & 15;
+        const unsigned dst = f32_smem_u32(logits_s + 16 * rank + i);
+        const unsigned mb = f32_smem_u32(lgbar);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];
+          const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
+          const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16) + bias_p2;
+          const unsigned s = (unsigned)(8 * q + j);
+          if ((int)s < nvalid) tc_st_async_f32(cl_mapa(dst, s), r, cl_mapa(mb, s));
+        }
+        TC_PF_ADD(8);
+        // ============================================================== softmax + draw + mu-law decode: CTA s owns stream s
+        if (rank < nvalid) {
+          wait_bar(lgbar, phlg);
+          if (lane == 0) mbar_expect(lgbar, TC_Q * 4);
+          const int b = b0 + rank;
+          float lg[8];
+#pragma unroll
+          for (int qi = 0; qi < 8; ++qi) lg[qi] = logits_s[lane + 32 * qi];
+          const int k = warp_softmax_draw(p, TC_Q, lg, b, t, lane, prob_s);
+          if (k >= 0 && lane < TC_CS) {
+            const float un = __ldg(p.enc_lut + k);
+            const int slot_n = (int)((t + 1) % TC_PK);
+            if (lane == 0) st_cg(p.u_hist + (long long)b * TC_PK + slot_n, un);
+            tc_st_async_f32(cl_mapa(f32_smem_u32(hist + rank * TC_PK + slot_n), (unsigned)lane), un,
+                            cl_mapa(f32_smem_u32(smpbar), (unsigned)lane));
+          }
+        }
+        TC_PF_ADD(9);
+      }
+    } else {
+      // ============================================================== loader warps: 5 (W_A, W_D), 6 (taps), 7 (W_B, W_C)
+      // the step-boundary tap MMAs (layer 0, issued behind the previous step's postprocess2) have released W_B / X_T1
+      if (lane == 0 && L > 1) {
+        if (warp == 7) { wait_bar(auxbar, phaux); issue_w(TC_OFF_WB, layer_w(1, TC_W1), TC_W1, wbarB); }
+        if (warp == 6) { wait_bar(auxbar, phaux); issue_tap(1, t, 1); }
+      }
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        acc_wait();      // S1 of layer l complete: W_A, W_C (its t-2d part was issued earlier) and X_T2 are free
+        if (lane == 0) {
+          if (warp == 5) {
+            if (!last) issue_w(TC_OFF_WA, layer_w(l + 1, 0), TC_W1, wbarA);
+            else issue_w(TC_OFF_WA, p.post1 + (size_t)rank * (TC_WP1 / 2), TC_WP1, wbarA);
+          } else if (warp == 7) {
+            if (!last) issue_w(TC_OFF_WC, layer_w(l + 1, 2 * TC_W1), TC_W1, wbarC);
+            else if (more) issue_w(TC_OFF_WC, layer_w(0, 2 * TC_W1), TC_W1, wbarC);
+          } else if (!last) issue_tap(l + 1, t, 2);
+        }
+        acc_wait();      // S2 of layer l complete: W_D, W_B (the next layer's t-d part was issued before it) and X_T1 are free
+        if (lane == 0) {
+          if (warp == 5) {
+            if (!last) issue_w(TC_OFF_WD, layer_w(l + 1, 3 * TC_W1), TC_W2, wbarD);
+            else issue_w(TC_OFF_WD, p.post2 + (size_t)rank * (TC_WP2 / 2), TC_WP2, wbarD);
+          } else if (l + 2 < L) {
+            if (warp == 7) issue_w(TC_OFF_WB, layer_w(l + 2, TC_W1), TC_W1, wbarB);
+            else issue_tap(l + 2, t, 1);
+          }
+        }
+      }
+      cl_arrive();
+      acc_wait();        // postprocess1 complete
+      cl_wait();         // ... and every CTA's ring stores of this step are visible
+      if (lane == 0 && more) {
+        if (warp == 5) issue_w(TC_OFF_WA, layer_w(0, 0), TC_W1, wbarA);
+        else if (warp == 7) issue_w(TC_OFF_WB, layer_w(0, TC_W1), TC_W1, wbarB);
+        else { issue_tap(0, t + 1, 1); issue_tap(0, t + 1, 2); }
+      }
+      acc_wait();        // postprocess2 complete
+      if (lane == 0 && more && warp == 5) issue_w(TC_OFF_WD, layer_w(0, 3 * TC_W1), TC_W2, wbarD);
     }
+    // ================================================================ all threads: the new samples of all streams are in hist
     if (!ext) {
-      spin_bar(smpbar, phsmp);
+      wait_bar(smpbar, phsmp);
       __syncthreads();
       if (tid == 0) mbar_expect(smpbar, 4u * (unsigned)nvalid);
     }
     TC_PF_ADD(10);
   }
   cl_barrier();
-  if (prof && rank == 0 && tid == 0) for (int i = 0; i < 16; ++i) p.prof[i] = pf[i];
-  if (prof && rank == 0 && tid == 128) for (int i = 0; i < 16; ++i) p.prof[16 + i] = pf[i];
-  if (prof && tid == 128) for (int i = 0; i < 5; ++i) p.prof[160 + rank * 5 + i] = pf[11 + i];
-#undef TC_TL
+  if (prof) for (int i = 0; i < 12; ++i) p.prof[(tid == 0 ? 0 : 16) + i] = pf[i];
 #undef TC_PF_START
 #undef TC_PF_ADD
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
-  (void)alive;
 }
 
 // float32 [K rows][ldw] row-major weights -> hi/lo bf16 K-major plane tiles per cluster CTA.
