@@ -658,8 +658,10 @@ int finish_timing(vqwn_handle* h) {
     }
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_tc_cluster") == 0) {
-    long long pf[32];
+    long long pf[48];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "[vqwn profile] tc bulk copies, cycles (issue / issue->landed): weight tile 32 KB layer 8: %lld / %lld, layer 20: %lld / %lld; tap 16 KB layer 8 (d=256): %lld / %lld, layer 20 (d=1): %lld / %lld\n",
+              pf[40], pf[41], pf[44], pf[45], pf[42], pf[43], pf[46], pf[47]);
       fprintf(stderr, "[vqwn profile] tc CTA0 epilogue thread 0 cycles: step_start=%lld S1_acc_wait=%lld S1_epilogue=%lld S1_push=%lld S2_acc_wait=%lld S2_epilogue=%lld S2_queue+push=%lld post1=%lld post2=%lld draw=%lld sample_wait=%lld (kernel %.3f ms)\n",
               pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7], pf[8], pf[9], pf[10], ms);
       fprintf(stderr, "[vqwn profile] tc CTA0 MMA thread cycles: step_start=%lld S1_weight_wait=%lld S1_slices+chain=%lld tap1=%lld S2_sync+weight_wait=%lld S2_slices+chain=%lld tap2=%lld post=%lld tail_taps=%lld sample_wait=%lld\n",

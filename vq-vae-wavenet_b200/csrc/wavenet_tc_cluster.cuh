@@ -157,6 +157,13 @@ __device__ __forceinline__ void tc_st_async_f32(unsigned addr, float v, unsigned
                ::"r"(addr), "r"(__float_as_uint(v)), "r"(mbar) : "memory");
 }
 
+__device__ __forceinline__ bool tc_test_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(f32_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcParams p_in) {
   extern __shared__ __align__(1024) uint8_t sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,7 +250,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
 #define TC_PF_ADD(i) do { if (prof) { const long long n_ = clock64(); pf[(i)] += n_ - pf_t; pf_t = n_; } } while (0)
   uint32_t elected = 0;
   if (warp == 4) asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
+  // instruction descriptors: fp32 accumulate, bf16 x bf16, N = 32; M = 128, and M = 64 for the gated-conv tiles (64 real
+  // rows: half the A-operand traffic; its accumulator occupies lanes 0-15 of each of the four TMEM lane quarters)
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NN >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NN >> 3) << 17) | ((64u >> 4) << 24);
   constexpr uint32_t D1A = 0, D1B = 32, D2 = 64;     // TMEM columns: gated conv (double-buffered) | everything else
   const uint32_t sm_u32 = f32_smem_u32(sm);
 
@@ -266,9 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
   auto issue_tap = [&](int l, long long t, int which) {
     const TcLayerDev& ly = p.layers[l];
     const unsigned d2 = 2u * (unsigned)ly.d;
-    const unsigned tt = (unsigned)(t & 0x3fffffff);                 // 2d is a power of two <= 2^30 for every supported dilation? no:
     const long long slot = (which == 1) ? ((t + ly.d) % (long long)d2) : (t % (long long)d2);
-    (void)tt;
     unsigned long long* bar = (which == 1) ? tapbar1 : tapbar2;
     mbar_expect(bar, TC_XB);
     bulk_g2s(reinterpret_cast<float*>(sm + (which == 1 ? TC_OFF_XT1 : TC_OFF_XT2)),
@@ -287,14 +295,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
   };
   auto ep_sync = [&]() { asm volatile("bar.sync 2, 128;" ::: "memory"); };
   // one MMA: D[128 x 32] (TMEM column d_col) (+)= A[128 x 16] . B[32 x 16]^T, K chunk `ks` of both tiles
-  auto mma1 = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, int ks, bool fresh) {
+  auto mma1 = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, int ks, bool fresh, bool m64) {
     const uint32_t a_lbo = a_rows * 16u;
+    const uint32_t id = m64 ? idesc64 : idesc;
     const uint64_t da = bc_desc(sm_u32 + (uint32_t)a_off + (uint32_t)ks * 2u * a_lbo, a_lbo);
     const uint64_t db = bc_desc(sm_u32 + (uint32_t)b_off + (uint32_t)ks * 2u * TC_PLANE, TC_PLANE);
     const uint32_t accf = fresh ? 0u : 1u;
     asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
                  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 ::"r"(tmem + d_col), "l"(da), "l"(db), "r"(idesc), "r"(accf), "r"(elected) : "memory");
+                 ::"r"(tmem + d_col), "l"(da), "l"(db), "r"(id), "r"(accf), "r"(elected) : "memory");
   };
   auto mma_commit_to = [&](unsigned long long* bar) {     // bar fires when every MMA issued so far has completed
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
@@ -307,11 +316,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
   };
   // warp 4: nks K chunks of a stage whose B operand is pushed by the 16 CTAs of the cluster (remote) or written locally
   auto w4_chain = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, int nks, unsigned long long* sbar, unsigned& sph,
-                      bool remote, bool fresh, unsigned rearm_bytes) {
+                      bool remote, bool fresh, unsigned rearm_bytes, bool m64) {
     if (remote) wait_bar(sbar, sph);
     operand_fence();
 #pragma unroll 1
-    for (int c = 0; c < nks; ++c) mma1(d_col, a_off, a_rows, b_off, c, fresh && c == 0);
+    for (int c = 0; c < nks; ++c) mma1(d_col, a_off, a_rows, b_off, c, fresh && c == 0, m64);
     if (remote && lane == 0) mbar_expect(sbar, rearm_bytes);
   };
   // warp 4: the chain-independent part of layer l's gated conv (one older tap), into that layer's accumulator
@@ -322,22 +331,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
     operand_fence();
     const int a_off = which == 1 ? TC_OFF_WB : TC_OFF_WC, b_off = which == 1 ? TC_OFF_XT1 : TC_OFF_XT2;
 #pragma unroll 1
-    for (int ks = 0; ks < 16; ++ks) mma1(dcol, a_off, TC_ROWS1, b_off, ks, which == 1 && ks == 0);
+    for (int ks = 0; ks < 16; ++ks) mma1(dcol, a_off, TC_ROWS1, b_off, ks, which == 1 && ks == 0, true);
   };
   // push the staged slice (nplanes planes, chunk c of 16 bytes at stg + 16 c) to `dst_off + 16 c` of every CTA of the
   // cluster; only the rows of valid streams travel.  Threads 0-127.
+  // shared::cluster address of this kernel's dynamic shared memory in the 8 peers a thread pushes 2-plane slices to
+  unsigned peer_sm[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) peer_sm[k] = cl_mapa(sm_u32, (unsigned)(rank + 1 + ((tid >> 6) & 1) + 2 * k) & (TC_CS - 1));
   auto push_slice = [&](int nplanes, int dst_off, unsigned long long* sbar) {
     const unsigned mb = f32_smem_u32(sbar);
     if (nplanes == 2) {
-      const int c = tid & 63, grp = tid >> 6;
+      const int c = tid & 63;
       if ((c & 15) < nvalid) {
         const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
-        const unsigned dst = sm_u32 + (unsigned)dst_off + (unsigned)c * 16u;
+        const unsigned doff = (unsigned)dst_off + (unsigned)c * 16u, moff = mb - sm_u32;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const unsigned pr = (unsigned)(rank + 1 + grp + 2 * k) & (TC_CS - 1);
-          cl_st_async_v4(cl_mapa(dst, pr), x, cl_mapa(mb, pr));
-        }
+        for (int k = 0; k < 8; ++k) cl_st_async_v4(peer_sm[k] + doff, x, peer_sm[k] + moff);
       }
     } else {
       const int c = tid;
@@ -374,6 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
     w4_tap(0, 2);
     mma_commit_to(auxbar);
   }
+  unsigned nA = 1, nT2 = 1;      // copies issued so far on wbarA / tapbar2 (development probe)
   long long cond_frame = -1;
   float cnd[8];       // warps 0-1: condition (+ bias) terms of the next gated conv / postprocess1 epilogue
 #pragma unroll
@@ -422,10 +433,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         for (int h = 0; h < 2; ++h) {
           const int s = 2 * sg + h;
           const float a = h ? a1 : a0;
-          int w_, lane_e, f;
-          if (st < L) { const int ch = cl_ & 15; w_ = ch >> 3; lane_e = 8 * (s >> 2) + (ch & 7); f = (cl_ >> 4) * 4 + (s & 3); }
-          else { w_ = cl_ >> 4; lane_e = 16 * (s >> 3) + (cl_ & 15); f = s & 7; }
-          __stcg(dst + (w_ * 32 + lane_e) * 8 + f, a);
+          int pos;
+          if (st < L) { const int ch = cl_ & 15; pos = ((ch >> 2) * 16 + 4 * (s >> 2) + (ch & 3)) * 8 + (cl_ >> 4) * 4 + (s & 3); }
+          else pos = ((cl_ >> 4) * 32 + 16 * (s >> 3) + (cl_ & 15)) * 8 + (s & 7);
+          __stcg(dst + pos, a);
         }
       }
       cond_frame = frame_t;
@@ -454,8 +465,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
       }
       __syncthreads();
       // warps 0-1 fetch the first layer's condition terms while the FIR runs
-      if (warp < 2) {
-        const float4* src = reinterpret_cast<const float4*>(ctab + (warp * 32 + lane) * 8);
+      if (warp < 4 && lane < 16) {
+        const float4* src = reinterpret_cast<const float4*>(ctab + (warp * 16 + lane) * 8);
         const float4 a = __ldcg(src), b = __ldcg(src + 1);
         cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w; cnd[4] = b.x; cnd[5] = b.y; cnd[6] = b.z; cnd[7] = b.w;
       }
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         if (l > 0) stage_sync5();
         wait_bar(wbarA, phA);
         TC_PF_ADD(1);
-        w4_chain((l & 1) ? D1B : D1A, TC_OFF_WA, TC_ROWS1, TC_OFF_XC, 16, xcbar, phxc, l > 0, false, RX1);
+        w4_chain((l & 1) ? D1B : D1A, TC_OFF_WA, TC_ROWS1, TC_OFF_XC, 16, xcbar, phxc, l > 0, false, RX1, true);
         mma_commit_to(accbar);
         TC_PF_ADD(2);
         if (!last) w4_tap(l + 1, 1);
@@ -515,7 +526,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         stage_sync5();
         wait_bar(wbarD, phD);
         TC_PF_ADD(4);
-        w4_chain(D2, TC_OFF_WD, TC_ROWS2, TC_OFF_XG, 16, xgbar, phxg, true, true, RX1);
+        w4_chain(D2, TC_OFF_WD, TC_ROWS2, TC_OFF_XG, 16, xgbar, phxg, true, true, RX1, false);
         mma_commit_to(accbar);
         TC_PF_ADD(5);
         if (!last) w4_tap(l + 1, 2);
@@ -524,12 +535,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
       cl_arrive();
       stage_sync5();
       wait_bar(wbarA, phA);
-      w4_chain(D2, TC_OFF_WA, TC_ROWSP1, TC_OFF_XT1, 32, xsbar, phxs, true, true, RX2);
+      w4_chain(D2, TC_OFF_WA, TC_ROWSP1, TC_OFF_XT1, 32, xsbar, phxs, true, true, RX2, false);
       mma_commit_to(accbar);
       cl_wait();
       stage_sync5();
       wait_bar(wbarD, phD);
-      w4_chain(D1B, TC_OFF_WD, TC_ROWSP2, TC_OFF_XC, 32, xnbar, phxn, true, true, RX2);
+      w4_chain(D1B, TC_OFF_WD, TC_ROWSP2, TC_OFF_XC, 32, xnbar, phxn, true, true, RX2, false);
       mma_commit_to(accbar);
       TC_PF_ADD(7);
       if (more) {
@@ -564,36 +575,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         if (l > 0) stage_sync5();
         acc_wait();
         TC_PF_ADD(1);
-        if (warp < 2) {
-          // lane = 8 qq + i: rows tanh-hi | sigmoid-hi | tanh-lo | sigmoid-lo of gate channel 16 rank + 8 warp + i
+        {
+          // M = 64 accumulator: warp w reads rows 16 w .. 16 w + 15 in its lanes 0-15; lane = 4 qq + c: row type qq (tanh-hi |
+          // sigmoid-hi | tanh-lo | sigmoid-lo) of gate channel 16 rank + 4 w + c.  Lanes 16-31 carry nothing.
           tc_ld32(my_taddr + d1, v);
-          const int qq = lane >> 3;
+          const int qq = (lane >> 2) & 3;
           float k8[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];       // streams j and 8 + j (hi + lo copies)
             const float keep = (qq & 2) ? hi_ : lo_, send = (qq & 2) ? lo_ : hi_;
-            k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);               // hi rows + lo rows
+            k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);                // hi rows + lo rows
           }
           float mine[4], other[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             mine[j] = (qq & 1) ? k8[4 + j] : k8[j];
             const float send = (qq & 1) ? k8[j] : k8[4 + j];
-            other[j] = __shfl_xor_sync(0xffffffffu, send, 8);                    // tanh <-> sigmoid partner
+            other[j] = __shfl_xor_sync(0xffffffffu, send, 4);                    // tanh <-> sigmoid partner
           }
-          const int i = lane & 7;
+          if (lane < 16) {
+            const int ch = 4 * warp + (lane & 3);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float at = ((qq & 1) ? other[j] : mine[j]) + cnd[j];
-            const float as = ((qq & 1) ? mine[j] : other[j]) + cnd[4 + j];
-            const float g = tc_tanh(at) * tc_sigmoid(as);                        // wavenet_ops.py:235-236
-            tc_st_split(stg + warp * TC_PLANE, 4 * qq + j, i, g);
+            for (int j = 0; j < 4; ++j) {
+              const float at = ((qq & 1) ? other[j] : mine[j]) + cnd[j];
+              const float as = ((qq & 1) ? mine[j] : other[j]) + cnd[4 + j];
+              const float g = tc_tanh(at) * tc_sigmoid(as);                      // wavenet_ops.py:235-236
+              tc_st_split(stg + (ch >> 3) * TC_PLANE, 4 * qq + j, ch & 7, g);
+            }
           }
-          // condition terms of the next epilogue of this kind (next layer, or postprocess1)
-          const float4* src = reinterpret_cast<const float4*>(ctab + (size_t)(l + 1) * 512 + (warp * 32 + lane) * 8);
-          const float4 a = __ldcg(src), b = __ldcg(src + 1);
-          cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w; cnd[4] = b.x; cnd[5] = b.y; cnd[6] = b.z; cnd[7] = b.w;
+          // condition terms of the next epilogue of this kind: next layer (all four warps, lanes 0-15), or postprocess1
+          // (warps 0-1, lane = 16 q + i)
+          if (!last ? (lane < 16) : (warp < 2)) {
+            const float4* src = reinterpret_cast<const float4*>(ctab + (size_t)(l + 1) * 512 + (last ? warp * 32 + lane : warp * 16 + lane) * 8);
+            const float4 a = __ldcg(src), b = __ldcg(src + 1);
+            cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w; cnd[4] = b.x; cnd[5] = b.y; cnd[6] = b.z; cnd[7] = b.w;
+          }
         }
         TC_PF_ADD(2);
         ep_sync();
@@ -630,15 +647,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         }
         TC_PF_ADD(5);
         ep_sync();
-        if (tid < 64) {
-          // queue push: this CTA's 2 planes of ring slot t mod 2d
-          const int slot_old = (int)(t % (2 * ly.d));
-          const float4 x = *reinterpret_cast<const float4*>(stq + tid * 16);
-          uint8_t* dst = reinterpret_cast<uint8_t*>(ly.ring + slot_old * ring_slot_elems + (long long)cluster * (TC_XB / 2)) +
-                         rank * 2 * TC_PLANE;
-          *reinterpret_cast<float4*>(dst + tid * 16) = x;
-          asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy ring stores vs later bulk-copy reads
-        }
         if (!last) {
           push_slice(2, TC_OFF_XC + rank * 2 * TC_PLANE, xcbar);
         } else {
@@ -649,6 +657,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
           }
           ep_sync();
           push_slice(4, TC_OFF_XT1 + rank * 4 * TC_PLANE, xsbar);
+        }
+        if (tid < 64) {
+          // queue push (off the chain, behind the hand-off): this CTA's 2 planes of ring slot t mod 2d
+          const int slot_old = (int)(t % (2 * ly.d));
+          const float4 x = *reinterpret_cast<const float4*>(stq + tid * 16);
+          uint8_t* dst = reinterpret_cast<uint8_t*>(ly.ring + slot_old * ring_slot_elems + (long long)cluster * (TC_XB / 2)) +
+                         rank * 2 * TC_PLANE;
+          *reinterpret_cast<float4*>(dst + tid * 16) = x;
+          asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy ring stores vs later bulk-copy reads
         }
         TC_PF_ADD(6);
       }
@@ -723,13 +740,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         const bool last = (l == L - 1);
         acc_wait();      // S1 of layer l complete: W_A, W_C (its t-2d part was issued earlier) and X_T2 are free
         if (lane == 0) {
+          // development probe (VQWN_PROFILE): latency of one weight tile copy and one tap copy, issue -> landed
+          const bool probe = (p.prof != nullptr) && blockIdx.x == 0 && p.cluster0 == 0 && t == p.t0 + 50 && (l == 7 || l == 19);
+          const long long c0 = probe ? clock64() : 0;
           if (warp == 5) {
             if (!last) issue_w(TC_OFF_WA, layer_w(l + 1, 0), TC_W1, wbarA);
             else issue_w(TC_OFF_WA, p.post1 + (size_t)rank * (TC_WP1 / 2), TC_WP1, wbarA);
+            nA += 1;
+            if (probe) {
+              const long long c1 = clock64();
+              while (!tc_test_wait(wbarA, (nA - 1) & 1u)) {}
+              p.prof[40 + (l == 19 ? 4 : 0)] = c1 - c0;
+              p.prof[41 + (l == 19 ? 4 : 0)] = clock64() - c0;
+            }
           } else if (warp == 7) {
             if (!last) issue_w(TC_OFF_WC, layer_w(l + 1, 2 * TC_W1), TC_W1, wbarC);
             else if (more) issue_w(TC_OFF_WC, layer_w(0, 2 * TC_W1), TC_W1, wbarC);
-          } else if (!last) issue_tap(l + 1, t, 2);
+          } else if (!last) {
+            issue_tap(l + 1, t, 2);
+            nT2 += 1;
+            if (probe) {
+              const long long c1 = clock64();
+              while (!tc_test_wait(tapbar2, (nT2 - 1) & 1u)) {}
+              p.prof[42 + (l == 19 ? 4 : 0)] = c1 - c0;
+              p.prof[43 + (l == 19 ? 4 : 0)] = clock64() - c0;
+            }
+          }
         }
         acc_wait();      // S2 of layer l complete: W_D, W_B (the next layer's t-d part was issued before it) and X_T1 are free
         if (lane == 0) {
@@ -746,9 +782,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
       acc_wait();        // postprocess1 complete
       cl_wait();         // ... and every CTA's ring stores of this step are visible
       if (lane == 0 && more) {
-        if (warp == 5) issue_w(TC_OFF_WA, layer_w(0, 0), TC_W1, wbarA);
+        if (warp == 5) { issue_w(TC_OFF_WA, layer_w(0, 0), TC_W1, wbarA); nA += 1; }
         else if (warp == 7) issue_w(TC_OFF_WB, layer_w(0, TC_W1), TC_W1, wbarB);
-        else { issue_tap(0, t + 1, 1); issue_tap(0, t + 1, 2); }
+        else { issue_tap(0, t + 1, 1); issue_tap(0, t + 1, 2); nT2 += 1; }
       }
       acc_wait();        // postprocess2 complete
       if (lane == 0 && more && warp == 5) issue_w(TC_OFF_WD, layer_w(0, 3 * TC_W1), TC_W2, wbarD);
@@ -773,7 +809,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
 // float32 [K rows][ldw] row-major weights -> hi/lo bf16 K-major plane tiles per cluster CTA.
 //   dst[cta * cta_stride + (plane * rows + row) * 8 + e] = hi or lo part of src[(k0 + 8 plane + e) * ldw + col(cta, row)]
 // row -> (column, part) by tile kind (the epilogue lane mappings of wavenet_tc_cluster):
-//   kind 0 (gated conv tap, 64 rows): row = 32 w + 8 qq + i: column (qq & 1 ? G : 0) + 16 cta + 8 w + i, part qq >> 1
+//   kind 0 (gated conv tap, 64 rows, M = 64 accumulator): row = 16 w + 4 qq + i: column (qq & 1 ? G : 0) + 16 cta + 4 w + i, part qq >> 1
 //   kind 1 (residual | skip, 96 rows): row < 32: column 16 cta + (row & 15), part row >> 4; 32..63: column R + 32 cta + row - 32
 //                                       (hi); 64..95: column R + 32 cta + row - 64 (lo)
 //   kind 2 (postprocess1, 64 rows): row = 32 w + 16 q + i: column 32 cta + 16 w + i, part q
@@ -790,8 +826,8 @@ __global__ void pack_tc_tiles_kernel(const float* __restrict__ src, int ldw, int
     const int plane = (int)(r / rows);
     int col, part;
     if (kind == 0) {
-      const int w = row >> 5, qq = (row >> 3) & 3, ii = row & 7;
-      col = ((qq & 1) ? TC_G : 0) + 16 * cta + 8 * w + ii; part = qq >> 1;
+      const int w = row >> 4, qq = (row >> 2) & 3, ii = row & 3;
+      col = ((qq & 1) ? TC_G : 0) + 16 * cta + 4 * w + ii; part = qq >> 1;
     } else if (kind == 1) {
       if (row < 32) { col = 16 * cta + (row & 15); part = row >> 4; }
       else if (row < 64) { col = TC_R + 32 * cta + (row - 32); part = 0; }
