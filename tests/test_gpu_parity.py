@@ -22,6 +22,9 @@ SMALL_WAVENET = dict(num_cycles=2, num_cycle_layers=3, dilation_rates=[1, 2, 4, 
 LOGIT_RTOL = 1e-3
 GREEDY_TIE = 1e-4
 SAMPLE_TIE = 1e-5
+# split-bf16 tensor-core arithmetic: operands carry 2^-17 relative error, the logits of the 30-layer stack ~1e-5 of
+# max |logit| (printed by the teacher-forced tests), which moves a cdf boundary by up to a few 1e-5: its near-tie band
+SAMPLE_TIE_OF = {"fp32": SAMPLE_TIE, "tc": 1e-4}
 # the two parity-grade arithmetic paths: float32 CUDA cores, and split-bf16 (hi + lo) tcgen05 tensor cores
 PRECISIONS = ["fp32", "tc"]
 KERNEL_OF = {"fp32": "wavenet_fp32_cluster", "tc": "wavenet_tc_cluster"}
@@ -611,9 +614,10 @@ def test_full_sample_same_uniforms(full, golden_dir):
     u = _ref_uniforms(r["full_sample_seed"], T, B)
     tag = "full/%s sample" % eng.precision_name
     audio, idx = eng.generate(cond[:, :T // 64], T, mode="sample", uniforms=u)
-    _check_sequences(idx, r["full_sample_idx"], r["full_sample_margin"], SAMPLE_TIE, 128, tag)
+    tie = SAMPLE_TIE_OF[eng.precision_name]
+    _check_sequences(idx, r["full_sample_idx"], r["full_sample_margin"], tie, 128, tag)
     _check_teacher_forced_draws(eng, cond[:, :T // 64], r["full_sample_idx"].astype(np.int64), r["full_sample_margin"],
-                                "sample", SAMPLE_TIE, uniforms=u, label=tag)
+                                "sample", tie, uniforms=u, label=tag)
 
 
 def test_full_size_properties(full):
