@@ -123,23 +123,29 @@ __global__ void __launch_bounds__(128, 1) probe_mma(int M, int N, int nmma, int 
     const long long t0 = clock64();
     long long t1 = 0;
     if (tid == 0) {
+      // descriptors advance by a constant per K chunk: the issue loop is two 64-bit adds + the MMA (a dependent chain of
+      // integer instructions in ONE thread costs ~4.5 cycles each and would otherwise hide the pipe cost)
+      uint64_t da0, db0, sa, sb;
+      if (layout == 0) {
+        da0 = desc_noswz(a_base, (uint32_t)M * 16u, 128); sa = (2u * (uint32_t)M * 16u) >> 4;
+        db0 = desc_noswz(b_base, (uint32_t)N * 16u, 128); sb = (2u * (uint32_t)N * 16u) >> 4;
+      } else if (layout == 2) {
+        da0 = desc_noswz(a_base, 128, 32 * 128); sa = 256 >> 4;
+        db0 = desc_noswz(b_base, 128, 32 * 128); sb = 256 >> 4;
+      } else {
+        da0 = desc_swz128(a_base); sa = 32 >> 4;      // within one 64-element K block (timing only)
+        db0 = desc_swz128(b_base); sb = 32 >> 4;
+      }
+      uint64_t da = da0, db = db0;
+#pragma unroll 4
       for (int ks = 0; ks < nmma; ++ks) {
-        uint64_t da, db;
-        const uint32_t kc = (uint32_t)(ks & 15);      // K = 256 tile, re-read by longer chains
-        if (layout == 0) {
-          da = desc_noswz(a_base + kc * 2u * (uint32_t)M * 16u, (uint32_t)M * 16u, 128);
-          db = desc_noswz(b_base + kc * 2u * (uint32_t)N * 16u, (uint32_t)N * 16u, 128);
-        } else if (layout == 2) {
-          da = desc_noswz(a_base + kc * 256u, 128, 32 * 128);      // 8-row groups of [K/8] core matrices
-          db = desc_noswz(b_base + kc * 256u, 128, 32 * 128);
-        } else {
-          da = desc_swz128(a_base + (kc >> 2) * (uint32_t)M * 128u + (kc & 3) * 32u);
-          db = desc_swz128(b_base + (kc >> 2) * (uint32_t)N * 128u + (kc & 3) * 32u);
-        }
         const uint32_t acc = ks > 0 ? 1u : 0u;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                      ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        da += sa; db += sb;
+        if ((ks & 3) == 3 && layout == 1) { da = da0; db = db0; }
+        if ((ks & 15) == 15) { da = da0; db = db0; }
       }
       t1 = clock64();
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(128, 1) probe_mma(int M, int N, int nmma, int 
 // slices, repeats.  method 0: 128 threads, st.async v4 (thread = 16-byte chunk, loops over peers); method 1: lanes of
 // warp 0 issue one bulk shared::cta -> shared::cluster copy per peer; method 2: as 1 but the 16 copies come from 16
 // different warps' lane 0 (512 threads)
-__global__ void probe_gather(int CS, int slice, int method, int iters, long long* out) {
+__global__ void probe_gather(int CS, int slice, int method, int iters, long long* out, uint8_t* gbuf) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t bar;
   uint8_t* rx = sm;                 // CS * slice
@@ -197,6 +203,18 @@ __global__ void probe_gather(int CS, int slice, int method, int iters, long long
         asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(mapa(rx_u, pr)), "r"(tx_u), "r"(slice), "r"(mapa(bar_u, pr)) : "memory");
       }
+    } else if (method == 3) {
+      // through L2: slice -> global, then ONE multicast bulk copy global -> the same offset of every CTA of the cluster
+      uint8_t* g = gbuf + ((size_t)blockIdx.x * 2 + (it & 1)) * 4096;
+      for (int c = tid; c < slice / 16; c += blockDim.x)
+        *reinterpret_cast<float4*>(g + c * 16) = *reinterpret_cast<const float4*>(tx + c * 16);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        const uint16_t mask = (uint16_t)((1u << CS) - 1u);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                     ::"r"(rx_u), "l"(g), "r"(slice), "r"(bar_u), "h"(mask) : "memory");
+      }
     } else {
       if (lane == 0 && warp < CS) {
         const uint32_t pr = (rank + 1 + warp) % CS;
@@ -215,6 +233,81 @@ __global__ void probe_gather(int CS, int slice, int method, int iters, long long
   const long long t1 = clock64();
   cl_sync();
   if (tid == 0) out[blockIdx.x] = t1 - t0;
+}
+
+// ------------------------------------------------------------------------------------------------ 2b. who pays the ~64 cycles?
+// `nw` warps (one elected thread each) issue nmma / nw MMAs each into their own accumulator (M = 128, N = 32, planes layout)
+// style 0: descriptor advanced by 64-bit adds; style 1: the 16-bit address field patched into a constant high word
+__global__ void __launch_bounds__(128, 1) probe_mma_multi(int nw, int nmma, int style, long long* out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, (uint32_t)nw);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  const int M = 128, N = 32;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (((uint32_t)M >> 4) << 24);
+  const uint32_t a_base = smem_u32(sm), b_base = smem_u32(sm) + 128 * 1024;
+  long long best = 1ll << 60;
+  uint32_t ph = 0;
+  for (int r = 0; r < 20; ++r) {
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp < nw && lane == 0) {
+      const int per = nmma / nw;
+      uint64_t da = desc_noswz(a_base + (uint32_t)warp * 16384u, (uint32_t)M * 16u, 128);
+      uint64_t db = desc_noswz(b_base + (uint32_t)warp * 4096u, (uint32_t)N * 16u, 128);
+      const uint32_t dcol = tmem + 32u * (uint32_t)warp;
+      if (style == 0) {
+        for (int ks = 0; ks < per; ++ks) {
+          const uint32_t acc = ks > 0 ? 1u : 0u;
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                       ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+          da += (2u * M * 16u) >> 4; db += (2u * N * 16u) >> 4;
+        }
+      } else {
+        // fully unrolled, descriptors are compile-time offsets from two base registers
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+          if (ks < per) {
+            const uint64_t da_k = da + (uint64_t)(ks * ((2 * 128 * 16) >> 4));
+            const uint64_t db_k = db + (uint64_t)(ks * ((2 * 32 * 16) >> 4));
+            if (ks == 0)
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 1;\n\tsetp.ne.b32 p, 0, 0;\n\t"
+                           "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                           ::"r"(dcol), "l"(da_k), "l"(db_k), "r"(idesc) : "memory");
+            else
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 1;\n\t"
+                           "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                           ::"r"(dcol), "l"(da_k), "l"(db_k), "r"(idesc) : "memory");
+          }
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    mbar_wait(&bar, ph);
+    ph ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const long long t2 = clock64();
+    if (tid == 0 && t2 - t0 < best) best = t2 - t0;
+  }
+  if (tid == 0) out[0] = best;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
 }
 
 int main() {
@@ -254,9 +347,9 @@ int main() {
   // ---- 2
   {
     CK(cudaFuncSetAttribute(probe_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    const int Ms[] = {64, 128};
-    const int Ns[] = {32, 64, 128};
-    const int nm[] = {1, 16, 48};
+    const int Ms[] = {128};
+    const int Ns[] = {32};
+    const int nm[] = {16, 48};
     for (int layout = 0; layout < 3; ++layout) for (int M : Ms) for (int N : Ns) for (int n : nm) {
       probe_mma<<<1, 128, 200 * 1024>>>(M, N, n, layout, 20, out);
       CK(cudaDeviceSynchronize());
@@ -265,13 +358,25 @@ int main() {
              h[0], h[1], (double)h[0] / n);
     }
   }
+  // ---- 2b
+  {
+    CK(cudaFuncSetAttribute(probe_mma_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int style = 0; style < 2; ++style) for (int nw : {1, 2, 4}) for (int n : {16}) {
+      probe_mma_multi<<<1, 128, 200 * 1024>>>(nw, n, style, out);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(h.data(), out, sizeof(long long), cudaMemcpyDeviceToHost));
+      printf("mma-multi style=%d issuing warps=%d total mma=%d: %lld cycles -> %.1f cyc/mma\n", style, nw, n, h[0], (double)h[0] / n);
+    }
+  }
   // ---- 3
   {
     CK(cudaFuncSetAttribute(probe_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(probe_gather, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    const int CSs[] = {8, 16};
-    const int slices[] = {512, 1024, 2048};
-    for (int CS : CSs) for (int slice : slices) for (int method = 0; method < 3; ++method) for (int ncl : {1, 4}) {
+    uint8_t* gbuf;
+    CK(cudaMalloc(&gbuf, 1 << 20));
+    const int CSs[] = {16};
+    const int slices[] = {1024};
+    for (int CS : CSs) for (int slice : slices) for (int method = 0; method < 4; ++method) for (int ncl : {1, 4}) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(CS * ncl);
       cfg.blockDim = dim3(method == 2 ? 512 : 128);
@@ -281,13 +386,13 @@ int main() {
       attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       const int iters = 2000;
-      CK(cudaLaunchKernelEx(&cfg, probe_gather, CS, slice, method, iters, out));
+      CK(cudaLaunchKernelEx(&cfg, probe_gather, CS, slice, method, iters, out, gbuf));
       CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(h.data(), out, CS * ncl * sizeof(long long), cudaMemcpyDeviceToHost));
       long long mx = 0;
       for (int i = 0; i < CS * ncl; ++i) mx = std::max(mx, h[i]);
       printf("gather CS=%2d slice=%4d B method=%d (%s) clusters=%d: %.0f cycles per all-gather round\n", CS, slice, method,
-             method == 0 ? "st.async" : (method == 1 ? "bulk, 1 warp" : "bulk, 16 warps"), ncl, (double)mx / iters);
+             method == 0 ? "st.async" : (method == 1 ? "bulk, 1 warp" : (method == 2 ? "bulk, 16 warps" : "L2 + multicast")), ncl, (double)mx / iters);
     }
   }
   printf("probe done\n");

@@ -88,6 +88,7 @@ struct vqwn_handle {
   size_t wtc_bytes = 0;
   size_t tc_persist_bytes = 0;             // persisting L2 set aside for the weight tiles (0: not available)
   float *tc_skf_k = nullptr, *tc_skf_b = nullptr, *tc_ctab = nullptr;
+  uint8_t* tc_gstage = nullptr;            // [co-resident cluster][TC_GSTAGE] hand-off staging
   const float** tc_b2_ptrs = nullptr;
   TcLayerDev* tc_layers_dev = nullptr;
   std::vector<TcLayerDev> tc_layers_host;
@@ -496,7 +497,7 @@ size_t tc_ring_bytes(const vqwn_handle* h, int B) {
   const size_t ncl = (size_t)(B + spc - 1) / spc;
   size_t dsum = 0;
   for (int l = 0; l < h->L; ++l) dsum += (size_t)h->cfg.dilations[l];
-  return 2 * dsum * ncl * TC_XB;
+  return (2 * dsum + (size_t)h->L) * ncl * TC_XB;      // 2d + 1 slots per layer
 }
 
 int launch_tc(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
@@ -518,12 +519,13 @@ int launch_tc(vqwn_handle* h, int mode, long long T, const float* cond, long lon
   uint8_t* rb = reinterpret_cast<uint8_t*>(h->ring_base);
   for (int l = 0; l < h->L; ++l) {
     h->tc_layers_host[l].ring = reinterpret_cast<__nv_bfloat16*>(rb + off);
-    off += (size_t)2 * h->cfg.dilations[l] * nclusters * TC_XB;
+    off += ((size_t)2 * h->cfg.dilations[l] + 1) * nclusters * TC_XB;
   }
   if (off > h->ring_floats * sizeof(float)) return fail(h, VQWN_ERR_INVALID, "tensor-core kernel: ring storage too small");
   CK(h, cudaMemcpyAsync(h->tc_layers_dev, h->tc_layers_host.data(), sizeof(TcLayerDev) * h->L, cudaMemcpyHostToDevice, h->stream));
   p.layers = h->tc_layers_dev;
   p.ctab = h->tc_ctab;
+  p.gstage = h->tc_gstage;
   p.enc_lut = h->enc_lut; p.dec_lut = h->dec_lut;
   p.u_hist = h->u_hist;
   p.t0 = h->t; p.T = T; p.mode = mode;
@@ -947,6 +949,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     CKC(cudaMalloc(&h->tc_skf_k, (size_t)TC_PK * TC_S * sizeof(float)));
     CKC(cudaMalloc(&h->tc_skf_b, (size_t)TC_S * sizeof(float)));
     CKC(cudaMalloc(&h->tc_ctab, (size_t)h->tc_max_clusters * TC_CS * (h->L + 1) * 512 * sizeof(float)));
+    CKC(cudaMalloc(&h->tc_gstage, (size_t)h->tc_max_clusters * TC_GSTAGE));
+    CKC(cudaMemset(h->tc_gstage, 0, (size_t)h->tc_max_clusters * TC_GSTAGE));
     CKC(cudaMalloc(&h->tc_b2_ptrs, sizeof(const float*) * h->L));
     CKC(cudaMalloc(&h->tc_layers_dev, sizeof(TcLayerDev) * h->L));
     h->tc_layers_host.resize(h->L);
@@ -1093,7 +1097,7 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
                      h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->wcl, h->cl_layers_dev, h->wbc, h->bc_layers_dev,
-                     h->wtc, h->tc_skf_k, h->tc_skf_b, h->tc_ctab, (void*)h->tc_b2_ptrs, h->tc_layers_dev};
+                     h->wtc, h->tc_skf_k, h->tc_skf_b, h->tc_ctab, h->tc_gstage, (void*)h->tc_b2_ptrs, h->tc_layers_dev};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,

@@ -13,9 +13,12 @@
 //   * weights: bf16 hi/lo tiles, K-major no-swizzle planes (plane p = k 8p..8p+7 of every row, 16 B per row), streamed
 //     from L2 with one cp.async.bulk per tile into four single buffers (current tap | tap t-d | tap t-2d | residual+skip),
 //     each re-filled as soon as the MMAs that read it have completed (tcgen05.commit);
-//   * activations: a CTA pushes its 16-channel slice (one K chunk of 16 = 1 KB of hi/lo bf16) into the shared memory of
-//     all 16 CTAs with st.async + complete_tx on a PER-SENDER mbarrier of the receiver; the MMA warp issues the K chunk
-//     of a sender as soon as that sender's barrier completes, so the tensor pipe runs while slices are still in flight;
+//   * activations: a CTA publishes its 16-channel slice (one K chunk of 16 = 1 KB of hi/lo bf16) through L2: one warp
+//     copies the staged slice to global memory and issues ONE multicast bulk copy (cp.async.bulk ... .multicast::cluster)
+//     that delivers it to the same offset of all 16 CTAs and counts its bytes on each receiver's mbarrier - measured 920
+//     cycles per 16-CTA all-gather round against 1650 for per-thread st.async and 1410 for 16 shared::cta ->
+//     shared::cluster bulk copies (tools/r2_probe.cu).  The layer-input slices are published straight from the dilation
+//     ring slot of the step, so the queue push (push_ops) and the hand-off are the same 1 KB store;
 //   * the parts of a layer's dilated conv that do not depend on this step's chain (taps t-d, t-2d from the HBM dilation
 //     rings) are issued into a second TMEM accumulator in the two hand-off gaps of the previous layer;
 //   * the local-condition projections (wavenet_ops.py:198-209; 30 layers + postprocess1) change once per `ratio` steps:
@@ -25,9 +28,10 @@
 //     and the skip start (wavenet.py:127-128) is folded into a 32-tap FIR with host-premultiplied weights;
 //   * the draw is distributed: CTA s owns stream s (softmax, greedy / sequential-cumsum sample, mu-law LUT) and
 //     broadcasts the new network input to the cluster.
-// The dilation queues are HBM rings [2d][cluster][32 planes][32 rows = 16 hi + 16 lo][8] bf16 in operand layout, so a tap
-// is one 16 KB bulk copy straight into the B operand.  One split cluster barrier per step orders the ring stores of a
-// step before the bulk reads of the next.  Geometry fixed to the reference's default (R = G = 256, S = 512, Q = 256,
+// The dilation queues are HBM rings [2d + 1][cluster][32 planes][32 rows = 16 hi + 16 lo][8] bf16 in operand layout (slot
+// t mod (2d + 1) = layer input of step t; one slot more than the reference's two chained queues of capacity d because the
+// slot of step t is written while the tap t - 2d is still being read), so a tap is one 16 KB bulk copy straight into the B
+// operand.  One split cluster barrier per step orders the ring stores of a step before the bulk reads of the next.  Geometry fixed to the reference's default (R = G = 256, S = 512, Q = 256,
 // C = 128, 32-tap preprocess, kernel_size 3).
 #pragma once
 #include <cuda_bf16.h>
@@ -60,8 +64,7 @@ constexpr int TC_OFF_XG = TC_OFF_XC + TC_XB;            // gate output         }
 constexpr int TC_OFF_XT1 = TC_OFF_XG + TC_XB;           // tap t-d             } postprocess1 input (K = 512)
 constexpr int TC_OFF_XT2 = TC_OFF_XT1 + TC_XB;          // tap t-2d            }
 constexpr int TC_OFF_STG = TC_OFF_XT2 + TC_XB;          // push staging: 4 planes
-constexpr int TC_OFF_STQ = TC_OFF_STG + 4 * TC_PLANE;   // queue staging: 2 planes
-constexpr int TC_OFF_HIST = TC_OFF_STQ + 2 * TC_PLANE;  // [16][32] fp32 network-input history ring (remote-written)
+constexpr int TC_OFF_HIST = TC_OFF_STG + 4 * TC_PLANE;  // [16][32] fp32 network-input history ring (remote-written)
 constexpr int TC_OFF_LOG = TC_OFF_HIST + TC_NS * TC_PK * 4;   // [256] fp32 logits of this CTA's stream (remote-written)
 constexpr int TC_OFF_US = TC_OFF_LOG + TC_Q * 4;        // [16][32] history in tap order     } 8 KB of CTA-local scratch,
 constexpr int TC_OFF_CUR0 = TC_OFF_US + TC_NS * TC_PK * 4;    // [16 ch][16] fp32 FIR output  } aliased by the condition rows
@@ -75,13 +78,16 @@ constexpr int TC_OFF_MISC = TC_OFF_BARS + TC_NBARS * 8;
 constexpr int TC_SMEM = TC_OFF_MISC + 16;
 static_assert(TC_OFF_PROB + TC_Q * 4 - TC_OFF_US == TC_NS * TC_C * 4, "condition rows alias exactly the local scratch");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
+// per-cluster global staging of the hand-offs that do not live in a ring: gate output (double-buffered by layer parity),
+// postprocess1 input, postprocess2 input
+constexpr int TC_GST_XG = 0, TC_GST_XS = 2 * TC_XB, TC_GST_XN = TC_GST_XS + 2 * TC_XB, TC_GSTAGE = TC_GST_XN + 2 * TC_XB;
 
 struct TcLayerDev {
   const __nv_bfloat16* w;     // [16 CTAs][W_A | W_B | W_C | W_D] hi/lo plane tiles
   const float* wlc;           // gated/local_condition/kernel [C][2G] float32 (row stride 2G)
   const float* b1;            // gated/bias [2G]
   const float* bres;          // residual/bias [R]
-  __nv_bfloat16* ring;        // [2d][nclusters][32 planes][32][8]
+  __nv_bfloat16* ring;        // [2d + 1][nclusters][32 planes][32][8]
   int d;
   int pad_;
 };
@@ -95,6 +101,7 @@ struct TcParams {
   const float *post1_lc, *post1_b, *post2_b;   // postprocess1/local_condition/kernel [C][S], biases
   const TcLayerDev* layers;
   float* ctab;                             // [launch cluster][16][L+1][512] condition table
+  uint8_t* gstage;                         // [launch cluster][TC_GSTAGE] hand-off staging in L2
   const float *enc_lut, *dec_lut;
   float* u_hist;
   long long t0, T;
@@ -157,6 +164,13 @@ __device__ __forceinline__ void tc_st_async_f32(unsigned addr, float v, unsigned
                ::"r"(addr), "r"(__float_as_uint(v)), "r"(mbar) : "memory");
 }
 
+// one bulk copy global -> the same shared-memory offset of every CTA in `mask`; each receiver's mbarrier (same offset)
+// counts the bytes
+__device__ __forceinline__ void tc_bulk_multicast(unsigned dst_smem, const void* gsrc, unsigned bytes, unsigned mbar, unsigned short mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst_smem), "l"(gsrc), "r"(bytes), "r"(mbar), "h"(mask) : "memory");
+}
+
 __device__ __forceinline__ bool tc_test_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -183,7 +197,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
 
   uint8_t* const xc = sm + TC_OFF_XC;
   uint8_t* const stg = sm + TC_OFF_STG;
-  uint8_t* const stq = sm + TC_OFF_STQ;
   float* const hist = reinterpret_cast<float*>(sm + TC_OFF_HIST);
   float* const logits_s = reinterpret_cast<float*>(sm + TC_OFF_LOG);
   float* const u_s = reinterpret_cast<float*>(sm + TC_OFF_US);
@@ -212,8 +225,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
   for (int i = tid; i < (TC_OFF_LAYERS - TC_OFF_XC) / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(sm + TC_OFF_XC)[i] = 0u;
   __syncthreads();
   const bool ext = (p.mode == GEN_STEP || p.mode == GEN_TEACHER);
-  const unsigned RX1 = TC_CS * 64u * (unsigned)nvalid;     // 16 senders x 16-channel slice: 2 planes x (hi + lo) x nvalid x 16 bytes
-  const unsigned RX2 = TC_CS * 128u * (unsigned)nvalid;    // 16 senders x 32-channel slice
+  const unsigned RX1 = TC_CS * 2u * TC_PLANE;     // 16 senders x 16-channel slice (2 planes, all 32 rows)
+  const unsigned RX2 = TC_CS * 4u * TC_PLANE;     // 16 senders x 32-channel slice
   if (tid == 0) {
     for (int i = 0; i < TC_NBARS; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(f32_smem_u32(&bars[i])));
@@ -272,15 +285,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
     cl_bulk_g2s_keep(reinterpret_cast<float*>(sm + dst_off), reinterpret_cast<const float*>(src), bytes, bar);
   };
   const long long ring_slot_elems = (long long)p.nclusters * (TC_XB / 2);
-  // which: 1 = tap t-d (slot (t+d) mod 2d), 2 = tap t-2d (slot t mod 2d)
+  // which: 1 = tap t-d, 2 = tap t-2d; slot of step s = s mod (2d + 1)
   auto issue_tap = [&](int l, long long t, int which) {
     const TcLayerDev& ly = p.layers[l];
-    const unsigned d2 = 2u * (unsigned)ly.d;
-    const long long slot = (which == 1) ? ((t + ly.d) % (long long)d2) : (t % (long long)d2);
+    const long long nslot = 2ll * ly.d + 1;
+    const long long slot = (which == 1) ? ((t + ly.d + 1) % nslot) : ((t + 1) % nslot);
     unsigned long long* bar = (which == 1) ? tapbar1 : tapbar2;
     mbar_expect(bar, TC_XB);
     bulk_g2s(reinterpret_cast<float*>(sm + (which == 1 ? TC_OFF_XT1 : TC_OFF_XT2)),
              reinterpret_cast<const float*>(ly.ring + slot * ring_slot_elems + (long long)cluster * (TC_XB / 2)), TC_XB, bar);
+  };
+  // this CTA's 1 KB slice of the ring slot that holds layer l's input of step t
+  auto ring_slice = [&](int l, long long t) {
+    const TcLayerDev& ly = p.layers[l];
+    const long long slot = t % (2ll * ly.d + 1);
+    return reinterpret_cast<uint8_t*>(ly.ring + slot * ring_slot_elems + (long long)cluster * (TC_XB / 2)) + rank * 2 * TC_PLANE;
   };
   auto layer_w = [&](int l, int off_bytes) {
     return reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const uint8_t*>(p.layers[l].w) +
@@ -294,21 +313,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
   auto ep_sync = [&]() { asm volatile("bar.sync 2, 128;" ::: "memory"); };
-  // one MMA: D[128 x 32] (TMEM column d_col) (+)= A[128 x 16] . B[32 x 16]^T, K chunk `ks` of both tiles
-  auto mma1 = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, int ks, bool fresh, bool m64) {
-    const uint32_t a_lbo = a_rows * 16u;
-    const uint32_t id = m64 ? idesc64 : idesc;
-    const uint64_t da = bc_desc(sm_u32 + (uint32_t)a_off + (uint32_t)ks * 2u * a_lbo, a_lbo);
-    const uint64_t db = bc_desc(sm_u32 + (uint32_t)b_off + (uint32_t)ks * 2u * TC_PLANE, TC_PLANE);
-    const uint32_t accf = fresh ? 0u : 1u;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 ::"r"(tmem + d_col), "l"(da), "l"(db), "r"(id), "r"(accf), "r"(elected) : "memory");
+  // a chain of nks MMAs, one per K chunk of 16: D[M x 32] (TMEM column d_col) (+)= A[M x 16] . B[32 x 16]^T.  Only the
+  // elected thread runs the loop (a real branch: predicating the instruction for the whole warp makes the compiler wrap
+  // every MMA in a per-lane loop), the descriptors advance by a constant - an MMA of this size occupies the pipe for ~64
+  // cycles whatever M and N are (tools/r2_probe.cu), the loop must not cost more than that
+  auto mma_chain = [&](uint32_t d_col, int a_off, uint32_t a_rows, int b_off, int nks, bool fresh, bool m64) {
+    if (elected) {
+      const uint32_t a_lbo = a_rows * 16u;
+      const uint32_t id = m64 ? idesc64 : idesc;
+      uint64_t da = bc_desc(sm_u32 + (uint32_t)a_off, a_lbo);
+      uint64_t db = bc_desc(sm_u32 + (uint32_t)b_off, TC_PLANE);
+      const uint64_t sa = (uint64_t)((2u * a_lbo) >> 4), sb = (uint64_t)((2u * TC_PLANE) >> 4);
+      uint32_t accf = fresh ? 0u : 1u;
+#pragma unroll 4
+      for (int ks = 0; ks < nks; ++ks) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                     ::"r"(tmem + d_col), "l"(da), "l"(db), "r"(id), "r"(accf) : "memory");
+        da += sa; db += sb; accf = 1u;
+      }
+    }
+    __syncwarp();
   };
   auto mma_commit_to = [&](unsigned long long* bar) {     // bar fires when every MMA issued so far has completed
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
-                 ::"r"(f32_smem_u32(bar)), "r"(elected) : "memory");
+    if (elected)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(f32_smem_u32(bar)) : "memory");
+    __syncwarp();
   };
   auto operand_fence = [&]() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -319,8 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
                       bool remote, bool fresh, unsigned rearm_bytes, bool m64) {
     if (remote) wait_bar(sbar, sph);
     operand_fence();
-#pragma unroll 1
-    for (int c = 0; c < nks; ++c) mma1(d_col, a_off, a_rows, b_off, c, fresh && c == 0, m64);
+    mma_chain(d_col, a_off, a_rows, b_off, nks, fresh, m64);
     if (remote && lane == 0) mbar_expect(sbar, rearm_bytes);
   };
   // warp 4: the chain-independent part of layer l's gated conv (one older tap), into that layer's accumulator
@@ -330,38 +359,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
     else { wait_bar(wbarC, phC); wait_bar(tapbar2, pht2); }
     operand_fence();
     const int a_off = which == 1 ? TC_OFF_WB : TC_OFF_WC, b_off = which == 1 ? TC_OFF_XT1 : TC_OFF_XT2;
-#pragma unroll 1
-    for (int ks = 0; ks < 16; ++ks) mma1(dcol, a_off, TC_ROWS1, b_off, ks, which == 1 && ks == 0, true);
+    mma_chain(dcol, a_off, TC_ROWS1, b_off, 16, which == 1, true);
   };
-  // push the staged slice (nplanes planes, chunk c of 16 bytes at stg + 16 c) to `dst_off + 16 c` of every CTA of the
-  // cluster; only the rows of valid streams travel.  Threads 0-127.
-  // shared::cluster address of this kernel's dynamic shared memory in the 8 peers a thread pushes 2-plane slices to
-  unsigned peer_sm[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) peer_sm[k] = cl_mapa(sm_u32, (unsigned)(rank + 1 + ((tid >> 6) & 1) + 2 * k) & (TC_CS - 1));
-  auto push_slice = [&](int nplanes, int dst_off, unsigned long long* sbar) {
-    const unsigned mb = f32_smem_u32(sbar);
-    if (nplanes == 2) {
-      const int c = tid & 63;
-      if ((c & 15) < nvalid) {
-        const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
-        const unsigned doff = (unsigned)dst_off + (unsigned)c * 16u, moff = mb - sm_u32;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cl_st_async_v4(peer_sm[k] + doff, x, peer_sm[k] + moff);
-      }
-    } else {
-      const int c = tid;
-      if ((c & 15) < nvalid) {
-        const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
-        const unsigned dst = sm_u32 + (unsigned)dst_off + (unsigned)c * 16u;
-#pragma unroll
-        for (int k = 0; k < TC_CS; ++k) {
-          const unsigned pr = (unsigned)(rank + 1 + k) & (TC_CS - 1);
-          cl_st_async_v4(cl_mapa(dst, pr), x, cl_mapa(mb, pr));
-        }
-      }
-    }
+  // warp 0: publish the staged slice (nplanes planes of this CTA's channels, stg) through L2: copy it to `gdst`, then ONE
+  // multicast bulk copy delivers it to offset dst_off of all 16 CTAs and counts its bytes on every receiver's `sbar`
+  auto publish = [&](uint8_t* gdst, int nplanes, int dst_off, unsigned long long* sbar) {
+    for (int c = lane; c < nplanes * (TC_PLANE / 16); c += 32)
+      *reinterpret_cast<float4*>(gdst + c * 16) = *reinterpret_cast<const float4*>(stg + c * 16);
+    asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy stores before the bulk copy's read
+    __syncwarp();
+    if (lane == 0)
+      tc_bulk_multicast(sm_u32 + (unsigned)dst_off, gdst, (unsigned)(nplanes * TC_PLANE), f32_smem_u32(sbar), (unsigned short)0xFFFF);
   };
+  uint8_t* const gst = p.gstage + (size_t)lcluster * TC_GSTAGE;
 
   const uint32_t my_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   float* const ctab = p.ctab + ((size_t)lcluster * TC_CS + rank) * (size_t)(L + 1) * 512;
@@ -507,6 +517,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // push_ops of layer 0: this CTA's slice of the first layer's input -> its dilation ring (loader warps 5-6)
+      if (tid >= 160 && tid < 224) {
+        const int c = tid - 160;
+        *reinterpret_cast<float4*>(ring_slice(0, t) + c * 16) = *reinterpret_cast<const float4*>(xc + rank * 2 * TC_PLANE + c * 16);
+        asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy ring stores vs later bulk-copy reads
+      }
     }
     TC_PF_ADD(0);
 
@@ -614,7 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         }
         TC_PF_ADD(2);
         ep_sync();
-        push_slice(2, TC_OFF_XG + rank * 2 * TC_PLANE, xgbar);
+        if (warp == 0) publish(gst + TC_GST_XG + (l & 1) * TC_XB + rank * 2 * TC_PLANE, 2, TC_OFF_XG + rank * 2 * TC_PLANE, xgbar);
         TC_PF_ADD(3);
         // ---------------------------------------------------------------- S2: residual + skip 1x1
         stage_sync5();
@@ -629,11 +645,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
             const float lo_ = v[j] + v[16 + j], hi_ = v[8 + j] + v[24 + j];
             const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
             const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            const float oldv = cur[j];
-            const float nv = oldv + (r + bres);                                  // wavenet.py:145
+            const float nv = cur[j] + (r + bres);                                // wavenet.py:145
             cur[j] = nv;
-            tc_st_split(stq, 8 * q + j, i, oldv);                                // push_ops: this step's layer input -> queue
             if (!last) tc_st_split(stg, 8 * q + j, i, nv);                       // the last residual is dead (wavenet.py:145)
+          }
+          // next layer's input of this step: one 1 KB store into its dilation ring (push_ops) that is also the source
+          // of the hand-off to the cluster
+          if (!last) {
+            __syncwarp();
+            publish(ring_slice(l + 1, t), 2, TC_OFF_XC + rank * 2 * TC_PLANE, xcbar);
           }
         } else if (warp < 3) {
           // lanes 32-63: skip rows hi, lanes 64-95: skip rows lo of channel 32 rank + lane
@@ -646,26 +666,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
           }
         }
         TC_PF_ADD(5);
-        ep_sync();
-        if (!last) {
-          push_slice(2, TC_OFF_XC + rank * 2 * TC_PLANE, xcbar);
-        } else {
+        if (last) {
           // relu(skip total) -> postprocess1 input slice (4 planes)
+          ep_sync();
           if (warp == 1) {
 #pragma unroll
             for (int s = 0; s < 16; ++s) tc_st_split(stg, s, lane, fmaxf(sk[s] + skx[lane * TC_NS + s], 0.f));     // wavenet.py:153
           }
           ep_sync();
-          push_slice(4, TC_OFF_XT1 + rank * 4 * TC_PLANE, xsbar);
-        }
-        if (tid < 64) {
-          // queue push (off the chain, behind the hand-off): this CTA's 2 planes of ring slot t mod 2d
-          const int slot_old = (int)(t % (2 * ly.d));
-          const float4 x = *reinterpret_cast<const float4*>(stq + tid * 16);
-          uint8_t* dst = reinterpret_cast<uint8_t*>(ly.ring + slot_old * ring_slot_elems + (long long)cluster * (TC_XB / 2)) +
-                         rank * 2 * TC_PLANE;
-          *reinterpret_cast<float4*>(dst + tid * 16) = x;
-          asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy ring stores vs later bulk-copy reads
+          if (warp == 0) publish(gst + TC_GST_XS + rank * 4 * TC_PLANE, 4, TC_OFF_XT1 + rank * 4 * TC_PLANE, xsbar);
         }
         TC_PF_ADD(6);
       }
@@ -689,7 +698,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wavenet_tc_cluster(const TcPara
         }
       }
       ep_sync();
-      push_slice(4, TC_OFF_XC + rank * 4 * TC_PLANE, xnbar);
+      if (warp == 0) publish(gst + TC_GST_XN + rank * 4 * TC_PLANE, 4, TC_OFF_XC + rank * 4 * TC_PLANE, xnbar);
       TC_PF_ADD(7);
       // ================================================================ postprocess2 -> logits, scattered to the drawing CTAs
       stage_sync5();
