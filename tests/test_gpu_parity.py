@@ -27,7 +27,7 @@ SAMPLE_TIE = 1e-5
 SAMPLE_TIE_OF = {"fp32": SAMPLE_TIE, "tc": 1e-4}
 # the two parity-grade arithmetic paths: float32 CUDA cores, and split-bf16 (hi + lo) tcgen05 tensor cores
 PRECISIONS = ["fp32", "tc"]
-KERNEL_OF = {"fp32": "wavenet_fp32_cluster", "tc": "wavenet_tc_cluster"}
+KERNEL_OF = {"fp32": "wavenet_fp32_cluster", "tc": "wavenet_tcf_cluster"}
 
 
 def _engine(wavenet=None, max_batch=64, weights=None, **kw):

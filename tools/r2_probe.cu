@@ -310,6 +310,85 @@ __global__ void __launch_bounds__(128, 1) probe_mma_multi(int nw, int nmma, int 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
 }
 
+// ------------------------------------------------------------------------------------------------ 2c. MMA chain under load
+// 64 MMAs (M = 128, N = 64, block layout LBO 128 / SBO 256) in groups of 4 with a commit per group (cgrp) or one commit at
+// the end, while warp 3 streams `bg` concurrent 16 KB bulk copies from L2 into other shared memory (0 = none)
+__global__ void __launch_bounds__(128, 1) probe_mma_load(const uint8_t* src, int cgrp, int bg, int N, long long* out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint64_t bar, gbar[4], lbar[8];
+  __shared__ uint32_t tmem_slot;
+  __shared__ volatile int stop;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&gbar[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&lbar[i], 1);
+    stop = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  if (warp == 3 && lane == 0 && bg > 0) {
+    // background stream: bg copies in flight, 16 KB each, into smem 128 KB..
+    long long n = 0;
+    size_t off = 0;
+    while (!stop) {
+      const int s = (int)(n % bg);
+      if (n >= bg) mbar_wait(&lbar[s], (uint32_t)((n / bg - 1) & 1));
+      mbar_expect(&lbar[s], 16384);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sm + 128 * 1024 + s * 16384)), "l"(src + off), "r"(16384), "r"(smem_u32(&lbar[s])) : "memory");
+      off = (off + 16384) % (4u << 20);
+      n += 1;
+    }
+    for (long long i = n; i < n + bg; ++i) { const int s = (int)(i % bg); if (i >= bg) mbar_wait(&lbar[s], (uint32_t)((i / bg - 1) & 1)); }
+    out[2] = n;
+  }
+  if (warp == 0) {
+    long long best = 1ll << 60;
+    uint32_t ph = 0;
+    for (int r = 0; r < 10; ++r) {
+      const long long t0 = clock64();
+      if (lane == 0) {
+        for (int g = 0; g < 16; ++g) {
+          uint64_t da = 0, db = 0;
+          da |= (uint64_t)(((smem_u32(sm) + (g & 3) * 16384) & 0x3FFFF) >> 4); da |= (uint64_t)(128 >> 4) << 16; da |= (uint64_t)(256 >> 4) << 32; da |= 1ull << 46;
+          db |= (uint64_t)(((smem_u32(sm) + 65536 + (g & 3) * 8192) & 0x3FFFF) >> 4); db |= (uint64_t)(128 >> 4) << 16; db |= (uint64_t)(256 >> 4) << 32; db |= 1ull << 46;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t acc = (g | j) ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                         ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            da += 4096 >> 4; db += 2048 >> 4;
+          }
+          if (cgrp) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&gbar[g & 3])) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      }
+      __syncwarp();
+      mbar_wait(&bar, ph);
+      ph ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const long long t2 = clock64();
+      if (t2 - t0 < best) best = t2 - t0;
+    }
+    if (lane == 0) { out[0] = best; stop = 1; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
 int main() {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -326,7 +405,7 @@ int main() {
     CK(cudaMalloc(&src, region * nregions));
     CK(cudaMemset(src, 0, region * nregions));
     CK(cudaFuncSetAttribute(probe_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    const int grids[] = {64};
+    const int grids[] = {};
     const int sizes[] = {32768};
     const int depths[] = {2, 4};
     for (int g : grids) for (int sz : sizes) for (int d : depths) {
@@ -350,7 +429,7 @@ int main() {
     const int Ms[] = {128};
     const int Ns[] = {32};
     const int nm[] = {16, 48};
-    for (int layout = 0; layout < 3; ++layout) for (int M : Ms) for (int N : Ns) for (int n : nm) {
+    for (int layout = 0; layout < 0; ++layout) for (int M : Ms) for (int N : Ns) for (int n : nm) {
       probe_mma<<<1, 128, 200 * 1024>>>(M, N, n, layout, 20, out);
       CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(h.data(), out, 2 * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -368,13 +447,26 @@ int main() {
       printf("mma-multi style=%d issuing warps=%d total mma=%d: %lld cycles -> %.1f cyc/mma\n", style, nw, n, h[0], (double)h[0] / n);
     }
   }
+  // ---- 2c
+  {
+    uint8_t* src2;
+    CK(cudaMalloc(&src2, 8u << 20));
+    CK(cudaMemset(src2, 0, 8u << 20));
+    CK(cudaFuncSetAttribute(probe_mma_load, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int N : {32, 64}) for (int cgrp = 0; cgrp < 2; ++cgrp) for (int bg : {0, 2, 4}) {
+      probe_mma_load<<<1, 128, 200 * 1024>>>(src2, cgrp, bg, N, out);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(h.data(), out, 3 * sizeof(long long), cudaMemcpyDeviceToHost));
+      printf("mma-load N=%d commit-per-4=%d background copies in flight=%d: 64 mma in %lld cycles -> %.1f cyc/mma\n", N, cgrp, bg, h[0], (double)h[0] / 64);
+    }
+  }
   // ---- 3
   {
     CK(cudaFuncSetAttribute(probe_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(probe_gather, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     uint8_t* gbuf;
     CK(cudaMalloc(&gbuf, 1 << 20));
-    const int CSs[] = {16};
+    const int CSs[] = {};
     const int slices[] = {1024};
     for (int CS : CSs) for (int slice : slices) for (int method = 0; method < 4; ++method) for (int ncl : {1, 4}) {
       cudaLaunchConfig_t cfg = {};

@@ -19,6 +19,7 @@
 #include "wavenet_fp32_cluster.cuh"
 #include "wavenet_bf16_cluster.cuh"
 #include "wavenet_tc_cluster.cuh"
+#include "wavenet_tcf_cluster.cuh"
 #include "sample.cuh"
 #include "encoder.cuh"
 
@@ -89,6 +90,16 @@ struct vqwn_handle {
   size_t tc_persist_bytes = 0;             // persisting L2 set aside for the weight tiles (0: not available)
   float *tc_skf_k = nullptr, *tc_skf_b = nullptr, *tc_ctab = nullptr;
   uint8_t* tc_gstage = nullptr;            // [co-resident cluster][TC_GSTAGE] hand-off staging
+  // one-hand-off-per-layer variant (wavenet_tcf_cluster.cuh): the default VQWN_PREC_TC kernel; VQWN_TC_KERNEL=v1 selects the older one
+  bool tf_use = true;
+  uint8_t* wtf = nullptr;                  // [16][tf_stream_bytes(L)] per-CTA weight streams
+  size_t wtf_bytes = 0;
+  float* tf_ptmp = nullptr;                // [G][2G] premultiplied W2_l . Wres_{l-1} of the layer being packed
+  float* tf_b1adj = nullptr;               // [L][2G] gated biases with W2_l . bres_{l-1} folded in
+  uint8_t* tf_gstage = nullptr;
+  long long* dbg_host = nullptr;
+  TfLayerDev* tf_layers_dev = nullptr;
+  std::vector<TfLayerDev> tf_layers_host;
   const float** tc_b2_ptrs = nullptr;
   TcLayerDev* tc_layers_dev = nullptr;
   std::vector<TcLayerDev> tc_layers_host;
@@ -297,6 +308,41 @@ int pack_weights(vqwn_handle* h) {
         TP(h, "decoder/skip/bias"), h->tc_b2_ptrs, h->L, h->tc_skf_k, h->tc_skf_b);
     h->launches += 1;
     CK(h, cudaGetLastError());
+    // weight streams of the one-hand-off-per-layer kernel: per cluster CTA, tiles in issue order
+    //   T_0 | A_0 T_1 | A_1 R_0 T_2 | ... | A_{L-1} R_{L-2} | R_{L-1} postprocess1 postprocess2
+    //   A_l = [P_l = W2_l . Wres_{l-1} | W2_l] (stacked inputs [gate_{l-1} | x_{l-1}]), T_l = [W1_l | W0_l] (taps t-d | t-2d)
+    {
+      const size_t SB = tf_stream_bytes(h->L);
+      auto pk = [&](const float* s0, const float* s1, int ldw, int ninstr, int rows, int kind, size_t off) {
+        const long long total = (long long)TF_CS * ninstr * rows * 16;
+        int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+        tf_pack_kernel<<<grid, 256, 0, h->stream>>>(s0, s1, ldw, ninstr, rows, kind, SB, h->wtf + off);
+        h->launches += 1;
+      };
+      const size_t tap = (size_t)R * 2 * G;      // w1 rows: current tap | tap t-d | tap t-2d | condition
+      size_t off = 0;
+      pk(h->w1[0] + tap, h->w1[0] + 2 * tap, 2 * G, 16, 128, 0, off); off += TF_TILE_A;
+      for (int l = 0; l < h->L; ++l) {
+        if (l == 0) {
+          pk(nullptr, h->w1[0], 2 * G, 16, 128, 0, off);
+          tf_fold_bias_kernel<<<(2 * G + 127) / 128, 128, 0, h->stream>>>(h->b1[0], nullptr, h->w1[0], h->tf_b1adj);
+        } else {
+          tf_premultiply_kernel<<<dim3((2 * G + 127) / 128, G), 128, 0, h->stream>>>(h->w2[l - 1], R + S, h->w1[l], h->tf_ptmp);
+          pk(h->tf_ptmp, h->w1[l], 2 * G, 16, 128, 0, off);
+          tf_fold_bias_kernel<<<(2 * G + 127) / 128, 128, 0, h->stream>>>(h->b1[l], h->b2[l - 1], h->w1[l],
+                                                                           h->tf_b1adj + (size_t)l * 2 * G);
+        }
+        h->launches += 2;
+        off += TF_TILE_A;
+        if (l >= 1) { pk(h->w2[l - 1], nullptr, R + S, 16, 96, 1, off); off += TF_TILE_R; }
+        if (l + 1 < h->L) { pk(h->w1[l + 1] + tap, h->w1[l + 1] + 2 * tap, 2 * G, 16, 128, 0, off); off += TF_TILE_A; }
+      }
+      pk(h->w2[h->L - 1], nullptr, R + S, 16, 96, 1, off); off += TF_TILE_R;
+      pk(h->post1_w, nullptr, S, 32, 64, 2, off); off += TF_TILE_P1;
+      pk(TP(h, "decoder/postprocess2/kernel"), nullptr, h->Q, 32, 32, 3, off); off += TF_TILE_P2;
+      if (off != SB) return fail(h, VQWN_ERR_INVALID, "tensor-core kernel: weight stream size mismatch");
+      CK(h, cudaGetLastError());
+    }
   }
   CK(h, cudaMemcpyAsync(h->enc_lut, TP(h, "lut/mu_law_encode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->dec_lut, TP(h, "lut/mu_law_decode"), (size_t)(h->Q + 1) * f, cudaMemcpyDeviceToDevice, h->stream));
@@ -497,7 +543,82 @@ size_t tc_ring_bytes(const vqwn_handle* h, int B) {
   const size_t ncl = (size_t)(B + spc - 1) / spc;
   size_t dsum = 0;
   for (int l = 0; l < h->L; ++l) dsum += (size_t)h->cfg.dilations[l];
-  return (2 * dsum + (size_t)h->L) * ncl * TC_XB;      // 2d + 1 slots per layer
+  // 2d + 1 slots per layer; the one-hand-off kernel stores pair blocks (both tap positions) of 32 KB
+  return (2 * dsum + (size_t)h->L) * ncl * (size_t)TF_PAIR;
+}
+
+int launch_tcf(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
+               const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
+               float* logits_out, float* probs_out) {
+  const int spc = tc_spc(h, h->B);
+  const int nclusters = (h->B + spc - 1) / spc;
+  if (h->t + T > 0x7fffffffLL) return fail(h, VQWN_ERR_INVALID, "tensor-core kernel: time index beyond 2^31 samples; call vqwn_reset");
+  TfParams p;
+  memset(&p, 0, sizeof p);
+  p.L = h->L; p.B = h->B; p.nclusters = nclusters; p.spc = spc;
+  p.pre_k = TP(h, "decoder/preprocess/kernel"); p.pre_b = TP(h, "decoder/preprocess/bias");
+  p.skf_k = h->tc_skf_k; p.skf_b = h->tc_skf_b;
+  p.wstream = h->wtf;
+  p.post1_lc = h->post1_w + (size_t)h->S * h->S;
+  p.post1_b = TP(h, "decoder/postprocess1/bias"); p.post2_b = TP(h, "decoder/postprocess2/bias");
+  size_t off = 0;
+  uint8_t* rb = reinterpret_cast<uint8_t*>(h->ring_base);
+  for (int l = 0; l < h->L; ++l) {
+    h->tf_layers_host[l].ring = rb + off;
+    off += ((size_t)2 * h->cfg.dilations[l] + 1) * nclusters * TF_PAIR;
+  }
+  if (off > h->ring_floats * sizeof(float)) return fail(h, VQWN_ERR_INVALID, "tensor-core kernel: ring storage too small");
+  CK(h, cudaMemcpyAsync(h->tf_layers_dev, h->tf_layers_host.data(), sizeof(TfLayerDev) * h->L, cudaMemcpyHostToDevice, h->stream));
+  p.layers = h->tf_layers_dev;
+  p.ctab = h->tc_ctab;
+  p.gstage = h->tf_gstage;
+  p.enc_lut = h->enc_lut; p.dec_lut = h->dec_lut;
+  p.u_hist = h->u_hist;
+  p.t0 = h->t; p.T = T; p.mode = mode;
+  p.cond = cond; p.cond_bstride = cond_bstride; p.ratio = ratio;
+  p.ext_audio = ext_audio; p.uniforms = uniforms; p.seed = seed; p.b_offset = h->stream_offset;
+  p.audio_out = audio_out; p.idx_out = idx_out; p.logits_out = logits_out; p.probs_out = probs_out;
+  p.prof = h->profile ? h->prof : nullptr;
+#ifdef TF_DEBUG_MARKS
+  static long long* dbg_host = nullptr;
+  if (!dbg_host) { cudaHostAlloc(&dbg_host, 4096, cudaHostAllocMapped); memset(dbg_host, 0, 4096); }
+  { long long* dp = nullptr; cudaHostGetDevicePointer(&dp, dbg_host, 0); p.prof = dp; }
+  h->dbg_host = dbg_host;
+#endif
+  p.err = h->gen_err;
+  CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.blockDim = dim3(TF_THREADS);
+  cfg.dynamicSmemBytes = TF_SMEM;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TF_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (h->tc_persist_bytes > 0 && !getenv("VQWN_TC_NO_PERSIST")) {
+    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[1].val.accessPolicyWindow.base_ptr = h->wtf;
+    attr[1].val.accessPolicyWindow.num_bytes = h->wtf_bytes;
+    attr[1].val.accessPolicyWindow.hitRatio = (float)((double)h->tc_persist_bytes >= (double)h->wtf_bytes
+                                                          ? 1.0 : (double)h->tc_persist_bytes / (double)h->wtf_bytes);
+    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 2;
+  }
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  for (int c0 = 0; c0 < nclusters; c0 += h->tc_max_clusters) {      // disjoint stream groups, one launch per co-resident set
+    const int nc = (nclusters - c0 < h->tc_max_clusters) ? (nclusters - c0) : h->tc_max_clusters;
+    p.cluster0 = c0;
+    cfg.gridDim = dim3(nc * TF_CS);
+    if (h->profile) CK(h, cudaLaunchKernelEx(&cfg, wavenet_tcf_cluster<true>, p));
+    else CK(h, cudaLaunchKernelEx(&cfg, wavenet_tcf_cluster<false>, p));
+    h->launches += 1;
+  }
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->last_kernel = "wavenet_tcf_cluster";
+  h->t += T;
+  return VQWN_OK;
 }
 
 int launch_tc(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
@@ -572,6 +693,9 @@ int launch_tc(vqwn_handle* h, int mode, long long T, const float* cond, long lon
 int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long long cond_bstride, int ratio,
                 const float* ext_audio, const double* uniforms, uint64_t seed, float* audio_out, int* idx_out,
                 float* logits_out, float* probs_out) {
+  if (h->precision == VQWN_PREC_TC && h->tf_use)
+    return launch_tcf(h, mode, T, cond, cond_bstride, ratio, ext_audio, uniforms, seed, audio_out, idx_out, logits_out,
+                      probs_out);
   if (h->precision == VQWN_PREC_TC)
     return launch_tc(h, mode, T, cond, cond_bstride, ratio, ext_audio, uniforms, seed, audio_out, idx_out, logits_out,
                      probs_out);
@@ -626,13 +750,27 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
 }
 
 int finish_timing(vqwn_handle* h) {
+#ifdef TF_DEBUG_MARKS
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess && h->dbg_host) {
+    fprintf(stderr, "[tcf debug marks]");
+    for (int i = 32; i < 32 + 24; ++i) fprintf(stderr, " %d:%lld", i - 32, h->dbg_host[i]);
+    fprintf(stderr, "\n");
+  }
+#endif
   CK(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
   if (strncmp(h->last_kernel, "wavenet_", 8) == 0) {
-    int e = 0;
-    CK(h, cudaMemcpy(&e, h->gen_err, sizeof(int), cudaMemcpyDeviceToHost));
+    int ev[8] = {0};
+    CK(h, cudaMemcpy(ev, h->gen_err, sizeof ev, cudaMemcpyDeviceToHost));
+    const int e = ev[0];
+    if (e && strcmp(h->last_kernel, "wavenet_tcf_cluster") == 0) {
+      char msg[200];
+      snprintf(msg, sizeof msg, "generation kernel: wait timed out (code %d, barrier at shared offset %d -> index %d, parity %d, thread %d, block %d)",
+               e, ev[1], (ev[1] - (int)TF_OFF_BARS) / 8, ev[2], ev[3], ev[4]);
+      return fail(h, VQWN_ERR_CUDA, msg);
+    }
     if (e) return fail(h, VQWN_ERR_CUDA, e == 2 ? "generation kernel: operand wait timed out" : (e == 4 ? "generation kernel: packet wait timed out" : "generation kernel: grid barrier timed out"));
   }
   if (h->profile && strcmp(h->last_kernel, "vq_tc_kernel") == 0) {
@@ -657,6 +795,17 @@ int finish_timing(vqwn_handle* h) {
       for (int c = 0; c < 3; ++c)
         fprintf(stderr, "[vqwn profile] bf16 CTA0 %s cycles: fir=%lld recv_wait=%lld operand_wait=%lld mma_chain=%lld tmem_ld=%lld ep_math=%lld ep_sync+queue=%lld push=%lld (kernel %.3f ms)\n",
                 cls[c], pf[8 * c + 0], pf[8 * c + 4], pf[8 * c + 1], pf[8 * c + 2], pf[8 * c + 7], pf[8 * c + 6], pf[8 * c + 3], pf[8 * c + 5], ms);
+    }
+  }
+  if (h->profile && strcmp(h->last_kernel, "wavenet_tcf_cluster") == 0) {
+    long long pf[48];
+    if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "[vqwn profile] tcf CTA0 epilogue thread 0 cycles: step_start=%lld gate_acc_wait=%lld gate_epilogue=%lld gate_publish=%lld res_skip=%lld tail_skip=%lld post1=%lld post2=%lld draw=%lld sample_wait=%lld (kernel %.3f ms)\n",
+              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7], pf[8], pf[10], ms);
+      const char* kn[7] = {"gate", "res+skip", "taps", "tail_skip", "post1", "post2", "next_taps"};
+      fprintf(stderr, "[vqwn profile] tcf CTA0 issuing thread (warp 4) cycles, wait / issue per chain kind:");
+      for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%lld/%lld", kn[k], pf[32 + 2 * k], pf[32 + 2 * k + 1]);
+      fprintf(stderr, " | step_start=%lld weight_chunk_wait=%lld operand_fence=%lld mma_issue=%lld chunk_commit=%lld chain_commits=%lld consume_total=%lld\n", pf[16], pf[25], pf[19], pf[20], pf[21], pf[22], pf[23]);
     }
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_tc_cluster") == 0) {
@@ -940,7 +1089,7 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     {
       int max_persist = 0;
       if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess && max_persist > 0) {
-        size_t want = h->wtc_bytes + (4u << 20);
+        size_t want = (size_t)TF_CS * tf_stream_bytes(h->L) + (4u << 20);      // the larger of the two kernels' weight sets
         if (want > (size_t)max_persist) want = (size_t)max_persist;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->tc_persist_bytes = want;
         else (void)cudaGetLastError();
@@ -949,6 +1098,32 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     CKC(cudaMalloc(&h->tc_skf_k, (size_t)TC_PK * TC_S * sizeof(float)));
     CKC(cudaMalloc(&h->tc_skf_b, (size_t)TC_S * sizeof(float)));
     CKC(cudaMalloc(&h->tc_ctab, (size_t)h->tc_max_clusters * TC_CS * (h->L + 1) * 512 * sizeof(float)));
+    {
+      CKC(cudaFuncSetAttribute((const void*)wavenet_tcf_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM));
+      CKC(cudaFuncSetAttribute((const void*)wavenet_tcf_cluster<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      CKC(cudaFuncSetAttribute((const void*)wavenet_tcf_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM));
+      CKC(cudaFuncSetAttribute((const void*)wavenet_tcf_cluster<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      const char* tk = getenv("VQWN_TC_KERNEL");
+      h->tf_use = !(tk && strcmp(tk, "v1") == 0);
+      h->wtf_bytes = (size_t)TF_CS * tf_stream_bytes(h->L);
+      CKC(cudaMalloc(&h->wtf, h->wtf_bytes));
+      CKC(cudaMalloc(&h->tf_ptmp, (size_t)G * 2 * G * sizeof(float)));
+      CKC(cudaMalloc(&h->tf_b1adj, (size_t)h->L * 2 * G * sizeof(float)));
+      CKC(cudaMalloc(&h->tf_gstage, (size_t)h->tc_max_clusters * TF_GSTAGE));
+      CKC(cudaMemset(h->tf_gstage, 0, (size_t)h->tc_max_clusters * TF_GSTAGE));
+      CKC(cudaMalloc(&h->tf_layers_dev, sizeof(TfLayerDev) * h->L));
+      h->tf_layers_host.resize(h->L);
+      for (int l = 0; l < h->L; ++l) {
+        TfLayerDev ld;
+        memset(&ld, 0, sizeof ld);
+        ld.wlc = h->w1[l] + (size_t)3 * R * 2 * G;
+        ld.b1 = h->tf_b1adj + (size_t)l * 2 * G;
+        ld.bres = h->b2[l];
+        ld.ring = nullptr;
+        ld.d = c.dilations[l];
+        h->tf_layers_host[l] = ld;
+      }
+    }
     CKC(cudaMalloc(&h->tc_gstage, (size_t)h->tc_max_clusters * TC_GSTAGE));
     CKC(cudaMemset(h->tc_gstage, 0, (size_t)h->tc_max_clusters * TC_GSTAGE));
     CKC(cudaMalloc(&h->tc_b2_ptrs, sizeof(const float*) * h->L));
@@ -1056,7 +1231,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     h->bc_max_clusters = nc;
     if (nc < 1) h->bc_ok = false;
   }
-  CKC(cudaMalloc(&h->gen_err, sizeof(int)));
+  CKC(cudaMalloc(&h->gen_err, 8 * sizeof(int)));
+  CKC(cudaMemset(h->gen_err, 0, 8 * sizeof(int)));
   if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "cluster") == 0 ? 3 : 0);
   h->actA_floats = FP32_TB * 3 * R;                       // gated conv: current | t-d | t-2d segments
   if (FP32_TB * S > h->actA_floats) h->actA_floats = FP32_TB * S;   // post1: relu(skip)
@@ -1097,7 +1273,8 @@ int vqwn_destroy(vqwn_handle* h) {
   for (auto p : h->b2) if (p) cudaFree(p);
   void* singles[] = {h->post1_w, h->layers_dev, h->enc_lut, h->dec_lut, h->ring_base, h->u_hist, h->cur, h->g,
                      h->skip, h->n1, h->logits, h->barrier, h->prof, h->emax_dev, h->vq_err, h->wtiles, h->gen_err, h->wcl, h->cl_layers_dev, h->wbc, h->bc_layers_dev,
-                     h->wtc, h->tc_skf_k, h->tc_skf_b, h->tc_ctab, h->tc_gstage, (void*)h->tc_b2_ptrs, h->tc_layers_dev};
+                     h->wtc, h->tc_skf_k, h->tc_skf_b, h->tc_ctab, h->tc_gstage, (void*)h->tc_b2_ptrs, h->tc_layers_dev,
+                     h->wtf, h->tf_ptmp, h->tf_b1adj, h->tf_gstage, h->tf_layers_dev};
   for (void* p : singles) if (p) cudaFree(p);
   DevBuf* bufs[] = {&h->cond_res, &h->uni_res, &h->audio_res, &h->idx_res, &h->logits_res, &h->x_res, &h->small_a,
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,
@@ -1647,6 +1824,13 @@ int vqwn_teacher_forced(vqwn_handle* h, const float* x, const float* cond, int B
   rc = launch_fp32(h, GEN_TEACHER, T, (const float*)h->cond_res.p, (long long)F * h->C, (int)(T / F),
                    (const float*)h->x_res.p, nullptr, 0, nullptr, nullptr, (float*)h->logits_res.p, nullptr);
   if (rc) return rc;
+#ifdef TF_DEBUG_MARKS
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess && h->dbg_host) {
+    fprintf(stderr, "[tcf debug marks]");
+    for (int i = 32; i < 32 + 24; ++i) fprintf(stderr, " %d:%lld", i - 32, h->dbg_host[i]);
+    fprintf(stderr, "\n");
+  }
+#endif
   CK(h, cudaMemcpyAsync(logits_out, h->logits_res.p, lbytes, cudaMemcpyDeviceToHost, h->stream));
   return finish_timing(h);
 }

@@ -1,0 +1,948 @@
+// WaveNet fast generation on the 5th-generation tensor cores at float32-grade accuracy, ONE hand-off per layer
+// (VQWN_PREC_TC).  Same reference semantics as the float32 kernels (wavenet.py:103-172, wavenet_ops.py:163-267,
+// utils.py:13-46, mu_law_ops.py:5-31).
+//
+// Arithmetic: split bfloat16 as in wavenet_tc_cluster.cuh (x = hi + lo, weight tiles stack hi and lo rows along M, the
+// activation operand stacks the hi and lo copies of the streams along N, fp32 accumulation in TMEM; biases, residual
+// chain, skip sum, gate, softmax and the draw are float32).
+//
+// What is new against wavenet_tc_cluster.cuh - the dependency chain of a time step is 30 hand-offs, not 60:
+//   * the reference's layer is gate_l = f(W2_l x_l + taps), x_{l+1} = x_l + Wres_l gate_l (wavenet_ops.py:240-267): two
+//     contractions that each need an all-gather of their input across the cluster.  Here the current-tap term is
+//     expanded once, W2_l x_l = W2_l x_{l-1} + (W2_l Wres_{l-1}) gate_{l-1} + W2_l bres_{l-1}, with P_l = W2_l Wres_{l-1}
+//     premultiplied on the host side (float64) and the bias term folded into the gated bias.  gate_{l-1} and x_{l-1}
+//     arrive together (both come out of stage l-1), so stage l needs ONE all-gather: [gate_{l-1} | x_{l-1}];
+//   * an MMA of this size occupies the tensor pipe for ~64 cycles whatever M <= 128 and N <= 128 are (tools/r2_probe.cu),
+//     so work is packed per instruction, not per FLOP: the activation operand stacks TWO inputs along N (64 columns), the
+//     weight tile puts the rows that multiply the first input in lanes 0-15 and those for the second in lanes 16-31 of
+//     every TMEM lane quarter: [P_l | W2_l] x [gate_{l-1} | x_{l-1}] is 16 instructions, both older taps
+//     [W1_l | W0_l] x [x_l(t-d) | x_l(t-2d)] another 16 (issued a stage ahead into the same accumulator), residual + skip
+//     rows 16 more; the off-diagonal blocks are never read;
+//   * weights stream through ONE FIFO of 16 KB chunks (4 instructions each) in issue order: a chunk's slot is released by
+//     tcgen05.commit and refilled by the loader lanes, so a layer's 176 KB of tiles never have to be resident at once;
+//   * hand-offs go through L2 as one multicast bulk copy per slice (see wavenet_tc_cluster.cuh); the dilation queues are
+//     HBM rings of PAIR blocks [2d + 1][cluster][16 senders][x(t-d) | x(t-2d)][1 KB]: a step's layer input is stored
+//     twice (1 KB each) so that both taps of a later step are ONE contiguous 32 KB bulk copy into the N-stacked operand.
+// Operand layout everywhere: per 16 channels (one MMA K step) a block [row groups of 8][2 x 8 channels][8 rows x 16 B];
+// descriptors: no swizzle, K-direction stride 128 B, row-group stride 256 B.
+// Geometry fixed to the reference's default (R = G = 256, S = 512, Q = 256, C = 128, 32-tap preprocess, kernel_size 3).
+#pragma once
+#include <cuda_bf16.h>
+#include "wavenet_tc_cluster.cuh"
+
+namespace vqwn {
+
+constexpr int TF_CS = 16;
+constexpr int TF_THREADS = 384;           // warps 0-3 epilogue | 4-7 MMA issue | 8-9 weight loaders | 10 tap loader | 11 idle
+constexpr int TF_NISSUE = 4;
+constexpr int TF_NS = 16;                  // streams per cluster (at most)
+constexpr int TF_R = 256, TF_G = 256, TF_S = 512, TF_Q = 256, TF_C = 128, TF_PK = 32;
+constexpr int TF_MAXL = 32;
+constexpr int TF_BLK = 1024;               // one K step (16 channels) of a 32-row activation operand
+constexpr int TF_PAIR = TF_CS * 2 * TF_BLK;    // N-stacked operand, K = 256: [16 senders][first | second][1 KB] = 32 KB
+constexpr int TF_SLOT = 16384;             // weight FIFO slot: 4 instructions x 128 rows x 32 B
+constexpr int TF_NSLOT = 7;
+constexpr int TF_CHUNK_A = 4 * 128 * 32, TF_CHUNK_R = 4 * 96 * 32, TF_CHUNK_P1 = 4 * 64 * 32, TF_CHUNK_P2 = 4 * 32 * 32;
+// per-CTA weight stream of one time step (bytes): T_0 | stage 0: A_0, T_1 | stage l: A_l, R_{l-1}, T_{l+1} | ... | tail
+constexpr int TF_TILE_A = 4 * TF_CHUNK_A, TF_TILE_R = 4 * TF_CHUNK_R, TF_TILE_P1 = 8 * TF_CHUNK_P1, TF_TILE_P2 = 8 * TF_CHUNK_P2;
+__host__ __device__ constexpr size_t tf_stream_bytes(int L) {
+  return (size_t)TF_TILE_A + (size_t)L * TF_TILE_A + (size_t)L * TF_TILE_R + (size_t)(L - 1) * TF_TILE_A + TF_TILE_P1 + TF_TILE_P2;
+}
+// shared memory map (bytes)
+constexpr int TF_OFF_W = 0;                                  // weight FIFO
+constexpr int TF_OFF_B1 = TF_OFF_W + TF_NSLOT * TF_SLOT;     // [2][gate | layer input] operands, by stage parity
+constexpr int TF_OFF_B2 = TF_OFF_B1 + 2 * TF_PAIR;           // [tap t-d | tap t-2d] operand; postprocess1 input
+constexpr int TF_OFF_STG = TF_OFF_B2 + TF_PAIR;              // publish staging: 2 blocks
+constexpr int TF_OFF_HIST = TF_OFF_STG + 2 * TF_BLK;         // [16][32] fp32 network-input history ring (remote-written)
+constexpr int TF_OFF_LOG = TF_OFF_HIST + TF_NS * TF_PK * 4;  // [256] fp32 logits of this CTA's stream (remote-written)
+constexpr int TF_OFF_US = TF_OFF_LOG + TF_Q * 4;             // [16][32] history in tap order     } 8 KB of CTA-local scratch,
+constexpr int TF_OFF_CUR0 = TF_OFF_US + TF_NS * TF_PK * 4;   // [16 ch][16] fp32 FIR output       } aliased by the condition
+constexpr int TF_OFF_SKF = TF_OFF_CUR0 + 16 * TF_NS * 4;     // [32 ch][16] skip FIR part         } rows [16][128] fp32 at a
+constexpr int TF_OFF_SKX = TF_OFF_SKF + 32 * TF_NS * 4;      // [32 ch][16] skip lo sums          } frame change
+constexpr int TF_OFF_PROB = TF_OFF_SKX + 32 * TF_NS * 4;     // [256] fp32 draw scratch           }
+constexpr int TF_OFF_LAYERS = TF_OFF_PROB + TF_Q * 4;
+constexpr int TF_OFF_BARS = TF_OFF_LAYERS + TF_MAXL * 48;
+constexpr int TF_NBARS = 32;
+constexpr int TF_OFF_MISC = TF_OFF_BARS + TF_NBARS * 8;
+constexpr int TF_OFF_PROF = TF_OFF_MISC + 16;            // [16] cycle counters of the issuing thread, by chain kind
+constexpr int TF_SMEM = TF_OFF_PROF + 16 * 8;
+static_assert(TF_OFF_PROB + TF_Q * 4 - TF_OFF_US == TF_NS * TF_C * 4, "condition rows alias exactly the local scratch");
+static_assert(TF_SMEM <= 232448, "shared memory budget");
+// per-cluster global staging of the hand-offs that do not live in a ring: gate output (double-buffered by layer parity),
+// postprocess1 input, postprocess2 input
+constexpr int TF_GST_XG = 0, TF_GST_XS = 2 * TF_CS * TF_BLK, TF_GST_XN = TF_GST_XS + 2 * TF_CS * TF_BLK,
+              TF_GSTAGE = TF_GST_XN + 2 * TF_CS * TF_BLK;
+
+struct TfLayerDev {
+  const float* wlc;           // gated/local_condition/kernel [C][2G] float32 (row stride 2G)
+  const float* b1;            // gated/bias [2G] + W2_l . residual/bias of layer l-1
+  const float* bres;          // residual/bias [R] (first R entries of the layer's [R + S] bias vector)
+  uint8_t* ring;              // [2d + 1][nclusters][TF_PAIR]
+  int d;
+  int pad_[3];
+};
+static_assert(sizeof(TfLayerDev) == 48, "layer record size");
+
+struct TfParams {
+  int L, B, nclusters, cluster0, spc;      // spc: streams per cluster; cluster c owns streams [c*spc, c*spc + spc)
+  const float *pre_k, *pre_b;              // preprocess/kernel [32][256], bias [256]
+  const float *skf_k, *skf_b;              // skip start folded into the FIR: [32][512] = pre_k . skip/kernel; [512] all skip biases
+  const uint8_t* wstream;                  // [16 CTAs][tf_stream_bytes(L)]
+  const float *post1_lc, *post1_b, *post2_b;   // postprocess1/local_condition/kernel [C][S], biases
+  const TfLayerDev* layers;
+  float* ctab;                             // [launch cluster][16][L+1][512] condition table
+  uint8_t* gstage;                         // [launch cluster][TF_GSTAGE] hand-off staging in L2
+  const float *enc_lut, *dec_lut;
+  float* u_hist;
+  long long t0, T;
+  int mode;
+  const float* cond;
+  long long cond_bstride;
+  int ratio;
+  const float* ext_audio;
+  const double* uniforms;
+  unsigned long long seed;
+  int b_offset;                            // global index of stream 0 (sharded runs): keys the seeded generator
+  int flags;                               // reserved
+  float* audio_out;
+  int* idx_out;
+  float* logits_out;
+  float* probs_out;
+  long long* prof;
+  int* err;
+};
+
+// element (row n, channel k of the 16-channel block) of an operand block: hi copy in row n, lo copy in row 16 + n
+__device__ __forceinline__ void tf_st_split(uint8_t* blk, int n, int k, float x) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  uint8_t* q = blk + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(q) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(q + 2 * 256) = lo;
+}
+__device__ __forceinline__ uint64_t tf_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;           // K direction: the two 8-channel halves of a K step
+  d |= (uint64_t)(256 >> 4) << 32;           // M / N direction: 8-row groups
+  d |= 1ull << 46;
+  return d;
+}
+__device__ __forceinline__ void tf_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// zero 32 accumulator columns of the warp's TMEM lane quarter
+__device__ __forceinline__ void tf_zero32(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tf_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f32_smem_u32(bar)) : "memory");
+}
+
+// one copy of the bounded wait loop for the whole kernel: the three warp roles run disjoint code and share the
+// instruction cache, every inlined copy costs all of them
+__device__ __noinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* err) {
+#pragma unroll 1
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    if (ok) return;
+    // a broken launch must end, not hang: once any wait has timed out every other wait gives up quickly
+    if ((spin & 1023) == 1023 && *reinterpret_cast<volatile int*>(err) != 0) return;
+  }
+  if (atomicCAS(err, 0, 2) == 0) {
+    // which wait: barrier offset in shared memory, parity, thread, block (read back by the host for the error message)
+    err[1] = (int)bar_addr; err[2] = (int)parity; err[3] = (int)threadIdx.x; err[4] = (int)blockIdx.x;
+  }
+}
+
+// PROF: in-kernel cycle counters (VQWN_PROFILE=1).  A separate instantiation: the issuing warps are bound by the length of
+// their own instruction stream, every time stamp costs them
+template <bool PROF>
+__global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfParams p_in) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  TfLayerDev* const layers_s = reinterpret_cast<TfLayerDev*>(sm + TF_OFF_LAYERS);
+  for (int i = tid; i < p_in.L * (int)(sizeof(TfLayerDev) / 4); i += TF_THREADS)
+    reinterpret_cast<uint32_t*>(layers_s)[i] = reinterpret_cast<const uint32_t*>(p_in.layers)[i];
+  TfParams p = p_in;
+  p.layers = layers_s;
+  unsigned rank_u;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
+  const int rank = (int)rank_u;
+  const int lcluster = (int)blockIdx.x / TF_CS;
+  const int cluster = p.cluster0 + lcluster;
+  const int b0 = cluster * p.spc;
+  const int nvalid = max(0, min(p.spc, p.B - b0));
+  const int L = p.L;
+
+  uint8_t* const b1buf = sm + TF_OFF_B1;
+  uint8_t* const b2buf = sm + TF_OFF_B2;
+  uint8_t* const stg = sm + TF_OFF_STG;
+  float* const hist = reinterpret_cast<float*>(sm + TF_OFF_HIST);
+  float* const logits_s = reinterpret_cast<float*>(sm + TF_OFF_LOG);
+  float* const u_s = reinterpret_cast<float*>(sm + TF_OFF_US);
+  float* const cur0 = reinterpret_cast<float*>(sm + TF_OFF_CUR0);
+  float* const skf = reinterpret_cast<float*>(sm + TF_OFF_SKF);
+  float* const skx = reinterpret_cast<float*>(sm + TF_OFF_SKX);
+  float* const prob_s = reinterpret_cast<float*>(sm + TF_OFF_PROB);
+  float* const ct_rows = reinterpret_cast<float*>(sm + TF_OFF_US);     // [16][128] condition rows (alias)
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm + TF_OFF_BARS);
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sm + TF_OFF_MISC);
+  unsigned long long* const wfull = bars + 0;          // [7] weight chunk landed
+  unsigned long long* const wfree = bars + 8;          // [7] the MMAs that read the slot completed
+  unsigned long long* const b1bar = bars + 16;         // [2] gathered operand of a stage landed (by stage parity)
+  unsigned long long* const tapbar = bars + 18;        // pair block of the next layer's taps landed in B2
+  unsigned long long* const tapfree = bars + 19;       // the MMAs that read B2 completed
+  unsigned long long* const xsbar = bars + 20;         // postprocess1 input slices landed in B2
+  unsigned long long* const accA = bars + 21;          // gate pre-activations / postprocess accumulators complete
+  unsigned long long* const accB = bars + 22;          // residual + skip accumulator complete
+  unsigned long long* const e1done = bars + 23;        // the gate epilogue has read its accumulator (4 warps)
+  unsigned long long* const e2done = bars + 24;        // the residual / skip epilogue has read its accumulator (3 warps)
+  unsigned long long* const lgbar = bars + 25;
+  unsigned long long* const smpbar = bars + 26;
+
+  for (int i = tid; i < (TF_OFF_LAYERS - TF_OFF_W) / 16; i += TF_THREADS) reinterpret_cast<uint4*>(sm + TF_OFF_W)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const bool ext = (p.mode == GEN_STEP || p.mode == GEN_TEACHER);
+  if (tid == 0) {
+    for (int i = 0; i < TF_NBARS; ++i) {
+      unsigned cnt = (bars + i == e1done) ? 4u : ((bars + i == e2done) ? 3u : 1u);
+      if (bars + i == accA || bars + i == accB || bars + i == tapfree) cnt = TF_NISSUE;      // one commit per issuing warp
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f32_smem_u32(&bars[i])), "r"(cnt));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // first use of the receive barriers in a step: stage 1 (gate_0 only, 16 KB) on parity 1, stage 2 on parity 0
+    mbar_expect(&b1bar[1], TF_CS * TF_BLK);
+    mbar_expect(&b1bar[0], (L > 2) ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
+    mbar_expect(xsbar, 2 * TF_CS * TF_BLK);
+    if (rank < nvalid) mbar_expect(lgbar, TF_Q * 4);
+    if (!ext) mbar_expect(smpbar, 4u * (unsigned)nvalid);
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(f32_smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < nvalid * TF_PK; i += TF_THREADS) hist[i] = ld_cg(p.u_hist + (long long)b0 * TF_PK + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  // every MMA chain accumulates (see consume): the accumulators start at zero and every epilogue re-zeroes what it read
+  if (warp < 4) {
+#pragma unroll
+    for (int c = 0; c < 224; c += 32) tf_zero32(tmem + ((uint32_t)(warp * 32) << 16) + c);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cl_barrier();      // every CTA's barriers are initialised and armed before any remote copy can arrive
+
+  const float mu = (float)(TF_Q - 1);
+  // in-kernel cycle counters (VQWN_PROFILE=1): CTA 0 of the first cluster, thread 0 (epilogue view) and thread 128 (MMA view)
+  const bool prof = PROF && (p.prof != nullptr) && blockIdx.x == 0 && p.cluster0 == 0 && (tid == 0 || tid == 128);
+  long long pf[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) pf[i] = 0;
+  long long pf_t = 0;
+#define TF_PF_START() do { if (prof) pf_t = clock64(); } while (0)
+#define TF_PF_ADD(i) do { if (prof) { const long long n_ = clock64(); pf[(i)] += n_ - pf_t; pf_t = n_; } } while (0)
+#ifdef TF_DEBUG_MARKS
+#define TF_MARK(slot, val) do { if (p.prof && lcluster == 0 && p.cluster0 == 0 && rank == 0 && lane == 0) { \
+    reinterpret_cast<volatile long long*>(p.prof)[32 + (slot)] = (long long)(val); __threadfence_system(); } } while (0)
+#else
+#define TF_MARK(slot, val) do { } while (0)
+#endif
+  uint32_t elected = 0;
+  const bool issuer = (warp >= 4 && warp < 4 + TF_NISSUE);
+  const unsigned iss = (unsigned)(warp - 4);
+  if (issuer) asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
+  // instruction descriptors: fp32 accumulate, bf16 x bf16, M = 128, N = 64 (stacked operands) or 32
+  const uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc32 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t ACC0 = 0, ACC1 = 64, ACCR = 128, ACCP1 = 160, ACCP2 = 192;     // TMEM columns
+  const uint32_t sm_u32 = f32_smem_u32(sm);
+
+  // ------------------------------------------------------------------ helpers
+  auto wait_bar = [&](unsigned long long* bar, unsigned& ph) {
+    tf_wait(f32_smem_u32(bar), ph, p.err);
+    ph ^= 1u;
+  };
+  const long long ring_slot_bytes = (long long)p.nclusters * TF_PAIR;
+  // pair block u of layer l: [16 senders][x(u - d) | x(u - 2d)][1 KB]
+  // (time indices stay below 2^31 - checked by the host - so the slot is a 32-bit modulo, not a 64-bit division routine
+  // inlined at every use)
+  auto pair_block = [&](int l, long long u) {
+    const TfLayerDev& ly = p.layers[l];
+    return ly.ring + (long long)((unsigned)u % (2u * (unsigned)ly.d + 1u)) * ring_slot_bytes + (long long)cluster * TF_PAIR;
+  };
+  // warp-level: publish `nblk` staged blocks through L2: copy them to `gdst` (and `gdst2` when given), then ONE multicast
+  // bulk copy delivers them to offset dst_off of all 16 CTAs and counts the bytes on every receiver's `sbar`
+  auto publish = [&](uint8_t* gdst, uint8_t* gdst2, int nblk, int dst_off, unsigned long long* sbar) {
+    for (int c = lane; c < nblk * (TF_BLK / 16); c += 32) {
+      const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
+      *reinterpret_cast<float4*>(gdst + c * 16) = x;
+      if (gdst2) *reinterpret_cast<float4*>(gdst2 + c * 16) = x;
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy stores before the bulk copies' reads
+    __syncwarp();
+    if (lane == 0 && sbar)
+      tc_bulk_multicast(sm_u32 + (unsigned)dst_off, gdst, (unsigned)(nblk * TF_BLK), f32_smem_u32(sbar), (unsigned short)0xFFFF);
+  };
+  uint8_t* const gst = p.gstage + (size_t)lcluster * TF_GSTAGE;
+  const uint32_t my_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  float* const ctab = p.ctab + ((size_t)lcluster * TF_CS + rank) * (size_t)(L + 1) * 512;
+  const uint8_t* const wsrc = p.wstream + (size_t)rank * tf_stream_bytes(L);
+
+  // ------------------------------------------------------------------ role state
+  // MMA thread: FIFO position and barrier phases
+  // (the FIFO position is NOT carried in a variable across the role branches: anything assigned under `if (warp == 4)`
+  // counts as thread-dependent, and slot addresses derived from it would need a register -> uniform-register transfer per
+  // MMA operand; it is recomputed per step from the step index: 4 prologue chunks + 12 L + 16 chunks per step)
+  unsigned ph_b10 = 0u, ph_b11 = 0u, ph_tap = 0u, ph_xs = 0u, ph_e1 = 0u, ph_e2 = 0u;
+  unsigned n_r = 0;                      // residual/skip chains issued so far
+  // consume `nch` chunks (4 instructions each) of `rows`-row tiles: D[128 x N] (TMEM column d_col) (+)= A . B^T with the B
+  // operand advancing b_step bytes per K step
+  // consume `nch` chunks (4 instructions each) of `rows`-row tiles: D[128 x N] (TMEM column d_col) += A . B^T with the B
+  // operand advancing b_step bytes per K step.  The chunks of a chain alternate between the issuing warps: one thread
+  // needs ~115 cycles of its own instruction stream per MMA (descriptor arithmetic, register -> uniform-register moves,
+  // the per-thread issue loop), the tensor pipe 64.  MMAs of different threads are not ordered, so every chain
+  // ACCUMULATES: the epilogue that reads an accumulator leaves it zeroed.
+  auto consume = [&](unsigned& ci, int nch, int rows, uint32_t d_col, bool n64, uint32_t b_addr, uint32_t b_step) {
+    const uint32_t a_step = (uint32_t)rows * 32u;
+    const uint64_t db0 = tf_desc(b_addr);
+    const uint64_t sb = (uint64_t)(b_step >> 4), sa = (uint64_t)(a_step >> 4);
+    const uint32_t id = n64 ? idesc64 : idesc32;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c, ++ci) {
+      if ((ci & (TF_NISSUE - 1)) != iss) continue;
+      const unsigned slot = ci % TF_NSLOT;
+      const long long w0_ = prof ? clock64() : 0;
+      tf_wait(f32_smem_u32(&wfull[slot]), (ci / TF_NSLOT) & 1u, p.err);
+      if (prof) pf[9] += clock64() - w0_;          // time the MMA thread waits for weight chunks
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const long long w1_ = prof ? clock64() : 0;
+      if (elected) {
+        uint64_t da = tf_desc(sm_u32 + TF_OFF_W + slot * TF_SLOT);
+        uint64_t db = db0 + (uint64_t)(4 * c) * sb;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                       ::"r"(tmem + d_col), "l"(da), "l"(db), "r"(id) : "memory");
+          da += sa; db += sb;
+        }
+        const long long w2_ = prof ? clock64() : 0;
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(f32_smem_u32(&wfree[slot])) : "memory");
+        if (prof) { pf[4] += w2_ - w1_; pf[5] += clock64() - w2_; }      // 4-MMA issue | commit
+      }
+      __syncwarp();
+    }
+  };
+  auto wait_b1 = [&](int par) {
+    if (par) wait_bar(&b1bar[1], ph_b11); else wait_bar(&b1bar[0], ph_b10);
+  };
+  auto commit_to = [&](unsigned long long* bar) {     // bar fires when every MMA issued so far has completed
+    if (elected)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(f32_smem_u32(bar)) : "memory");
+    __syncwarp();
+  };
+  auto operand_fence = [&]() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+  // loader lanes (warp 5 lane 0: even chunks, warp 7 lane 0: odd chunks): chunks issued so far, stream position
+  unsigned li = 0;
+  size_t woff = 0;
+  const bool wloader = (lane == 0) && (warp == 8 || warp == 9);
+  const unsigned wmine = (warp == 9) ? 1u : 0u;
+  const bool tloader = (lane == 0) && (warp == 10);
+  unsigned long long wpol = 0;
+  if (wloader) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(wpol));
+  auto load_chunks = [&](int nch, int bytes) {
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      if ((li & 1u) == wmine) {
+        const unsigned slot = li % TF_NSLOT;
+        if (li >= TF_NSLOT) tf_wait(f32_smem_u32(&wfree[slot]), ((li / TF_NSLOT) - 1u) & 1u, p.err);
+        mbar_expect(&wfull[slot], (unsigned)bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(sm_u32 + TF_OFF_W + slot * TF_SLOT), "l"(wsrc + woff), "r"(bytes), "r"(f32_smem_u32(&wfull[slot])), "l"(wpol) : "memory");
+      }
+      li += 1;
+      woff += (size_t)bytes;
+    }
+  };
+  // tap loader (warp 6 lane 0)
+  unsigned ph_tapfree = 0u;
+  auto load_taps = [&](int l, long long t) {
+    mbar_expect(tapbar, TF_PAIR);
+    bulk_g2s(reinterpret_cast<float*>(b2buf), reinterpret_cast<const float*>(pair_block(l, t)), TF_PAIR, tapbar);
+  };
+  // epilogue phases
+  unsigned ph_accA = 0u, ph_accB = 0u, ph_lg = 0u, ph_smp = 0u;
+
+  // ------------------------------------------------------------------ prologue: the first step's layer-0 taps
+  if (tloader) load_taps(0, p.t0);
+  if (wloader) load_chunks(8, TF_CHUNK_A);          // T_0 and A_0 sit at the head of the stream
+  if (issuer) {
+    wait_bar(tapbar, ph_tap);
+    operand_fence();
+    unsigned ci = 0u;
+    consume(ci, 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
+    commit_to(tapfree);
+  }
+  TF_MARK(warp, 1);
+  long long cond_frame = -1;
+  float cnd[8];       // condition (+ bias) terms of the next gate / postprocess1 epilogue
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cnd[j] = 0.f;
+
+  for (long long t = p.t0; t < p.t0 + p.T; ++t) {
+    const long long frame_t = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
+    const bool more = (t + 1 < p.t0 + p.T);
+    TF_PF_START();
+    // ================================================================ all threads: frame change -> condition table
+    if (frame_t != cond_frame) {
+      for (int idx = tid; idx < TF_NS * (TF_C / 4); idx += TF_THREADS) {
+        const int n = idx >> 5, c4 = idx & 31;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < nvalid)
+          x = __ldg(reinterpret_cast<const float4*>(p.cond + (long long)(b0 + n) * p.cond_bstride + frame_t * TF_C) + c4);
+        reinterpret_cast<float4*>(ct_rows)[idx] = x;
+      }
+      __syncthreads();
+      const int cl_ = tid & 31, sg = (tid >> 5) & 7;
+      const float* r0 = ct_rows + (2 * sg) * TF_C;
+      const float* r1 = r0 + TF_C;
+#pragma unroll 1
+      for (int st = 0; st <= (tid < 256 ? L : -1); ++st) {
+        const float* wsrc_;
+        int ld, col;
+        float bias;
+        if (st < L) {
+          wsrc_ = p.layers[st].wlc; ld = 2 * TF_G;
+          col = ((cl_ >> 4) ? TF_G : 0) + 16 * rank + (cl_ & 15);
+          bias = __ldg(p.layers[st].b1 + col);
+        } else {
+          wsrc_ = p.post1_lc; ld = TF_S;
+          col = 32 * rank + cl_;
+          bias = __ldg(p.post1_b + col);
+        }
+        float a0 = bias, a1 = bias;
+#pragma unroll 8
+        for (int k = 0; k < TF_C; ++k) {
+          const float w = __ldg(wsrc_ + (size_t)k * ld + col);
+          a0 = fmaf(r0[k], w, a0);
+          a1 = fmaf(r1[k], w, a1);
+        }
+        float* dst = ctab + (size_t)st * 512;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int s = 2 * sg + h;
+          const float a = h ? a1 : a0;
+          int pos;
+          if (st < L) {
+            // gate epilogue: warp w = ch >> 2, lane = 16 blk + 4 qq + c handles channel 4 w + c, streams
+            // 8 blk + 4 (qq >> 1) + 2 (qq & 1) + {0, 1}; entry 2 type + e
+            const int ch = cl_ & 15, ty = cl_ >> 4;
+            const int ln = 16 * (s >> 3) + 4 * ((s >> 1) & 3) + (ch & 3);
+            pos = ((ch >> 2) * 32 + ln) * 4 + 2 * ty + (s & 1);
+          } else pos = ((cl_ >> 4) * 32 + 16 * (s >> 3) + (cl_ & 15)) * 8 + (s & 7);
+          __stcg(dst + pos, a);
+        }
+      }
+      cond_frame = frame_t;
+      __syncthreads();
+    }
+    // ================================================================ all threads: history -> FIR -> layer-0 input, skip FIR part
+    {
+      const int slot_t = (int)(t % TF_PK);
+      if (ext) {
+        if (tid < TF_NS) {
+          const int b = b0 + tid;
+          float x = 0.f;
+          if (tid < nvalid) {
+            if (p.mode == GEN_STEP) x = p.ext_audio[b];
+            else x = (t > p.t0) ? p.ext_audio[(long long)b * p.T + (t - p.t0 - 1)] : 0.f;
+          }
+          const float u = mu_law_encode_dev(x, mu, 0.f);
+          hist[tid * TF_PK + slot_t] = u;
+          if (rank == 0 && tid < nvalid) st_cg(p.u_hist + (long long)b * TF_PK + slot_t, u);
+        }
+        __syncthreads();
+      }
+      for (int idx = tid; idx < TF_NS * TF_PK; idx += TF_THREADS) {
+        const int i = idx / TF_PK, j = idx - i * TF_PK;
+        u_s[idx] = hist[i * TF_PK + ((slot_t - j) & (TF_PK - 1))];
+      }
+      __syncthreads();
+      // the first layer's condition terms are fetched while the FIR runs
+      if (warp < 4) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(ctab + (warp * 32 + lane) * 4));
+        cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w;
+      }
+      // h0 = (u0*K[PK-1] + b) + u1*K[PK-2] + ...   thread = channel (wavenet_ops.py:178,193: kernel[k-1] is the current sample)
+      if (tid < TF_R) {
+        float acc[TF_NS];
+        const float fb = __ldg(p.pre_b + tid);
+#pragma unroll
+        for (int i = 0; i < TF_NS; ++i) acc[i] = fb;
+#pragma unroll 4
+        for (int j = 0; j < TF_PK; ++j) {
+          const float w = __ldg(p.pre_k + (TF_PK - 1 - j) * TF_R + tid);
+#pragma unroll
+          for (int i = 0; i < TF_NS; ++i) acc[i] = fmaf(u_s[i * TF_PK + j], w, acc[i]);
+        }
+        // layer input of stage 0 = second operand of its stacked pair (the first, "gate of layer -1", multiplies zero weights)
+        uint8_t* const yblk = b1buf + (tid >> 4) * 2 * TF_BLK + TF_BLK;
+#pragma unroll
+        for (int i = 0; i < TF_NS; ++i) {
+          tf_st_split(yblk, i, tid & 15, acc[i]);
+          if ((tid >> 4) == rank) cur0[(tid & 15) * TF_NS + i] = acc[i];
+        }
+      }
+      // skip start folded into the FIR (wavenet.py:127-128): skf[ch][s], ch = 32 rank + (tid & 31), streams 2 (tid >> 5) + {0,1}
+      if (tid < 256) {
+        const int ch = tid & 31, sg = tid >> 5;
+        const float* kp = p.skf_k + 32 * rank + ch;
+        float a0 = __ldg(p.skf_b + 32 * rank + ch), a1 = a0;
+        const float* u0 = u_s + (2 * sg) * TF_PK;
+#pragma unroll 8
+        for (int j = 0; j < TF_PK; ++j) {
+          const float w = __ldg(kp + (TF_PK - 1 - j) * TF_S);
+          a0 = fmaf(u0[j], w, a0);
+          a1 = fmaf(u0[TF_PK + j], w, a1);
+        }
+        skf[ch * TF_NS + 2 * sg] = a0;
+        skf[ch * TF_NS + 2 * sg + 1] = a1;
+      }
+      __syncthreads();
+      // stage 1 reads the same layer input next to gate_0: copy the 16 blocks into the other parity's operand
+      for (int i = tid; i < TF_CS * (TF_BLK / 16); i += TF_THREADS) {
+        const int blk = i >> 6, c = i & 63;
+        *reinterpret_cast<float4*>(b1buf + TF_PAIR + blk * 2 * TF_BLK + TF_BLK + c * 16) =
+            *reinterpret_cast<const float4*>(b1buf + blk * 2 * TF_BLK + TF_BLK + c * 16);
+      }
+      // push_ops of layer 0: this CTA's slice of the first layer's input -> its dilation ring, once per tap position
+      if (tid >= 192 && tid < 256) {
+        const int c = tid - 192;
+        const int d0 = p.layers[0].d;
+        const float4 x = *reinterpret_cast<const float4*>(b1buf + rank * 2 * TF_BLK + TF_BLK + c * 16);
+        *reinterpret_cast<float4*>(pair_block(0, t + d0) + rank * 2 * TF_BLK + c * 16) = x;
+        *reinterpret_cast<float4*>(pair_block(0, t + 2 * d0) + rank * 2 * TF_BLK + TF_BLK + c * 16) = x;
+        asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy ring stores vs later bulk-copy reads
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    TF_PF_ADD(0);
+    TF_MARK(16 + warp, 100000 * (t - p.t0) + 7);
+
+    if (issuer) {
+      // ============================================================== MMA issue warps (both run the same loop)
+      // One loop over the chains of a step, ONE copy of the issue code (instruction-cache footprint): op = 3 l + k for the
+      // stages (k = 0: gate chain of layer l, 1: residual + skip rows of layer l-1, 2: taps of layer l+1), then the tail:
+      // 3 L: skip rows of the last layer, + 1: postprocess1, + 2: postprocess2, + 3: next step's layer-0 taps
+      unsigned ci = 4u + (unsigned)(t - p.t0) * (12u * (unsigned)L + 16u);       // chunks consumed before this step
+#pragma unroll 1
+      for (int op = 0; op < 3 * L + 4; ++op) {
+        const int l = (op < 3 * L) ? op / 3 : L;
+        const int k = (op < 3 * L) ? op - 3 * l : 3 + (op - 3 * L);
+        if ((k == 1 && l == 0) || (k == 2 && l + 1 >= L) || (k == 6 && !more)) continue;
+        const int par = l & 1;
+        int nch = 4, rows = 128;
+        uint32_t d_col, b_addr = sm_u32 + TF_OFF_B1 + par * TF_PAIR, b_step = 2 * TF_BLK;
+        bool n64 = true;
+        if (k == 0) {
+          // the gate epilogue of layer l-1 has read its accumulator (the taps of layer l+1 overwrite it below).  Waited
+          // for HERE, where it is at most one event behind: after this stage's first chain the epilogue of layer l may
+          // arrive too, and a waiter two phases behind would read the barrier's parity as "not yet"
+          if (l > 0) {
+            wait_bar(e1done, ph_e1);
+            wait_b1(par);
+            // next use of this parity's barrier: stage l + 2 (gate + layer input), else the tail (gate only on parity
+            // L & 1, postprocess2 input on parity 1)
+            if (lane == 0 && iss == 0) mbar_expect(&b1bar[par], (l + 2 < L || par != (L & 1)) ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
+          }
+          d_col = par ? ACC1 : ACC0;                         // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
+        } else if (k == 1 || k == 3) {
+          if (k == 3) {
+            wait_bar(e1done, ph_e1);                         // the last gate epilogue of the step
+            wait_b1(par);
+            // parity L & 1 next: postprocess2 input (parity 1), or stage 2 of the next step
+            if (lane == 0 && iss == 0) mbar_expect(&b1bar[par], (par == 1 || L > 2) ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
+          }
+          if (n_r > 0) wait_bar(e2done, ph_e2);              // the previous residual / skip epilogue has read ACCR
+          n_r += 1;
+          rows = 96; d_col = ACCR; n64 = false;              // residual + skip rows x gate
+        } else if (k == 2 || k == 6) {
+          wait_bar(tapbar, ph_tap);
+          d_col = (k == 6 || par) ? ACC0 : ACC1;             // taps of layer l+1 (of layer 0 of the next step)
+          b_addr = sm_u32 + TF_OFF_B2;
+        } else if (k == 4) {
+          wait_bar(xsbar, ph_xs);
+          if (lane == 0 && iss == 0) mbar_expect(xsbar, 2 * TF_CS * TF_BLK);
+          nch = 8; rows = 64; d_col = ACCP1; n64 = false; b_addr = sm_u32 + TF_OFF_B2; b_step = TF_BLK;
+        } else {
+          cl_wait();
+          wait_b1(1);
+          if (lane == 0 && iss == 0) mbar_expect(&b1bar[1], TF_CS * TF_BLK);          // stage 1 of the next step: gate_0 only
+          nch = 8; rows = 32; d_col = ACCP2; n64 = false; b_addr = sm_u32 + TF_OFF_B1 + TF_PAIR; b_step = TF_BLK;
+        }
+        long long* const pfs = reinterpret_cast<long long*>(sm + TF_OFF_PROF);
+        if (prof) { const long long n_ = clock64(); pfs[2 * k] += n_ - pf_t; pf_t = n_; }          // waits of this chain
+        { const long long f0_ = prof ? clock64() : 0; operand_fence(); if (prof) pf[3] += clock64() - f0_; }
+        { const long long q0_ = prof ? clock64() : 0; consume(ci, nch, rows, d_col, n64, b_addr, b_step); if (prof) pf[7] += clock64() - q0_; }
+        const long long c0_ = prof ? clock64() : 0;
+        if (k == 0 || k == 4 || k == 5) commit_to(accA);
+        if (k == 1 || k == 3) commit_to(accB);
+        if (k == 2 || k == 4 || k == 6) commit_to(tapfree);
+        if (k == 3) cl_arrive();
+        if (prof) { const long long n_ = clock64(); pfs[2 * k + 1] += n_ - pf_t; pf_t = n_; pf[6] += n_ - c0_; }      // issue of this chain
+      }
+    } else if (warp < 4) {
+      // ============================================================== epilogue warps
+      uint32_t v0[32], v1[32];
+      float cur[8];       // warp 0: float32 residual chain, channel 16 rank + (lane & 15), streams 8 (lane >> 4) .. +8
+      float sk[16];       // warp 1 / 2: skip sums (hi / lo rows) of channel 32 rank + lane, 16 streams
+      if (warp == 0) {
+        const int i = lane & 15, q = lane >> 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = cur0[i * TF_NS + 8 * q + j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < 16; ++s) sk[s] = (warp == 1) ? skf[lane * TF_NS + s] : 0.f;
+      const int blk = lane >> 4, qq = (lane >> 2) & 3, cc = lane & 3;
+      // residual + skip epilogue of layer `lr` (its rows were multiplied with gate_lr): x_{lr+1} = x_lr + res + b
+      auto res_skip_epilogue = [&](int lr) {
+        const bool dead = (lr == L - 1);                      // the last residual is dead (wavenet.py:145)
+        const float bres = (warp == 0 && !dead) ? __ldg(p.layers[lr].bres + 16 * rank + (lane & 15)) : 0.f;
+        wait_bar(accB, ph_accB);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp < 3 && !(dead && warp == 0)) {
+          tf_ld32_issue(my_taddr + ACCR, v0);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (warp < 3) {
+          tf_zero32(my_taddr + ACCR);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) tf_mbar_arrive(e2done);
+        }
+        if (warp == 0 && !dead) {
+          // lane = 16 q + i: residual rows hi | lo of channel 16 rank + i
+          const int q = lane >> 4, i = lane & 15;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float lo_ = __uint_as_float(v0[j]) + __uint_as_float(v0[16 + j]);
+            const float hi_ = __uint_as_float(v0[8 + j]) + __uint_as_float(v0[24 + j]);
+            const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
+            const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            const float nv = cur[j] + (r + bres);                                // wavenet.py:145
+            cur[j] = nv;
+            tf_st_split(stg, 8 * q + j, i, nv);
+          }
+          __syncwarp();
+          // layer lr+1's input of this step: stored once per tap position of its dilation ring (push_ops); the first
+          // copy is also the source of the hand-off to the cluster (second operand of stage lr+2's stacked pair)
+          const int ln = lr + 1;
+          const int dn = p.layers[ln].d;
+          uint8_t* g1 = pair_block(ln, t + dn) + rank * 2 * TF_BLK;
+          uint8_t* g2 = pair_block(ln, t + 2 * dn) + rank * 2 * TF_BLK + TF_BLK;
+          const bool needed = (ln + 1 < L);
+          publish(g1, g2, 1, TF_OFF_B1 + ((ln + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK + TF_BLK, needed ? &b1bar[(ln + 1) & 1] : nullptr);
+        } else if (warp == 1 || warp == 2) {
+          // lanes 32-63: skip rows hi, lanes 64-95: skip rows lo of channel 32 rank + lane
+#pragma unroll
+          for (int s = 0; s < 16; ++s) sk[s] += __uint_as_float(v0[s]) + __uint_as_float(v0[16 + s]);
+        }
+      };
+#pragma unroll 1
+      for (int l = 0; l <= L; ++l) {
+        const uint32_t acc = (l & 1) ? ACC1 : ACC0;
+        TF_MARK(10 + warp, 100000 * (t - p.t0) + 10 * l);
+        if (l < L) {
+        // ---------------------------------------------------------------- gate of layer l
+        wait_bar(accA, ph_accA);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TF_PF_ADD(1);
+        tf_ld32_issue(my_taddr + acc, v0);
+        tf_ld32_issue(my_taddr + acc + 32, v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tf_zero32(my_taddr + acc);
+        tf_zero32(my_taddr + acc + 32);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (lane == 0) tf_mbar_arrive(e1done);
+        {
+          // lanes 0-15 of the warp hold the rows that multiplied the first stacked input (columns 0-31), lanes 16-31 those
+          // for the second (columns 32-63); columns = 16 hi copies | 16 lo copies of the streams
+          float a8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float m0 = blk ? (__uint_as_float(v1[j]) + __uint_as_float(v1[16 + j])) : (__uint_as_float(v0[j]) + __uint_as_float(v0[16 + j]));
+            const float m1 = blk ? (__uint_as_float(v1[8 + j]) + __uint_as_float(v1[24 + j])) : (__uint_as_float(v0[8 + j]) + __uint_as_float(v0[24 + j]));
+            const float keep = blk ? m1 : m0, send = blk ? m0 : m1;             // keep streams 8 blk + j
+            a8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);              // first + second stacked product
+          }
+          float b4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float keep = (qq & 2) ? a8[4 + j] : a8[j], send = (qq & 2) ? a8[j] : a8[4 + j];
+            b4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);               // hi rows + lo rows; streams 8 blk + 4 (qq >> 1) + j
+          }
+          // tanh lanes (qq & 1 = 0) finish streams j = 0, 1, sigmoid lanes streams j = 2, 3
+          const float s0 = (qq & 1) ? b4[0] : b4[2], s1 = (qq & 1) ? b4[1] : b4[3];
+          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 4), r1 = __shfl_xor_sync(0xffffffffu, s1, 4);
+          const float at0 = ((qq & 1) ? r0 : b4[0]) + cnd[0], at1 = ((qq & 1) ? r1 : b4[1]) + cnd[1];
+          const float as0 = ((qq & 1) ? b4[2] : r0) + cnd[2], as1 = ((qq & 1) ? b4[3] : r1) + cnd[3];
+          const int sbase = 8 * blk + 4 * (qq >> 1) + 2 * (qq & 1);
+          tf_st_split(stg, sbase, 4 * warp + cc, tc_tanh(at0) * tc_sigmoid(as0));       // wavenet_ops.py:235-236
+          tf_st_split(stg, sbase + 1, 4 * warp + cc, tc_tanh(at1) * tc_sigmoid(as1));
+          // condition terms of the next epilogue of this kind: next layer, or postprocess1 (warps 0-1, lane = 16 q + i)
+          if (l + 1 < L) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(ctab + (size_t)(l + 1) * 512 + (warp * 32 + lane) * 4));
+            cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w;
+          } else if (warp < 2) {
+            const float4* src = reinterpret_cast<const float4*>(ctab + (size_t)L * 512 + (warp * 32 + lane) * 8);
+            const float4 a = __ldcg(src), b = __ldcg(src + 1);
+            cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w; cnd[4] = b.x; cnd[5] = b.y; cnd[6] = b.z; cnd[7] = b.w;
+          }
+        }
+        TF_PF_ADD(2);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        // gate_l: first input of stage l+1's stacked pair (and of the last layer's skip rows in the tail)
+        if (warp == 0)
+          publish(gst + TF_GST_XG + (l & 1) * TF_CS * TF_BLK + rank * TF_BLK, nullptr, 1,
+                  TF_OFF_B1 + ((l + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK, &b1bar[(l + 1) & 1]);
+        TF_PF_ADD(3);
+        }
+        // ---------------------------------------------------------------- residual + skip of layer l-1 (l = L: the tail's
+        // skip rows of the last layer)
+        if (l > 0) res_skip_epilogue(l - 1);
+        TF_PF_ADD(4);
+        if (l < L) asm volatile("bar.sync 2, 128;" ::: "memory");       // the staging buffer is free for the next gate epilogue
+      }
+      // ================================================================ tail: relu(skip total) -> postprocess1
+      // every ring store of this step is issued: split cluster barrier (waited for before the next step's tap loads)
+      cl_arrive();
+      if (warp == 2) {
+#pragma unroll
+        for (int s = 0; s < 16; ++s) skx[lane * TF_NS + s] = sk[s];
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (warp == 1) {
+        // skip channel 32 rank + lane = K step 2 rank + (lane >> 4) of postprocess1's input
+#pragma unroll
+        for (int s = 0; s < 16; ++s)
+          tf_st_split(stg + (lane >> 4) * TF_BLK, s, lane & 15, fmaxf(sk[s] + skx[lane * TF_NS + s], 0.f));     // wavenet.py:153
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (warp == 0) publish(gst + TF_GST_XS + rank * 2 * TF_BLK, nullptr, 2, TF_OFF_B2 + rank * 2 * TF_BLK, xsbar);
+      TF_PF_ADD(5);
+      // ================================================================ postprocess1 (+ condition), relu
+      wait_bar(accA, ph_accA);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      cl_wait();
+      const float bias_p2 = (warp == 0) ? __ldg(p.post2_b + 16 * rank + (lane & 15)) : 0.f;
+      if (warp < 2) {
+        // lane = 16 q + i: rows hi | lo of postprocess1 channel 32 rank + 16 warp + i
+        tf_ld32_issue(my_taddr + ACCP1, v0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tf_zero32(my_taddr + ACCP1);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        const int q = lane >> 4, i = lane & 15;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float lo_ = __uint_as_float(v0[j]) + __uint_as_float(v0[16 + j]);
+          const float hi_ = __uint_as_float(v0[8 + j]) + __uint_as_float(v0[24 + j]);
+          const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
+          const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16) + cnd[j];
+          tf_st_split(stg + warp * TF_BLK, 8 * q + j, i, fmaxf(r, 0.f));     // wavenet.py:163
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (warp == 0) publish(gst + TF_GST_XN + rank * 2 * TF_BLK, nullptr, 2, TF_OFF_B1 + TF_PAIR + rank * 2 * TF_BLK, &b1bar[1]);
+      TF_PF_ADD(6);
+      // ================================================================ postprocess2 -> logits, scattered to the drawing CTAs
+      wait_bar(accA, ph_accA);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 0) {
+        // lane = 16 q + i: rows hi | lo of logit 16 rank + i
+        tf_ld32_issue(my_taddr + ACCP2, v0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tf_zero32(my_taddr + ACCP2);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        const int q = lane >> 4, i = lane & 15;
+        const unsigned dst = f32_smem_u32(logits_s + 16 * rank + i);
+        const unsigned mb = f32_smem_u32(lgbar);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float lo_ = __uint_as_float(v0[j]) + __uint_as_float(v0[16 + j]);
+          const float hi_ = __uint_as_float(v0[8 + j]) + __uint_as_float(v0[24 + j]);
+          const float keep = q ? hi_ : lo_, send = q ? lo_ : hi_;
+          const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16) + bias_p2;
+          const unsigned s = (unsigned)(8 * q + j);
+          if ((int)s < nvalid) tc_st_async_f32(cl_mapa(dst, s), r, cl_mapa(mb, s));
+        }
+        TF_PF_ADD(7);
+        // ============================================================== softmax + draw + mu-law decode: CTA s owns stream s
+        if (rank < nvalid) {
+          wait_bar(lgbar, ph_lg);
+          if (lane == 0) mbar_expect(lgbar, TF_Q * 4);
+          const int b = b0 + rank;
+          float lg[8];
+#pragma unroll
+          for (int qi = 0; qi < 8; ++qi) lg[qi] = logits_s[lane + 32 * qi];
+          const int k = warp_softmax_draw(p, TF_Q, lg, b, t, lane, prob_s);
+          if (k >= 0 && lane < TF_CS) {
+            const float un = __ldg(p.enc_lut + k);
+            const int slot_n = (int)((t + 1) % TF_PK);
+            if (lane == 0) st_cg(p.u_hist + (long long)b * TF_PK + slot_n, un);
+            tc_st_async_f32(cl_mapa(f32_smem_u32(hist + rank * TF_PK + slot_n), (unsigned)lane), un,
+                            cl_mapa(f32_smem_u32(smpbar), (unsigned)lane));
+          }
+        }
+        TF_PF_ADD(8);
+      }
+    } else {
+      // ============================================================== loader warps: 8 / 9 (lane 0) weight stream, 10 (lane 0) taps
+      // their part of the step's ring stores is done: arrive at the step's cluster barrier first - the MMA warps wait on it
+      // in the tail while the weight FIFO is still being fed
+      cl_arrive();
+      if (wloader) {
+        // the same chain order as the MMA warps' (op = 3 l + k, tail 3 L ..); the first gate tile of a step was requested
+        // at the end of the previous one, and this step ends with the next step's T_0 and A_0 (stream offset wraps to 0)
+#pragma unroll 1
+        for (int op = 1; op < 3 * L + 3; ++op) {
+          const int l = (op < 3 * L) ? op / 3 : L;
+          const int k = (op < 3 * L) ? op - 3 * l : 3 + (op - 3 * L);
+          if ((k == 1 && l == 0) || (k == 2 && l + 1 >= L)) continue;
+          const int nch = (k == 4 || k == 5) ? 8 : 4;
+          const int bytes = (k == 1 || k == 3) ? TF_CHUNK_R : (k == 4 ? TF_CHUNK_P1 : (k == 5 ? TF_CHUNK_P2 : TF_CHUNK_A));
+          load_chunks(nch, bytes);
+        }
+        if (more) { woff = 0; load_chunks(8, TF_CHUNK_A); }           // T_0 and A_0 of the next step
+      }
+      if (tloader) {
+#pragma unroll 1
+        for (int l = 0; l + 1 < L; ++l) {
+          wait_bar(tapfree, ph_tapfree);       // the previous pair block (layer l's taps) has been consumed
+          load_taps(l + 1, t);
+        }
+        wait_bar(tapfree, ph_tapfree);         // layer L-1's taps consumed: B2 now receives postprocess1's input
+        wait_bar(tapfree, ph_tapfree);         // postprocess1 consumed it
+      }
+      __syncwarp();
+      cl_wait();                               // every CTA's ring stores of this step are visible
+      if (tloader && more) load_taps(0, t + 1);
+    }
+    // ================================================================ all threads: the new samples of all streams are in hist
+    if (!ext) wait_bar(smpbar, ph_smp);
+    // Free-running modes: a CTA leaves the step only with the new samples of ALL streams, i.e. after every CTA's
+    // postprocess2 - nobody can publish into the next step's operands (or count bytes on a receive barrier) while a
+    // neighbour still works on this step.  With external inputs nothing couples the CTAs: a cluster barrier does.
+    if (ext) cl_barrier();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();       // also: the step's scratch (skip sums, draw) is free before the next step rewrites it
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ext && tid == 0) mbar_expect(smpbar, 4u * (unsigned)nvalid);
+    TF_PF_ADD(10);
+  }
+  cl_barrier();
+  if (prof) for (int i = 0; i < 12; ++i) p.prof[(tid == 0 ? 0 : 16) + i] = pf[i];
+  if (prof && tid == 128) for (int i = 0; i < 14; ++i) p.prof[32 + i] = reinterpret_cast<long long*>(sm + TF_OFF_PROF)[i];
+#undef TF_PF_START
+#undef TF_PF_ADD
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight stream builder
+// ---------------------------------------------------------------------------------------------------------------------
+// P[k][n] = sum_m Wres[k][m] W2[m][n] (float64 accumulation): Wres = w2prev [G][ldr] columns 0..R-1 (gate channel k ->
+// residual channel m), W2 = current-tap rows of w1cur [R][2G]
+__global__ void tf_premultiply_kernel(const float* __restrict__ w2prev, int ldr, const float* __restrict__ w1cur,
+                                      float* __restrict__ P) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;     // 0 .. 2G-1
+  const int k = blockIdx.y;                                // 0 .. G-1
+  if (n >= 2 * TF_G) return;
+  double a = 0.0;
+  for (int m = 0; m < TF_R; ++m) a += (double)w2prev[(size_t)k * ldr + m] * (double)w1cur[(size_t)m * 2 * TF_G + n];
+  P[(size_t)k * 2 * TF_G + n] = (float)a;
+}
+// b1adj[n] = b1[n] + sum_m bres_prev[m] W2[m][n]   (bres_prev null: copy)
+__global__ void tf_fold_bias_kernel(const float* __restrict__ b1, const float* __restrict__ bres_prev,
+                                    const float* __restrict__ w1cur, float* __restrict__ b1adj) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= 2 * TF_G) return;
+  double a = (double)b1[n];
+  if (bres_prev)
+    for (int m = 0; m < TF_R; ++m) a += (double)bres_prev[m] * (double)w1cur[(size_t)m * 2 * TF_G + n];
+  b1adj[n] = (float)a;
+}
+// one tile of `ninstr` K steps x `rows` rows for every cluster CTA:
+//   dst[cta * cta_stride + kk * rows * 32 + (m >> 3) * 256 + (e >> 3) * 128 + (m & 7) * 16 + (e & 7) * 2] = hi or lo part of
+//   the weight that multiplies input channel kk * 16 + e in row m.  Row -> (source, column, part) by tile kind:
+//   kind 0 (stacked gate tile, 128 rows): m = 32 w + 16 blk + 4 qq + c: column (qq & 1 ? G : 0) + 16 cta + 4 w + c, part
+//           qq >> 1, source src0 for blk 0 and src1 for blk 1 (either may be null = zero rows), both [K][2G]
+//   kind 1 (residual | skip, 96 rows): m < 32: column 16 cta + (m & 15), part m >> 4; 32..63: column R + 32 cta + m - 32 (hi);
+//           64..95: column R + 32 cta + m - 64 (lo); src0 [K][R + S]
+//   kind 2 (postprocess1, 64 rows): m = 32 w + 16 q + i: column 32 cta + 16 w + i, part q; src0 [K][S]
+//   kind 3 (postprocess2, 32 rows): m = 16 q + i: column 16 cta + i, part q; src0 [K][Q]
+__global__ void tf_pack_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int ldw, int ninstr, int rows,
+                               int kind, size_t cta_stride, uint8_t* __restrict__ dst) {
+  const long long per_cta = (long long)ninstr * rows * 16;
+  const long long total = (long long)TF_CS * per_cta;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cta = (int)(i / per_cta);
+    long long r = i % per_cta;
+    const int e = (int)(r % 16); r /= 16;
+    const int m = (int)(r % rows);
+    const int kk = (int)(r / rows);
+    int col, part;
+    const float* src = src0;
+    if (kind == 0) {
+      const int w = m >> 5, blk = (m >> 4) & 1, qq = (m >> 2) & 3, c = m & 3;
+      col = ((qq & 1) ? TF_G : 0) + 16 * cta + 4 * w + c; part = qq >> 1;
+      src = blk ? src1 : src0;
+    } else if (kind == 1) {
+      if (m < 32) { col = 16 * cta + (m & 15); part = m >> 4; }
+      else if (m < 64) { col = TF_R + 32 * cta + (m - 32); part = 0; }
+      else { col = TF_R + 32 * cta + (m - 64); part = 1; }
+    } else if (kind == 2) {
+      const int w = m >> 5, q = (m >> 4) & 1, ii = m & 15;
+      col = 32 * cta + 16 * w + ii; part = q;
+    } else {
+      col = 16 * cta + (m & 15); part = m >> 4;
+    }
+    const float x = src ? src[(size_t)(kk * 16 + e) * ldw + col] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 v = part ? __float2bfloat16_rn(x - __bfloat162float(hi)) : hi;
+    *reinterpret_cast<__nv_bfloat16*>(dst + (size_t)cta * cta_stride + (size_t)kk * rows * 32 + (m >> 3) * 256 + (e >> 3) * 128 +
+                                      (m & 7) * 16 + (e & 7) * 2) = v;
+  }
+}
+
+}  // namespace vqwn
