@@ -95,6 +95,13 @@ int vqwn_set_stream(vqwn_handle* h, void* cuda_stream);
  * and float32 residual / skip / softmax (logits within 2e-2); the reference's default WaveNet geometry only, otherwise
  * VQWN_ERR_NOTIMPL.  Set it before vqwn_reset / the first generate call of a run: the dilation-queue layout differs. */
 int vqwn_set_precision(vqwn_handle* h, int precision);
+/* VQWN_PREC_TC only.  The tensor-core kernel splits every contraction over four MMA-issuing warps that accumulate into
+ * one TMEM tile; by default the tensor pipe receives their instructions in arrival order, so float32 rounding differs in
+ * the last bits from run to run (~1e-6 relative on the logits; a draw can flip only on such a near-tie).  on != 0: the
+ * warps take turns in a fixed order - results are bit-reproducible (a run equals its prefix, a shard equals the unsharded
+ * run, the step API equals the loop) at ~25 % lower throughput.  The float32 path (VQWN_PREC_FP32) is always
+ * bit-reproducible.  The reference makes no such promise either way (TensorFlow CPU MatMul threading). */
+int vqwn_set_reproducible(vqwn_handle* h, int on);
 int vqwn_set_vq_kernel(vqwn_handle* h, int kernel);
 /* sharded runs (generate.py:34: the batch is the list of -speakers, cut into contiguous slices per GPU): global index of
  * this handle's stream 0.  It keys the counter-based generator that stands in for np.random.rand (utils.py:22) when

@@ -92,6 +92,7 @@ struct vqwn_handle {
   uint8_t* tc_gstage = nullptr;            // [co-resident cluster][TC_GSTAGE] hand-off staging
   // one-hand-off-per-layer variant (wavenet_tcf_cluster.cuh): the default VQWN_PREC_TC kernel; VQWN_TC_KERNEL=v1 selects the older one
   bool tf_use = true;
+  bool tc_reproducible = false;            // vqwn_set_reproducible: fixed accumulation order in the tensor-core kernel
   uint8_t* wtf = nullptr;                  // [16][tf_stream_bytes(L)] per-CTA weight streams
   size_t wtf_bytes = 0;
   float* tf_ptmp = nullptr;                // [G][2G] premultiplied W2_l . Wres_{l-1} of the layer being packed
@@ -559,6 +560,7 @@ int launch_tcf(vqwn_handle* h, int mode, long long T, const float* cond, long lo
   p.pre_k = TP(h, "decoder/preprocess/kernel"); p.pre_b = TP(h, "decoder/preprocess/bias");
   p.skf_k = h->tc_skf_k; p.skf_b = h->tc_skf_b;
   p.wstream = h->wtf;
+  p.flags = h->tc_reproducible ? 1 : 0;
   p.post1_lc = h->post1_w + (size_t)h->S * h->S;
   p.post1_b = TP(h, "decoder/postprocess1/bias"); p.post2_b = TP(h, "decoder/postprocess2/bias");
   size_t off = 0;
@@ -800,8 +802,8 @@ int finish_timing(vqwn_handle* h) {
   if (h->profile && strcmp(h->last_kernel, "wavenet_tcf_cluster") == 0) {
     long long pf[48];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess) {
-      fprintf(stderr, "[vqwn profile] tcf CTA0 epilogue thread 0 cycles: step_start=%lld gate_acc_wait=%lld gate_epilogue=%lld gate_publish=%lld res_skip=%lld tail_skip=%lld post1=%lld post2=%lld draw=%lld sample_wait=%lld (kernel %.3f ms)\n",
-              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7], pf[8], pf[10], ms);
+      fprintf(stderr, "[vqwn profile] tcf CTA0 epilogue thread 0 cycles: step_start=%lld gate_acc_wait=%lld gate_epilogue=%lld gate_publish=%lld res_skip=%lld tail_skip=%lld post1=%lld post2=%lld draw=%lld sample_wait=%lld | inside res_skip: accB_wait=%lld tmem_read_zero_sync=%lld (kernel %.3f ms)\n",
+              pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7], pf[8], pf[10], pf[9], pf[11], ms);
       const char* kn[7] = {"gate", "res+skip", "taps", "tail_skip", "post1", "post2", "next_taps"};
       fprintf(stderr, "[vqwn profile] tcf CTA0 issuing thread (warp 4) cycles, wait / issue per chain kind:");
       for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%lld/%lld", kn[k], pf[32 + 2 * k], pf[32 + 2 * k + 1]);
@@ -1291,6 +1293,12 @@ int vqwn_set_stream(vqwn_handle* h, void* cuda_stream) {
   ENTER(h);
   CK(h, cudaStreamSynchronize(h->stream));
   h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return VQWN_OK;
+}
+
+int vqwn_set_reproducible(vqwn_handle* h, int on) {
+  if (!h) return VQWN_ERR_INVALID;
+  h->tc_reproducible = (on != 0);
   return VQWN_OK;
 }
 

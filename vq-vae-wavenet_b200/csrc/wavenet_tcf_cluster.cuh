@@ -103,7 +103,7 @@ struct TfParams {
   const double* uniforms;
   unsigned long long seed;
   int b_offset;                            // global index of stream 0 (sharded runs): keys the seeded generator
-  int flags;                               // reserved
+  int flags;                               // bit 0: reproducible accumulation order (issuing warps take turns)
   float* audio_out;
   int* idx_out;
   float* logits_out;
@@ -167,6 +167,45 @@ __device__ __noinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* er
   }
 }
 
+// One weight chunk (4 K steps): wait for it, issue its 4 MMAs D[128 x N] += A . B^T, release its FIFO slot.  A real
+// function: the issuing warps are bound by the length of their own instruction stream (every MMA costs ~17 instructions
+// of descriptor arithmetic, register -> uniform-register moves and the per-thread issue loop), one copy keeps it short
+// and in the instruction cache.  d_tmem: accumulator address; b_addr: B operand of the chunk's first K step.
+__device__ __noinline__ void tf_issue_chunk(unsigned ci, uint32_t a_step, uint32_t d_tmem, uint32_t idesc, uint32_t b_addr,
+                                            uint32_t b_step, uint32_t sm_u32, uint32_t elected, int* err, bool have_weights, unsigned* turn_ptr) {
+  const unsigned slot = ci % TF_NSLOT;
+  if (!have_weights) tf_wait(sm_u32 + TF_OFF_BARS + slot * 8u, (ci / TF_NSLOT) & 1u, err);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (elected) {
+    uint64_t da = tf_desc(sm_u32 + TF_OFF_W + slot * TF_SLOT);
+    uint64_t db = tf_desc(b_addr);
+    const uint64_t sa = (uint64_t)(a_step >> 4), sb = (uint64_t)(b_step >> 4);
+    // The chunks of a chain accumulate into one TMEM tile from four different threads, and float32 accumulation depends
+    // on the order in which the tensor pipe receives them (last-bit differences from run to run, ~1e-6 relative).
+    // Reproducible mode (vqwn_set_reproducible): the issuing warps take turns in FIFO order, a counter in shared memory,
+    // so the pipe sees the MMAs in exactly the order one thread would have issued them; the waits and the descriptor
+    // arithmetic of the four warps still overlap, the issue itself (~80 cycles per MMA) no longer does.
+    volatile unsigned* const turn = reinterpret_cast<volatile unsigned*>(turn_ptr);
+    if (turn) while (*turn != ci) { }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                   "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                   ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc) : "memory");
+      da += sa; db += sb;
+    }
+    if (turn) *turn = ci + 1u;
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sm_u32 + TF_OFF_BARS + (8u + slot) * 8u) : "memory");
+  }
+  __syncwarp();
+}
+// the barrier fires when every MMA this thread has issued so far has completed
+__device__ __noinline__ void tf_commit(uint32_t bar_addr, uint32_t elected) {
+  if (elected)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+  __syncwarp();
+}
+
 // PROF: in-kernel cycle counters (VQWN_PROFILE=1).  A separate instantiation: the issuing warps are bound by the length of
 // their own instruction stream, every time stamp costs them
 template <bool PROF>
@@ -200,6 +239,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   float* const ct_rows = reinterpret_cast<float*>(sm + TF_OFF_US);     // [16][128] condition rows (alias)
   unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm + TF_OFF_BARS);
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sm + TF_OFF_MISC);
+  // reproducible mode (flags bit 0): next FIFO chunk whose MMAs may be issued
+  unsigned* const turn_s = (p.flags & 1) ? reinterpret_cast<unsigned*>(sm + TF_OFF_MISC + 8) : nullptr;
   unsigned long long* const wfull = bars + 0;          // [7] weight chunk landed
   unsigned long long* const wfree = bars + 8;          // [7] the MMAs that read the slot completed
   unsigned long long* const b1bar = bars + 16;         // [2] gathered operand of a stage landed (by stage parity)
@@ -217,15 +258,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   __syncthreads();
   const bool ext = (p.mode == GEN_STEP || p.mode == GEN_TEACHER);
   if (tid == 0) {
+    *reinterpret_cast<unsigned*>(sm + TF_OFF_MISC + 8) = 0u;
     for (int i = 0; i < TF_NBARS; ++i) {
       unsigned cnt = (bars + i == e1done) ? 4u : ((bars + i == e2done) ? 3u : 1u);
       if (bars + i == accA || bars + i == accB || bars + i == tapfree) cnt = TF_NISSUE;      // one commit per issuing warp
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f32_smem_u32(&bars[i])), "r"(cnt));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // first use of the receive barriers in a step: stage 1 (gate_0 only, 16 KB) on parity 1, stage 2 on parity 0
-    mbar_expect(&b1bar[1], TF_CS * TF_BLK);
-    mbar_expect(&b1bar[0], (L > 2) ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
+    // first use of the receive barriers in a step: stage 0 (layer input only, 16 KB) on parity 0, stage 1 on parity 1
+    mbar_expect(&b1bar[0], TF_CS * TF_BLK);
+    mbar_expect(&b1bar[1], 2 * TF_CS * TF_BLK);
     mbar_expect(xsbar, 2 * TF_CS * TF_BLK);
     if (rank < nvalid) mbar_expect(lgbar, TF_Q * 4);
     if (!ext) mbar_expect(smpbar, 4u * (unsigned)nvalid);
@@ -291,9 +333,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   };
   // warp-level: publish `nblk` staged blocks through L2: copy them to `gdst` (and `gdst2` when given), then ONE multicast
   // bulk copy delivers them to offset dst_off of all 16 CTAs and counts the bytes on every receiver's `sbar`
-  auto publish = [&](uint8_t* gdst, uint8_t* gdst2, int nblk, int dst_off, unsigned long long* sbar) {
+  auto publish = [&](const uint8_t* src, uint8_t* gdst, uint8_t* gdst2, int nblk, int dst_off, unsigned long long* sbar) {
     for (int c = lane; c < nblk * (TF_BLK / 16); c += 32) {
-      const float4 x = *reinterpret_cast<const float4*>(stg + c * 16);
+      const float4 x = *reinterpret_cast<const float4*>(src + c * 16);
       *reinterpret_cast<float4*>(gdst + c * 16) = x;
       if (gdst2) *reinterpret_cast<float4*>(gdst2 + c * 16) = x;
     }
@@ -314,52 +356,24 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   // MMA operand; it is recomputed per step from the step index: 4 prologue chunks + 12 L + 16 chunks per step)
   unsigned ph_b10 = 0u, ph_b11 = 0u, ph_tap = 0u, ph_xs = 0u, ph_e1 = 0u, ph_e2 = 0u;
   unsigned n_r = 0;                      // residual/skip chains issued so far
-  // consume `nch` chunks (4 instructions each) of `rows`-row tiles: D[128 x N] (TMEM column d_col) (+)= A . B^T with the B
-  // operand advancing b_step bytes per K step
-  // consume `nch` chunks (4 instructions each) of `rows`-row tiles: D[128 x N] (TMEM column d_col) += A . B^T with the B
-  // operand advancing b_step bytes per K step.  The chunks of a chain alternate between the issuing warps: one thread
-  // needs ~115 cycles of its own instruction stream per MMA (descriptor arithmetic, register -> uniform-register moves,
-  // the per-thread issue loop), the tensor pipe 64.  MMAs of different threads are not ordered, so every chain
-  // ACCUMULATES: the epilogue that reads an accumulator leaves it zeroed.
-  auto consume = [&](unsigned& ci, int nch, int rows, uint32_t d_col, bool n64, uint32_t b_addr, uint32_t b_step) {
-    const uint32_t a_step = (uint32_t)rows * 32u;
-    const uint64_t db0 = tf_desc(b_addr);
-    const uint64_t sb = (uint64_t)(b_step >> 4), sa = (uint64_t)(a_step >> 4);
+  // this warp's chunk(s) of a chain of `nch` chunks (4 or 8) of `rows`-row tiles that starts at FIFO position ci0: chunk
+  // iss (and 4 + iss).  The chunks of a chain go to the four issuing warps: MMAs of different threads are not ordered, so
+  // every chain ACCUMULATES - the epilogue that reads an accumulator leaves it zeroed.
+  auto consume = [&](unsigned ci0, int nch, int rows, uint32_t d_col, bool n64, uint32_t b_addr, uint32_t b_step, bool have_weights = false) {
     const uint32_t id = n64 ? idesc64 : idesc32;
-#pragma unroll 1
-    for (int c = 0; c < nch; ++c, ++ci) {
-      if ((ci & (TF_NISSUE - 1)) != iss) continue;
-      const unsigned slot = ci % TF_NSLOT;
-      const long long w0_ = prof ? clock64() : 0;
-      tf_wait(f32_smem_u32(&wfull[slot]), (ci / TF_NSLOT) & 1u, p.err);
-      if (prof) pf[9] += clock64() - w0_;          // time the MMA thread waits for weight chunks
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const long long w1_ = prof ? clock64() : 0;
-      if (elected) {
-        uint64_t da = tf_desc(sm_u32 + TF_OFF_W + slot * TF_SLOT);
-        uint64_t db = db0 + (uint64_t)(4 * c) * sb;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-                       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                       ::"r"(tmem + d_col), "l"(da), "l"(db), "r"(id) : "memory");
-          da += sa; db += sb;
-        }
-        const long long w2_ = prof ? clock64() : 0;
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(f32_smem_u32(&wfree[slot])) : "memory");
-        if (prof) { pf[4] += w2_ - w1_; pf[5] += clock64() - w2_; }      // 4-MMA issue | commit
-      }
-      __syncwarp();
-    }
+    tf_issue_chunk(ci0 + iss, (uint32_t)rows * 32u, tmem + d_col, id, b_addr + 4u * iss * b_step, b_step, sm_u32, elected, p.err, have_weights, turn_s);
+    if (nch == 8)
+      tf_issue_chunk(ci0 + 4u + iss, (uint32_t)rows * 32u, tmem + d_col, id, b_addr + 4u * (4u + iss) * b_step, b_step, sm_u32, elected, p.err, false, turn_s);
+  };
+  // the weight chunk of the chain that is waiting for a gather: checked BEFORE the gather wait, off the critical path
+  auto weights_ready = [&](unsigned ci0) {
+    const unsigned c_ = ci0 + iss;
+    tf_wait(sm_u32 + TF_OFF_BARS + (c_ % TF_NSLOT) * 8u, (c_ / TF_NSLOT) & 1u, p.err);
   };
   auto wait_b1 = [&](int par) {
     if (par) wait_bar(&b1bar[1], ph_b11); else wait_bar(&b1bar[0], ph_b10);
   };
-  auto commit_to = [&](unsigned long long* bar) {     // bar fires when every MMA issued so far has completed
-    if (elected)
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(f32_smem_u32(bar)) : "memory");
-    __syncwarp();
-  };
+  auto commit_to = [&](unsigned long long* bar) { tf_commit(f32_smem_u32(bar), elected); };
   auto operand_fence = [&]() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -401,8 +415,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   if (issuer) {
     wait_bar(tapbar, ph_tap);
     operand_fence();
-    unsigned ci = 0u;
-    consume(ci, 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
+    consume(0u, 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
     commit_to(tapfree);
   }
   TF_MARK(warp, 1);
@@ -495,56 +508,53 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         const float4 a = __ldcg(reinterpret_cast<const float4*>(ctab + (warp * 32 + lane) * 4));
         cnd[0] = a.x; cnd[1] = a.y; cnd[2] = a.z; cnd[3] = a.w;
       }
-      // h0 = (u0*K[PK-1] + b) + u1*K[PK-2] + ...   thread = channel (wavenet_ops.py:178,193: kernel[k-1] is the current sample)
-      if (tid < TF_R) {
-        float acc[TF_NS];
-        const float fb = __ldg(p.pre_b + tid);
+      // Warps 4-11 (256 threads; the epilogue warps keep their registers): this CTA's OWN 16 channels of the preprocess
+      // FIR - the cluster gets them like every other layer input, as one 1 KB slice - and its 32 channels of the skip
+      // start.  h0 = (u0*K[PK-1] + b) + u1*K[PK-2] + ... (wavenet_ops.py:178,193: kernel[k-1] is the current sample); the
+      // tap weights of a thread are fetched together (one L2 round trip), not one dependent load per tap.
+      if (tid >= 128) {
+        const int q = tid - 128;
+        {
+          const int c = q & 15, s_ = q >> 4;
+          float w[TF_PK];
 #pragma unroll
-        for (int i = 0; i < TF_NS; ++i) acc[i] = fb;
-#pragma unroll 4
-        for (int j = 0; j < TF_PK; ++j) {
-          const float w = __ldg(p.pre_k + (TF_PK - 1 - j) * TF_R + tid);
+          for (int j = 0; j < TF_PK; ++j) w[j] = __ldg(p.pre_k + (TF_PK - 1 - j) * TF_R + 16 * rank + c);
+          float a = __ldg(p.pre_b + 16 * rank + c);
+          const float* u0 = u_s + s_ * TF_PK;
 #pragma unroll
-          for (int i = 0; i < TF_NS; ++i) acc[i] = fmaf(u_s[i * TF_PK + j], w, acc[i]);
+          for (int j = 0; j < TF_PK; ++j) a = fmaf(u0[j], w[j], a);
+          cur0[c * TF_NS + s_] = a;
+          tf_st_split(stg, s_, c, a);
         }
-        // layer input of stage 0 = second operand of its stacked pair (the first, "gate of layer -1", multiplies zero weights)
-        uint8_t* const yblk = b1buf + (tid >> 4) * 2 * TF_BLK + TF_BLK;
+        {
+          // skip start folded into the FIR (wavenet.py:127-128): skf[ch][s], ch = 32 rank + (q & 31), streams 2 (q >> 5) + {0,1}
+          const int ch = q & 31, sg = q >> 5;
+          const float* kp = p.skf_k + 32 * rank + ch;
+          float w[TF_PK];
 #pragma unroll
-        for (int i = 0; i < TF_NS; ++i) {
-          tf_st_split(yblk, i, tid & 15, acc[i]);
-          if ((tid >> 4) == rank) cur0[(tid & 15) * TF_NS + i] = acc[i];
+          for (int j = 0; j < TF_PK; ++j) w[j] = __ldg(kp + (TF_PK - 1 - j) * TF_S);
+          float a0 = __ldg(p.skf_b + 32 * rank + ch), a1 = a0;
+          const float* u0 = u_s + (2 * sg) * TF_PK;
+#pragma unroll
+          for (int j = 0; j < TF_PK; ++j) {
+            a0 = fmaf(u0[j], w[j], a0);
+            a1 = fmaf(u0[TF_PK + j], w[j], a1);
+          }
+          skf[ch * TF_NS + 2 * sg] = a0;
+          skf[ch * TF_NS + 2 * sg + 1] = a1;
         }
-      }
-      // skip start folded into the FIR (wavenet.py:127-128): skf[ch][s], ch = 32 rank + (tid & 31), streams 2 (tid >> 5) + {0,1}
-      if (tid < 256) {
-        const int ch = tid & 31, sg = tid >> 5;
-        const float* kp = p.skf_k + 32 * rank + ch;
-        float a0 = __ldg(p.skf_b + 32 * rank + ch), a1 = a0;
-        const float* u0 = u_s + (2 * sg) * TF_PK;
-#pragma unroll 8
-        for (int j = 0; j < TF_PK; ++j) {
-          const float w = __ldg(kp + (TF_PK - 1 - j) * TF_S);
-          a0 = fmaf(u0[j], w, a0);
-          a1 = fmaf(u0[TF_PK + j], w, a1);
-        }
-        skf[ch * TF_NS + 2 * sg] = a0;
-        skf[ch * TF_NS + 2 * sg + 1] = a1;
       }
       __syncthreads();
-      // stage 1 reads the same layer input next to gate_0: copy the 16 blocks into the other parity's operand
-      for (int i = tid; i < TF_CS * (TF_BLK / 16); i += TF_THREADS) {
-        const int blk = i >> 6, c = i & 63;
-        *reinterpret_cast<float4*>(b1buf + TF_PAIR + blk * 2 * TF_BLK + TF_BLK + c * 16) =
-            *reinterpret_cast<const float4*>(b1buf + blk * 2 * TF_BLK + TF_BLK + c * 16);
-      }
-      // push_ops of layer 0: this CTA's slice of the first layer's input -> its dilation ring, once per tap position
-      if (tid >= 192 && tid < 256) {
-        const int c = tid - 192;
+      // push_ops of layer 0 + hand-off (warp 11): the slice goes to the dilation ring once per tap position, and from there
+      // to the layer-input half of BOTH stage operands (stage 0 pairs it with zero weights, stage 1 with gate_0)
+      if (warp == 11) {
         const int d0 = p.layers[0].d;
-        const float4 x = *reinterpret_cast<const float4*>(b1buf + rank * 2 * TF_BLK + TF_BLK + c * 16);
-        *reinterpret_cast<float4*>(pair_block(0, t + d0) + rank * 2 * TF_BLK + c * 16) = x;
-        *reinterpret_cast<float4*>(pair_block(0, t + 2 * d0) + rank * 2 * TF_BLK + TF_BLK + c * 16) = x;
-        asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy ring stores vs later bulk-copy reads
+        uint8_t* g1 = pair_block(0, t + d0) + rank * 2 * TF_BLK;
+        uint8_t* g2 = pair_block(0, t + 2 * d0) + rank * 2 * TF_BLK + TF_BLK;
+        publish(stg, g1, g2, 1, TF_OFF_B1 + rank * 2 * TF_BLK + TF_BLK, &b1bar[0]);
+        if (lane == 0)
+          tc_bulk_multicast(sm_u32 + (unsigned)(TF_OFF_B1 + TF_PAIR + rank * 2 * TF_BLK + TF_BLK), g1, TF_BLK, f32_smem_u32(&b1bar[1]),
+                            (unsigned short)0xFFFF);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -555,66 +565,70 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
     TF_MARK(16 + warp, 100000 * (t - p.t0) + 7);
 
     if (issuer) {
-      // ============================================================== MMA issue warps (both run the same loop)
-      // One loop over the chains of a step, ONE copy of the issue code (instruction-cache footprint): op = 3 l + k for the
-      // stages (k = 0: gate chain of layer l, 1: residual + skip rows of layer l-1, 2: taps of layer l+1), then the tail:
-      // 3 L: skip rows of the last layer, + 1: postprocess1, + 2: postprocess2, + 3: next step's layer-0 taps
+      // ============================================================== MMA issue warps (all four run the same sequence)
+      // Accumulator reuse needs no barrier of its own: the gather a stage waits for contains this CTA's own slices, which
+      // the epilogue publishes only after it has read (and zeroed) the accumulators of the previous stage.  The one
+      // exception is the tail's skip chain (e2done).
       unsigned ci = 4u + (unsigned)(t - p.t0) * (12u * (unsigned)L + 16u);       // chunks consumed before this step
 #pragma unroll 1
-      for (int op = 0; op < 3 * L + 4; ++op) {
-        const int l = (op < 3 * L) ? op / 3 : L;
-        const int k = (op < 3 * L) ? op - 3 * l : 3 + (op - 3 * L);
-        if ((k == 1 && l == 0) || (k == 2 && l + 1 >= L) || (k == 6 && !more)) continue;
+      for (int l = 0; l < L; ++l) {
         const int par = l & 1;
-        int nch = 4, rows = 128;
-        uint32_t d_col, b_addr = sm_u32 + TF_OFF_B1 + par * TF_PAIR, b_step = 2 * TF_BLK;
-        bool n64 = true;
-        if (k == 0) {
-          // the gate epilogue of layer l-1 has read its accumulator (the taps of layer l+1 overwrite it below).  Waited
-          // for HERE, where it is at most one event behind: after this stage's first chain the epilogue of layer l may
-          // arrive too, and a waiter two phases behind would read the barrier's parity as "not yet"
-          if (l > 0) {
-            wait_bar(e1done, ph_e1);
-            wait_b1(par);
-            // next use of this parity's barrier: stage l + 2 (gate + layer input), else the tail (gate only on parity
-            // L & 1, postprocess2 input on parity 1)
-            if (lane == 0 && iss == 0) mbar_expect(&b1bar[par], (l + 2 < L || par != (L & 1)) ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
-          }
-          d_col = par ? ACC1 : ACC0;                         // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
-        } else if (k == 1 || k == 3) {
-          if (k == 3) {
-            wait_bar(e1done, ph_e1);                         // the last gate epilogue of the step
-            wait_b1(par);
-            // parity L & 1 next: postprocess2 input (parity 1), or stage 2 of the next step
-            if (lane == 0 && iss == 0) mbar_expect(&b1bar[par], (par == 1 || L > 2) ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
-          }
-          if (n_r > 0) wait_bar(e2done, ph_e2);              // the previous residual / skip epilogue has read ACCR
-          n_r += 1;
-          rows = 96; d_col = ACCR; n64 = false;              // residual + skip rows x gate
-        } else if (k == 2 || k == 6) {
-          wait_bar(tapbar, ph_tap);
-          d_col = (k == 6 || par) ? ACC0 : ACC1;             // taps of layer l+1 (of layer 0 of the next step)
-          b_addr = sm_u32 + TF_OFF_B2;
-        } else if (k == 4) {
-          wait_bar(xsbar, ph_xs);
-          if (lane == 0 && iss == 0) mbar_expect(xsbar, 2 * TF_CS * TF_BLK);
-          nch = 8; rows = 64; d_col = ACCP1; n64 = false; b_addr = sm_u32 + TF_OFF_B2; b_step = TF_BLK;
-        } else {
-          cl_wait();
-          wait_b1(1);
-          if (lane == 0 && iss == 0) mbar_expect(&b1bar[1], TF_CS * TF_BLK);          // stage 1 of the next step: gate_0 only
-          nch = 8; rows = 32; d_col = ACCP2; n64 = false; b_addr = sm_u32 + TF_OFF_B1 + TF_PAIR; b_step = TF_BLK;
+        const uint32_t b1a = sm_u32 + TF_OFF_B1 + par * TF_PAIR;
+        weights_ready(ci);
+        wait_b1(par);
+        // next use of this parity's barrier: stage l + 2 (gate + layer input, 32 KB); else the tail's gate (parity L & 1,
+        // 16 KB), postprocess2's input (the other parity if it is 1, 32 KB), or the next step's stage 0 (16 KB)
+        if (lane == 0 && iss == 0)
+          mbar_expect(&b1bar[par], (l + 2 < L || (par != (L & 1) && par == 1)) ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
+        operand_fence();
+        consume(ci, 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, true);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
+        commit_to(accA);
+        ci += 4u;
+        if (l > 0) {
+          consume(ci, 4, 96, ACCR, false, b1a, 2 * TF_BLK);                     // residual + skip rows of layer l-1 x gate_{l-1}
+          commit_to(accB);
+          ci += 4u;
         }
-        long long* const pfs = reinterpret_cast<long long*>(sm + TF_OFF_PROF);
-        if (prof) { const long long n_ = clock64(); pfs[2 * k] += n_ - pf_t; pf_t = n_; }          // waits of this chain
-        { const long long f0_ = prof ? clock64() : 0; operand_fence(); if (prof) pf[3] += clock64() - f0_; }
-        { const long long q0_ = prof ? clock64() : 0; consume(ci, nch, rows, d_col, n64, b_addr, b_step); if (prof) pf[7] += clock64() - q0_; }
-        const long long c0_ = prof ? clock64() : 0;
-        if (k == 0 || k == 4 || k == 5) commit_to(accA);
-        if (k == 1 || k == 3) commit_to(accB);
-        if (k == 2 || k == 4 || k == 6) commit_to(tapfree);
-        if (k == 3) cl_arrive();
-        if (prof) { const long long n_ = clock64(); pfs[2 * k + 1] += n_ - pf_t; pf_t = n_; pf[6] += n_ - c0_; }      // issue of this chain
+        if (l + 1 < L) {
+          wait_bar(tapbar, ph_tap);
+          operand_fence();
+          consume(ci, 4, 128, par ? ACC0 : ACC1, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);      // taps of layer l+1
+          commit_to(tapfree);
+          ci += 4u;
+        }
+      }
+      // ---- tail: skip rows of the last layer, postprocess1, postprocess2, next step's layer-0 taps
+      {
+        const int par = L & 1;
+        wait_b1(par);
+        // parity L & 1 next: postprocess2 input (parity 1, 32 KB), or stage 0 of the next step (16 KB)
+        if (lane == 0 && iss == 0) mbar_expect(&b1bar[par], par == 1 ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
+        wait_bar(e2done, ph_e2);       // the residual / skip epilogue of layer L-2 has read ACCR (nothing it publishes is waited for)
+        operand_fence();
+        consume(ci, 4, 96, ACCR, false, sm_u32 + TF_OFF_B1 + par * TF_PAIR, 2 * TF_BLK);
+        commit_to(accB);
+        ci += 4u;
+        cl_arrive();
+        wait_bar(xsbar, ph_xs);
+        if (lane == 0 && iss == 0) mbar_expect(xsbar, 2 * TF_CS * TF_BLK);
+        operand_fence();
+        consume(ci, 8, 64, ACCP1, false, sm_u32 + TF_OFF_B2, TF_BLK);
+        commit_to(accA);
+        commit_to(tapfree);
+        ci += 8u;
+        cl_wait();
+        wait_b1(1);
+        if (lane == 0 && iss == 0) mbar_expect(&b1bar[1], 2 * TF_CS * TF_BLK);      // stage 1 of the next step
+        operand_fence();
+        consume(ci, 8, 32, ACCP2, false, sm_u32 + TF_OFF_B1 + TF_PAIR, TF_BLK);
+        commit_to(accA);
+        ci += 8u;
+        if (more) {
+          wait_bar(tapbar, ph_tap);
+          operand_fence();
+          consume(ci, 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
+          commit_to(tapfree);
+        }
       }
     } else if (warp < 4) {
       // ============================================================== epilogue warps
@@ -636,8 +650,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       auto res_skip_epilogue = [&](int lr) {
         const bool dead = (lr == L - 1);                      // the last residual is dead (wavenet.py:145)
         const float bres = (warp == 0 && !dead) ? __ldg(p.layers[lr].bres + 16 * rank + (lane & 15)) : 0.f;
+        const long long r0_ = prof ? clock64() : 0;
         wait_bar(accB, ph_accB);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long r1_ = prof ? clock64() : 0;
         if (warp < 3 && !(dead && warp == 0)) {
           tf_ld32_issue(my_taddr + ACCR, v0);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -646,8 +662,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           tf_zero32(my_taddr + ACCR);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) tf_mbar_arrive(e2done);
+          if (lane == 0 && lr == L - 2) tf_mbar_arrive(e2done);       // waited for by the tail's skip chain only
+          // warps 0-2 have all read and zeroed their rows before warp 0 publishes the layer input that lets the next
+          // residual + skip chain start
+          asm volatile("bar.sync 3, 96;" ::: "memory");
         }
+        const long long r2_ = prof ? clock64() : 0;
+        if (prof) { pf[9] += r1_ - r0_; pf[11] += r2_ - r1_; }       // accB wait | TMEM read + zero + 3-warp barrier
         if (warp == 0 && !dead) {
           // lane = 16 q + i: residual rows hi | lo of channel 16 rank + i
           const int q = lane >> 4, i = lane & 15;
@@ -659,7 +680,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
             const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             const float nv = cur[j] + (r + bres);                                // wavenet.py:145
             cur[j] = nv;
-            tf_st_split(stg, 8 * q + j, i, nv);
+            tf_st_split(stg + TF_BLK, 8 * q + j, i, nv);
           }
           __syncwarp();
           // layer lr+1's input of this step: stored once per tap position of its dilation ring (push_ops); the first
@@ -669,7 +690,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           uint8_t* g1 = pair_block(ln, t + dn) + rank * 2 * TF_BLK;
           uint8_t* g2 = pair_block(ln, t + 2 * dn) + rank * 2 * TF_BLK + TF_BLK;
           const bool needed = (ln + 1 < L);
-          publish(g1, g2, 1, TF_OFF_B1 + ((ln + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK + TF_BLK, needed ? &b1bar[(ln + 1) & 1] : nullptr);
+          publish(stg + TF_BLK, g1, g2, 1, TF_OFF_B1 + ((ln + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK + TF_BLK, needed ? &b1bar[(ln + 1) & 1] : nullptr);
         } else if (warp == 1 || warp == 2) {
           // lanes 32-63: skip rows hi, lanes 64-95: skip rows lo of channel 32 rank + lane
 #pragma unroll
@@ -692,7 +713,6 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         tf_zero32(my_taddr + acc + 32);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (lane == 0) tf_mbar_arrive(e1done);
         {
           // lanes 0-15 of the warp hold the rows that multiplied the first stacked input (columns 0-31), lanes 16-31 those
           // for the second (columns 32-63); columns = 16 hi copies | 16 lo copies of the streams
@@ -731,8 +751,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         TF_PF_ADD(2);
         asm volatile("bar.sync 2, 128;" ::: "memory");
         // gate_l: first input of stage l+1's stacked pair (and of the last layer's skip rows in the tail)
-        if (warp == 0)
-          publish(gst + TF_GST_XG + (l & 1) * TF_CS * TF_BLK + rank * TF_BLK, nullptr, 1,
+        // (warp 3 publishes; warp 0 goes straight on to the residual rows - the layer input it produces is the later of the
+        // two slices the next stage waits for)
+        if (warp == 3)
+          publish(stg, gst + TF_GST_XG + (l & 1) * TF_CS * TF_BLK + rank * TF_BLK, nullptr, 1,
                   TF_OFF_B1 + ((l + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK, &b1bar[(l + 1) & 1]);
         TF_PF_ADD(3);
         }
@@ -757,7 +779,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           tf_st_split(stg + (lane >> 4) * TF_BLK, s, lane & 15, fmaxf(sk[s] + skx[lane * TF_NS + s], 0.f));     // wavenet.py:153
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (warp == 0) publish(gst + TF_GST_XS + rank * 2 * TF_BLK, nullptr, 2, TF_OFF_B2 + rank * 2 * TF_BLK, xsbar);
+      if (warp == 0) publish(stg, gst + TF_GST_XS + rank * 2 * TF_BLK, nullptr, 2, TF_OFF_B2 + rank * 2 * TF_BLK, xsbar);
       TF_PF_ADD(5);
       // ================================================================ postprocess1 (+ condition), relu
       wait_bar(accA, ph_accA);
@@ -781,7 +803,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         }
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (warp == 0) publish(gst + TF_GST_XN + rank * 2 * TF_BLK, nullptr, 2, TF_OFF_B1 + TF_PAIR + rank * 2 * TF_BLK, &b1bar[1]);
+      if (warp == 0) publish(stg, gst + TF_GST_XN + rank * 2 * TF_BLK, nullptr, 2, TF_OFF_B1 + TF_PAIR + rank * 2 * TF_BLK, &b1bar[1]);
       TF_PF_ADD(6);
       // ================================================================ postprocess2 -> logits, scattered to the drawing CTAs
       wait_bar(accA, ph_accA);

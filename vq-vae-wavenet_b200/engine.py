@@ -147,6 +147,12 @@ class Engine:
         self._ck(self.lib.vqwn_set_precision(self._h, {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "tc": _lib.PREC_TC}[name]))
         self._B = None
 
+    def set_reproducible(self, on=True):
+        """"tc" precision only: fixed accumulation order of the four MMA-issuing warps - bit-reproducible results (a run
+        equals its prefix, a shard the unsharded run, the step API the loop) at ~25 % lower throughput.  Default off: the
+        last bits of the float32 accumulation vary from run to run (~1e-6 relative)."""
+        self._ck(self.lib.vqwn_set_reproducible(self._h, 1 if on else 0))
+
     def set_stream_offset(self, offset):
         """global index of this engine's stream 0 in a sharded run (keys the seeded sample-mode generator)"""
         self._ck(self.lib.vqwn_set_stream_offset(self._h, int(offset)))
