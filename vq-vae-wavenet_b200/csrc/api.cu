@@ -68,6 +68,8 @@ struct vqwn_handle {
   std::vector<size_t> off_w1t, off_w2t;
   size_t off_skip0t = 0, off_post1t = 0, off_post2t = 0;
   int* gen_err = nullptr;
+  int* tf_err_host = nullptr;      // host-mapped error record of the one-hand-off tensor-core kernel (readable after a trap)
+  int* tf_err_dev = nullptr;
   int gen_kernel = 0;                      // 0 auto (cluster kernel when it applies), 1 barrier, 3 cluster
   // cluster kernel (wavenet_fp32_cluster.cuh)
   bool cl_ok = false;                      // geometry constraints hold and 16-CTA clusters can be scheduled
@@ -554,6 +556,7 @@ int launch_tcf(vqwn_handle* h, int mode, long long T, const float* cond, long lo
   const int spc = tc_spc(h, h->B);
   const int nclusters = (h->B + spc - 1) / spc;
   if (h->t + T > 0x7fffffffLL) return fail(h, VQWN_ERR_INVALID, "tensor-core kernel: time index beyond 2^31 samples; call vqwn_reset");
+  if (T > 10000000LL) return fail(h, VQWN_ERR_INVALID, "tensor-core kernel: at most 10^7 time steps per call (32-bit weight-FIFO position)");
   TfParams p;
   memset(&p, 0, sizeof p);
   p.L = h->L; p.B = h->B; p.nclusters = nclusters; p.spc = spc;
@@ -583,12 +586,18 @@ int launch_tcf(vqwn_handle* h, int mode, long long T, const float* cond, long lo
   p.prof = h->profile ? h->prof : nullptr;
 #ifdef TF_DEBUG_MARKS
   static long long* dbg_host = nullptr;
-  if (!dbg_host) { cudaHostAlloc(&dbg_host, 4096, cudaHostAllocMapped); memset(dbg_host, 0, 4096); }
+  if (!dbg_host) { cudaHostAlloc(&dbg_host, 131072, cudaHostAllocMapped); memset(dbg_host, 0, 131072); }
   { long long* dp = nullptr; cudaHostGetDevicePointer(&dp, dbg_host, 0); p.prof = dp; }
   h->dbg_host = dbg_host;
 #endif
-  p.err = h->gen_err;
+  // the error record lives in host-mapped memory: a wait that times out traps, and device memory is unreadable afterwards
   CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  memset(h->tf_err_host, 0, 8 * sizeof(int));
+  p.err = h->tf_err_dev;
+#ifdef TF_DEBUG_MARKS
+  { memset(dbg_host + 1024, 0, 3072 * 8); memset(dbg_host + 4096, 0, 32768); p.err = reinterpret_cast<int*>(p.prof + 4096); }
+#endif
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.blockDim = dim3(TF_THREADS);
@@ -751,28 +760,58 @@ int launch_fp32(vqwn_handle* h, int mode, long long T, const float* cond, long l
   return VQWN_OK;
 }
 
-int finish_timing(vqwn_handle* h) {
 #ifdef TF_DEBUG_MARKS
-  if (cudaStreamSynchronize(h->stream) != cudaSuccess && h->dbg_host) {
-    fprintf(stderr, "[tcf debug marks]");
-    for (int i = 32; i < 32 + 24; ++i) fprintf(stderr, " %d:%lld", i - 32, h->dbg_host[i]);
+// development build: what the host-mapped debug area says after a failed launch
+static void tf_debug_dump(vqwn_handle* h) {
+  if (!h->dbg_host) return;
+  const int* e = reinterpret_cast<const int*>(h->dbg_host + 4096);
+  fprintf(stderr, "[tcf first timeout] code %d barrier index %d parity %d thread %d block %d\n", e[0],
+          ((e[1] & 0x3ffff) - 1024 - (int)TF_OFF_BARS) / 8, e[2], e[3], e[4]);
+  for (int c = 0; c < 112; ++c) {
+    int any = 0;
+    for (int w = 0; w < 12; ++w) any |= e[64 + (c * 12 + w) * 2 + 1];
+    if (!any) continue;
+    fprintf(stderr, "[tcf stuck] cta %3d:", c);
+    for (int w = 0; w < 12; ++w) {
+      const int a = e[64 + (c * 12 + w) * 2], pr = e[64 + (c * 12 + w) * 2 + 1];
+      if (pr) fprintf(stderr, " w%d:bar%d/p%d", w, ((a & 0x3ffff) - 1024 - (int)TF_OFF_BARS) / 8, pr - 100);
+    }
     fprintf(stderr, "\n");
   }
+  for (int c = 0; c < 112; ++c) {
+    const long long* m = h->dbg_host + 1024 + c * 12;
+    long long any = 0;
+    for (int w = 0; w < 12; ++w) any |= m[w];
+    if (!any) continue;
+    fprintf(stderr, "[tcf marks] cta %3d:", c);
+    for (int w = 0; w < 12; ++w) fprintf(stderr, " %lld", m[w]);
+    fprintf(stderr, "\n");
+  }
+}
 #endif
-  CK(h, cudaStreamSynchronize(h->stream));
+
+int finish_timing(vqwn_handle* h) {
+#ifdef TF_DEBUG_MARKS
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) tf_debug_dump(h);
+#endif
+  {
+    const cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess && strcmp(h->last_kernel, "wavenet_tcf_cluster") == 0 && h->tf_err_host && h->tf_err_host[0]) {
+      const int* ev = h->tf_err_host;
+      char msg[320];
+      snprintf(msg, sizeof msg, "generation kernel stopped: wait timed out (barrier index %d, parity %d, thread %d, block %d): %s",
+               ((ev[1] & 0x3ffff) - 1024 - (int)TF_OFF_BARS) / 8, ev[2], ev[3], ev[4], cudaGetErrorString(se));
+      return fail(h, VQWN_ERR_CUDA, msg);
+    }
+    CK(h, se);
+  }
   float ms = 0.f;
   CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
-  if (strncmp(h->last_kernel, "wavenet_", 8) == 0) {
+  if (strncmp(h->last_kernel, "wavenet_", 8) == 0 && strcmp(h->last_kernel, "wavenet_tcf_cluster") != 0) {
     int ev[8] = {0};
     CK(h, cudaMemcpy(ev, h->gen_err, sizeof ev, cudaMemcpyDeviceToHost));
     const int e = ev[0];
-    if (e && strcmp(h->last_kernel, "wavenet_tcf_cluster") == 0) {
-      char msg[200];
-      snprintf(msg, sizeof msg, "generation kernel: wait timed out (code %d, barrier at shared offset %d -> index %d, parity %d, thread %d, block %d)",
-               e, ev[1], (ev[1] - (int)TF_OFF_BARS) / 8, ev[2], ev[3], ev[4]);
-      return fail(h, VQWN_ERR_CUDA, msg);
-    }
     if (e) return fail(h, VQWN_ERR_CUDA, e == 2 ? "generation kernel: operand wait timed out" : (e == 4 ? "generation kernel: packet wait timed out" : "generation kernel: grid barrier timed out"));
   }
   if (h->profile && strcmp(h->last_kernel, "vq_tc_kernel") == 0) {
@@ -1107,6 +1146,7 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
       CKC(cudaFuncSetAttribute((const void*)wavenet_tcf_cluster<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       const char* tk = getenv("VQWN_TC_KERNEL");
       h->tf_use = !(tk && strcmp(tk, "v1") == 0);
+      if (const char* rp = getenv("VQWN_TC_REPRODUCIBLE")) h->tc_reproducible = (atoi(rp) != 0);
       h->wtf_bytes = (size_t)TF_CS * tf_stream_bytes(h->L);
       CKC(cudaMalloc(&h->wtf, h->wtf_bytes));
       CKC(cudaMalloc(&h->tf_ptmp, (size_t)G * 2 * G * sizeof(float)));
@@ -1235,6 +1275,9 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   }
   CKC(cudaMalloc(&h->gen_err, 8 * sizeof(int)));
   CKC(cudaMemset(h->gen_err, 0, 8 * sizeof(int)));
+  CKC(cudaHostAlloc(&h->tf_err_host, 64 * sizeof(int), cudaHostAllocMapped));
+  memset(h->tf_err_host, 0, 64 * sizeof(int));
+  CKC(cudaHostGetDevicePointer(&h->tf_err_dev, h->tf_err_host, 0));
   if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "cluster") == 0 ? 3 : 0);
   h->actA_floats = FP32_TB * 3 * R;                       // gated conv: current | t-d | t-2d segments
   if (FP32_TB * S > h->actA_floats) h->actA_floats = FP32_TB * S;   // post1: relu(skip)
@@ -1282,6 +1325,7 @@ int vqwn_destroy(vqwn_handle* h) {
                     &h->small_b, &h->small_c, &h->small_d, &h->vq_z, &h->vq_idx, &h->vq_out, &h->spk_idx,
                     &h->enc_x, &h->enc_a, &h->enc_b, &h->enc_fold, &h->enc_z, &h->enc_c, &h->enc_d, &h->enc_e, &h->enc_f};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  if (h->tf_err_host) cudaFreeHost(h->tf_err_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1833,11 +1877,7 @@ int vqwn_teacher_forced(vqwn_handle* h, const float* x, const float* cond, int B
                    (const float*)h->x_res.p, nullptr, 0, nullptr, nullptr, (float*)h->logits_res.p, nullptr);
   if (rc) return rc;
 #ifdef TF_DEBUG_MARKS
-  if (cudaStreamSynchronize(h->stream) != cudaSuccess && h->dbg_host) {
-    fprintf(stderr, "[tcf debug marks]");
-    for (int i = 32; i < 32 + 24; ++i) fprintf(stderr, " %d:%lld", i - 32, h->dbg_host[i]);
-    fprintf(stderr, "\n");
-  }
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) tf_debug_dump(h);
 #endif
   CK(h, cudaMemcpyAsync(logits_out, h->logits_res.p, lbytes, cudaMemcpyDeviceToHost, h->stream));
   return finish_timing(h);

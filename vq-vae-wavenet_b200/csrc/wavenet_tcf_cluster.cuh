@@ -62,7 +62,8 @@ constexpr int TF_OFF_SKX = TF_OFF_SKF + 32 * TF_NS * 4;      // [32 ch][16] skip
 constexpr int TF_OFF_PROB = TF_OFF_SKX + 32 * TF_NS * 4;     // [256] fp32 draw scratch           }
 constexpr int TF_OFF_LAYERS = TF_OFF_PROB + TF_Q * 4;
 constexpr int TF_OFF_BARS = TF_OFF_LAYERS + TF_MAXL * 48;
-constexpr int TF_NBARS = 32;
+constexpr int TF_NBARS = 40;
+constexpr int TF_WFULL1 = 32;               // second set of weight-arrival barriers (odd tenancies of a slot)
 constexpr int TF_OFF_MISC = TF_OFF_BARS + TF_NBARS * 8;
 constexpr int TF_OFF_PROF = TF_OFF_MISC + 16;            // [16] cycle counters of the issuing thread, by chain kind
 constexpr int TF_SMEM = TF_OFF_PROF + 16 * 8;
@@ -153,19 +154,43 @@ __device__ __forceinline__ void tf_mbar_arrive(unsigned long long* bar) {
 // instruction cache, every inlined copy costs all of them
 __device__ __noinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* err) {
 #pragma unroll 1
-  for (int spin = 0; spin < (1 << 22); ++spin) {
+  for (int spin = 0; spin < (1 << 26); ++spin) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
     if (ok) return;
-    // a broken launch must end, not hang: once any wait has timed out every other wait gives up quickly
-    if ((spin & 1023) == 1023 && *reinterpret_cast<volatile int*>(err) != 0) return;
+#ifdef TF_DEBUG_MARKS
+    // development: every waiter that has been stuck for half the bound records what it waits for (host-mapped memory)
+    if (spin == (1 << 25) && (threadIdx.x & 31) == 0) {
+      volatile int* d = reinterpret_cast<volatile int*>(err) + 64 + (blockIdx.x * 12 + (threadIdx.x >> 5)) * 2;
+      d[0] = (int)bar_addr; d[1] = (int)parity + 100;
+      __threadfence_system();
+    }
+#endif
   }
-  if (atomicCAS(err, 0, 2) == 0) {
-    // which wait: barrier offset in shared memory, parity, thread, block (read back by the host for the error message)
-    err[1] = (int)bar_addr; err[2] = (int)parity; err[3] = (int)threadIdx.x; err[4] = (int)blockIdx.x;
-  }
+  // A wait that never completes is a broken launch: record which one (barrier offset in shared memory, parity, thread,
+  // block - read back by the host for the error message) and stop the grid instead of running on with missing operands
+  if (atomicCAS(err, 0, 2) == 0) { err[1] = (int)bar_addr; err[2] = (int)parity; err[3] = (int)threadIdx.x; err[4] = (int)blockIdx.x; }
+  __threadfence_system();
+  __trap();
 }
+
+// Weight FIFO barriers and parity waits.  An mbarrier parity wait is valid only while the waiter is at most one phase
+// away from the barrier (a waiter that asks for phase n while phase n - 1 is still open sees "the other parity" and
+// passes at once), and the FIFO's producers and consumers are only loosely coupled: two loader lanes, four issuing warps.
+//   * release barriers wfree[slot]: every slot belongs to ONE loader lane (even slots: warp 8, odd slots: warp 9), which
+//     therefore sees every phase of its barriers, in order;
+//   * arrival barriers: TWO per slot, used alternately (wfull[tenancy & 1][slot]).  Consecutive phases of one barrier are
+//     chunks ci and ci + 14; chunk ci - 14 lies three or four chains back, and every chain that far back has completed
+//     in all four issuing warps before any of them can reach chunk ci (gate chain l+1 needs the gather of gate l, i.e.
+//     all four accA commits of chain l; the residual chain of l needs x_l, i.e. accB of l-1; the tap chain of l+2 needs
+//     its pair block, loaded after all four tapfree commits of l+1; the tail is ordered the same way by xsbar / b1bar).
+//     With one barrier per slot the distance would be 7 chunks - less than two chains - and nothing orders those.
+__device__ __forceinline__ unsigned tf_wfull_bar(unsigned sm_u32, unsigned ci) {
+  const unsigned u = ci / TF_NSLOT, slot = ci - u * TF_NSLOT;
+  return sm_u32 + TF_OFF_BARS + ((u & 1u) ? (TF_WFULL1 + slot) : slot) * 8u;
+}
+__device__ __forceinline__ unsigned tf_wfull_parity(unsigned ci) { return ((ci / TF_NSLOT) >> 1) & 1u; }
 
 // One weight chunk (4 K steps): wait for it, issue its 4 MMAs D[128 x N] += A . B^T, release its FIFO slot.  A real
 // function: the issuing warps are bound by the length of their own instruction stream (every MMA costs ~17 instructions
@@ -174,7 +199,7 @@ __device__ __noinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* er
 __device__ __noinline__ void tf_issue_chunk(unsigned ci, uint32_t a_step, uint32_t d_tmem, uint32_t idesc, uint32_t b_addr,
                                             uint32_t b_step, uint32_t sm_u32, uint32_t elected, int* err, bool have_weights, unsigned* turn_ptr) {
   const unsigned slot = ci % TF_NSLOT;
-  if (!have_weights) tf_wait(sm_u32 + TF_OFF_BARS + slot * 8u, (ci / TF_NSLOT) & 1u, err);
+  if (!have_weights) tf_wait(tf_wfull_bar(sm_u32, ci), tf_wfull_parity(ci), err);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (elected) {
     uint64_t da = tf_desc(sm_u32 + TF_OFF_W + slot * TF_SLOT);
@@ -241,7 +266,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sm + TF_OFF_MISC);
   // reproducible mode (flags bit 0): next FIFO chunk whose MMAs may be issued
   unsigned* const turn_s = (p.flags & 1) ? reinterpret_cast<unsigned*>(sm + TF_OFF_MISC + 8) : nullptr;
-  unsigned long long* const wfull = bars + 0;          // [7] weight chunk landed
+  // bars 0..6 and 32..38: weight chunk landed (even / odd tenancy of the slot, see tf_wfull_bar)
   unsigned long long* const wfree = bars + 8;          // [7] the MMAs that read the slot completed
   unsigned long long* const b1bar = bars + 16;         // [2] gathered operand of a stage landed (by stage parity)
   unsigned long long* const tapbar = bars + 18;        // pair block of the next layer's taps landed in B2
@@ -303,11 +328,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
 #define TF_PF_START() do { if (prof) pf_t = clock64(); } while (0)
 #define TF_PF_ADD(i) do { if (prof) { const long long n_ = clock64(); pf[(i)] += n_ - pf_t; pf_t = n_; } } while (0)
 #ifdef TF_DEBUG_MARKS
-#define TF_MARK(slot, val) do { if (p.prof && lcluster == 0 && p.cluster0 == 0 && rank == 0 && lane == 0) { \
-    reinterpret_cast<volatile long long*>(p.prof)[32 + (slot)] = (long long)(val); __threadfence_system(); } } while (0)
+  // development: every warp of every CTA leaves its last program point in host-mapped memory (posted stores, no fence)
+#define TF_MARK(code) do { if (p.prof && lane == 0) { \
+    reinterpret_cast<volatile long long*>(p.prof)[1024 + blockIdx.x * 12 + warp] = (long long)(t_mark * 1000 + (code)); } } while (0)
 #else
-#define TF_MARK(slot, val) do { } while (0)
+#define TF_MARK(code) do { } while (0)
 #endif
+  long long t_mark = -1;
   uint32_t elected = 0;
   const bool issuer = (warp >= 4 && warp < 4 + TF_NISSUE);
   const unsigned iss = (unsigned)(warp - 4);
@@ -368,7 +395,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   // the weight chunk of the chain that is waiting for a gather: checked BEFORE the gather wait, off the critical path
   auto weights_ready = [&](unsigned ci0) {
     const unsigned c_ = ci0 + iss;
-    tf_wait(sm_u32 + TF_OFF_BARS + (c_ % TF_NSLOT) * 8u, (c_ / TF_NSLOT) & 1u, p.err);
+    tf_wait(tf_wfull_bar(sm_u32, c_), tf_wfull_parity(c_), p.err);
   };
   auto wait_b1 = [&](int par) {
     if (par) wait_bar(&b1bar[1], ph_b11); else wait_bar(&b1bar[0], ph_b10);
@@ -378,7 +405,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
-  // loader lanes (warp 5 lane 0: even chunks, warp 7 lane 0: odd chunks): chunks issued so far, stream position
+  // loader lanes (warp 8 lane 0: even FIFO slots, warp 9 lane 0: odd slots): chunks issued so far, stream position
   unsigned li = 0;
   size_t woff = 0;
   const bool wloader = (lane == 0) && (warp == 8 || warp == 9);
@@ -389,12 +416,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   auto load_chunks = [&](int nch, int bytes) {
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
-      if ((li & 1u) == wmine) {
-        const unsigned slot = li % TF_NSLOT;
+      const unsigned slot = li % TF_NSLOT;
+      if ((slot & 1u) == wmine) {
         if (li >= TF_NSLOT) tf_wait(f32_smem_u32(&wfree[slot]), ((li / TF_NSLOT) - 1u) & 1u, p.err);
-        mbar_expect(&wfull[slot], (unsigned)bytes);
+        const unsigned fb = tf_wfull_bar(sm_u32, li);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((unsigned)bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                     ::"r"(sm_u32 + TF_OFF_W + slot * TF_SLOT), "l"(wsrc + woff), "r"(bytes), "r"(f32_smem_u32(&wfull[slot])), "l"(wpol) : "memory");
+                     ::"r"(sm_u32 + TF_OFF_W + slot * TF_SLOT), "l"(wsrc + woff), "r"(bytes), "r"(fb), "l"(wpol) : "memory");
       }
       li += 1;
       woff += (size_t)bytes;
@@ -418,7 +446,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
     consume(0u, 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
     commit_to(tapfree);
   }
-  TF_MARK(warp, 1);
+  TF_MARK(1);
   long long cond_frame = -1;
   float cnd[8];       // condition (+ bias) terms of the next gate / postprocess1 epilogue
 #pragma unroll
@@ -427,6 +455,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   for (long long t = p.t0; t < p.t0 + p.T; ++t) {
     const long long frame_t = (p.ratio > 0) ? (t - p.t0) / p.ratio : 0;
     const bool more = (t + 1 < p.t0 + p.T);
+    t_mark = t - p.t0;
+    TF_MARK(2);
     TF_PF_START();
     // ================================================================ all threads: frame change -> condition table
     if (frame_t != cond_frame) {
@@ -562,7 +592,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     TF_PF_ADD(0);
-    TF_MARK(16 + warp, 100000 * (t - p.t0) + 7);
+    TF_MARK(7);
 
     if (issuer) {
       // ============================================================== MMA issue warps (all four run the same sequence)
@@ -574,6 +604,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       for (int l = 0; l < L; ++l) {
         const int par = l & 1;
         const uint32_t b1a = sm_u32 + TF_OFF_B1 + par * TF_PAIR;
+        TF_MARK(100 + l);
         weights_ready(ci);
         wait_b1(par);
         // next use of this parity's barrier: stage l + 2 (gate + layer input, 32 KB); else the tail's gate (parity L & 1,
@@ -600,6 +631,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       // ---- tail: skip rows of the last layer, postprocess1, postprocess2, next step's layer-0 taps
       {
         const int par = L & 1;
+        TF_MARK(150);
         wait_b1(par);
         // parity L & 1 next: postprocess2 input (parity 1, 32 KB), or stage 0 of the next step (16 KB)
         if (lane == 0 && iss == 0) mbar_expect(&b1bar[par], par == 1 ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
@@ -609,6 +641,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         commit_to(accB);
         ci += 4u;
         cl_arrive();
+        TF_MARK(151);
         wait_bar(xsbar, ph_xs);
         if (lane == 0 && iss == 0) mbar_expect(xsbar, 2 * TF_CS * TF_BLK);
         operand_fence();
@@ -616,13 +649,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         commit_to(accA);
         commit_to(tapfree);
         ci += 8u;
+        TF_MARK(152);
         cl_wait();
+        TF_MARK(153);
         wait_b1(1);
         if (lane == 0 && iss == 0) mbar_expect(&b1bar[1], 2 * TF_CS * TF_BLK);      // stage 1 of the next step
         operand_fence();
         consume(ci, 8, 32, ACCP2, false, sm_u32 + TF_OFF_B1 + TF_PAIR, TF_BLK);
         commit_to(accA);
         ci += 8u;
+        TF_MARK(154);
         if (more) {
           wait_bar(tapbar, ph_tap);
           operand_fence();
@@ -700,7 +736,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
 #pragma unroll 1
       for (int l = 0; l <= L; ++l) {
         const uint32_t acc = (l & 1) ? ACC1 : ACC0;
-        TF_MARK(10 + warp, 100000 * (t - p.t0) + 10 * l);
+        TF_MARK(200 + l);
         if (l < L) {
         // ---------------------------------------------------------------- gate of layer l
         wait_bar(accA, ph_accA);
@@ -766,6 +802,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       }
       // ================================================================ tail: relu(skip total) -> postprocess1
       // every ring store of this step is issued: split cluster barrier (waited for before the next step's tap loads)
+      TF_MARK(250);
       cl_arrive();
       if (warp == 2) {
 #pragma unroll
@@ -782,9 +819,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       if (warp == 0) publish(stg, gst + TF_GST_XS + rank * 2 * TF_BLK, nullptr, 2, TF_OFF_B2 + rank * 2 * TF_BLK, xsbar);
       TF_PF_ADD(5);
       // ================================================================ postprocess1 (+ condition), relu
+      TF_MARK(251);
       wait_bar(accA, ph_accA);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      TF_MARK(252);
       cl_wait();
+      TF_MARK(253);
       const float bias_p2 = (warp == 0) ? __ldg(p.post2_b + 16 * rank + (lane & 15)) : 0.f;
       if (warp < 2) {
         // lane = 16 q + i: rows hi | lo of postprocess1 channel 32 rank + 16 warp + i
@@ -806,7 +846,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       if (warp == 0) publish(stg, gst + TF_GST_XN + rank * 2 * TF_BLK, nullptr, 2, TF_OFF_B1 + TF_PAIR + rank * 2 * TF_BLK, &b1bar[1]);
       TF_PF_ADD(6);
       // ================================================================ postprocess2 -> logits, scattered to the drawing CTAs
+      TF_MARK(254);
       wait_bar(accA, ph_accA);
+      TF_MARK(255);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (warp == 0) {
         // lane = 16 q + i: rows hi | lo of logit 16 rank + i
@@ -829,7 +871,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         TF_PF_ADD(7);
         // ============================================================== softmax + draw + mu-law decode: CTA s owns stream s
         if (rank < nvalid) {
+          TF_MARK(256);
           wait_bar(lgbar, ph_lg);
+          TF_MARK(257);
           if (lane == 0) mbar_expect(lgbar, TF_Q * 4);
           const int b = b0 + rank;
           float lg[8];
@@ -860,6 +904,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           const int k = (op < 3 * L) ? op - 3 * l : 3 + (op - 3 * L);
           if ((k == 1 && l == 0) || (k == 2 && l + 1 >= L)) continue;
           const int nch = (k == 4 || k == 5) ? 8 : 4;
+          TF_MARK(300 + op);
           const int bytes = (k == 1 || k == 3) ? TF_CHUNK_R : (k == 4 ? TF_CHUNK_P1 : (k == 5 ? TF_CHUNK_P2 : TF_CHUNK_A));
           load_chunks(nch, bytes);
         }
@@ -868,18 +913,22 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       if (tloader) {
 #pragma unroll 1
         for (int l = 0; l + 1 < L; ++l) {
+          TF_MARK(400 + l);
           wait_bar(tapfree, ph_tapfree);       // the previous pair block (layer l's taps) has been consumed
           load_taps(l + 1, t);
         }
         wait_bar(tapfree, ph_tapfree);         // layer L-1's taps consumed: B2 now receives postprocess1's input
         wait_bar(tapfree, ph_tapfree);         // postprocess1 consumed it
       }
+      TF_MARK(450);
       __syncwarp();
       cl_wait();                               // every CTA's ring stores of this step are visible
       if (tloader && more) load_taps(0, t + 1);
     }
     // ================================================================ all threads: the new samples of all streams are in hist
+    TF_MARK(500);
     if (!ext) wait_bar(smpbar, ph_smp);
+    TF_MARK(501);
     // Free-running modes: a CTA leaves the step only with the new samples of ALL streams, i.e. after every CTA's
     // postprocess2 - nobody can publish into the next step's operands (or count bytes on a receive barrier) while a
     // neighbour still works on this step.  With external inputs nothing couples the CTAs: a cluster barrier does.
@@ -890,7 +939,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
     if (!ext && tid == 0) mbar_expect(smpbar, 4u * (unsigned)nvalid);
     TF_PF_ADD(10);
   }
+  TF_MARK(600);
   cl_barrier();
+  TF_MARK(601);
   if (prof) for (int i = 0; i < 12; ++i) p.prof[(tid == 0 ? 0 : 16) + i] = pf[i];
   if (prof && tid == 128) for (int i = 0; i < 14; ++i) p.prof[32 + i] = reinterpret_cast<long long*>(sm + TF_OFF_PROF)[i];
 #undef TF_PF_START
