@@ -502,6 +502,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) wavenet_bf16_cluster(const BcPa
           const float4 x = *reinterpret_cast<const float4*>(stage + 8 * BC_STAGE_PLANE + tid * 16 + (tid >> 4) * 16);
           __nv_bfloat16* dst = ly.ring + slot_old * ring_slot_elems + (long long)cluster * BC_R * BC_NS + (rank * 4) * (BC_PLANE_B / 2);
           *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + tid * 16) = x;
+          // generic-proxy ring store, read by a later step's bulk copy (async proxy)
+          asm volatile("fence.proxy.async.global;" ::: "memory");
         }
       }
       BC_PF_ADD(3);

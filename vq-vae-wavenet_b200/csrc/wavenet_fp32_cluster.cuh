@@ -494,6 +494,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) wavenet_fp32_cluster(const ClPa
             stage[o] = fmaxf(sk, 0.f);     // only read after the last layer (wavenet.py:153)
           }
         }
+        // the ring stores above are generic-proxy writes that a later step reads with bulk copies (async proxy)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
       }
       __syncthreads();
       CL_PF_ADD(5);
