@@ -593,7 +593,7 @@ int launch_tcf(vqwn_handle* h, int mode, long long T, const float* cond, long lo
   // the error record lives in host-mapped memory: a wait that times out traps, and device memory is unreadable afterwards
   CK(h, cudaMemsetAsync(h->gen_err, 0, sizeof(int), h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
-  memset(h->tf_err_host, 0, 8 * sizeof(int));
+  memset(h->tf_err_host, 0, 4096 * sizeof(int));
   p.err = h->tf_err_dev;
 #ifdef TF_DEBUG_MARKS
   { memset(dbg_host + 1024, 0, 3072 * 8); memset(dbg_host + 4096, 0, 32768); p.err = reinterpret_cast<int*>(p.prof + 4096); }
@@ -798,6 +798,19 @@ int finish_timing(vqwn_handle* h) {
     const cudaError_t se = cudaStreamSynchronize(h->stream);
     if (se != cudaSuccess && strcmp(h->last_kernel, "wavenet_tcf_cluster") == 0 && h->tf_err_host && h->tf_err_host[0]) {
       const int* ev = h->tf_err_host;
+      if (getenv("VQWN_DEBUG")) {
+        for (int c = 0; c < 112; ++c) {
+          int any = 0;
+          for (int w = 0; w < 12; ++w) any |= ev[64 + (c * 12 + w) * 2 + 1];
+          if (!any) continue;
+          fprintf(stderr, "[tcf stuck] cta %3d:", c);
+          for (int w = 0; w < 12; ++w) {
+            const int a = ev[64 + (c * 12 + w) * 2], pr = ev[64 + (c * 12 + w) * 2 + 1];
+            if (pr) fprintf(stderr, " w%d:bar%d/p%d", w, ((a & 0x3ffff) - 1024 - (int)TF_OFF_BARS) / 8, pr - 100);
+          }
+          fprintf(stderr, "\n");
+        }
+      }
       char msg[320];
       snprintf(msg, sizeof msg, "generation kernel stopped: wait timed out (barrier index %d, parity %d, thread %d, block %d): %s",
                ((ev[1] & 0x3ffff) - 1024 - (int)TF_OFF_BARS) / 8, ev[2], ev[3], ev[4], cudaGetErrorString(se));
@@ -1275,8 +1288,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   }
   CKC(cudaMalloc(&h->gen_err, 8 * sizeof(int)));
   CKC(cudaMemset(h->gen_err, 0, 8 * sizeof(int)));
-  CKC(cudaHostAlloc(&h->tf_err_host, 64 * sizeof(int), cudaHostAllocMapped));
-  memset(h->tf_err_host, 0, 64 * sizeof(int));
+  CKC(cudaHostAlloc(&h->tf_err_host, 4096 * sizeof(int), cudaHostAllocMapped));
+  memset(h->tf_err_host, 0, 4096 * sizeof(int));
   CKC(cudaHostGetDevicePointer(&h->tf_err_dev, h->tf_err_host, 0));
   if (const char* gk = getenv("VQWN_GEN_KERNEL")) h->gen_kernel = (strcmp(gk, "barrier") == 0) ? 1 : (strcmp(gk, "cluster") == 0 ? 3 : 0);
   h->actA_floats = FP32_TB * 3 * R;                       // gated conv: current | t-d | t-2d segments

@@ -153,20 +153,29 @@ __device__ __forceinline__ void tf_mbar_arrive(unsigned long long* bar) {
 // one copy of the bounded wait loop for the whole kernel: the three warp roles run disjoint code and share the
 // instruction cache, every inlined copy costs all of them
 __device__ __noinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* err) {
+  unsigned long long t_start = 0;
+  bool noted = false;
 #pragma unroll 1
-  for (int spin = 0; spin < (1 << 26); ++spin) {
+  for (unsigned spin = 0;; ++spin) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
     if (ok) return;
-#ifdef TF_DEBUG_MARKS
-    // development: every waiter that has been stuck for half the bound records what it waits for (host-mapped memory)
-    if (spin == (1 << 25) && (threadIdx.x & 31) == 0) {
-      volatile int* d = reinterpret_cast<volatile int*>(err) + 64 + (blockIdx.x * 12 + (threadIdx.x >> 5)) * 2;
-      d[0] = (int)bar_addr; d[1] = (int)parity + 100;
-      __threadfence_system();
+    if ((spin & 1023u) == 1023u) {
+      // bounded by wall time (the spin rate depends on how many lanes wait): a waiter stuck for 0.25 s records what it
+      // waits for in host-mapped memory (VQWN_DEBUG=1 prints the table after a failed launch), after 2 s the launch is
+      // declared broken
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_start == 0) t_start = now;
+      if (!noted && now - t_start > 250000000ull && (threadIdx.x & 31) == 0) {
+        volatile int* d = reinterpret_cast<volatile int*>(err) + 64 + (blockIdx.x * 12 + (threadIdx.x >> 5)) * 2;
+        d[0] = (int)bar_addr; d[1] = (int)parity + 100;
+        __threadfence_system();
+        noted = true;
+      }
+      if (now - t_start > 2000000000ull) break;
     }
-#endif
   }
   // A wait that never completes is a broken launch: record which one (barrier offset in shared memory, parity, thread,
   // block - read back by the host for the error message) and stop the grid instead of running on with missing operands
