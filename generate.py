@@ -11,8 +11,9 @@ own GPU.  Outputs, as the reference writes them (generate.py:94-101,115-117):
 Weights: the reference's own TensorFlow checkpoint `<restore>.index` / `<restore>.data-*` (read without TensorFlow,
 EMA shadows preferred as `ema.variables_to_restore()` does), or `<restore>.npz` holding arrays keyed by the
 reference's variable names.
-Encoder: Encoder_64 ("encoder": "64") and Encoder_Magenta ("Magenta") run on the device; for Encoder_2019
-pass the encoder output with -z_e <file.npy> ([F,latent_dim] or [B,F,latent_dim]); -audio then only fixes the length.
+Encoder: Encoder_64 ("encoder": "64"), Encoder_Magenta ("Magenta") and Encoder_2019 ("2019", hop 320: the trimmed audio
+length must also be a multiple of 320) run on the device; -z_e <file.npy> ([F,latent_dim] or [B,F,latent_dim]) supplies
+an encoder output instead, -audio then only fixes the length.
 """
 import os
 import sys
@@ -71,15 +72,15 @@ def main(argv=None):
     wav = wavio.prepare_audio(wavio.read_wav(args.audio_path, 16000), batch_size)        # generate.py:36-44
     length = wav.shape[1]
     z_e = None
+    if cfg.model['encoder'] == '2019' and args.z_e_path is None and length % 320 != 0:
+        # the reference fails inside add_condition's reshape for such lengths; say why
+        raise ValueError("Encoder_2019 needs an audio length that is a multiple of 320 samples after the 512-trim, got %d" % length)
     if args.z_e_path is not None:
         z_e = np.load(args.z_e_path).astype(np.float32)
         if z_e.ndim == 2:
             z_e = np.tile(z_e[None], (batch_size, 1, 1))
         if length % z_e.shape[1] != 0:
             raise ValueError("audio length %d is not a multiple of the %d encoder frames" % (length, z_e.shape[1]))
-    elif cfg.model['encoder'] not in ('64', 'Magenta'):
-        raise NotImplementedError("encoder %s not implemented on the device (SURVEY 8f #1): pass -z_e"
-                                  % cfg.model['encoder'])
 
     from vqvae_wavenet_b200 import tf_checkpoint
     weights_file = args.restore_path + '.npz'
@@ -104,7 +105,7 @@ def main(argv=None):
     encoder = None
     if z_e is None:
         # generate.py:40 tiles ONE utterance over the batch: encode it once, tile the result
-        enc_cls = pkg.Encoder_64 if cfg.model['encoder'] == '64' else pkg.Encoder_Magenta        # generate.py:65-69
+        enc_cls = {'64': pkg.Encoder_64, 'Magenta': pkg.Encoder_Magenta, '2019': pkg.Encoder_2019}[cfg.model['encoder']]   # generate.py:65-69
         encoder = enc_cls(cfg.model['latent_dim'], engine)
         z_e = np.tile(encoder.build(wav[:1]), (batch_size, 1, 1))
     model = pkg.VQVAE({'x': wav, 'z_e': z_e, 'speaker': speaker, 'encoder': encoder,

@@ -41,6 +41,7 @@ extern "C" {
 #define VQWN_ENCODER_NONE 0
 #define VQWN_ENCODER_MAGENTA 1   /* Encoder_Magenta (Encoder/encoder.py:29-64) */
 #define VQWN_ENCODER_64 64       /* Encoder_64 (Encoder/encoder.py:8-26) */
+#define VQWN_ENCODER_2019 2019   /* Encoder_2019 (Encoder/encoder.py:66-98; MFCC front end Encoder/encoder_ops.py:14-43), hop 320 */
 
 /* arithmetic of the decoder step (vqwn_set_precision) */
 #define VQWN_PREC_FP32 0   /* fp32 CUDA-core contraction; the parity anchor                 */
@@ -129,12 +130,16 @@ int vqwn_tensor_info(const vqwn_handle* h, int i, char* name_out, int name_cap,
 
 /* ---- encoder ----------------------------------------------------------- */
 /* replaces Encoder_64.build / Encoder_Magenta.build (Encoder/encoder.py:8-26, 29-64; model.py:36-42): x [B,T] float
- * audio -> z_e_out [B, T/64, latent_dim].  T must be a multiple of 64.
+ * audio -> z_e_out [B, T/64, latent_dim].  T must be a multiple of 64 (Encoder_2019: 320, see below).
  * cfg.encoder == VQWN_ENCODER_64: keras variables "encoder/conv1d[_i]/{kernel,bias}", "encoder/batch_normalization[_i]/
  *   {gamma,beta,moving_mean,moving_variance}" (i = 1..6, the first without suffix; BatchNorm in inference form, eps 1e-3).
  * cfg.encoder == VQWN_ENCODER_MAGENTA: "encoder/preprocess/{kernel,bias}", "encoder/cycle_1/layer_l/{dilated,gate,filter,
  *   residual}/{kernel,bias}" (l = 1..6), "encoder/postprocess/{kernel,bias}"; shift_right + mu_law_encode on the input.
- * Encoder_2019 (MFCC front end) is not built: VQWN_ERR_NOTIMPL. */
+ * cfg.encoder == VQWN_ENCODER_2019 (Encoder/encoder.py:66-98): keras variables "encoder/conv1d[_i]/{kernel,bias}", i = 1..9:
+ *   MFCC front end (25 ms periodic-hann frames every 10 ms, pad_end, |DFT| 201 bins, 80 HTK mel bands 20-8000 Hz,
+ *   log(. + 1e-6), 13 DCT-II coefficients x rsqrt(160): Encoder/encoder_ops.py:14-43), conv k3 + (conv k3 + skip),
+ *   conv k4 stride 2, 2 x (conv k3 + skip), 4 x (conv k3, doubled: the reference's `relu + relu`), 1x1 to latent_dim.
+ *   Hop 320: T must be a multiple of 320 and z_e_out is [B, T/320, latent_dim]. */
 int vqwn_encode_audio(vqwn_handle* h, const float* x, int B, int64_t T, float* z_e_out);
 
 /* ---- VQ bottleneck + conditioning ---------------------------------------------------- */

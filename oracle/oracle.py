@@ -592,6 +592,125 @@ def encoder_magenta_forward(cfg, weights, x):
     return conv1d_v2(en, weights["encoder/postprocess/kernel"], weights["encoder/postprocess/bias"])
 
 
+# ---------------------------------------------------------------------------------------------
+# Encoder_2019 (Encoder/encoder.py:66-98, Encoder/encoder_ops.py:14-69) - SURVEY 8f #1, third encoder
+# ---------------------------------------------------------------------------------------------
+# The conv stack is the reference's own code; the MFCC front end calls tf.contrib.signal (TensorFlow r1.12-1.14, a
+# third-party dependency absent from /root/reference), whose published algorithms are restated here:
+#   stft(frame_length=400, frame_step=160, fft_length=400, periodic hann window, pad_end=True) -> |rfft| (201 bins);
+#   linear_to_mel_weight_matrix(80, 201, 16000, 20, 8000): HTK mel scale 1127 ln(1 + f / 700), triangles on the mel
+#     axis between 82 equally spaced edges, DC bin zeroed;
+#   log(mel + 1e-6); mfccs_from_log_mel_spectrograms = DCT-II (unnormalised, factor 2) * rsqrt(2 * 80); first 13.
+# PARITY of this front end is pinned only to the restatement that tests/golden/tf_shim.py shares (no TensorFlow here).
+MFCC_SR, MFCC_FRAME, MFCC_STEP, MFCC_MELS, MFCC_COEFS = 16000, 400, 160, 80, 13
+MFCC_LOWER_HZ, MFCC_UPPER_HZ = 20.0, 8000.0
+ENC2019_HOP = 2 * MFCC_STEP          # one stride-2 conv after the 10 ms frames (encoder.py:82)
+
+
+def hann_window_periodic(n):
+    """tf.contrib.signal.hann_window(periodic=True): 0.5 - 0.5 cos(2 pi i / n)"""
+    return (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)).astype(F32)
+
+
+def linear_to_mel_weight_matrix(num_mel_bins=MFCC_MELS, num_spectrogram_bins=MFCC_FRAME // 2 + 1, sample_rate=MFCC_SR,
+                                lower_edge_hertz=MFCC_LOWER_HZ, upper_edge_hertz=MFCC_UPPER_HZ):
+    """tf.contrib.signal.linear_to_mel_weight_matrix (mel_ops.py), evaluated in float64 and rounded to float32"""
+    def hz_to_mel(f):
+        return 1127.0 * np.log(1.0 + np.asarray(f, dtype=np.float64) / 700.0)
+    nyquist = sample_rate / 2.0
+    lin = np.linspace(0.0, nyquist, num_spectrogram_bins)[1:]                 # bands_to_zero = 1 (the DC bin)
+    spec_mel = hz_to_mel(lin)[:, None]
+    edges = np.linspace(hz_to_mel(lower_edge_hertz), hz_to_mel(upper_edge_hertz), num_mel_bins + 2)
+    lower, center, upper = edges[:-2][None, :], edges[1:-1][None, :], edges[2:][None, :]
+    lower_slopes = (spec_mel - lower) / (center - lower)
+    upper_slopes = (upper - spec_mel) / (upper - center)
+    w = np.maximum(0.0, np.minimum(lower_slopes, upper_slopes))
+    return np.pad(w, [(1, 0), (0, 0)]).astype(F32)                             # [201, 80]
+
+
+def dct2_matrix(n=MFCC_MELS, k=MFCC_COEFS):
+    """mfccs_from_log_mel_spectrograms: dct(type=2) (X_c = 2 sum_m x_m cos(pi c (2m+1) / (2n))) * rsqrt(2n); [n, k]"""
+    m = np.arange(n)[:, None]
+    c = np.arange(k)[None, :]
+    return (2.0 * np.cos(np.pi * c * (2 * m + 1) / (2.0 * n)) / np.sqrt(2.0 * n)).astype(F32)
+
+
+def mfcc(batch_wav):
+    """Encoder/encoder_ops.py:14-43.  batch_wav [B,T] -> [B, ceil(T/160), 13]"""
+    x = np.asarray(batch_wav, dtype=F32)
+    B, T = x.shape
+    nfr = -(-T // MFCC_STEP)                                                   # pad_end=True
+    xp = np.pad(x, [(0, 0), (0, (nfr - 1) * MFCC_STEP + MFCC_FRAME - T)])
+    idx = np.arange(nfr)[:, None] * MFCC_STEP + np.arange(MFCC_FRAME)[None, :]
+    frames = xp[:, idx] * hann_window_periodic(MFCC_FRAME)
+    mag = np.abs(np.fft.rfft(frames.astype(F32), n=MFCC_FRAME, axis=-1)).astype(F32)
+    mel = (mag @ linear_to_mel_weight_matrix()).astype(F32)
+    logmel = np.log(mel + F32(1e-6)).astype(F32)
+    return (logmel @ dct2_matrix()).astype(F32)
+
+
+def encoder2019_specs(cfg):
+    """keras auto-names inside variable_scope('encoder'): conv1d, conv1d_1, ..., conv1d_9 in creation order
+    (encoder.py:75-96): 2 x conv_3_768, strided_conv_4_768, 2 + 4 x conv_3_768, linear_64"""
+    specs = []
+    shapes = [(3, MFCC_COEFS, 768), (3, 768, 768), (4, 768, 768)] + [(3, 768, 768)] * 6 + [(1, 768, cfg.D)]
+    for i, shp in enumerate(shapes):
+        sfx = "" if i == 0 else "_%d" % i
+        specs += [("encoder/conv1d%s/kernel" % sfx, shp), ("encoder/conv1d%s/bias" % sfx, (shp[2],))]
+    return specs
+
+
+def make_encoder2019_weights(cfg, seed=4323):
+    """seeded synthetic weights: glorot-uniform kernels (keras default) scaled down so the 2x 'relu + relu' blocks
+    (encoder.py:91-93) keep activations O(1), small biases"""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in encoder2019_specs(cfg):
+        if name.endswith("kernel"):
+            lim = np.sqrt(6.0 / (shape[0] * shape[1] + shape[0] * shape[2]))
+            a = rng.uniform(-lim, lim, size=shape)
+        else:
+            a = rng.uniform(-0.1, 0.1, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=F32)
+    return out
+
+
+def _keras_conv1d_same(net, K, b, stride, relu):
+    k = K.shape[0]
+    T = net.shape[1]
+    To = (T + stride - 1) // stride
+    total = max((To - 1) * stride + k - T, 0)
+    left = total // 2
+    xp = np.pad(net, [(0, 0), (left, total - left), (0, 0)])
+    out = None
+    for j in range(k):
+        term = xp[:, j: j + (To - 1) * stride + 1: stride] @ K[j]
+        out = term if out is None else out + term
+    out = (out + b).astype(F32)
+    return np.maximum(out, 0) if relu else out
+
+
+def encoder2019_forward(cfg, weights, x):
+    """Encoder/encoder.py:72-98.  x [B,T,1] (T a multiple of 320) -> z_e [B,T/320,latent_dim].  Quirk Q17: the four
+    'relu layers' are `relu + relu` (twice the conv output, no skip connection)."""
+    def conv(i, net, stride=1, relu=True):
+        sfx = "" if i == 0 else "_%d" % i
+        return _keras_conv1d_same(net, weights["encoder/conv1d%s/kernel" % sfx], weights["encoder/conv1d%s/bias" % sfx], stride, relu)
+    net = mfcc(np.asarray(x, dtype=F32)[:, :, 0])
+    net = conv(0, net)
+    net = conv(1, net) + net
+    net = conv(2, net, stride=2)
+    i = 3
+    for _ in range(2):
+        net = conv(i, net) + net
+        i += 1
+    for _ in range(4):
+        r = conv(i, net)
+        net = r + r
+        i += 1
+    return conv(9, net, relu=False)
+
+
 def synthetic_z_e(cfg, weights, B, F, seed=1235, kind="normal"):
     rng = np.random.default_rng(seed)
     E = weights["embedding/embedding"]

@@ -45,7 +45,7 @@ import model as ref_model  # noqa: E402
 import utils as ref_utils  # noqa: E402
 import mu_law_ops as ref_mu  # noqa: E402
 from Decoder.decoder import WavenetDecoder  # noqa: E402
-from Encoder.encoder import Encoder_64, Encoder_Magenta  # noqa: E402
+from Encoder.encoder import Encoder_64, Encoder_Magenta, Encoder_2019  # noqa: E402
 
 sys.path.insert(1, ROOT)
 from oracle import oracle as O  # noqa: E402
@@ -358,8 +358,65 @@ def section_encoders(out):
         print("%s: z_e %s, oracle diff %.3g (max |z| %.3g)" % (name, z.shape, np.abs(fwd(cfg, ew, x) - z).max(), np.abs(z).max()))
 
 
+def section_enc2019(out):
+    """Encoder/encoder.py:66-98 + Encoder/encoder_ops.py:14-69 on a short input (T a multiple of 320, quirk Q10).  The
+    conv stack, its residual / `relu + relu` structure and the variable names are the reference's code; the
+    tf.contrib.signal leaf operators are tf_shim's restatement of TensorFlow's published algorithms."""
+    cfg = O.Config()
+    B, T = 2, 7680
+    x = O.synthetic_audio(B, T, seed=1237)[:, :, None]
+    sess = tf.Session()
+    w = dict(O.make_weights(O.Config(wavenet=SMALL_WAVENET)))
+    ew = O.make_encoder2019_weights(cfg)
+    w.update(ew)
+    m = build_model(w, wavenet_json(SMALL_WAVENET), Encoder_2019(64), x, [0, 1])
+    m.build_generator()
+    z = sess.run(m.z_e)
+    created = dict(tf_shim.created_variables())
+    assert all(k in created and created[k] == v.shape for k, v in ew.items()), "encoder variable names differ"
+    out["enc2019_z_e"] = z.astype(np.float32)
+    zo = O.encoder2019_forward(cfg, ew, x)
+    print("enc2019: z_e %s, oracle diff %.3g (max |z| %.3g)" % (z.shape, np.abs(zo - z).max(), np.abs(z).max()))
+
+
+def section_cfg5_e2e(out):
+    """BASELINE config 5 end to end for the three encoder variants: audio -> Encoder_* -> VQ -> speaker concat ->
+    teacher-forced conv-form decoder (model.py:36-42,57-87,76-83; decoder.py:12-37; wavenet.py:24-100), default 30-layer
+    WaveNet, batch 8.  '64' and 'Magenta': T = 6656 (hop 64, 104 frames).  '2019': T = 7680 (hop 320, 24 frames) - the
+    reference cannot run this encoder at 6656 (21 frames do not divide 6656)."""
+    cfg = O.Config()
+    B = 2 if QUICK else 8
+    spk = [b % 4 for b in range(B)]
+    for tag, cls, mk, T, hop in (("e2e64", Encoder_64, O.make_encoder64_weights, 6656, 64),
+                                 ("e2emag", Encoder_Magenta, O.make_encoder_magenta_weights, 6656, 64),
+                                 ("e2e2019", Encoder_2019, O.make_encoder2019_weights, 7680, 320)):
+        if QUICK:
+            T = hop * 4
+        w = dict(O.make_weights(cfg, seed=1234))
+        w.update(mk(cfg))
+        x = O.synthetic_audio(B, T, seed=1237)
+        t0 = time.time()
+        parts = []
+        for b0 in range(0, B, 2):                                          # streams are independent: two at a time (memory)
+            m = build_model(w, wavenet_json(None), cls(64), x[b0:b0 + 2, :, None], spk[b0:b0 + 2])
+            m._build()
+            with tf.variable_scope("decoder"):
+                m._build_decoder()
+            parts.append(tf.Session().run([m.z_e, m.q_z_x, m.x_z_q]))
+        z_e = np.concatenate([p_[0] for p_ in parts])
+        idx = np.concatenate([p_[1] for p_ in parts])
+        logits = np.concatenate([p_[2].reshape(-1, T, 256) for p_ in parts])
+        print("%s: end-to-end conv form [%d x %d], %d frames, in %.1fs" % (tag, B, T, z_e.shape[1], time.time() - t0), flush=True)
+        out[tag + "_T"] = np.int64(T)
+        out[tag + "_z_e"] = z_e.astype(np.float32)
+        out[tag + "_idx"] = idx.astype(np.int16)
+        out[tag + "_logits"] = logits[:, 127::128].astype(np.float32)
+        out[tag + "_last_logits"] = logits[:, -8:].astype(np.float32)
+        out[tag + "_logit_sum"] = logits.astype(np.float64).sum(-1)[:, ::16]
+
+
 def main():
-    sections = [("ref_vars", section_variables), ("ref_vq", section_vq), ("ref_kat", section_kat),
+    sections = [("ref_enc2019", section_enc2019), ("ref_cfg5_e2e", section_cfg5_e2e), ("ref_vars", section_variables), ("ref_vq", section_vq), ("ref_kat", section_kat),
                 ("ref_small", section_small), ("ref_encoders", section_encoders), ("ref_cfg5", section_cfg5),
                 ("ref_full", section_full)]
     only = [a for a in sys.argv[1:] if not a.startswith("--")]

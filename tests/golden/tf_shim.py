@@ -294,7 +294,8 @@ def sign(x):
 
 
 def abs(x):  # noqa: A001 - mirrors tf.abs
-    return _unary(np.abs, x)
+    x = _wrap(x)
+    return _unary(np.abs, x, dtype=np.float32 if x.dtype == np.complex64 else None)      # tf.abs(complex64) is float32
 
 
 def reshape(x, shape):
@@ -600,6 +601,56 @@ class _BatchNormalization:
             var = get_variable("moving_variance", [c], trainable=False)
         inv = _unary(lambda v: (np.float32(1) / np.sqrt(v + np.float32(1e-3))).astype(np.float32), var)
         return (net - mean) * (gamma * inv) + beta
+
+
+# ---- tf.contrib.signal (TensorFlow r1.12-1.14), used by Encoder/encoder_ops.py:14-43.  The library itself is absent:
+# these are restatements of its published algorithms (signal/python/ops: spectral_ops.stft, window_ops.hann_window,
+# mel_ops.linear_to_mel_weight_matrix, mfcc_ops.mfccs_from_log_mel_spectrograms), float32 like the TF kernels.
+def _hann_window(window_length, periodic=True, dtype=np.float32):
+    n = window_length if periodic else window_length - 1
+    return (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(window_length) / n)).astype(np.float32)
+
+
+def _stft(signals, frame_length, frame_step, fft_length=None, window_fn=_hann_window, pad_end=False):
+    signals = _wrap(signals)
+    fft_length = fft_length or frame_length
+    T = signals._shape[-1]
+    nfr = -(-T // frame_step) if pad_end else 1 + (T - frame_length) // frame_step
+    win = window_fn(frame_length)
+
+    def run(x):
+        xp = np.pad(x, [(0, 0)] * (x.ndim - 1) + [(0, max((nfr - 1) * frame_step + frame_length - T, 0))])
+        idx = np.arange(nfr)[:, None] * frame_step + np.arange(frame_length)[None, :]
+        frames = (xp[..., idx] * win).astype(np.float32)
+        return np.fft.rfft(frames, n=fft_length, axis=-1).astype(np.complex64)
+    return Tensor(run, [signals], list(signals._shape.dims[:-1]) + [nfr, fft_length // 2 + 1], np.complex64)
+
+
+def _linear_to_mel_weight_matrix(num_mel_bins=20, num_spectrogram_bins=129, sample_rate=8000, lower_edge_hertz=125.0,
+                                 upper_edge_hertz=3800.0, dtype=np.float32):
+    def hz_to_mel(f):
+        return 1127.0 * np.log(1.0 + np.asarray(f, dtype=np.float64) / 700.0)
+    nsb = int(num_spectrogram_bins)
+    lin = np.linspace(0.0, sample_rate / 2.0, nsb)[1:]
+    spec_mel = hz_to_mel(lin)[:, None]
+    edges = np.linspace(hz_to_mel(lower_edge_hertz), hz_to_mel(upper_edge_hertz), num_mel_bins + 2)
+    lower, center, upper = edges[:-2][None, :], edges[1:-1][None, :], edges[2:][None, :]
+    w = np.maximum(0.0, np.minimum((spec_mel - lower) / (center - lower), (upper - spec_mel) / (upper - center)))
+    return constant(np.pad(w, [(1, 0), (0, 0)]).astype(np.float32))
+
+
+def _mfccs_from_log_mel_spectrograms(log_mel):
+    log_mel = _wrap(log_mel)
+    n = log_mel._shape[-1]
+    m = np.arange(n)[:, None]
+    c = np.arange(n)[None, :]
+    dct = (2.0 * np.cos(np.pi * c * (2 * m + 1) / (2.0 * n)) / np.sqrt(2.0 * n)).astype(np.float32)
+    return Tensor(lambda v: (v @ dct).astype(np.float32), [log_mel], log_mel._shape.dims)
+
+
+contrib = types.SimpleNamespace(signal=types.SimpleNamespace(
+    stft=_stft, hann_window=_hann_window, linear_to_mel_weight_matrix=_linear_to_mel_weight_matrix,
+    mfccs_from_log_mel_spectrograms=_mfccs_from_log_mel_spectrograms))
 
 
 keras = types.SimpleNamespace(

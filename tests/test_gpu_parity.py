@@ -260,10 +260,36 @@ def test_encoder64_matches_oracle():
     assert np.array_equal(enc.build(x[:, :, None]), z)
     with pytest.raises(ValueError):
         eng.encode_audio(x[:, :100])
-    none = pkg.Engine(pkg.EngineConfig(wavenet=SMALL_WAVENET, model=dict(encoder="2019")), device=0, max_batch=1)
-    with pytest.raises(NotImplementedError):
-        none.encode_audio(x)
-    none.close()
+    eng.close()
+
+
+def test_encoder_2019_matches_oracle_and_reference(golden_dir):
+    """Encoder_2019 (Encoder/encoder.py:66-98) on the device: MFCC front end (Encoder/encoder_ops.py:14-43) + conv stack
+    with the reference's `relu + relu` blocks, hop 320.  Targets: the output of the reference's own code on the shim
+    (ref_enc2019.npz) and the NumPy restatement on other shapes.  The device evaluates the 400-point DFT directly in
+    float32 where TensorFlow / NumPy run an FFT; measured 2.6e-6 of max |z_e|, gate 1e-4 like the other encoders."""
+    import vqvae_wavenet_b200 as pkg
+    cfg = O.Config()
+    w = O.make_encoder2019_weights(cfg)
+    eng = pkg.Engine(pkg.EngineConfig(wavenet=SMALL_WAVENET, model=dict(encoder="2019")), device=0, max_batch=4)
+    eng.set_weights(w)
+    g = np.load(os.path.join(golden_dir, "ref_enc2019.npz"))["enc2019_z_e"]
+    x = O.synthetic_audio(2, 7680, seed=1237)
+    z = eng.encode_audio(x)
+    assert z.shape == g.shape == (2, 24, 64)
+    err = np.abs(z - g).max() / np.abs(g).max()
+    print("Encoder_2019 vs reference fixture: %.3g of max |z_e|" % err)
+    assert err <= 1e-4
+    for B, T in ((1, 320), (3, 2560), (2, 64000)):
+        x = O.synthetic_audio(B, T, seed=5)
+        z = eng.encode_audio(x)
+        oz = O.encoder2019_forward(cfg, w, x[:, :, None])
+        assert z.shape == oz.shape == (B, T // 320, 64)
+        assert np.abs(z - oz).max() <= 1e-4 * max(1.0, np.abs(oz).max())
+    enc = pkg.Encoder_2019(64, eng)
+    assert np.array_equal(enc.build(x[:, :, None]), z)
+    with pytest.raises(ValueError):
+        eng.encode_audio(x[:, :6656])                  # 6656 is not a multiple of 320 (SURVEY Q10)
     eng.close()
 
 
@@ -798,6 +824,49 @@ def test_cfg5_teacher_forced_full_size(monkeypatch, golden_dir):
     assert np.abs(out["fp32"] - out["barrier"]).max() <= 2e-5 * scale
     assert np.abs(out["tc"] - out["fp32"]).max() <= LOGIT_RTOL * scale
     assert np.abs(out["bf16"] - out["fp32"]).max() <= BF16_LOGIT_RTOL * scale
+
+
+@pytest.mark.parametrize("variant", ["64", "Magenta", "2019"])
+def test_cfg5_end_to_end_encoder_variants(variant, golden_dir):
+    """BASELINE config 5 for each encoder variant, end to end against the reference's own graph (ref_cfg5_e2e.npz:
+    audio -> Encoder_* -> VQ -> speaker concat -> conv-form decoder, run by make_ref_golden.py): batch 8, default
+    30-layer WaveNet; '64' / 'Magenta' at T = 6656 (hop 64), '2019' at T = 7680 (hop 320 - the reference cannot run it at
+    6656).  The device encoder output is checked against the reference's; the VQ indices of the
+    reference's z_e must be the reference's; the teacher-forced logits are computed from the reference's z_e so that a
+    near-tie flip of one code cannot hide behind (or masquerade as) a decoder error."""
+    import vqvae_wavenet_b200 as pkg
+    tag = {"64": "e2e64", "Magenta": "e2emag", "2019": "e2e2019"}[variant]
+    r = np.load(os.path.join(golden_dir, "ref_cfg5_e2e.npz"))
+    cfg = O.Config()
+    w = dict(O.make_weights(cfg, seed=1234))
+    w.update({"64": O.make_encoder64_weights, "Magenta": O.make_encoder_magenta_weights, "2019": O.make_encoder2019_weights}[variant](cfg))
+    B, T = 8, int(r[tag + "_T"])
+    x = O.synthetic_audio(B, T, seed=1237)
+    eng = pkg.Engine(pkg.EngineConfig(model=dict(encoder=variant)), device=0, max_batch=B)
+    eng.set_weights(w)
+    z = eng.encode_audio(x)
+    zr = r[tag + "_z_e"]
+    assert z.shape == zr.shape
+    ez = np.abs(z - zr).max() / np.abs(zr).max()
+    spk = np.arange(B, dtype=np.int32) % 4
+    idx_dev, _ = eng.encode_condition(z, spk)
+    idx, cond = eng.encode_condition(zr, spk)
+    assert np.array_equal(idx, r[tag + "_idx"].astype(np.int64))                 # VQ of the reference's z_e: bit-exact
+    flips = int((idx_dev != idx).sum())
+    print("cfg5 %s: encoder %.3g of max |z_e|, %d of %d codes differ when the device's own z_e is quantised" % (variant, ez, flips, idx.size))
+    assert ez <= 1e-4
+    assert flips <= idx.size // 100
+    scale = np.abs(r[tag + "_logits"]).max()
+    for prec, tol in (("fp32", LOGIT_RTOL), ("tc", LOGIT_RTOL)):
+        eng.set_precision(prec)
+        lg = eng.teacher_forced(x, cond)
+        assert lg.shape == (B, T, 256)
+        e1 = np.abs(lg[:, 127::128] - r[tag + "_logits"]).max() / scale
+        e2 = np.abs(lg[:, -8:] - r[tag + "_last_logits"]).max() / scale
+        e3 = np.abs(lg[:, ::16].astype(np.float64).sum(-1) - r[tag + "_logit_sum"]).max() / (256 * scale)
+        print("cfg5 %s %s vs reference end-to-end graph: %.3g / %.3g / checksum %.3g of max |logit|" % (variant, prec, e1, e2, e3))
+        assert max(e1, e2, e3) <= tol
+    eng.close()
 
 
 def test_tc_default_order_agrees_with_reproducible_order(golden_dir):

@@ -104,5 +104,6 @@ def test_synthetic_magenta_encoder_weights_equal_oracle():
     assert sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) for k in a)
     with pytest.raises(RuntimeError):
         pkg.Encoder_Magenta(64).build(np.zeros((1, 64, 1), np.float32))
-    with pytest.raises(NotImplementedError):
-        pkg.Encoder_2019(64)
+    with pytest.raises(RuntimeError):
+        pkg.Encoder_2019(64).build(np.zeros((1, 320, 1), np.float32))     # like the others: no engine, no CPU fallback
+    assert pkg.EngineConfig(model=dict(encoder="2019")).to_c().encoder == 2019

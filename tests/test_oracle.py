@@ -190,3 +190,58 @@ def test_encoder_magenta_against_torch_witness():
     x2 = x.copy()
     x2[:, 64 * 10:] = 0
     assert np.array_equal(O.encoder_magenta_forward(cfg, w, x2)[:, :10], z[:, :10])
+
+
+def test_mfcc_front_end_properties():
+    """Encoder/encoder_ops.py:14-43 restated (tf.contrib.signal): shapes, the mel matrix's structure, the DCT's
+    orthogonality up to its scale, a pure tone landing in the right mel band, pad_end framing"""
+    W = O.linear_to_mel_weight_matrix()
+    assert W.shape == (201, 80) and W.dtype == np.float32
+    assert np.all(W >= 0) and np.all(W[0] == 0)                       # DC bin zeroed
+    assert np.all(W.max(0) > 0)                                       # every band has support
+    centers = (W * np.arange(201)[:, None]).sum(0) / W.sum(0)
+    assert np.all(np.diff(centers) >= 0) and centers[-1] > 150       # bands ordered in frequency (the lowest share 40 Hz bins)
+    assert W[:, 0].nonzero()[0].min() >= 1 and W[:, -1].nonzero()[0].max() <= 200
+    D = O.dct2_matrix(80, 80).astype(np.float64)
+    G = D.T @ D
+    assert np.allclose(np.diag(G)[1:], 1.0, atol=1e-5) and np.allclose(G - np.diag(np.diag(G)), 0.0, atol=1e-5)
+    assert np.allclose(G[0, 0], 2.0, atol=1e-5)                       # TF's unnormalised type-2 DCT: c = 0 is not rescaled
+    win = O.hann_window_periodic(400)
+    assert win[0] == 0 and abs(win[200] - 1.0) < 1e-7 and abs(win[1] - win[399]) < 1e-7
+    t = np.arange(1600)
+    x = (0.5 * np.sin(2 * np.pi * 1000.0 * t / 16000.0)).astype(np.float32)[None]
+    m = O.mfcc(x)
+    assert m.shape == (1, 10, 13) and m.dtype == np.float32 and np.isfinite(m).all()
+    # a direct (float64 DFT) evaluation of one interior frame
+    fr = x[0, 160:560].astype(np.float64) * win
+    n = np.arange(400)
+    mag = np.abs(np.array([np.sum(fr * np.exp(-2j * np.pi * k * n / 400)) for k in range(201)]))
+    assert mag.argmax() == 25                                         # 1000 Hz / (16000 / 400)
+    # (a pure tone leaves most bands at rounding-noise level, where log(. + 1e-6) amplifies float32 FFT noise: the
+    # value check uses the broadband synthetic signal)
+    xs = O.synthetic_audio(1, 1600, seed=9)
+    ms = O.mfcc(xs)
+    fr = xs[0, 160:560].astype(np.float64) * win
+    mag = np.abs(np.array([np.sum(fr * np.exp(-2j * np.pi * k * n / 400)) for k in range(201)]))
+    ref = np.log(mag @ W.astype(np.float64) + 1e-6) @ O.dct2_matrix().astype(np.float64)
+    assert np.abs(ref - ms[0, 1]).max() < 2e-3
+    # the last frames see zero padding (pad_end=True): frame 9 covers samples 1440..1839, 160 real ones
+    assert O.mfcc(x[:, :1500]).shape == (1, 10, 13)
+
+
+def test_encoder2019_structure():
+    """Encoder/encoder.py:72-98: hop 320, ten convs in creation order, `relu + relu` doubles (quirk Q17)"""
+    cfg = O.Config()
+    w = O.make_encoder2019_weights(cfg)
+    names = [n for n, _ in O.encoder2019_specs(cfg)]
+    assert names[0] == "encoder/conv1d/kernel" and names[-1] == "encoder/conv1d_9/bias" and len(names) == 20
+    assert w["encoder/conv1d/kernel"].shape == (3, 13, 768) and w["encoder/conv1d_2/kernel"].shape == (4, 768, 768)
+    x = O.synthetic_audio(2, 1280, seed=3)[:, :, None]
+    z = O.encoder2019_forward(cfg, w, x)
+    assert z.shape == (2, 4, 64) and np.isfinite(z).all()
+    # doubling the last block's kernel and bias == what `relu + relu` does to a plain conv: scale the final linear map instead
+    w2 = dict(w)
+    w2["encoder/conv1d_9/kernel"] = w["encoder/conv1d_9/kernel"] * np.float32(0.5)
+    z2 = O.encoder2019_forward(cfg, w2, x)
+    b = w["encoder/conv1d_9/bias"]
+    assert np.allclose((z - b) * 0.5, z2 - b, atol=1e-4)

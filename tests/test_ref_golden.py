@@ -159,3 +159,32 @@ def test_encoders_match_reference(golden_dir):
     assert np.abs(z - g["enc64_z_e"]).max() < 1e-5
     z = O.encoder_magenta_forward(cfg, O.make_encoder_magenta_weights(cfg), x)
     assert np.abs(z - g["encmag_z_e"]).max() < 2e-5
+
+
+def test_encoder2019_matches_reference(golden_dir):
+    """Encoder_2019 (Encoder/encoder.py:66-98 run by make_ref_golden.py; its tf.contrib.signal leaf operators are
+    tf_shim's restatement of TensorFlow's published MFCC pipeline): oracle == reference output"""
+    g = _load(golden_dir, "ref_enc2019.npz")
+    cfg = O.Config()
+    x = O.synthetic_audio(2, 7680, seed=1237)[:, :, None]
+    z = O.encoder2019_forward(cfg, O.make_encoder2019_weights(cfg), x)
+    assert z.shape == g["enc2019_z_e"].shape == (2, 24, 64)
+    assert np.abs(z - g["enc2019_z_e"]).max() < 1e-4
+
+
+def test_cfg5_end_to_end_fixture_front_half(golden_dir):
+    """ref_cfg5_e2e.npz (the reference's whole graph per encoder variant): the oracle's encoders and VQ reproduce its
+    z_e and code indices; the decoder half is checked on the GPU (tests/test_gpu_parity.py) and, for the conv form
+    itself, by the cfg5 test above"""
+    g = _load(golden_dir, "ref_cfg5_e2e.npz")
+    cfg = O.Config()
+    E = O.make_weights(cfg, seed=1234)["embedding/embedding"]
+    for tag, mk, fwd, tol in (("e2e64", O.make_encoder64_weights, O.encoder64_forward, 2e-5),
+                              ("e2emag", O.make_encoder_magenta_weights, O.encoder_magenta_forward, 5e-5),
+                              ("e2e2019", O.make_encoder2019_weights, O.encoder2019_forward, 2e-4)):
+        T = int(g[tag + "_T"])
+        x = O.synthetic_audio(8, T, seed=1237)[:2, :, None]
+        z = fwd(cfg, mk(cfg), x)
+        assert np.abs(z - g[tag + "_z_e"][:2]).max() < tol * max(1.0, np.abs(z).max()), tag
+        idx = O.vq_discretise(g[tag + "_z_e"], E)[0]
+        assert np.array_equal(idx, g[tag + "_idx"].astype(np.int64)), tag

@@ -974,7 +974,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   if (c.pre_kernel_size < 1 || c.pre_kernel_size > 64) return fail(nullptr, VQWN_ERR_INVALID, "preprocess.kernel_size out of range");
   if (c.use_vq && (c.k < 1 || c.k > 512)) return fail(nullptr, VQWN_ERR_NOTIMPL, "k must be <= 512");
   if (c.latent_dim != 32 && c.latent_dim != 64) return fail(nullptr, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
-  if (c.encoder != VQWN_ENCODER_NONE && c.encoder != VQWN_ENCODER_64 && c.encoder != VQWN_ENCODER_MAGENTA)
+  if (c.encoder != VQWN_ENCODER_NONE && c.encoder != VQWN_ENCODER_64 && c.encoder != VQWN_ENCODER_MAGENTA &&
+      c.encoder != VQWN_ENCODER_2019)
     return fail(nullptr, VQWN_ERR_NOTIMPL, "encoders on the device: Encoder_64 (64), Encoder_Magenta (1), or none (0)");
   if (c.encoder != VQWN_ENCODER_NONE && c.latent_dim != 64)
     return fail(nullptr, VQWN_ERR_NOTIMPL, "the device encoders need latent_dim = 64");
@@ -1077,6 +1078,16 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
     }
     add_tensor(h, "encoder/postprocess/kernel", {1, MC, c.latent_dim}, false);
     add_tensor(h, "encoder/postprocess/bias", {c.latent_dim}, false);
+  }
+  if (c.encoder == VQWN_ENCODER_2019) {
+    // Encoder/encoder.py:75-96: ten unnamed keras Conv1D layers in creation order
+    const int shp[10][3] = {{3, MFCC_COEFS, 768}, {3, 768, 768}, {4, 768, 768}, {3, 768, 768}, {3, 768, 768}, {3, 768, 768},
+                            {3, 768, 768}, {3, 768, 768}, {3, 768, 768}, {1, 768, c.latent_dim}};
+    for (int i = 0; i < 10; ++i) {
+      const std::string sfx = i == 0 ? "" : "_" + std::to_string(i);
+      add_tensor(h, "encoder/conv1d" + sfx + "/kernel", {shp[i][0], shp[i][1], shp[i][2]}, false);
+      add_tensor(h, "encoder/conv1d" + sfx + "/bias", {shp[i][2]}, false);
+    }
   }
   add_tensor(h, "lut/mu_law_decode", {Q + 1}, false);
   add_tensor(h, "lut/mu_law_encode", {Q + 1}, false);
@@ -1534,11 +1545,117 @@ static int encode_magenta(vqwn_handle* h, const float* x, int B, int64_t T, floa
   return finish_timing(h);
 }
 
+// Encoder_2019 (Encoder/encoder.py:72-98) on the device: MFCC front end (one fused kernel), then the conv stack through
+// the implicit-GEMM kernel.  The front end's constants (hann window, mel weights, DCT matrix) are built here in
+// float64 from the published definitions of tf.contrib.signal (Encoder/encoder_ops.py:14-43) and rounded to float32.
+static int encode_2019(vqwn_handle* h, const float* x, int B, int64_t T, float* z_e_out) {
+  int rc;
+  const int D = h->D;
+  for (int i = 0; i < 10; ++i) {
+    const std::string base = "encoder/conv1d" + (i == 0 ? std::string() : "_" + std::to_string(i));
+    if ((rc = check_tensor_ready(h, (base + "/kernel").c_str()))) return rc;
+    if ((rc = check_tensor_ready(h, (base + "/bias").c_str()))) return rc;
+  }
+  const int F1 = (int)((T + MFCC_STEP - 1) / MFCC_STEP), F2 = (F1 + 1) / 2;
+  // constants + identity scale / shift + the first kernel padded to 16 input channels: one small buffer
+  const size_t n_win = MFCC_FRAME, n_mel = (size_t)MFCC_BINS * MFCC_MELS, n_dct = (size_t)MFCC_MELS * MFCC_COEFS;
+  const size_t n_w0 = (size_t)3 * MFCC_CPAD * 768;
+  const size_t off_win = 2 * 768, off_mel = off_win + n_win, off_dct = off_mel + n_mel, off_w0 = off_dct + n_dct + 4;
+  if ((rc = ensure(h, h->enc_fold, (off_w0 + n_w0) * sizeof(float)))) return rc;
+  {
+    std::vector<float> c(off_w0, 0.f);
+    for (int i = 0; i < 768; ++i) c[i] = 1.f;
+    const double PI = 3.14159265358979323846;
+    for (int n = 0; n < MFCC_FRAME; ++n) c[off_win + n] = (float)(0.5 - 0.5 * cos(2.0 * PI * n / MFCC_FRAME));
+    auto mel = [](double f) { return 1127.0 * log(1.0 + f / 700.0); };
+    const double lo = mel(20.0), hi = mel(8000.0);
+    for (int k = 1; k < MFCC_BINS; ++k) {                       // the DC bin stays zero
+      const double sm = mel(8000.0 * k / (MFCC_BINS - 1));
+      for (int m = 0; m < MFCC_MELS; ++m) {
+        const double e0 = lo + (hi - lo) * m / (MFCC_MELS + 1), e1 = lo + (hi - lo) * (m + 1) / (MFCC_MELS + 1),
+                     e2 = lo + (hi - lo) * (m + 2) / (MFCC_MELS + 1);
+        const double w = fmin((sm - e0) / (e1 - e0), (e2 - sm) / (e2 - e1));
+        c[off_mel + (size_t)k * MFCC_MELS + m] = (float)(w > 0.0 ? w : 0.0);
+      }
+    }
+    for (int m = 0; m < MFCC_MELS; ++m)
+      for (int q = 0; q < MFCC_COEFS; ++q)
+        c[off_dct + (size_t)m * MFCC_COEFS + q] = (float)(2.0 * cos(PI * q * (2 * m + 1) / (2.0 * MFCC_MELS)) / sqrt(2.0 * MFCC_MELS));
+    CK(h, cudaMemcpyAsync(h->enc_fold.p, c.data(), c.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
+  const float* one = (const float*)h->enc_fold.p;
+  const float* zero = one + 768;
+  float* w0p = (float*)h->enc_fold.p + off_w0;
+  pad_cin_kernel<<<64, 256, 0, h->stream>>>(TP(h, "encoder/conv1d/kernel"), w0p, 3, MFCC_COEFS, MFCC_CPAD, 768);
+  h->launches += 1;
+  const size_t per_stream = (size_t)T * sizeof(float) + 3 * (size_t)F1 * 768 * sizeof(float);
+  size_t gsz = ((size_t)1 << 30) / per_stream;
+  if (gsz < 1) gsz = 1;
+  const int group = gsz > (size_t)B ? B : (int)gsz;
+  if ((rc = ensure(h, h->enc_x, (size_t)group * T * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->enc_a, (size_t)group * F1 * 768 * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->enc_b, (size_t)group * F1 * 768 * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->enc_c, (size_t)group * F1 * 768 * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->enc_z, (size_t)group * F2 * D * sizeof(float)))) return rc;
+  auto ew_grid = [](long long n) { return (int)((n + 255) / 256 < 65535 ? (n + 255) / 256 : 65535); };
+  // keras Conv1D(padding='same'): Tout = ceil(Tin / stride), total pad = max((Tout-1) stride + k - Tin, 0), left = total / 2
+  auto conv = [&](const float* in, int layer, const float* Wk, float* out, int g, int Tin, int cin, int cout, int k, int stride, int relu) {
+    const int Tout = (Tin + stride - 1) / stride;
+    int total_pad = (Tout - 1) * stride + k - Tin;
+    if (total_pad < 0) total_pad = 0;
+    const std::string base = "encoder/conv1d" + (layer == 0 ? std::string() : "_" + std::to_string(layer));
+    const long long M = (long long)g * Tout;
+    dim3 grid((unsigned)((M + ENC_BM - 1) / ENC_BM), (unsigned)(cout / ENC_BN));
+    conv1d_gemm_kernel<<<grid, 256, 0, h->stream>>>(in, Wk ? Wk : TP(h, base + "/kernel"), TP(h, base + "/bias"), one, zero, out, g, Tin,
+                                                    cin, Tout, cout, k, stride, total_pad / 2, relu);
+    h->launches += 1;
+    return Tout;
+  };
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int g = (B - b0 < group) ? (B - b0) : group;
+    CK(h, cudaMemcpyAsync(h->enc_x.p, x + (size_t)b0 * T, (size_t)g * T * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    float* a = (float*)h->enc_a.p;
+    float* b = (float*)h->enc_b.p;
+    float* c = (float*)h->enc_c.p;
+    mfcc_kernel<<<g * F1, 256, 0, h->stream>>>((const float*)h->enc_x.p, one + off_win, one + off_mel, one + off_dct, c, (int)T, F1);
+    h->launches += 1;
+    conv(c, 0, w0p, a, g, F1, MFCC_CPAD, 768, 3, 1, 1);                         // net = conv_3_768(mfcc)
+    conv(a, 1, nullptr, b, g, F1, 768, 768, 3, 1, 1);                            // conv = conv_3_768(net)
+    enc_add_kernel<<<ew_grid((long long)g * F1 * 768), 256, 0, h->stream>>>(b, a, a, (long long)g * F1 * 768);    // net = conv + net
+    conv(a, 2, nullptr, b, g, F1, 768, 768, 4, 2, 1);                            // strided_conv_4_768 -> b [F2]
+    float* net = b;
+    float* tmp = a;
+    const long long n2 = (long long)g * F2 * 768;
+    for (int i = 3; i < 5; ++i) {                                                // 2 x (conv + net)
+      conv(net, i, nullptr, tmp, g, F2, 768, 768, 3, 1, 1);
+      enc_add_kernel<<<ew_grid(n2), 256, 0, h->stream>>>(tmp, net, net, n2);
+    }
+    for (int i = 5; i < 9; ++i) {                                                // 4 x (relu + relu), quirk Q17
+      conv(net, i, nullptr, tmp, g, F2, 768, 768, 3, 1, 1);
+      enc_add_kernel<<<ew_grid(n2), 256, 0, h->stream>>>(tmp, tmp, tmp, n2);
+      float* t_ = net; net = tmp; tmp = t_;
+    }
+    h->launches += 7;
+    conv(net, 9, nullptr, (float*)h->enc_z.p, g, F2, 768, D, 1, 1, 0);           // linear_64
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(z_e_out + (size_t)b0 * F2 * D, h->enc_z.p, (size_t)g * F2 * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->last_kernel = "conv1d_gemm_kernel";
+  return finish_timing(h);
+}
+
 int vqwn_encode_audio(vqwn_handle* h, const float* x, int B, int64_t T, float* z_e_out) {
   ENTER(h);
   if (!x || !z_e_out || B < 1 || T < 64) return fail(h, VQWN_ERR_INVALID, "bad argument");
   if (h->cfg.encoder == VQWN_ENCODER_NONE)
-    return fail(h, VQWN_ERR_NOTIMPL, "no encoder configured on the device (vqwn_config.encoder = 64 or 1)");
+    return fail(h, VQWN_ERR_NOTIMPL, "no encoder configured on the device (vqwn_config.encoder = 64, 1 or 2019)");
+  if (h->cfg.encoder == VQWN_ENCODER_2019) {
+    if (T % (2 * MFCC_STEP) != 0) return fail(h, VQWN_ERR_INVALID, "T must be a multiple of 320 (Encoder_2019 hop)");
+    return encode_2019(h, x, B, T, z_e_out);
+  }
   if (T % 64 != 0) return fail(h, VQWN_ERR_INVALID, "T must be a multiple of 64 (encoder hop)");
   if (h->cfg.encoder == VQWN_ENCODER_MAGENTA) return encode_magenta(h, x, B, T, z_e_out);
   int rc;

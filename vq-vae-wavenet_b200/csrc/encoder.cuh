@@ -136,4 +136,62 @@ __global__ void magenta_add_kernel(const float* __restrict__ d, const float* __r
     out[i] = d[i] + r[i];
 }
 
+// ---- Encoder_2019 pieces (Encoder/encoder.py:66-98, Encoder/encoder_ops.py:14-43)
+// MFCC front end, one CTA per (utterance, 10 ms frame): 400-sample frame (zero past the end: pad_end) x periodic hann
+// window -> |DFT| at 201 bins (direct form, twiddles cos/sin(2 pi j / 400) from a shared-memory table indexed by k n
+// mod 400) -> 80 mel bands (weights [201][80]) -> log(. + 1e-6) -> 13 DCT-II coefficients (matrix [80][13], factor
+// 2 / sqrt(160) folded in).  Output channels-last [B][frames][16]: 13 coefficients + 3 zeros, so the first
+// convolution runs through the same implicit-GEMM kernel as every other layer (its K chunk is 16 channels).
+constexpr int MFCC_FRAME = 400, MFCC_STEP = 160, MFCC_BINS = 201, MFCC_MELS = 80, MFCC_COEFS = 13, MFCC_CPAD = 16;
+__global__ void __launch_bounds__(256) mfcc_kernel(const float* __restrict__ x, const float* __restrict__ window,
+                                                   const float* __restrict__ melw, const float* __restrict__ dct,
+                                                   float* __restrict__ out, int T, int frames) {
+  __shared__ float fr[MFCC_FRAME], ct[MFCC_FRAME], st[MFCC_FRAME], mag[MFCC_BINS + 3], lm[MFCC_MELS];
+  const int f = blockIdx.x % frames, b = blockIdx.x / frames, tid = threadIdx.x;
+  for (int n = tid; n < MFCC_FRAME; n += 256) {
+    const long long ti = (long long)f * MFCC_STEP + n;
+    fr[n] = (ti < T ? x[(long long)b * T + ti] : 0.f) * window[n];
+    ct[n] = cospif((float)n * (1.0f / 200.0f));
+    st[n] = sinpif((float)n * (1.0f / 200.0f));
+  }
+  __syncthreads();
+  if (tid < MFCC_BINS) {
+    float re = 0.f, im = 0.f;
+    int j = 0;
+    for (int n = 0; n < MFCC_FRAME; ++n) {
+      re = fmaf(fr[n], ct[j], re);
+      im = fmaf(fr[n], st[j], im);
+      j += tid;
+      if (j >= MFCC_FRAME) j -= MFCC_FRAME;
+    }
+    mag[tid] = sqrtf(re * re + im * im);
+  }
+  __syncthreads();
+  if (tid < MFCC_MELS) {
+    float a = 0.f;
+    for (int k = 0; k < MFCC_BINS; ++k) a = fmaf(mag[k], __ldg(melw + k * MFCC_MELS + tid), a);
+    lm[tid] = logf(a + 1e-6f);
+  }
+  __syncthreads();
+  if (tid < MFCC_CPAD) {
+    float a = 0.f;
+    if (tid < MFCC_COEFS)
+      for (int m = 0; m < MFCC_MELS; ++m) a = fmaf(lm[m], __ldg(dct + m * MFCC_COEFS + tid), a);
+    out[((long long)b * frames + f) * MFCC_CPAD + tid] = a;
+  }
+}
+// W [k][cin][cout] -> Wp [k][cin_pad][cout] with zero rows for the padded input channels
+__global__ void pad_cin_kernel(const float* __restrict__ W, float* __restrict__ Wp, int k, int cin, int cin_pad, int cout) {
+  const int total = k * cin_pad * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cout, ci = (i / cout) % cin_pad, j = i / (cout * cin_pad);
+    Wp[i] = ci < cin ? W[((long long)j * cin + ci) * cout + co] : 0.f;
+  }
+}
+// out = a + b (Encoder_2019's residual adds; a == b gives its `relu + relu`)
+__global__ void enc_add_kernel(const float* a, const float* b, float* out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i] + b[i];
+}
+
 }  // namespace vqwn

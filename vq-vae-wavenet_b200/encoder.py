@@ -1,6 +1,5 @@
 """Mirror of Encoder/encoder.py as generate.py uses it (generate.py:65-69): an object with .build(x) -> z_e.
-Encoder_64 and Encoder_Magenta run on the device; Encoder_2019 (MFCC front end) raises
-NotImplementedError."""
+Encoder_64, Encoder_Magenta and Encoder_2019 all run on the device."""
 import numpy as np
 
 
@@ -35,5 +34,16 @@ class Encoder_Magenta:
 
 
 class Encoder_2019:
+    """MFCC front end (25 ms periodic-hann frames every 10 ms, |DFT|, 80 mel bands, log, 13 DCT coefficients:
+    Encoder/encoder_ops.py:14-43), conv k3 + (conv k3 + skip), conv k4 stride 2, 2 x (conv k3 + skip), 4 x `relu + relu`
+    (twice the conv output, reference quirk), 1x1 to latent_dim; hop 320 (Encoder/encoder.py:66-98), executed by
+    vqwn_encode_audio with vqwn_config.encoder = VQWN_ENCODER_2019.  T must be a multiple of 320."""
+
     def __init__(self, latent_dim, engine=None):
-        raise NotImplementedError("encoder 2019 not implemented")
+        self.latent_dim = latent_dim
+        self.engine = engine
+
+    def build(self, net):
+        if self.engine is None:
+            raise RuntimeError("Encoder_2019 needs the Engine that holds its weights (no CPU fallback)")
+        return self.engine.encode_audio(np.asarray(net, dtype=np.float32))

@@ -72,7 +72,7 @@ class EngineConfig:
         c.speaker_dim = m["speaker_embedding"]
         c.num_speakers = self.num_speakers
         c.use_vq = 1 if m["use_vq"] else 0
-        c.encoder = {"64": 64, "Magenta": 1}.get(str(m.get("encoder")), 0)      # VQWN_ENCODER_64 / _MAGENTA / _NONE
+        c.encoder = {"64": 64, "Magenta": 1, "2019": 2019}.get(str(m.get("encoder")), 0)   # VQWN_ENCODER_64 / _MAGENTA / _2019 / _NONE
         return c
 
 
@@ -102,6 +102,7 @@ class Engine:
         self.q = self.config.wavenet["quantization_channels"]
         self.C = self.config.cond_channels
         self.D = self.config.model["latent_dim"]
+        self.encoder_hop = 320 if str(self.config.model.get("encoder")) == "2019" else 64      # audio samples per z_e frame
         # NumPy-built mu-law tables (same expressions as the reference's NumPy decode)
         self.set_tensor("lut/mu_law_decode", mu_law_ops.decode_lut(self.q))
         self.set_tensor("lut/mu_law_encode", mu_law_ops.encode_lut(self.q))
@@ -188,12 +189,12 @@ class Engine:
 
     # ------------------------------------------------------------------ encoder
     def encode_audio(self, x):
-        """Encoder_64.build: x [B,T] or [B,T,1] float audio -> z_e [B,T/64,latent_dim]"""
+        """Encoder_*.build: x [B,T] or [B,T,1] float audio -> z_e [B,T/hop,latent_dim] (hop 64; Encoder_2019: 320)"""
         xx = _f32(x)
         if xx.ndim == 3:
             xx = np.ascontiguousarray(xx[:, :, 0])
         B, T = xx.shape
-        z = np.empty((B, T // 64, self.D), dtype=np.float32)
+        z = np.empty((B, T // self.encoder_hop, self.D), dtype=np.float32)
         self._ck(self.lib.vqwn_encode_audio(self._h, _ptr(xx, C.c_float), B, T, _ptr(z, C.c_float)))
         return z
 
