@@ -52,6 +52,9 @@ extern "C" {
 #define VQWN_VQ_AUTO   0   /* tensor-core kernel when k = 512 and latent_dim = 64, else direct  */
 #define VQWN_VQ_DIRECT 1   /* float32 CUDA-core direct form                                      */
 #define VQWN_VQ_TENSOR 2   /* tcgen05 tf32 ranking + exact float32 re-evaluation of near-minima  */
+/* what the VQ hands to the decoder (vqwn_set_vq_output) */
+#define VQWN_VQ_OUT_STRAIGHT_THROUGH 0   /* z_e + (e_k - z_e): model.py:73,85-87 (differs from e_k in the last bit) */
+#define VQWN_VQ_OUT_CODE 1               /* e_k itself: Magenta/config.py:240-242 (`self.encoding = e_k`)                     */
 
 /* model_parameters.json + wavenet_parameters.json (generate.py:63-64, wavenet.py:10-21) */
 typedef struct vqwn_config {
@@ -104,6 +107,10 @@ int vqwn_set_precision(vqwn_handle* h, int precision);
  * bit-reproducible.  The reference makes no such promise either way (TensorFlow CPU MatMul threading). */
 int vqwn_set_reproducible(vqwn_handle* h, int on);
 int vqwn_set_vq_kernel(vqwn_handle* h, int kernel);
+/* replaces the choice between model.py:73 (`z_q = z_e + stop_gradient(e_k - z_e)`, what conditions the default decoder)
+ * and Magenta/config.py:242 (`self.encoding = e_k`, what Magenta/generate.py:67 feeds): applies to vqwn_vq_lookup's
+ * zq_out and vqwn_encode_condition's condition rows */
+int vqwn_set_vq_output(vqwn_handle* h, int output);
 /* sharded runs (generate.py:34: the batch is the list of -speakers, cut into contiguous slices per GPU): global index of
  * this handle's stream 0.  It keys the counter-based generator that stands in for np.random.rand (utils.py:22) when
  * vqwn_generate gets no uniforms, so that a slice draws exactly what the unsharded run draws for the same streams. */

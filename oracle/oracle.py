@@ -711,6 +711,125 @@ def encoder2019_forward(cfg, weights, x):
     return conv(9, net, relu=False)
 
 
+# ---------------------------------------------------------------------------------------------
+# Magenta/ fast-generation topology: Magenta/config.py:18-138 (FastGenerationConfig.build),
+# Magenta/masked.py:133-174 (causal_linear, linear), Magenta/generate.py:52-87 (host loop)
+# ---------------------------------------------------------------------------------------------
+MAGENTA_NUM_STAGES, MAGENTA_NUM_LAYERS, MAGENTA_FILTER_LENGTH = 10, 50, 2      # config.py:5-7
+MAGENTA_WIDTH, MAGENTA_SKIP_WIDTH, MAGENTA_BOTTLENECK, MAGENTA_K = 256, 512, 64, 512      # config.py:8-9,15-16
+MAGENTA_SPEAKERS = 109                                                         # config.py:42
+
+
+def magenta_fastgen_specs(num_layers=MAGENTA_NUM_LAYERS):
+    """variables FastGenerationConfig.build creates, by name (config.py:40-130; masked.py:146-151,167-171), plus the
+    codebook Config.build owns (config.py:229)"""
+    W, S, E = MAGENTA_WIDTH, MAGENTA_SKIP_WIDTH, MAGENTA_BOTTLENECK
+    specs = [("embedding", (MAGENTA_K, E)), ("speaker_emb", (MAGENTA_SPEAKERS, E)),
+             ("startconv/W", (1, MAGENTA_FILTER_LENGTH, 1, W)), ("startconv/biases", (W,)),
+             ("skip_start/W", (1, 1, W, S)), ("skip_start/biases", (S,))]
+    for i in range(1, num_layers + 1):
+        specs += [("dilatedconv_%d/W" % i, (1, MAGENTA_FILTER_LENGTH, W, 2 * W)), ("dilatedconv_%d/biases" % i, (2 * W,)),
+                  ("cond_map_%d/W" % i, (1, 1, E, 2 * W)), ("cond_map_%d/biases" % i, (2 * W,)),
+                  ("gc_%d/kernel" % i, (1, E, 2 * W)), ("gc_%d/bias" % i, (2 * W,)),
+                  ("res_%d/W" % i, (1, 1, W, W)), ("res_%d/biases" % i, (W,)),
+                  ("skip_%d/W" % i, (1, 1, W, S)), ("skip_%d/biases" % i, (S,))]
+    specs += [("out1/W", (1, 1, S, S)), ("out1/biases", (S,)), ("cond_map_out1/W", (1, 1, E, S)), ("cond_map_out1/biases", (S,)),
+              ("gc_final/kernel", (1, E, S)), ("gc_final/bias", (S,)), ("logits/W", (1, 1, S, 256)), ("logits/biases", (256,))]
+    return specs
+
+
+def make_magenta_fastgen_weights(seed=4324, num_layers=MAGENTA_NUM_LAYERS, peaked=False):
+    """seeded synthetic weights: kernels U(+-sqrt(3 / fan_in)), biases U(+-0.05) except the gc biases around their
+    initial value 1.0 (config.py:33), codebook / speaker table as make_weights"""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in magenta_fastgen_specs(num_layers):
+        if name == "embedding":
+            a = rng.uniform(-0.130, 0.130, size=shape)
+        elif name == "speaker_emb":
+            a = rng.uniform(-0.332, 0.332, size=shape)
+        elif name.endswith("/W") or name.endswith("/kernel"):
+            lim = np.sqrt(3.0 / float(np.prod(shape[:-1])))
+            a = rng.uniform(-lim, lim, size=shape)
+            if peaked and name == "logits/W":
+                a = a * 8.0
+        elif name.startswith("gc_"):
+            a = 1.0 + rng.uniform(-0.05, 0.05, size=shape)
+        else:
+            a = rng.uniform(-0.05, 0.05, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=F32)
+    return out
+
+
+class MagentaFastWavenet:
+    """FastGenerationConfig.build as one step (config.py:36-138): queues of capacity `rate` zero-filled (masked.py:135-137),
+    y = state_1 . W[0,0] + x . W[0,1] + b (masked.py:165-169), local condition cond_map_i(en) and global condition gc_i(gc)
+    each WITH bias (the gc bias initialised to 1), gate = sigmoid(first half) * tanh(second half) (config.py:103)."""
+
+    def __init__(self, weights, batch, speaker_idx, num_layers=MAGENTA_NUM_LAYERS):
+        self.w, self.batch, self.L = weights, batch, num_layers
+        self.gc = weights["speaker_emb"][np.asarray(speaker_idx, dtype=np.int64)]          # config.py:41-43
+        self.init_ops()
+
+    def init_ops(self):
+        z1 = np.zeros((self.batch, 1), dtype=F32)
+        zw = np.zeros((self.batch, MAGENTA_WIDTH), dtype=F32)
+        self.q0 = deque([z1])                                                               # startconv: rate 1
+        self.q = [deque([zw] * (2 ** (i % MAGENTA_NUM_STAGES))) for i in range(self.L)]     # config.py:75
+
+    @staticmethod
+    def _causal_linear(q, x, W, b):
+        state_1 = q.popleft()                                                               # masked.py:137
+        q.append(x)                                                                         # masked.py:138
+        return ((state_1 @ W[0, 0] + x @ W[0, 1]) + b).astype(F32)                          # masked.py:165-169
+
+    def step(self, input_t, encoding_t):
+        w = self.w
+        x = mu_law_encode(np.asarray(input_t, dtype=F32).reshape(self.batch, 1))            # config.py:47 (masked.py:31-35)
+        en = np.asarray(encoding_t, dtype=F32)
+        lin = lambda v, name: ((v @ w[name + "/W"][0, 0]) + w[name + "/biases"]).astype(F32)        # masked.py:163-172
+        gcl = lambda scope: ((self.gc @ w[scope + "/kernel"][0]) + w[scope + "/bias"]).astype(F32)   # config.py:22-35
+        l = self._causal_linear(self.q0, x, w["startconv/W"], w["startconv/biases"])
+        s = lin(l, "skip_start")
+        m = MAGENTA_WIDTH
+        for i in range(self.L):
+            d = self._causal_linear(self.q[i], l, w["dilatedconv_%d/W" % (i + 1)], w["dilatedconv_%d/biases" % (i + 1)])
+            d = d + lin(en, "cond_map_%d" % (i + 1))                                        # config.py:93
+            d = d + gcl("gc_%d" % (i + 1))                                                  # config.py:96-97
+            d = (_sigmoid(d[:, :m]) * np.tanh(d[:, m:])).astype(F32)                        # config.py:103
+            l = l + lin(d, "res_%d" % (i + 1))                                              # config.py:106
+            s = s + lin(d, "skip_%d" % (i + 1))                                             # config.py:109
+        s = np.maximum(s, 0)
+        s = lin(s, "out1") + lin(en, "cond_map_out1")                                       # config.py:112-113
+        s = s + gcl("gc_final")
+        s = np.maximum(s, 0)
+        logits = lin(s, "logits")
+        return softmax(logits), logits
+
+
+def magenta_generate(weights, encoding, speaker_idx, length, mode="greedy", uniforms=None, teacher=None,
+                     num_layers=MAGENTA_NUM_LAYERS):
+    """Magenta/generate.py:73-84 (the same loop as generate.py:103-113).  encoding [B,F,64] = e_k (config.py:242).
+    Returns (audio, idx, logits, margins)."""
+    B = encoding.shape[0]
+    net = MagentaFastWavenet(weights, B, speaker_idx, num_layers)
+    audio = np.zeros([B, 1], dtype=F32)
+    to_write = np.zeros([B, length], dtype=F32)
+    idx_out = np.zeros([B, length], dtype=np.int32)
+    logits_out = np.zeros([B, length, 256], dtype=F32)
+    margins = np.zeros([B, length], dtype=F32)
+    ratio = length // encoding.shape[1]
+    for i in range(length):
+        probs, logits = net.step(audio, encoding[:, i // ratio])
+        u = None if uniforms is None else uniforms[i]
+        idx = decode_indices(probs, mode, u)
+        margins[:, i] = draw_margin(probs, mode, u)
+        decoded = mu_law_decode_np(idx.astype(F32), 256)
+        to_write[:, i], idx_out[:, i], logits_out[:, i] = decoded, idx, logits
+        audio = np.expand_dims(decoded, -1) if teacher is None else np.asarray(teacher[:, i:i + 1], dtype=F32)
+    return to_write, idx_out, logits_out, margins
+
+
 def synthetic_z_e(cfg, weights, B, F, seed=1235, kind="normal"):
     rng = np.random.default_rng(seed)
     E = weights["embedding/embedding"]

@@ -415,8 +415,86 @@ def section_cfg5_e2e(out):
         out[tag + "_logit_sum"] = logits.astype(np.float64).sum(-1)[:, ::16]
 
 
+def section_magenta(out):
+    """Magenta/ fast generation: the reference's FastGenerationConfig.build (Magenta/config.py:18-138 over
+    Magenta/masked.py:31-35,133-174) is imported unmodified and driven by Magenta/generate.py:73-84's loop (re-typed: it is
+    module-level script code), full size: 50 layers, width 256, skip 512, k = 2.  The local condition fed per step is
+    e_k (config.py:242), here rows of the synthetic codebook."""
+    import importlib.util
+    mdir = os.path.join(REF, "Magenta")
+    sys.path.append(mdir)                                              # `from masked import *`
+    spec = importlib.util.spec_from_file_location("magenta_config", os.path.join(mdir, "config.py"))
+    mcfg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mcfg)
+    B, T = 3, 192
+    spk = [0, 5, 17]
+    mw = O.make_magenta_fastgen_weights(peaked=True)
+    rng = np.random.default_rng(1239)
+    codes = rng.integers(0, 512, size=(B, T // 64))
+    encoding = mw["embedding"][codes]                                  # e_k rows
+    out["magenta_codes"] = codes.astype(np.int16)
+    out["magenta_speakers"] = np.array(spk)
+    sess = tf.Session()
+
+    def fresh():
+        tf.reset_default_graph()
+        tf.set_variable_values({k: v for k, v in mw.items() if k != "embedding"})
+        gen = mcfg.FastGenerationConfig(batch_size=B)
+        x_t = tf.placeholder(tf.float32, shape=[B, 1])
+        net = gen.build(inputs=x_t, gc=tf.constant(onehot(spk, 109)[:, 0]))
+        created = dict(tf_shim.created_variables())
+        want = dict((k, v.shape) for k, v in mw.items() if k != "embedding")
+        assert created == want, "Magenta variable names / shapes differ from the oracle's table"
+        return x_t, net
+
+    def loop(x_t, net, length, mode, teacher=None, seed=None):        # Magenta/generate.py:73-84
+        audio = np.zeros([B, 1], dtype=np.float32)
+        to_write = np.zeros([B, length], dtype=np.float32)
+        probs_all = np.zeros([B, length, 256], dtype=np.float32)
+        logits_all = np.zeros([B, length, 256], dtype=np.float32)
+        logits_node = net["predictions"].inputs[0]
+        sess.run(net["init_ops"])
+        if seed is not None:
+            np.random.seed(seed)
+        ratio = length // encoding.shape[1]
+        for i in range(length):
+            probs, _, lg = sess.run([net["predictions"], net["push_ops"], logits_node],
+                                    {x_t: audio, net["encoding"]: encoding[:, i // ratio]})
+            decoded = ref_utils.decode(probs, mode=mode)
+            to_write[:, i], probs_all[:, i], logits_all[:, i] = decoded, probs, lg
+            audio = decoded.reshape([B, 1]) if teacher is None else np.asarray(teacher[:, i:i + 1], dtype=np.float32)
+        return to_write, probs_all, logits_all
+
+    x = O.synthetic_audio(B, T, seed=1237)
+    t0 = time.time()
+    x_t, net = fresh()
+    _, probs, logits = loop(x_t, net, T, "greedy", teacher=x)
+    _, _, o_logits, _ = O.magenta_generate(mw, encoding, spk, T, mode="greedy", teacher=x)
+    print("magenta: teacher-forced %d steps in %.1fs; oracle logit diff %.3g (max |logit| %.3g)"
+          % (T, time.time() - t0, np.abs(o_logits - logits).max(), np.abs(logits).max()))
+    out["magenta_teacher_logits"] = logits.astype(np.float32)
+    x_t, net = fresh()
+    audio, probs, _ = loop(x_t, net, T, "greedy")
+    gidx = audio_to_index(audio)
+    out["magenta_greedy_idx"] = gidx
+    out["magenta_greedy_margin"] = np.stack([O.draw_margin(probs[:, i], "greedy") for i in range(T)], 1).astype(np.float32)
+    _, o_gidx, _, _ = O.magenta_generate(mw, encoding, spk, T, mode="greedy")
+    print("magenta: greedy oracle mismatching draws %d, distinct values %d" % (int((o_gidx != gidx).sum()), len(np.unique(gidx))))
+    seed = 1240
+    x_t, net = fresh()
+    audio, probs, _ = loop(x_t, net, T, "sample", seed=seed)
+    sidx = audio_to_index(audio)
+    np.random.seed(seed)
+    u = np.stack([np.random.rand(B) for _ in range(T)])
+    out["magenta_sample_idx"] = sidx
+    out["magenta_sample_seed"] = np.int64(seed)
+    out["magenta_sample_margin"] = np.stack([O.draw_margin(probs[:, i], "sample", u[i]) for i in range(T)], 1).astype(np.float32)
+    _, o_sidx, _, _ = O.magenta_generate(mw, encoding, spk, T, mode="sample", uniforms=u)
+    print("magenta: sample oracle mismatching draws %d" % int((o_sidx != sidx).sum()))
+
+
 def main():
-    sections = [("ref_enc2019", section_enc2019), ("ref_cfg5_e2e", section_cfg5_e2e), ("ref_vars", section_variables), ("ref_vq", section_vq), ("ref_kat", section_kat),
+    sections = [("ref_magenta", section_magenta), ("ref_enc2019", section_enc2019), ("ref_cfg5_e2e", section_cfg5_e2e), ("ref_vars", section_variables), ("ref_vq", section_vq), ("ref_kat", section_kat),
                 ("ref_small", section_small), ("ref_encoders", section_encoders), ("ref_cfg5", section_cfg5),
                 ("ref_full", section_full)]
     only = [a for a in sys.argv[1:] if not a.startswith("--")]

@@ -436,11 +436,22 @@ def _moments(x, axes):
     return m, m
 
 
+def sigmoid(x):
+    """tf.sigmoid (Magenta/config.py:103)"""
+    return _unary(_sigmoid, x)
+
+
+def tanh(x):
+    """tf.tanh (Magenta/config.py:103)"""
+    return _unary(np.tanh, x)
+
+
 nn = types.SimpleNamespace(
     tanh=lambda x: _unary(np.tanh, x),
     sigmoid=lambda x: _unary(_sigmoid, x),
     relu=lambda x: _unary(lambda v: np.maximum(v, np.float32(0)), x),
-    softmax=lambda x: _unary(_softmax, x),
+    softmax=lambda x, name=None: _unary(_softmax, x),
+    bias_add=lambda value, bias: value + bias,            # tf.nn.bias_add on [batch, channels] (Magenta/masked.py:159,169,172)
     conv2d=_conv2d,
     embedding_lookup=_embedding_lookup,
     moments=_moments,
@@ -470,8 +481,9 @@ class FIFOQueue:
         return Operation(run, [vals])
 
     def enqueue(self, vals):
-        (val,) = vals
-        val = _wrap(val)
+        if isinstance(vals, (list, tuple)):       # wavenet_ops.py:188 passes a one-element list, Magenta/masked.py:138 the tensor
+            (vals,) = vals
+        val = _wrap(vals)
 
         def run(v):
             assert v.shape == self.item_shape, (v.shape, self.item_shape)

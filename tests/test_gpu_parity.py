@@ -869,6 +869,55 @@ def test_cfg5_end_to_end_encoder_variants(variant, golden_dir):
     eng.close()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tc"])
+def test_magenta_fast_generation(prec, golden_dir):
+    """Magenta/ fast generation (50 layers, k = 2, cond_map + gc with biases, sigmoid-first gate, e_k as the
+    condition) through the same kernels via vq-vae-wavenet_b200/magenta.py's re-arrangement of the checkpoint.  Target:
+    what the reference's own FastGenerationConfig.build + Magenta/generate.py loop produced (ref_magenta.npz)."""
+    from vqvae_wavenet_b200 import magenta
+    g = np.load(os.path.join(golden_dir, "ref_magenta.npz"))
+    mw = O.make_magenta_fastgen_weights(peaked=True)
+    codes = g["magenta_codes"].astype(np.int64)
+    spk = g["magenta_speakers"].astype(np.int64)
+    B, T = g["magenta_greedy_idx"].shape
+    gen = magenta.FastGenerationConfig(batch_size=B, precision=prec)
+    gen.restore(mw)
+    onehot = np.zeros((B, 109), np.float32)
+    onehot[np.arange(B), spk] = 1
+    gen.build(onehot)
+    assert np.array_equal(gen.embedding, mw["embedding"]) and np.array_equal(gen.speaker_emb, mw["speaker_emb"])
+    e_k = mw["embedding"][codes]
+    cond = gen.condition_from_codes(e_k)
+    assert np.array_equal(cond[..., :64], e_k) and np.array_equal(cond[:, 0, 64:], mw["speaker_emb"][spk])
+    # the VQ hands e_k itself to the decoder (Magenta/config.py:242), not z_e + (e_k - z_e)
+    z_e = (e_k + np.random.default_rng(5).normal(0, 1e-3, e_k.shape)).astype(np.float32)
+    idx, cond2 = gen.quantise(z_e)
+    assert np.array_equal(idx, codes) and np.array_equal(cond2, cond)
+    gen.engine.set_vq_output("straight_through")
+    _, cond3 = gen.quantise(z_e)
+    assert np.array_equal(cond3[..., :64], z_e + (e_k - z_e)) and not np.array_equal(cond3, cond)
+    gen.engine.set_vq_output("code")
+    # teacher-forced logits
+    x = O.synthetic_audio(B, T, seed=1237)
+    lg = gen.teacher_forced(x, cond)
+    want = g["magenta_teacher_logits"]
+    err = np.abs(lg - want).max() / np.abs(want).max()
+    print("magenta %s: kernel %s, teacher-forced logits vs reference %.3g of max |logit|" % (prec, gen.engine.last_kernel_name, err))
+    assert err <= LOGIT_RTOL
+    # free-running sequences
+    gtie = GREEDY_TIE_FULL_OF[prec]
+    audio, gi = gen.generate(cond, T, mode="greedy")
+    _check_sequences(gi, g["magenta_greedy_idx"], g["magenta_greedy_margin"], gtie, 32, "magenta/%s greedy" % prec)
+    assert np.array_equal(audio, O.decode_lut()[gi])
+    u = _ref_uniforms(g["magenta_sample_seed"], T, B)
+    _, si = gen.generate(cond, T, mode="sample", uniforms=u)
+    _check_sequences(si, g["magenta_sample_idx"], g["magenta_sample_margin"], SAMPLE_TIE_OF[prec], 32, "magenta/%s sample" % prec)
+    gen.engine.eng = None
+    _check_teacher_forced_draws(gen.engine, cond, g["magenta_greedy_idx"].astype(np.int64), g["magenta_greedy_margin"], "greedy", gtie,
+                                label="magenta/%s greedy" % prec)
+    gen.close()
+
+
 def test_tc_default_order_agrees_with_reproducible_order(golden_dir):
     """VQWN_PREC_TC in its default mode (four issuing warps, accumulation in arrival order) against the fixed order:
     teacher-forced logits agree to float32 rounding (<= 2e-5 of max |logit|), far inside the 1e-3 parity tolerance"""

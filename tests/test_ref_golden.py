@@ -188,3 +188,48 @@ def test_cfg5_end_to_end_fixture_front_half(golden_dir):
         assert np.abs(z - g[tag + "_z_e"][:2]).max() < tol * max(1.0, np.abs(z).max()), tag
         idx = O.vq_discretise(g[tag + "_z_e"], E)[0]
         assert np.array_equal(idx, g[tag + "_idx"].astype(np.int64)), tag
+
+
+def test_magenta_fastgen_oracle_matches_reference(golden_dir):
+    """Magenta/ fast generation (Magenta/config.py:18-138 + masked.py:133-174 run unmodified by make_ref_golden.py, full size:
+    50 layers): the oracle's restatement gives the same logits bit for bit and the same greedy / seeded-sample sequences"""
+    g = _load(golden_dir, "ref_magenta.npz")
+    mw = O.make_magenta_fastgen_weights(peaked=True)
+    enc = mw["embedding"][g["magenta_codes"].astype(np.int64)]
+    spk = [int(v) for v in g["magenta_speakers"]]
+    B, T = g["magenta_greedy_idx"].shape
+    n = T if LONG else 48
+    x = O.synthetic_audio(B, T, seed=1237)
+    _, _, lg, _ = O.magenta_generate(mw, enc, spk, n, mode="greedy", teacher=x[:, :n]) if n == T else \
+        O.magenta_generate(mw, np.repeat(enc, 64, axis=1)[:, :n], spk, n, mode="greedy", teacher=x[:, :n])
+    assert np.array_equal(lg, g["magenta_teacher_logits"][:, :n])
+    _, gi, _, _ = O.magenta_generate(mw, np.repeat(enc, 64, axis=1)[:, :n], spk, n, mode="greedy")
+    assert np.array_equal(gi, g["magenta_greedy_idx"][:, :n])
+    u = _uniforms(g["magenta_sample_seed"], T, B)
+    _, si, _, _ = O.magenta_generate(mw, np.repeat(enc, 64, axis=1)[:, :n], spk, n, mode="sample", uniforms=u[:n])
+    assert np.array_equal(si, g["magenta_sample_idx"][:, :n])
+
+
+def test_magenta_weight_mapping_onto_default_topology(golden_dir):
+    """the product's re-arrangement of a Magenta checkpoint (vq-vae-wavenet_b200/magenta.py: zero oldest tap, swapped gate
+    halves, [cond_map | gc] stacked as one local-condition kernel, biases folded) evaluated by the DEFAULT generator's
+    restatement (wavenet.py:103-172) reproduces the Magenta reference's logits: the mapping is exact up to float32
+    summation order"""
+    from vqvae_wavenet_b200 import magenta
+    g = _load(golden_dir, "ref_magenta.npz")
+    mw = O.make_magenta_fastgen_weights(peaked=True)
+    assert {k: v.shape for k, v in mw.items()} == magenta.variable_shapes()
+    w = magenta.convert_weights(mw)
+    cfg = O.Config(wavenet=magenta.wavenet_parameters())
+    assert cfg.receptive_field == sum(cfg.dilations) * 2 + 1 + 31
+    spk = g["magenta_speakers"].astype(np.int64)
+    enc = mw["embedding"][g["magenta_codes"].astype(np.int64)]
+    B = enc.shape[0]
+    n = 32
+    cond = np.concatenate([np.repeat(enc, 64, axis=1)[:, :n], np.repeat(mw["speaker_emb"][spk][:, None], n, axis=1)], -1)
+    x = O.synthetic_audio(B, g["magenta_greedy_idx"].shape[1], seed=1237)[:, :n]
+    _, _, lg = O.generate(cfg, w, cond, n, mode="greedy", teacher=x, return_logits=True)
+    want = g["magenta_teacher_logits"][:, :n]
+    assert np.abs(lg - want).max() <= 2e-5 * np.abs(want).max()
+    with pytest.raises(KeyError):
+        magenta.convert_weights({k: v for k, v in mw.items() if k != "gc_7/bias"})

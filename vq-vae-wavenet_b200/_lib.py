@@ -60,6 +60,7 @@ PROTOTYPES = {
     "vqwn_set_precision": (C.c_int, [_H, C.c_int]),
     "vqwn_set_reproducible": (C.c_int, [_H, C.c_int]),
     "vqwn_set_vq_kernel": (C.c_int, [_H, C.c_int]),
+    "vqwn_set_vq_output": (C.c_int, [_H, C.c_int]),
     "vqwn_set_stream_offset": (C.c_int, [_H, C.c_int64]),
     "vqwn_set_tensor": (C.c_int, [_H, C.c_char_p, _f32p, _i64p, C.c_int]),
     "vqwn_get_tensor": (C.c_int, [_H, C.c_char_p, _f32p, C.c_int64]),

@@ -68,6 +68,7 @@ struct vqwn_handle {
   std::vector<size_t> off_w1t, off_w2t;
   size_t off_skip0t = 0, off_post1t = 0, off_post2t = 0;
   int* gen_err = nullptr;
+  int vq_out_code = 0;             // 1: the VQ emits e_k (Magenta/config.py:242) instead of z_e + (e_k - z_e) (model.py:73)
   int* tf_err_host = nullptr;      // host-mapped error record of the one-hand-off tensor-core kernel (readable after a trap)
   int* tf_err_dev = nullptr;
   int gen_kernel = 0;                      // 0 auto (cluster kernel when it applies), 1 barrier, 3 cluster
@@ -90,6 +91,7 @@ struct vqwn_handle {
   __nv_bfloat16* wtc = nullptr;            // [L][16][144 KB] hi/lo tiles, then postprocess1 [16][64 KB], postprocess2 [16][32 KB]
   size_t wtc_bytes = 0;
   size_t tc_persist_bytes = 0;             // persisting L2 set aside for the weight tiles (0: not available)
+  size_t tc_max_window = 0;                // cudaDevAttrMaxAccessPolicyWindowSize
   float *tc_skf_k = nullptr, *tc_skf_b = nullptr, *tc_ctab = nullptr;
   uint8_t* tc_gstage = nullptr;            // [co-resident cluster][TC_GSTAGE] hand-off staging
   // one-hand-off-per-layer variant (wavenet_tcf_cluster.cuh): the default VQWN_PREC_TC kernel; VQWN_TC_KERNEL=v1 selects the older one
@@ -609,10 +611,11 @@ int launch_tcf(vqwn_handle* h, int mode, long long T, const float* cond, long lo
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (h->tc_persist_bytes > 0 && !getenv("VQWN_TC_NO_PERSIST")) {
     attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    // (a 50-layer stream - the Magenta topology - is larger than the largest window the device accepts)
+    const size_t win = h->wtf_bytes < h->tc_max_window ? h->wtf_bytes : h->tc_max_window;
     attr[1].val.accessPolicyWindow.base_ptr = h->wtf;
-    attr[1].val.accessPolicyWindow.num_bytes = h->wtf_bytes;
-    attr[1].val.accessPolicyWindow.hitRatio = (float)((double)h->tc_persist_bytes >= (double)h->wtf_bytes
-                                                          ? 1.0 : (double)h->tc_persist_bytes / (double)h->wtf_bytes);
+    attr[1].val.accessPolicyWindow.num_bytes = win;
+    attr[1].val.accessPolicyWindow.hitRatio = (float)((double)h->tc_persist_bytes >= (double)win ? 1.0 : (double)h->tc_persist_bytes / (double)win);
     attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cfg.numAttrs = 2;
@@ -679,9 +682,9 @@ int launch_tc(vqwn_handle* h, int mode, long long T, const float* cond, long lon
   if (h->tc_persist_bytes > 0 && !getenv("VQWN_TC_NO_PERSIST")) {
     attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
     attr[1].val.accessPolicyWindow.base_ptr = h->wtc;
-    attr[1].val.accessPolicyWindow.num_bytes = h->wtc_bytes;
-    attr[1].val.accessPolicyWindow.hitRatio = (float)((double)h->tc_persist_bytes >= (double)h->wtc_bytes
-                                                          ? 1.0 : (double)h->tc_persist_bytes / (double)h->wtc_bytes);
+    const size_t win = h->wtc_bytes < h->tc_max_window ? h->wtc_bytes : h->tc_max_window;
+    attr[1].val.accessPolicyWindow.num_bytes = win;
+    attr[1].val.accessPolicyWindow.hitRatio = (float)((double)h->tc_persist_bytes >= (double)win ? 1.0 : (double)h->tc_persist_bytes / (double)win);
     attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cfg.numAttrs = 2;
@@ -904,7 +907,7 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
     if (grid < 1) grid = 1;
     CK(h, cudaMemsetAsync(h->vq_err, 0, sizeof(int), h->stream));
     vq_tc_kernel<<<grid, VT_THREADS, VT_SMEM, h->stream>>>(z, E, n, idx, out, out_stride, spk, spk_idx, spk_dim, F,
-                                                           h->emax_dev, h->vq_err, h->profile ? h->prof : nullptr);
+                                                           h->emax_dev, h->vq_err, h->profile ? h->prof : nullptr, h->vq_out_code);
     h->last_kernel = "vq_tc_kernel";
   } else {
     // at least 128 threads: the kernel stages 4 vectors with VB*D/4 <= 64 threads and reduces with one warp per vector
@@ -915,9 +918,9 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
     int grid = (int)((nblocks < (long long)h->num_sms * 1) ? nblocks : (long long)h->num_sms);
     if (grid < 1) grid = 1;
     if (h->D == 64)
-      vq_direct_kernel<64, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F);
+      vq_direct_kernel<64, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F, h->vq_out_code);
     else if (h->D == 32)
-      vq_direct_kernel<32, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F);
+      vq_direct_kernel<32, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F, h->vq_out_code);
     else
       return fail(h, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
     h->last_kernel = "vq_direct_kernel";
@@ -1158,6 +1161,10 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
         if (want > (size_t)max_persist) want = (size_t)max_persist;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->tc_persist_bytes = want;
         else (void)cudaGetLastError();
+        int max_win = 0;
+        if (cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device) == cudaSuccess && max_win > 0)
+          h->tc_max_window = (size_t)max_win;
+        else { (void)cudaGetLastError(); h->tc_persist_bytes = 0; }
       } else (void)cudaGetLastError();
     }
     CKC(cudaMalloc(&h->tc_skf_k, (size_t)TC_PK * TC_S * sizeof(float)));
@@ -1407,6 +1414,13 @@ int vqwn_set_vq_kernel(vqwn_handle* h, int kernel) {
   ENTER(h);
   if (kernel < VQWN_VQ_AUTO || kernel > VQWN_VQ_TENSOR) return fail(h, VQWN_ERR_INVALID, "unknown VQ kernel id");
   h->vq_kernel = kernel;
+  return VQWN_OK;
+}
+
+int vqwn_set_vq_output(vqwn_handle* h, int output) {
+  ENTER(h);
+  if (output != VQWN_VQ_OUT_STRAIGHT_THROUGH && output != VQWN_VQ_OUT_CODE) return fail(h, VQWN_ERR_INVALID, "unknown VQ output id");
+  h->vq_out_code = output == VQWN_VQ_OUT_CODE ? 1 : 0;
   return VQWN_OK;
 }
 

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(512, 1)
 vq_direct_kernel(const float* __restrict__ z, const float* __restrict__ E, int K, long long N,
                  long long* __restrict__ idx_out, float* __restrict__ zq_out, int out_stride,
                  const float* __restrict__ spk_table, const int* __restrict__ spk_idx,
-                 int spk_dim, int F) {
+                 int spk_dim, int F, int out_code) {
   __shared__ __align__(16) float zs[VB][D];
   __shared__ float wmin_d[VB][16];
   __shared__ int wmin_k[VB][16];
@@ -104,7 +104,7 @@ vq_direct_kernel(const float* __restrict__ z, const float* __restrict__ E, int K
           if (c < D) {
             const float zz = zs[v][c];
             const float ek = __ldg(E + (size_t)best_k[v] * D + c);
-            o = __fadd_rn(zz, __fsub_rn(ek, zz));          // model.py:73
+            o = out_code ? ek : __fadd_rn(zz, __fsub_rn(ek, zz));      // Magenta/config.py:242 (e_k) : model.py:73
           } else {
             const int b = (int)(gv / F);
             o = __ldg(spk_table + (size_t)spk_idx[b] * spk_dim + (c - D));

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1)
 vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long N,
              long long* __restrict__ idx_out, float* __restrict__ zq_out, int out_stride,
              const float* __restrict__ spk_table, const int* __restrict__ spk_idx, int spk_dim, int F,
-             const float* __restrict__ emax_p, int* __restrict__ err, long long* __restrict__ prof) {
+             const float* __restrict__ emax_p, int* __restrict__ err, long long* __restrict__ prof, int out_code) {
   extern __shared__ __align__(1024) uint8_t vt_smem_raw[];
   uint8_t* smem = vt_smem_raw;
   uint8_t* sE = smem;
@@ -415,7 +415,7 @@ vq_tc_kernel(const float* __restrict__ z, const float* __restrict__ E, long long
           o.y = __fadd_rn(zz.y, __fsub_rn(ee.y, zz.y));
           o.z = __fadd_rn(zz.z, __fsub_rn(ee.z, zz.z));
           o.w = __fadd_rn(zz.w, __fsub_rn(ee.w, zz.w));
-          if (gv < N) *reinterpret_cast<float4*>(zq_out + (size_t)gv * out_stride + 4 * ch) = o;
+          if (gv < N) *reinterpret_cast<float4*>(zq_out + (size_t)gv * out_stride + 4 * ch) = out_code ? ee : o;     // Magenta/config.py:242
         }
         if (spk_dim > 0) {
           for (int j = 0; j < 8; ++j) {

@@ -45,7 +45,7 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_NS = 16;                 // streams per cluster (at most)
 constexpr int TC_NN = 32;                 // MMA N: 16 hi rows + 16 lo rows
 constexpr int TC_R = 256, TC_G = 256, TC_S = 512, TC_Q = 256, TC_C = 128, TC_PK = 32;
-constexpr int TC_MAXL = 32;
+constexpr int TC_MAXL = 64;
 constexpr int TC_PLANE = TC_NN * 16;      // bytes of one activation plane
 constexpr int TC_XB = 32 * TC_PLANE;      // K = 256 activation operand: 16 KB
 constexpr int TC_ROWS1 = 64, TC_ROWS2 = 96, TC_ROWSP1 = 64, TC_ROWSP2 = 32;

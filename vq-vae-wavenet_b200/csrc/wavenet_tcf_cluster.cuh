@@ -37,7 +37,7 @@ constexpr int TF_THREADS = 384;           // warps 0-3 epilogue | 4-7 MMA issue 
 constexpr int TF_NISSUE = 4;
 constexpr int TF_NS = 16;                  // streams per cluster (at most)
 constexpr int TF_R = 256, TF_G = 256, TF_S = 512, TF_Q = 256, TF_C = 128, TF_PK = 32;
-constexpr int TF_MAXL = 32;
+constexpr int TF_MAXL = 64;
 constexpr int TF_BLK = 1024;               // one K step (16 channels) of a 32-row activation operand
 constexpr int TF_PAIR = TF_CS * 2 * TF_BLK;    // N-stacked operand, K = 256: [16 senders][first | second][1 KB] = 32 KB
 constexpr int TF_SLOT = 16384;             // weight FIFO slot: 4 instructions x 128 rows x 32 B

@@ -161,6 +161,10 @@ class Engine:
     def set_vq_kernel(self, name):
         self._ck(self.lib.vqwn_set_vq_kernel(self._h, {"auto": _lib.VQ_AUTO, "direct": _lib.VQ_DIRECT, "tensor": _lib.VQ_TENSOR}[name]))
 
+    def set_vq_output(self, name):
+        """'straight_through': z_e + (e_k - z_e) (model.py:73); 'code': e_k itself (Magenta/config.py:242)"""
+        self._ck(self.lib.vqwn_set_vq_output(self._h, {"straight_through": 0, "code": 1}[name]))
+
     # ------------------------------------------------------------------ weights
     def set_tensor(self, name, array):
         a = _f32(array)
