@@ -31,7 +31,8 @@ FLOP_PER_SAMPLE = 36386816          # minimal algorithmic work per ge
 QUEUE_BYTES_PER_SAMPLE = 92160 + 512 + 4
 # dram read + write per time step at 64 streams, from the committed ncu --set full captures of the same kernels
 # (profiles/): not measured by this run, hence "from_profile" in the line
-NCU_DRAM_BYTES_PER_STEP = {"wavenet_fp32_cluster": 85.3e6, "wavenet_tcf_cluster": None}
+# wavenet_tcf_cluster: profiles/r2_tcf_full_summary.txt, T = 64 launch: 4.497 GB read + 0.482 GB written
+NCU_DRAM_BYTES_PER_STEP = {"wavenet_fp32_cluster": 85.3e6, "wavenet_tcf_cluster": (4.497320e9 + 482.103040e6) / 64}
 METRIC = "generated audio samples/sec"
 DTYPE = {"fp32": "f32", "tc": "bf16x2-split (hi+lo operands, f32 accumulate, f32-grade)", "bf16": "bf16 (f32 accumulate)"}
 
@@ -406,10 +407,12 @@ def main():
         per_step = NCU_DRAM_BYTES_PER_STEP.get(kernel_name)
         traffic = per_step * T if (per_step and B == 64) else None
         roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved_tf / peaks["tensor_sustained"], "traffic": traffic, "traffic_source": "from_profile",
+                    "frac": achieved_tf / peaks["tensor_sustained"], "traffic": traffic,
+                    "traffic_source": "from_profile (ncu --set full of a T = 64 launch at 64 streams, profiles/, per time step x T)",
                     "note": "algorithmic FLOP (36.39 MFLOP per sample per stream) over the sustained bf16 peak; the split-bf16 "
                             "kernel executes ~4x that on the tensor pipe (hi/lo operand quadrants) and is bound by the "
-                            "30-stage dependency chain of a time step, not by FLOPs (DESIGN.md 4.5)",
+                            "30-stage dependency chain of a time step and, inside a stage, by the latency x depth of the "
+                            "weight FIFO (12 chunks of 16 KB per stage through 7 slots), not by FLOPs (DESIGN.md 4.5)",
                     "kernel": kernel_name, "kernel_ms": k_ms, "us_per_time_step": step_s * 1e6,
                     "roofline_us_per_time_step": roof_step * 1e6, "hbm_achieved_gbs": achieved_gbs,
                     "hbm_frac": achieved_gbs / peaks["hbm"], "peak_source": peaks["source"] + ", sustained bf16"}

@@ -12,10 +12,12 @@
 // instruction sequence as vq_direct_kernel (sequential __fsub_rn/__fmaf_rn over d, lowest index
 // on ties), reading the untouched fp32 rows that already sit in shared memory as MMA operands.
 //
-// One persistent CTA per SM, 192 threads:
-//   warps 0-3  epilogue: thread = vector = TMEM lane; single TMEM read per accumulator half
-//   warp  4    MMA issue (one elected lane), TMEM allocation
-//   warp  5    loader: cp.async z tiles (fp32, K-major core-matrix layout), ||z||, K-augmentation
+// One persistent CTA per SM, 416 threads:
+//   warps 0-7   epilogue: thread = vector = TMEM lane, two warps per lane quadrant (one per accumulator half = 256
+//               codes); two passes over the half: maximum, then the codes within the threshold of the maximum;
+//               rows with several candidates are queued and re-evaluated exactly, one (row, candidate) pair per thread
+//   warp  8     MMA issue (one elected lane), TMEM allocation
+//   warps 9-12  loaders: cp.async z tiles (fp32, K-chunk plane layout), ||z||, K-augmentation; 32 rows each
 // Shared memory: codebook [512 x 72] fp32 as the B operand (144 KB, loaded once), 2 stages of
 // z tile [128 x 72] fp32 as the A operand (36 KB each), candidate lists (6 KB).
 // TMEM: 512 columns = two 256-column accumulator halves (codes 0-255 / 256-511), double-buffered

@@ -11,11 +11,15 @@
 // 16 CTAs owns MS streams (MS <= 10) for the whole run and splits every stage by OUTPUT
 // CHANNELS: CTA r computes channels [r*N/16, (r+1)*N/16) of all MS streams.  The activations
 // never leave shared memory: a CTA pushes its slice of the stage output into the shared memory
-// of all 16 CTAs (st.shared::cluster, DSMEM) and the hand-off is a hardware cluster barrier
-// (~1.2-1.7k cycles measured for push + barrier, tools/cluster_probe.cu).  Clusters are
-// independent of each other: no grid-wide synchronisation exists.  The price is that every
-// cluster streams all weights (18 MB, L2-resident) once per step; per CTA that is 1.15 MB per
-// step through cp.async.bulk, double-buffered one stage ahead (S1 buffer / S2 buffer).
+// of all 16 CTAs with st.async.shared::cluster ... mbarrier::complete_tx (SASS STAS): every store
+// also counts its bytes on the RECEIVER's mbarrier, so a receiver waits on its own barrier for the
+// bytes of all 16 senders - no cluster-wide barrier per hand-off and no release stall on the sender
+// (two hardware cluster barriers per step remain: logits -> CTA 0, new sample -> all; they also
+// order the HBM ring stores against later bulk-copy reads).  Clusters are independent of each
+// other: no grid-wide synchronisation exists.  The price is that every cluster streams all float32
+// weights (78.6 MB) once per step, 4.9 MB per CTA, through cp.async.bulk with an L2 evict-last
+// hint, one stage ahead (S1 buffer / S2 buffer); they do not stay in L2 (85 MB of DRAM reads per
+// step, profiles/r1_cluster_full_summary.txt).
 //
 // Stage -> per-CTA tile (MS streams x NC columns, K), default geometry:
 //   skip start   MS x 32 skip channels,                 K = R          (input: local FIR, no hand-off)
