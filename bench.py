@@ -22,7 +22,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs (reference arm, cpu_baseline) are NumPy matmuls whose
+# BLAS reads that variable when NumPy is imported - drop it first so they get every host core at any N
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    if os.environ.get(_v) == "1":
+        del os.environ[_v]
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -136,6 +142,11 @@ def cpu_baseline_window(B, steps, warm):
     """the oracle port (FastWavenet: per-step matmuls + FIFO deques + NumPy decode) on host cores"""
     import torch
     torch.set_num_threads(os.cpu_count() or 1)          # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    try:                                                 # the BLAS behind NumPy's matmul (what the port actually runs on)
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     from oracle import oracle as O
     cfg = O.Config()
     w = O.make_weights(cfg, seed=1234, peaked=True)
