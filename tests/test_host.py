@@ -107,3 +107,34 @@ def test_synthetic_magenta_encoder_weights_equal_oracle():
     with pytest.raises(RuntimeError):
         pkg.Encoder_2019(64).build(np.zeros((1, 320, 1), np.float32))     # like the others: no engine, no CPU fallback
     assert pkg.EngineConfig(model=dict(encoder="2019")).to_c().encoder == 2019
+
+
+def test_wav_extensible_subformat(tmp_path):
+    """WAVE_FORMAT_EXTENSIBLE: the plain format tag is read from the sub-format GUID (bytes 24:26 of the fmt body), so
+    32-bit PCM is not mistaken for float because a 03 00 happens to occur in the header"""
+    import struct
+    from vqvae_wavenet_b200 import wavio
+    guid_tail = bytes.fromhex("000000001000800000aa00389b71")
+
+    def write(path, subtag, payload, bits, mask=3):           # mask = 3 puts the bytes 03 00 into the header
+        fmt = struct.pack("<HHIIHH", 0xFFFE, 1, 16000, 16000 * bits // 8, bits // 8, bits) + struct.pack("<HHI", 22, bits, mask) \
+            + struct.pack("<H", subtag) + guid_tail
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(payload)) + payload
+        with open(path, "wb") as f:
+            f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    ints = (np.array([0, 1 << 30, -(1 << 30), (1 << 31) - 1], dtype="<i4"))
+    write(tmp_path / "pcm32.wav", 1, ints.tobytes(), 32)
+    x = wavio.read_wav(str(tmp_path / "pcm32.wav"))
+    assert np.allclose(x, ints.astype(np.float64) / 2147483648.0)
+    fl = np.array([0.0, 0.5, -0.25, 1.0], dtype="<f4")
+    write(tmp_path / "f32.wav", 3, fl.tobytes(), 32)
+    assert np.array_equal(wavio.read_wav(str(tmp_path / "f32.wav")), fl)
+
+
+def test_crc32c_vectorised_equals_bytewise():
+    from vqvae_wavenet_b200 import tf_checkpoint as T
+    assert T.crc32c(b"123456789") == 0xE3069283                      # the published check value of CRC-32C
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 16383, 16384, 16385, 100003, 300000):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert T.crc32c(d) == (T._crc_bytes(0xFFFFFFFF, d) ^ 0xFFFFFFFF), n

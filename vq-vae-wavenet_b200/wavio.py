@@ -12,20 +12,25 @@ def read_wav(path, sample_rate=16000):
         data = f.read()
     if data[:4] != b"RIFF" or data[8:12] != b"WAVE":
         raise ValueError("%s is not a RIFF/WAVE file" % path)
-    pos, fmt, raw = 12, None, None
+    pos, fmt, raw, fmt_body = 12, None, None, b""
     while pos + 8 <= len(data):
         cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
         body = data[pos + 8:pos + 8 + size]
         if cid == b"fmt ":
             fmt = struct.unpack("<HHIIHH", body[:16])
+            fmt_body = body
         elif cid == b"data":
             raw = body
         pos += 8 + size + (size & 1)
     if fmt is None or raw is None:
         raise ValueError("missing fmt/data chunk in %s" % path)
     tag, channels, rate, _, _, bits = fmt
-    if tag == 0xFFFE and len(data) >= 44:        # WAVE_FORMAT_EXTENSIBLE: sub-format in the first 2 bytes
-        tag = 3 if bits == 32 and b"\x03\x00" in data[36:60] else 1
+    if tag == 0xFFFE:
+        # WAVE_FORMAT_EXTENSIBLE: cbSize (2) + valid bits (2) + channel mask (4), then the sub-format GUID whose first two
+        # bytes are the plain format tag (1 = PCM, 3 = IEEE float): bytes 24:26 of the fmt chunk body
+        if len(fmt_body) < 26:
+            raise ValueError("truncated WAVE_FORMAT_EXTENSIBLE fmt chunk in %s" % path)
+        tag = struct.unpack("<H", fmt_body[24:26])[0]
     if tag == 3 and bits == 32:
         x = np.frombuffer(raw, dtype="<f4").astype(np.float32)
     elif tag == 3 and bits == 64:
