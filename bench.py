@@ -121,7 +121,7 @@ def vq_bench(eng, vq_n):
     zbig = (0.13 * rng.standard_normal((vq_n, 64))).astype(np.float32)
     eng.vq_upload(zbig)
     hbm = load_peaks()["hbm"]
-    for kern in ("tensor", "direct"):
+    for kern in ("tensor", "tensor_bf16", "direct"):      # tf32 ranking (default), split-bf16 ranking (experiment), float32 anchor
         eng.set_vq_kernel(kern)
         for n in (6656, vq_n):
             for _ in range(3):

@@ -124,7 +124,7 @@ def _check_teacher_forced_draws(eng, cond, want_idx, margin, mode, tie, uniforms
 
 
 # ----------------------------------------------------------------------------------------- VQ
-@pytest.mark.parametrize("kernel", ["direct", "tensor"])
+@pytest.mark.parametrize("kernel", ["direct", "tensor", "tensor_bf16"])
 @pytest.mark.parametrize("kind", ["normal", "near_code", "scaled"])
 def test_vq_cfg2_bit_exact(kind, kernel, golden_dir):
     cfg = O.Config()
@@ -148,7 +148,7 @@ def test_vq_cfg2_bit_exact(kind, kernel, golden_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("kernel", ["direct", "tensor"])
+@pytest.mark.parametrize("kernel", ["direct", "tensor", "tensor_bf16"])
 def test_vq_ties_ragged_and_empty(kernel):
     cfg = O.Config()
     w = O.make_weights(cfg, seed=1234)
@@ -194,18 +194,26 @@ def test_vq_tensor_equals_direct():
     eng.set_vq_kernel("direct")
     i_d, q_d = eng.vq_lookup(z)
     assert eng.last_kernel_name == "vq_direct_kernel"
-    eng.set_vq_kernel("tensor")
-    i_t, q_t = eng.vq_lookup(z)
-    assert eng.last_kernel_name == "vq_tc_kernel"
-    assert np.array_equal(i_d, i_t)
-    assert np.array_equal(q_d, q_t)
     spk = np.array([1, 2], dtype=np.int32)
     zc = z[:2 * 300].reshape(2, 300, 64)
-    eng.set_vq_kernel("direct")
     a = eng.encode_condition(zc, spk)
-    eng.set_vq_kernel("tensor")
-    b = eng.encode_condition(zc, spk)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for name, kname in (("tensor", "vq_tc_kernel"), ("tensor_bf16", "vq_tc2_kernel")):     # tf32 / split-bf16 ranking
+        eng.set_vq_kernel(name)
+        i_t, q_t = eng.vq_lookup(z)
+        assert eng.last_kernel_name == kname
+        assert np.array_equal(i_d, i_t), name
+        assert np.array_equal(q_d, q_t), name
+        b = eng.encode_condition(zc, spk)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), name
+    # a vector exactly between MANY codes, and a codebook of identical rows: every code is inside the band
+    E2 = np.tile(E[3], (512, 1)).astype(np.float32)
+    w3 = dict(w2)
+    w3["embedding/embedding"] = E2
+    eng.set_weights({"embedding/embedding": E2})
+    for name in ("direct", "tensor", "tensor_bf16"):
+        eng.set_vq_kernel(name)
+        i_s, _ = eng.vq_lookup(z[:300])
+        assert np.all(i_s == 0), name
     eng.close()
 
 

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "vq.cuh"
 #include "vq_tc.cuh"
+#include "vq_tc2.cuh"
 #include "wavenet_fp32.cuh"
 #include "wavenet_fp32_cluster.cuh"
 #include "wavenet_bf16_cluster.cuh"
@@ -830,7 +831,7 @@ int finish_timing(vqwn_handle* h) {
     const int e = ev[0];
     if (e) return fail(h, VQWN_ERR_CUDA, e == 2 ? "generation kernel: operand wait timed out" : (e == 4 ? "generation kernel: packet wait timed out" : "generation kernel: grid barrier timed out"));
   }
-  if (h->profile && strcmp(h->last_kernel, "vq_tc_kernel") == 0) {
+  if (h->profile && strncmp(h->last_kernel, "vq_tc", 5) == 0) {
     long long pf[32];
     if (cudaMemcpy(pf, h->prof, sizeof pf, cudaMemcpyDeviceToHost) == cudaSuccess)
       fprintf(stderr, "[vqwn profile] vq_tc CTA0 epilogue-warp0 cycles: setup=%lld wait_z=%lld wait_acc=%lld pass1=%lld pass2=%lld decide=%lld output=%lld (kernel %.3f ms)\n",
@@ -891,7 +892,7 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
   const float* E = TP(h, "embedding/embedding");
   const float* spk = spk_dim > 0 ? TP(h, "speaker_embedding") : nullptr;
   const bool tensor_ok = (K == VT_K && h->D == VT_D);
-  if (h->vq_kernel == VQWN_VQ_TENSOR && !tensor_ok)
+  if ((h->vq_kernel == VQWN_VQ_TENSOR || h->vq_kernel == VQWN_VQ_TENSOR_BF16) && !tensor_ok)
     return fail(h, VQWN_ERR_NOTIMPL, "tensor-core VQ kernel needs k = 512 and latent_dim = 64");
   const bool use_tensor = tensor_ok && h->vq_kernel != VQWN_VQ_DIRECT;
   if (use_tensor && !h->emax_valid) {
@@ -906,9 +907,15 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
     int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
     if (grid < 1) grid = 1;
     CK(h, cudaMemsetAsync(h->vq_err, 0, sizeof(int), h->stream));
-    vq_tc_kernel<<<grid, VT_THREADS, VT_SMEM, h->stream>>>(z, E, n, idx, out, out_stride, spk, spk_idx, spk_dim, F,
-                                                           h->emax_dev, h->vq_err, h->profile ? h->prof : nullptr, h->vq_out_code);
-    h->last_kernel = "vq_tc_kernel";
+    if (h->vq_kernel != VQWN_VQ_TENSOR_BF16) {
+      vq_tc_kernel<<<grid, VT_THREADS, VT_SMEM, h->stream>>>(z, E, n, idx, out, out_stride, spk, spk_idx, spk_dim, F,
+                                                             h->emax_dev, h->vq_err, h->profile ? h->prof : nullptr, h->vq_out_code);
+      h->last_kernel = "vq_tc_kernel";
+    } else {
+      vq_tc2_kernel<<<grid, VT_THREADS, V2_SMEM, h->stream>>>(z, E, n, idx, out, out_stride, spk, spk_idx, spk_dim, F,
+                                                              h->emax_dev, h->vq_err, h->profile ? h->prof : nullptr, h->vq_out_code);
+      h->last_kernel = "vq_tc2_kernel";
+    }
   } else {
     // at least 128 threads: the kernel stages 4 vectors with VB*D/4 <= 64 threads and reduces with one warp per vector
     // (VB = 4 warps); threads beyond k hold no code (has_code guards)
@@ -932,10 +939,10 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
 }
 
 int check_vq_error(vqwn_handle* h) {
-  if (strcmp(h->last_kernel, "vq_tc_kernel") != 0) return VQWN_OK;
+  if (strncmp(h->last_kernel, "vq_tc", 5) != 0) return VQWN_OK;
   int e = 0;
   CK(h, cudaMemcpy(&e, h->vq_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (e) return fail(h, VQWN_ERR_CUDA, "vq_tc_kernel: pipeline wait timed out");
+  if (e) return fail(h, VQWN_ERR_CUDA, "tensor-core VQ kernel: pipeline wait timed out");
   return VQWN_OK;
 }
 
@@ -1120,6 +1127,7 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   CKC(cudaMalloc(&h->emax_dev, sizeof(float)));
   CKC(cudaMalloc(&h->vq_err, sizeof(int)));
   CKC(cudaFuncSetAttribute((const void*)vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VT_SMEM));
+  CKC(cudaFuncSetAttribute((const void*)vq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM));
   CKC(cudaMalloc(&h->dec_lut, (Q + 1) * sizeof(float)));
 
   // state
@@ -1412,7 +1420,7 @@ int vqwn_set_stream_offset(vqwn_handle* h, int64_t offset) {
 
 int vqwn_set_vq_kernel(vqwn_handle* h, int kernel) {
   ENTER(h);
-  if (kernel < VQWN_VQ_AUTO || kernel > VQWN_VQ_TENSOR) return fail(h, VQWN_ERR_INVALID, "unknown VQ kernel id");
+  if (kernel < VQWN_VQ_AUTO || kernel > VQWN_VQ_TENSOR_BF16) return fail(h, VQWN_ERR_INVALID, "unknown VQ kernel id");
   h->vq_kernel = kernel;
   return VQWN_OK;
 }
