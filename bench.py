@@ -138,6 +138,35 @@ def vq_bench(eng, vq_n):
     return out
 
 
+def encoder_bench(pkg, device):
+    """SURVEY 8f #1 (the step before the path): one 4 s utterance x 8 through each device encoder; runs once per
+    utterance in generate.py.  ms = CUDA events around the whole vqwn_encode_audio call (H2D of the audio and D2H of
+    z_e included); GFLOP = the conv stacks' multiply-adds x 2."""
+    from vqvae_wavenet_b200 import synthetic
+    out = {}
+    Bx, T = 8, 64000
+    x = (0.1 * np.random.default_rng(5).standard_normal((Bx, T))).astype(np.float32)
+    gflop = {"64": 2 * (T / 2 * 5 * 768 + sum(T / 2 ** (i + 1) * 5 * 768 * 768 for i in range(1, 6)) + T / 64 * 768 * 64) / 1e9,
+             "Magenta": 2 * (T * 5 * 128 + sum(T / 2 ** (i + 1) * (128 * 128 * (1 + 5 + 5 + 1)) for i in range(6)) + T / 64 * 128 * 64) / 1e9,
+             "2019": 2 * (T / 160 * (400 * 402 + 201 * 80 + 80 * 13 + 3 * 13 * 768 + 3 * 768 * 768) +
+                          T / 320 * (4 * 768 * 768 + 6 * 3 * 768 * 768 + 768 * 64)) / 1e9}
+    for name, mk in (("64", synthetic.make_encoder64_weights), ("Magenta", synthetic.make_encoder_magenta_weights),
+                     ("2019", synthetic.make_encoder2019_weights)):
+        cfg = pkg.EngineConfig(model=dict(encoder=name))
+        e = pkg.Engine(cfg, device=device, max_batch=1)
+        e.set_weights(mk(cfg))
+        e.encode_audio(x)
+        ts = []
+        for _ in range(3):
+            e.encode_audio(x)
+            ts.append(e.last_kernel_ms)
+        ms = float(np.median(ts))
+        out[name] = {"ms_per_8_utterances_of_4s": ms, "utterances_per_s": Bx / (ms * 1e-3), "gflop_per_utterance": gflop[name],
+                     "achieved_tflops": Bx * gflop[name] / ms, "kernel": "conv1d_gemm_kernel (float32 CUDA cores)"}
+        e.close()
+    return out
+
+
 def cpu_baseline_window(B, steps, warm):
     """the oracle port (FastWavenet: per-step matmuls + FIFO deques + NumPy decode) on host cores"""
     import torch
@@ -404,6 +433,12 @@ def main():
 
     # ---------------------------------------------------------------- VQ lookups/s (secondary metric)
     vq = vq_bench(eng, args.vq_n) if rank == 0 else {}
+    encoders = {}
+    if rank == 0 and not args.no_bf16:
+        try:
+            encoders = encoder_bench(pkg, local_rank)
+        except Exception as e:                                   # a secondary block never takes the headline down
+            encoders = {"error": str(e)[:200]}
 
     # ---------------------------------------------------------------- roofline + CPU baseline + report
     if rank == 0:
@@ -458,7 +493,7 @@ def main():
             "cpu_baseline_single_stream": cpu1,
             "secondary": secondary,
             "single_stream_latency": latency,
-            "vq": vq,
+            "vq": vq, "encoders": encoders,
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -325,6 +325,51 @@ def test_encoder_magenta_matches_oracle():
     eng.close()
 
 
+def test_cli_encoder_2019(tmp_path, monkeypatch):
+    """generate.py with "encoder": "2019" in the -params file: audio -> MFCC + conv stack (hop 320) -> VQ -> WaveNet"""
+    import json
+    import generate
+    from conftest import write_speaker_table
+    write_speaker_table(tmp_path)
+    monkeypatch.setenv("VQWN_SPEAKER_TABLES", str(tmp_path))
+    import vqvae_wavenet_b200 as pkg
+    from vqvae_wavenet_b200 import synthetic, wavio
+    root = os.path.dirname(generate.__file__)
+    with open(os.path.join(root, "model_parameters.json")) as f:
+        mp = json.load(f)
+    mp["encoder"] = "2019"
+    mp["wavenet_parameters"] = os.path.join(root, "wavenet_parameters.json")
+    with open(str(tmp_path / "model_2019.json"), "w") as f:
+        json.dump(mp, f)
+    cfg = pkg.EngineConfig.from_files(str(tmp_path / "model_2019.json"))
+    w = synthetic.make_weights(cfg, seed=1234, peaked=True)
+    w.update(synthetic.make_encoder2019_weights(cfg))
+    run = tmp_path / "run"
+    run.mkdir()
+    np.savez(str(run / "weights-9.npz"), **w)
+    x = O.synthetic_audio(1, 2700, seed=9)[0]
+    wavio.write_wav_float32(str(tmp_path / "in.wav"), 16000, x)
+    generate.main(["-restore", str(run / "weights-9"), "-audio", str(tmp_path / "in.wav"), "-speakers", "p225",
+                   "-mode", "greedy", "-params", str(tmp_path / "model_2019.json")])
+    a = wavio.read_wav(str(run / "9_p225.wav"))
+    assert a.shape == (2560,)                                 # 2700 trimmed to a multiple of 512 = 8 frames of 320
+    eng = pkg.Engine(cfg, 0, 1)
+    eng.set_weights(w)
+    z = eng.encode_audio(x[None, :2560])
+    assert z.shape == (1, 8, 64)
+    assert np.abs(z - O.encoder2019_forward(O.Config(), w, x[None, :2560, None])).max() < 1e-4 * np.abs(z).max()
+    table = pkg.utils.get_speaker_to_int(pkg.utils.find_speaker_table("vctk", roots=()))
+    _, cond = eng.encode_condition(z, [table["p225"]])
+    audio, _ = eng.generate(cond, 2560, mode="greedy")
+    assert np.array_equal(audio[0], a)
+    eng.close()
+    # a trimmed length that is not a multiple of 320 is refused with a reason (the reference fails inside a reshape)
+    wavio.write_wav_float32(str(tmp_path / "short.wav"), 16000, x[:1100])
+    with pytest.raises(ValueError):
+        generate.main(["-restore", str(run / "weights-9"), "-audio", str(tmp_path / "short.wav"), "-speakers", "p225",
+                       "-mode", "greedy", "-params", str(tmp_path / "model_2019.json")])
+
+
 def test_cli_end_to_end(tmp_path, monkeypatch):
     """generate.py with the reference's flags, TF-free: audio -> Encoder_64 -> VQ -> WaveNet -> WAVs"""
     import generate

@@ -138,3 +138,12 @@ def test_crc32c_vectorised_equals_bytewise():
     for n in (0, 1, 16383, 16384, 16385, 100003, 300000):
         d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
         assert T.crc32c(d) == (T._crc_bytes(0xFFFFFFFF, d) ^ 0xFFFFFFFF), n
+
+
+def test_synthetic_encoder2019_weights_equal_oracle():
+    import vqvae_wavenet_b200 as pkg
+    from vqvae_wavenet_b200 import synthetic
+    from oracle import oracle as O
+    a = synthetic.make_encoder2019_weights(pkg.EngineConfig(model=dict(encoder="2019")))
+    b = O.make_encoder2019_weights(O.Config())
+    assert sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) for k in a)

@@ -110,3 +110,27 @@ def make_encoder_magenta_weights(config, seed=4322):
             a = rng.uniform(-0.05, 0.05, size=shape)
         out[name] = np.ascontiguousarray(a, dtype=np.float32)
     return out
+
+
+def encoder2019_specs(config):
+    """keras Conv1D variables of Encoder_2019 under variable_scope('encoder') (Encoder/encoder.py:75-96): conv1d ... conv1d_9"""
+    D = config.model["latent_dim"]
+    shapes = [(3, 13, 768), (3, 768, 768), (4, 768, 768)] + [(3, 768, 768)] * 6 + [(1, 768, D)]
+    specs = []
+    for i, shp in enumerate(shapes):
+        sfx = "" if i == 0 else "_%d" % i
+        specs += [("encoder/conv1d%s/kernel" % sfx, shp), ("encoder/conv1d%s/bias" % sfx, (shp[2],))]
+    return specs
+
+
+def make_encoder2019_weights(config, seed=4323):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in encoder2019_specs(config):
+        if name.endswith("kernel"):
+            lim = np.sqrt(6.0 / (shape[0] * shape[1] + shape[0] * shape[2]))
+            a = rng.uniform(-lim, lim, size=shape)
+        else:
+            a = rng.uniform(-0.1, 0.1, size=shape)
+        out[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return out
