@@ -405,6 +405,26 @@ def main():
                 eng2.close()
             except Exception as e:                                            # noqa: BLE001 - secondary figure only
                 secondary["config4_sample_b512"] = {"error": str(e)}
+        if args.precision == "tc" and B == 64 and args.mode == "greedy":
+            # the step is latency-bound, not throughput-bound: one co-resident set of clusters (7 x 16 streams on a B200)
+            # runs at the same time per step as 64 streams - the per-GPU throughput at its best batch
+            nb = 112
+            try:
+                eng2 = pkg.Engine(cfg, device=local_rank, max_batch=nb)
+                eng2.set_weights(w)
+                eng2.set_stream(stream.cuda_stream)
+                z2 = np.concatenate([z_e] * ((nb + B - 1) // B), 0)[:nb]
+                s2 = (np.arange(nb, dtype=np.int32) + rank * nb) % 4
+                _, c2 = eng2.encode_condition(z2, s2)
+                eng2.upload_condition(c2)
+                eng_keep, eng = eng, eng2
+                secondary["greedy_112_streams"] = one_timed("tc", "greedy", nb)
+                secondary["greedy_112_streams"]["note"] = ("same kernel, 112 streams per GPU = one co-resident set of 7 clusters x 16 "
+                                                           "streams: the best per-GPU batch (x real time = value / 16000 / n_gpus)")
+                eng = eng_keep
+                eng2.close()
+            except Exception as e:                                            # noqa: BLE001 - secondary figure only
+                secondary["greedy_112_streams"] = {"error": str(e)}
         eng.set_precision(args.precision)
         if u is not None:
             eng.upload_uniforms(u)
