@@ -329,6 +329,10 @@ int pack_weights(vqwn_handle* h) {
       size_t off = 0;
       pk(h->w1[0] + tap, h->w1[0] + 2 * tap, 2 * G, 16, 128, 0, off); off += TF_TILE_A;
       for (int l = 0; l < h->L; ++l) {
+#ifdef TF_ORDER_RA
+        // stage l: R_{l-1} before A_l (the kernel issues the residual + skip chain first)
+        if (l >= 1) { pk(h->w2[l - 1], nullptr, R + S, 16, 96, 1, off); off += TF_TILE_R; }
+#endif
         if (l == 0) {
           pk(nullptr, h->w1[0], 2 * G, 16, 128, 0, off);
           tf_fold_bias_kernel<<<(2 * G + 127) / 128, 128, 0, h->stream>>>(h->b1[0], nullptr, h->w1[0], h->tf_b1adj);
@@ -340,7 +344,9 @@ int pack_weights(vqwn_handle* h) {
         }
         h->launches += 2;
         off += TF_TILE_A;
+#ifndef TF_ORDER_RA
         if (l >= 1) { pk(h->w2[l - 1], nullptr, R + S, 16, 96, 1, off); off += TF_TILE_R; }
+#endif
         if (l + 1 < h->L) { pk(h->w1[l + 1] + tap, h->w1[l + 1] + 2 * tap, 2 * G, 16, 128, 0, off); off += TF_TILE_A; }
       }
       pk(h->w2[h->L - 1], nullptr, R + S, 16, 96, 1, off); off += TF_TILE_R;

@@ -40,8 +40,16 @@ constexpr int TF_R = 256, TF_G = 256, TF_S = 512, TF_Q = 256, TF_C = 128, TF_PK 
 constexpr int TF_MAXL = 64;
 constexpr int TF_BLK = 1024;               // one K step (16 channels) of a 32-row activation operand
 constexpr int TF_PAIR = TF_CS * 2 * TF_BLK;    // N-stacked operand, K = 256: [16 senders][first | second][1 KB] = 32 KB
-constexpr int TF_SLOT = 16384;             // weight FIFO slot: 4 instructions x 128 rows x 32 B
+// weight FIFO: a chunk is one bulk copy = TF_CPW x 4 instructions (TF_CPW issuing warps share it); the copy unit of an SM
+// takes a few hundred cycles per bulk copy whatever its size up to 48 KB (tools/r2_probe.cu), so fewer, larger chunks
+#ifdef TF_CHUNK32
+constexpr int TF_CPW = 2;
+constexpr int TF_NSLOT = 3;
+#else
+constexpr int TF_CPW = 1;
 constexpr int TF_NSLOT = 7;
+#endif
+constexpr int TF_SLOT = 16384 * TF_CPW;    // slot: TF_CPW x 4 instructions x 128 rows x 32 B
 constexpr int TF_CHUNK_A = 4 * 128 * 32, TF_CHUNK_R = 4 * 96 * 32, TF_CHUNK_P1 = 4 * 64 * 32, TF_CHUNK_P2 = 4 * 32 * 32;
 // per-CTA weight stream of one time step (bytes): T_0 | stage 0: A_0, T_1 | stage l: A_l, R_{l-1}, T_{l+1} | ... | tail
 constexpr int TF_TILE_A = 4 * TF_CHUNK_A, TF_TILE_R = 4 * TF_CHUNK_R, TF_TILE_P1 = 8 * TF_CHUNK_P1, TF_TILE_P2 = 8 * TF_CHUNK_P2;
@@ -207,11 +215,13 @@ __device__ __forceinline__ unsigned tf_wfull_parity(unsigned ci) { return ((ci /
 // and in the instruction cache.  d_tmem: accumulator address; b_addr: B operand of the chunk's first K step.
 __device__ __noinline__ void tf_issue_chunk(unsigned ci, uint32_t a_step, uint32_t d_tmem, uint32_t idesc, uint32_t b_addr,
                                             uint32_t b_step, uint32_t sm_u32, uint32_t elected, int* err, bool have_weights, unsigned* turn_ptr) {
-  const unsigned slot = ci % TF_NSLOT;
-  if (!have_weights) tf_wait(tf_wfull_bar(sm_u32, ci), tf_wfull_parity(ci), err);
+  // ci counts quarter-tiles (4 instructions); the FIFO chunk that holds it is ci / TF_CPW, at sub-position ci % TF_CPW
+  const unsigned chunk = ci / TF_CPW, sub = ci - chunk * TF_CPW;
+  const unsigned slot = chunk % TF_NSLOT;
+  if (!have_weights) tf_wait(tf_wfull_bar(sm_u32, chunk), tf_wfull_parity(chunk), err);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (elected) {
-    uint64_t da = tf_desc(sm_u32 + TF_OFF_W + slot * TF_SLOT);
+    uint64_t da = tf_desc(sm_u32 + TF_OFF_W + slot * TF_SLOT + sub * 4u * a_step);
     uint64_t db = tf_desc(b_addr);
     const uint64_t sa = (uint64_t)(a_step >> 4), sb = (uint64_t)(b_step >> 4);
     // The chunks of a chain accumulate into one TMEM tile from four different threads, and float32 accumulation depends
@@ -296,6 +306,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
     for (int i = 0; i < TF_NBARS; ++i) {
       unsigned cnt = (bars + i == e1done) ? 4u : ((bars + i == e2done) ? 3u : 1u);
       if (bars + i == accA || bars + i == accB || bars + i == tapfree) cnt = TF_NISSUE;      // one commit per issuing warp
+      if (i >= 8 && i < 8 + TF_NSLOT) cnt = TF_CPW;                                          // wfree: one commit per issuing warp of the chunk
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f32_smem_u32(&bars[i])), "r"(cnt));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -403,7 +414,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   };
   // the weight chunk of the chain that is waiting for a gather: checked BEFORE the gather wait, off the critical path
   auto weights_ready = [&](unsigned ci0) {
-    const unsigned c_ = ci0 + iss;
+    const unsigned c_ = (ci0 + iss) / TF_CPW;
     tf_wait(tf_wfull_bar(sm_u32, c_), tf_wfull_parity(c_), p.err);
   };
   auto wait_b1 = [&](int par) {
@@ -448,7 +459,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
 
   // ------------------------------------------------------------------ prologue: the first step's layer-0 taps
   if (tloader) load_taps(0, p.t0);
-  if (wloader) load_chunks(8, TF_CHUNK_A);          // T_0 and A_0 sit at the head of the stream
+  if (wloader) load_chunks(8 / TF_CPW, TF_CHUNK_A * TF_CPW);          // T_0 and A_0 sit at the head of the stream
   if (issuer) {
     wait_bar(tapbar, ph_tap);
     operand_fence();
@@ -621,6 +632,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         if (lane == 0 && iss == 0)
           mbar_expect(&b1bar[par], (l + 2 < L || (par != (L & 1) && par == 1)) ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
         operand_fence();
+#ifdef TF_ORDER_RA
+        // residual + skip chain first: its result x_l is the LATER of the two hand-offs of the stage (it is published
+        // behind the gate epilogue) and its operand gate_{l-1} is in the same gather
+        if (l > 0) {
+          consume(ci, 4, 96, ACCR, false, b1a, 2 * TF_BLK, true);               // residual + skip rows of layer l-1 x gate_{l-1}
+          commit_to(accB);
+          ci += 4u;
+        }
+        consume(ci, 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, l == 0);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
+        commit_to(accA);
+        ci += 4u;
+#else
         consume(ci, 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, true);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
         commit_to(accA);
         ci += 4u;
@@ -629,6 +652,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           commit_to(accB);
           ci += 4u;
         }
+#endif
         if (l + 1 < L) {
           wait_bar(tapbar, ph_tap);
           operand_fence();
@@ -746,10 +770,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       for (int l = 0; l <= L; ++l) {
         const uint32_t acc = (l & 1) ? ACC1 : ACC0;
         TF_MARK(200 + l);
+#ifdef TF_ORDER_RA
+        if (l > 0) res_skip_epilogue(l - 1);       // its chain is issued first in the stage
+#endif
         if (l < L) {
         // ---------------------------------------------------------------- gate of layer l
         wait_bar(accA, ph_accA);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef TF_ORDER_RA
+        asm volatile("bar.sync 2, 128;" ::: "memory");       // warp 3 has published the previous gate: the staging buffer is free
+#endif
         TF_PF_ADD(1);
         tf_ld32_issue(my_taddr + acc, v0);
         tf_ld32_issue(my_taddr + acc + 32, v1);
@@ -805,9 +835,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         }
         // ---------------------------------------------------------------- residual + skip of layer l-1 (l = L: the tail's
         // skip rows of the last layer)
+#ifndef TF_ORDER_RA
         if (l > 0) res_skip_epilogue(l - 1);
         TF_PF_ADD(4);
         if (l < L) asm volatile("bar.sync 2, 128;" ::: "memory");       // the staging buffer is free for the next gate epilogue
+#endif
       }
       // ================================================================ tail: relu(skip total) -> postprocess1
       // every ring store of this step is issued: split cluster barrier (waited for before the next step's tap loads)
@@ -908,16 +940,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         // the same chain order as the MMA warps' (op = 3 l + k, tail 3 L ..); the first gate tile of a step was requested
         // at the end of the previous one, and this step ends with the next step's T_0 and A_0 (stream offset wraps to 0)
 #pragma unroll 1
-        for (int op = 1; op < 3 * L + 3; ++op) {
+#ifdef TF_ORDER_RA
+        constexpr int K_RES = 0, OP0 = 2;       // stage l: R_{l-1}, A_l, T_{l+1}; A_0 came with the previous step's tail
+#else
+        constexpr int K_RES = 1, OP0 = 1;       // stage l: A_l, R_{l-1}, T_{l+1}
+#endif
+        for (int op = OP0; op < 3 * L + 3; ++op) {
           const int l = (op < 3 * L) ? op / 3 : L;
           const int k = (op < 3 * L) ? op - 3 * l : 3 + (op - 3 * L);
-          if ((k == 1 && l == 0) || (k == 2 && l + 1 >= L)) continue;
+          if ((k == K_RES && l == 0) || (k == 2 && l + 1 >= L)) continue;
           const int nch = (k == 4 || k == 5) ? 8 : 4;
           TF_MARK(300 + op);
-          const int bytes = (k == 1 || k == 3) ? TF_CHUNK_R : (k == 4 ? TF_CHUNK_P1 : (k == 5 ? TF_CHUNK_P2 : TF_CHUNK_A));
-          load_chunks(nch, bytes);
+          const int bytes = (k == K_RES || k == 3) ? TF_CHUNK_R : (k == 4 ? TF_CHUNK_P1 : (k == 5 ? TF_CHUNK_P2 : TF_CHUNK_A));
+          load_chunks(nch / TF_CPW, bytes * TF_CPW);
         }
-        if (more) { woff = 0; load_chunks(8, TF_CHUNK_A); }           // T_0 and A_0 of the next step
+        if (more) { woff = 0; load_chunks(8 / TF_CPW, TF_CHUNK_A * TF_CPW); }           // T_0 and A_0 of the next step
       }
       if (tloader) {
 #pragma unroll 1
