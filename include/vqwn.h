@@ -48,12 +48,14 @@ extern "C" {
 #define VQWN_PREC_BF16 1   /* bf16 tcgen05 contraction, fp32 accumulate (tolerance 2e-2)    */
 #define VQWN_PREC_TC   2   /* split-bf16 (hi + lo) tcgen05 contraction, fp32 accumulate: float32-grade (logits ~1e-5) */
 
-/* VQ kernel selection (vqwn_set_vq_kernel); both give identical indices and z_q */
+/* VQ kernel selection (vqwn_set_vq_kernel); AUTO / DIRECT / TENSOR / TENSOR_BF16 give identical indices and z_q */
 #define VQWN_VQ_AUTO   0   /* tensor-core kernel when k = 512 and latent_dim = 64, else direct  */
 #define VQWN_VQ_DIRECT 1   /* float32 CUDA-core direct form                                      */
 #define VQWN_VQ_TENSOR 2   /* tcgen05 tf32 ranking + exact float32 re-evaluation of near-minima  */
 #define VQWN_VQ_TENSOR_BF16 3   /* experiment (vq_tc2.cuh): split-bf16 ranking, 15x fewer near-minima to re-evaluate, same results;
                                  * measured slower (its float32 rows come from L2, not shared memory) - DESIGN.md 4.1 */
+#define VQWN_VQ_EXPANDED 4      /* Magenta/sonnet.py:91-98: ||z||^2 - 2 z.w + ||w||^2 in float32, first minimum; picks the direct
+                                 * form's code except on near-ties of the two formulations */
 /* what the VQ hands to the decoder (vqwn_set_vq_output) */
 #define VQWN_VQ_OUT_STRAIGHT_THROUGH 0   /* z_e + (e_k - z_e): model.py:73,85-87 (differs from e_k in the last bit) */
 #define VQWN_VQ_OUT_CODE 1               /* e_k itself: Magenta/config.py:240-242 (`self.encoding = e_k`)                     */

@@ -217,6 +217,36 @@ def test_vq_tensor_equals_direct():
     eng.close()
 
 
+def test_vq_expanded_distance_mode():
+    """Magenta/sonnet.py:91-98 as a device mode (VQWN_VQ_EXPANDED): ||z||^2 - 2 z.w + ||w||^2 in float32, first minimum.
+    Against the NumPy restatement of the same formula (BLAS summation order differs from the device's sequential one):
+    identical codes except where the two best expanded distances are within 1e-5 relative; and the direct form's codes
+    except on such near-ties (what tests/test_oracle.py shows for the two formulations)."""
+    cfg = O.Config()
+    w = O.make_weights(cfg, seed=1234)
+    E = w["embedding/embedding"]
+    eng = _engine(None, 1, w)
+    for kind in ("normal", "near_code", "scaled"):
+        z = O.synthetic_z_e(cfg, w, 64, 104, seed=1235, kind=kind)
+        eng.set_vq_kernel("expanded")
+        idx, zq = eng.vq_lookup(z)
+        assert eng.last_kernel_name == "vq_direct_kernel"
+        want = O.vq_discretise_expanded(z, E)
+        d = O.vq_distances_f64(z.reshape(-1, 64), E)
+        srt = np.sort(d, axis=1)
+        gap = (srt[:, 1] - srt[:, 0]) / np.maximum(srt[:, 0], 1e-30)
+        bad = (idx.reshape(-1) != want.reshape(-1))
+        assert np.all(gap[bad] < 1e-5), "%s: %d codes differ from the expanded-form restatement away from a near-tie" % (kind, int(bad.sum()))
+        eng.set_vq_kernel("direct")
+        idx_d, _ = eng.vq_lookup(z)
+        bad_d = (idx.reshape(-1) != idx_d.reshape(-1))
+        assert np.all(gap[bad_d] < 1e-5)
+        assert np.array_equal(zq, (z + (E[idx] - z)).astype(np.float32))
+        print("expanded VQ %s: %d / %d codes differ from the NumPy expanded form, %d from the direct form (all near-ties)"
+              % (kind, int(bad.sum()), bad.size, int(bad_d.sum())))
+    eng.close()
+
+
 def test_vq_large_property():
     """N = 2^16 vectors: the chosen code attains the float64 minimum distance up to 1e-5 relative,
     and the lookup is idempotent (VQ of z_q's code row returns the same index)."""

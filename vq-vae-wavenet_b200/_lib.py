@@ -8,7 +8,7 @@ MAX_LAYERS = 64
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOTIMPL, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MODE_GREEDY, MODE_SAMPLE = 0, 1
 PREC_FP32, PREC_BF16, PREC_TC = 0, 1, 2
-VQ_AUTO, VQ_DIRECT, VQ_TENSOR, VQ_TENSOR_BF16 = 0, 1, 2, 3
+VQ_AUTO, VQ_DIRECT, VQ_TENSOR, VQ_TENSOR_BF16, VQ_EXPANDED = 0, 1, 2, 3, 4
 
 
 class VqwnError(RuntimeError):

@@ -900,7 +900,7 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
   const bool tensor_ok = (K == VT_K && h->D == VT_D);
   if ((h->vq_kernel == VQWN_VQ_TENSOR || h->vq_kernel == VQWN_VQ_TENSOR_BF16) && !tensor_ok)
     return fail(h, VQWN_ERR_NOTIMPL, "tensor-core VQ kernel needs k = 512 and latent_dim = 64");
-  const bool use_tensor = tensor_ok && h->vq_kernel != VQWN_VQ_DIRECT;
+  const bool use_tensor = tensor_ok && h->vq_kernel != VQWN_VQ_DIRECT && h->vq_kernel != VQWN_VQ_EXPANDED;
   if (use_tensor && !h->emax_valid) {
     vq_emax_kernel<<<1, (K + 31) / 32 * 32, 0, h->stream>>>(E, K, h->D, h->emax_dev);
     CK(h, cudaGetLastError());
@@ -931,9 +931,10 @@ int launch_vq(vqwn_handle* h, const float* z, long long n, long long* idx, float
     int grid = (int)((nblocks < (long long)h->num_sms * 1) ? nblocks : (long long)h->num_sms);
     if (grid < 1) grid = 1;
     if (h->D == 64)
-      vq_direct_kernel<64, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F, h->vq_out_code);
+      vq_direct_kernel<64, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F, h->vq_out_code, h->vq_kernel == VQWN_VQ_EXPANDED);
     else if (h->D == 32)
-      vq_direct_kernel<32, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F, h->vq_out_code);
+      vq_direct_kernel<32, 4><<<grid, threads, 0, h->stream>>>(z, E, K, n, idx, out, out_stride, spk, spk_idx, spk_dim, F, h->vq_out_code,
+                                                               h->vq_kernel == VQWN_VQ_EXPANDED);
     else
       return fail(h, VQWN_ERR_NOTIMPL, "latent_dim must be 32 or 64");
     h->last_kernel = "vq_direct_kernel";
@@ -1426,7 +1427,7 @@ int vqwn_set_stream_offset(vqwn_handle* h, int64_t offset) {
 
 int vqwn_set_vq_kernel(vqwn_handle* h, int kernel) {
   ENTER(h);
-  if (kernel < VQWN_VQ_AUTO || kernel > VQWN_VQ_TENSOR_BF16) return fail(h, VQWN_ERR_INVALID, "unknown VQ kernel id");
+  if (kernel < VQWN_VQ_AUTO || kernel > VQWN_VQ_EXPANDED) return fail(h, VQWN_ERR_INVALID, "unknown VQ kernel id");
   h->vq_kernel = kernel;
   return VQWN_OK;
 }

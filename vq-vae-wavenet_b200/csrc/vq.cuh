@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(512, 1)
 vq_direct_kernel(const float* __restrict__ z, const float* __restrict__ E, int K, long long N,
                  long long* __restrict__ idx_out, float* __restrict__ zq_out, int out_stride,
                  const float* __restrict__ spk_table, const int* __restrict__ spk_idx,
-                 int spk_dim, int F, int out_code) {
+                 int spk_dim, int F, int out_code, int expanded = 0) {
   __shared__ __align__(16) float zs[VB][D];
   __shared__ float wmin_d[VB][16];
   __shared__ int wmin_k[VB][16];
@@ -52,16 +52,34 @@ vq_direct_kernel(const float* __restrict__ z, const float* __restrict__ E, int K
     float dist[VB];
 #pragma unroll
     for (int v = 0; v < VB; ++v) dist[v] = 0.f;
+    if (!expanded) {
 #pragma unroll
-    for (int d = 0; d < D; d += 4) {
+      for (int d = 0; d < D; d += 4) {
+#pragma unroll
+        for (int v = 0; v < VB; ++v) {
+          const float4 zv = *reinterpret_cast<const float4*>(&zs[v][d]);
+          float t;
+          t = __fsub_rn(zv.x, e[d]);     dist[v] = __fmaf_rn(t, t, dist[v]);
+          t = __fsub_rn(zv.y, e[d + 1]); dist[v] = __fmaf_rn(t, t, dist[v]);
+          t = __fsub_rn(zv.z, e[d + 2]); dist[v] = __fmaf_rn(t, t, dist[v]);
+          t = __fsub_rn(zv.w, e[d + 3]); dist[v] = __fmaf_rn(t, t, dist[v]);
+        }
+      }
+    } else {
+      // Magenta/sonnet.py:91-95: ||z||^2 - 2 z.w + ||w||^2 (the three terms formed separately, then combined in that order)
+      float ee = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) ee = __fmaf_rn(e[d], e[d], ee);
 #pragma unroll
       for (int v = 0; v < VB; ++v) {
-        const float4 zv = *reinterpret_cast<const float4*>(&zs[v][d]);
-        float t;
-        t = __fsub_rn(zv.x, e[d]);     dist[v] = __fmaf_rn(t, t, dist[v]);
-        t = __fsub_rn(zv.y, e[d + 1]); dist[v] = __fmaf_rn(t, t, dist[v]);
-        t = __fsub_rn(zv.z, e[d + 2]); dist[v] = __fmaf_rn(t, t, dist[v]);
-        t = __fsub_rn(zv.w, e[d + 3]); dist[v] = __fmaf_rn(t, t, dist[v]);
+        float zz = 0.f, dot = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float zv = zs[v][d];
+          zz = __fmaf_rn(zv, zv, zz);
+          dot = __fmaf_rn(zv, e[d], dot);
+        }
+        dist[v] = __fadd_rn(__fsub_rn(zz, __fmul_rn(2.0f, dot)), ee);
       }
     }
     // warp argmin, lowest index on ties (tf.argmin de-facto order)

@@ -159,7 +159,7 @@ class Engine:
         self._ck(self.lib.vqwn_set_stream_offset(self._h, int(offset)))
 
     def set_vq_kernel(self, name):
-        self._ck(self.lib.vqwn_set_vq_kernel(self._h, {"auto": _lib.VQ_AUTO, "direct": _lib.VQ_DIRECT, "tensor": _lib.VQ_TENSOR, "tensor_bf16": _lib.VQ_TENSOR_BF16}[name]))
+        self._ck(self.lib.vqwn_set_vq_kernel(self._h, {"auto": _lib.VQ_AUTO, "direct": _lib.VQ_DIRECT, "tensor": _lib.VQ_TENSOR, "tensor_bf16": _lib.VQ_TENSOR_BF16, "expanded": _lib.VQ_EXPANDED}[name]))
 
     def set_vq_output(self, name):
         """'straight_through': z_e + (e_k - z_e) (model.py:73); 'code': e_k itself (Magenta/config.py:242)"""
