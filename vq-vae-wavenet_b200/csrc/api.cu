@@ -319,39 +319,58 @@ int pack_weights(vqwn_handle* h) {
     //   A_l = [P_l = W2_l . Wres_{l-1} | W2_l] (stacked inputs [gate_{l-1} | x_{l-1}]), T_l = [W1_l | W0_l] (taps t-d | t-2d)
     {
       const size_t SB = tf_stream_bytes(h->L);
-      auto pk = [&](const float* s0, const float* s1, int ldw, int ninstr, int rows, int kind, size_t off) {
+#ifdef TF_FIFO2
+      // two streams per CTA (the kernel's two weight FIFOs): [16][gate / tap tiles in issue order], then [16][the rest]
+      const size_t SBig = tf_big_bytes(h->L), SSmall = tf_small_bytes(h->L);
+      uint8_t* const base_small = h->wtf + (size_t)TF_CS * SBig;
+      size_t offb = 0, offs = 0;
+      auto pk = [&](const float* s0, const float* s1, int ldw, int ninstr, int rows, int kind, size_t bytes) {
+        const bool big = (kind == 0);
+        const long long total = (long long)TF_CS * ninstr * rows * 16;
+        int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+        tf_pack_kernel<<<grid, 256, 0, h->stream>>>(s0, s1, ldw, ninstr, rows, kind, big ? SBig : SSmall,
+                                                    big ? h->wtf + offb : base_small + offs);
+        if (big) offb += bytes; else offs += bytes;
+        h->launches += 1;
+      };
+#else
+      size_t off = 0;
+      auto pk = [&](const float* s0, const float* s1, int ldw, int ninstr, int rows, int kind, size_t bytes) {
         const long long total = (long long)TF_CS * ninstr * rows * 16;
         int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
         tf_pack_kernel<<<grid, 256, 0, h->stream>>>(s0, s1, ldw, ninstr, rows, kind, SB, h->wtf + off);
+        off += bytes;
         h->launches += 1;
       };
+#endif
       const size_t tap = (size_t)R * 2 * G;      // w1 rows: current tap | tap t-d | tap t-2d | condition
-      size_t off = 0;
-      pk(h->w1[0] + tap, h->w1[0] + 2 * tap, 2 * G, 16, 128, 0, off); off += TF_TILE_A;
+      pk(h->w1[0] + tap, h->w1[0] + 2 * tap, 2 * G, 16, 128, 0, TF_TILE_A);
       for (int l = 0; l < h->L; ++l) {
 #ifdef TF_ORDER_RA
         // stage l: R_{l-1} before A_l (the kernel issues the residual + skip chain first)
-        if (l >= 1) { pk(h->w2[l - 1], nullptr, R + S, 16, 96, 1, off); off += TF_TILE_R; }
+        if (l >= 1) pk(h->w2[l - 1], nullptr, R + S, 16, 96, 1, TF_TILE_R);
 #endif
         if (l == 0) {
-          pk(nullptr, h->w1[0], 2 * G, 16, 128, 0, off);
+          pk(nullptr, h->w1[0], 2 * G, 16, 128, 0, TF_TILE_A);
           tf_fold_bias_kernel<<<(2 * G + 127) / 128, 128, 0, h->stream>>>(h->b1[0], nullptr, h->w1[0], h->tf_b1adj);
         } else {
           tf_premultiply_kernel<<<dim3((2 * G + 127) / 128, G), 128, 0, h->stream>>>(h->w2[l - 1], R + S, h->w1[l], h->tf_ptmp);
-          pk(h->tf_ptmp, h->w1[l], 2 * G, 16, 128, 0, off);
+          pk(h->tf_ptmp, h->w1[l], 2 * G, 16, 128, 0, TF_TILE_A);
           tf_fold_bias_kernel<<<(2 * G + 127) / 128, 128, 0, h->stream>>>(h->b1[l], h->b2[l - 1], h->w1[l],
                                                                            h->tf_b1adj + (size_t)l * 2 * G);
         }
         h->launches += 2;
-        off += TF_TILE_A;
 #ifndef TF_ORDER_RA
-        if (l >= 1) { pk(h->w2[l - 1], nullptr, R + S, 16, 96, 1, off); off += TF_TILE_R; }
+        if (l >= 1) pk(h->w2[l - 1], nullptr, R + S, 16, 96, 1, TF_TILE_R);
 #endif
-        if (l + 1 < h->L) { pk(h->w1[l + 1] + tap, h->w1[l + 1] + 2 * tap, 2 * G, 16, 128, 0, off); off += TF_TILE_A; }
+        if (l + 1 < h->L) pk(h->w1[l + 1] + tap, h->w1[l + 1] + 2 * tap, 2 * G, 16, 128, 0, TF_TILE_A);
       }
-      pk(h->w2[h->L - 1], nullptr, R + S, 16, 96, 1, off); off += TF_TILE_R;
-      pk(h->post1_w, nullptr, S, 32, 64, 2, off); off += TF_TILE_P1;
-      pk(TP(h, "decoder/postprocess2/kernel"), nullptr, h->Q, 32, 32, 3, off); off += TF_TILE_P2;
+      pk(h->w2[h->L - 1], nullptr, R + S, 16, 96, 1, TF_TILE_R);
+      pk(h->post1_w, nullptr, S, 32, 64, 2, TF_TILE_P1);
+      pk(TP(h, "decoder/postprocess2/kernel"), nullptr, h->Q, 32, 32, 3, TF_TILE_P2);
+#ifdef TF_FIFO2
+      const size_t off = (offb == SBig && offs == SSmall) ? SB : 0;
+#endif
       if (off != SB) return fail(h, VQWN_ERR_INVALID, "tensor-core kernel: weight stream size mismatch");
       CK(h, cudaGetLastError());
     }
@@ -871,6 +890,20 @@ int finish_timing(vqwn_handle* h) {
       for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%lld/%lld", kn[k], pf[32 + 2 * k], pf[32 + 2 * k + 1]);
       fprintf(stderr, " | step_start=%lld weight_chunk_wait=%lld operand_fence=%lld mma_issue=%lld chunk_commit=%lld chain_commits=%lld consume_total=%lld\n", pf[16], pf[25], pf[19], pf[20], pf[21], pf[22], pf[23]);
     }
+    if (const char* tp = getenv("VQWN_TRACE_FILE")) {
+      // one time step's event trace of CTA 0 (kernel: TF_TR): "warp event layer cycles" lines for tools/tcf_trace.py
+      std::vector<long long> tr(12 * TF_TRACE_N);
+      if (cudaMemcpy(tr.data(), h->prof + 256, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        if (FILE* f = fopen(tp, "w")) {
+          for (int w = 0; w < 12; ++w)
+            for (int i = 0; i < TF_TRACE_N; ++i) {
+              const long long v = tr[(size_t)w * TF_TRACE_N + i];
+              if (v) fprintf(f, "%d %lld %lld %lld\n", w, (v >> 8) & 255, v & 255, v >> 16);
+            }
+          fclose(f);
+        }
+      }
+    }
   }
   if (h->profile && strcmp(h->last_kernel, "wavenet_tc_cluster") == 0) {
     long long pf[48];
@@ -1229,7 +1262,8 @@ int vqwn_create(const vqwn_config* cfg, int device, int max_batch, vqwn_handle**
   CKC(cudaMalloc(&h->n1, Bp * S * sizeof(float)));
   CKC(cudaMalloc(&h->logits, Bp * Q * sizeof(float)));
   CKC(cudaMalloc(&h->barrier, 32 * sizeof(unsigned long long)));
-  CKC(cudaMalloc(&h->prof, 256 * sizeof(long long)));
+  CKC(cudaMalloc(&h->prof, (256 + 12 * TF_TRACE_N) * sizeof(long long)));       // counters + one step's event trace (VQWN_PROFILE=1)
+  CKC(cudaMemset(h->prof, 0, (256 + 12 * TF_TRACE_N) * sizeof(long long)));
   CKC(cudaMemset(h->prof, 0, 256 * sizeof(long long)));
   h->profile = getenv("VQWN_PROFILE") != nullptr;
 

@@ -38,6 +38,7 @@ constexpr int TF_NISSUE = 4;
 constexpr int TF_NS = 16;                  // streams per cluster (at most)
 constexpr int TF_R = 256, TF_G = 256, TF_S = 512, TF_Q = 256, TF_C = 128, TF_PK = 32;
 constexpr int TF_MAXL = 64;
+constexpr int TF_TRACE_N = 320;            // trace events per warp (profile build)
 constexpr int TF_BLK = 1024;               // one K step (16 channels) of a 32-row activation operand
 constexpr int TF_PAIR = TF_CS * 2 * TF_BLK;    // N-stacked operand, K = 256: [16 senders][first | second][1 KB] = 32 KB
 // weight FIFO: a chunk is one bulk copy = TF_CPW x 4 instructions (TF_CPW issuing warps share it); the copy unit of an SM
@@ -56,6 +57,9 @@ constexpr int TF_TILE_A = 4 * TF_CHUNK_A, TF_TILE_R = 4 * TF_CHUNK_R, TF_TILE_P1
 __host__ __device__ constexpr size_t tf_stream_bytes(int L) {
   return (size_t)TF_TILE_A + (size_t)L * TF_TILE_A + (size_t)L * TF_TILE_R + (size_t)(L - 1) * TF_TILE_A + TF_TILE_P1 + TF_TILE_P2;
 }
+// TF_FIFO2: the two per-CTA streams of a time step: gate / tap tiles, and everything else
+__host__ __device__ constexpr size_t tf_big_bytes(int L) { return (size_t)2 * L * TF_TILE_A; }
+__host__ __device__ constexpr size_t tf_small_bytes(int L) { return (size_t)L * TF_TILE_R + TF_TILE_P1 + TF_TILE_P2; }
 // shared memory map (bytes)
 constexpr int TF_OFF_W = 0;                                  // weight FIFO
 constexpr int TF_OFF_B1 = TF_OFF_W + TF_NSLOT * TF_SLOT;     // [2][gate | layer input] operands, by stage parity
@@ -203,25 +207,54 @@ __device__ __noinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* er
 //     all four accA commits of chain l; the residual chain of l needs x_l, i.e. accB of l-1; the tap chain of l+2 needs
 //     its pair block, loaded after all four tapfree commits of l+1; the tail is ordered the same way by xsbar / b1bar).
 //     With one barrier per slot the distance would be 7 chunks - less than two chains - and nothing orders those.
+#ifdef TF_FIFO2
+// TWO weight FIFOs in the same 112 KB: class 0 = 4 slots x 16 KB for the gate and tap tiles, class 1 = 4 slots x 12 KB for
+// the residual + skip tiles (and the postprocess tiles, 8 / 4 KB chunks).  With one FIFO of seven 16 KB slots the eighth
+// chunk of a stage - the last quarter of the residual + skip tile - is requested only when the gate chain has released a
+// slot and lands ~2k cycles into the stage; with the 12 KB class beside it a stage's gate tile AND residual + skip tile
+// (64 + 48 KB) are resident when its gather completes.  A chunk id is (class << 31) | index within the class; each class
+// has one loader lane (warp 8: class 0, warp 9: class 1), so every release barrier is still watched by one lane, and
+// consecutive phases of an arrival barrier are 8 chunks = two chains of the class apart (see above).
+constexpr int TF_SLOT_R = 12288;
+constexpr int TF_OFF_WR = TF_OFF_W + 4 * 16384;
+static_assert(TF_CPW == 1 && TF_OFF_WR + 4 * TF_SLOT_R == TF_OFF_W + TF_NSLOT * TF_SLOT, "two FIFOs fill the weight area exactly");
+__device__ __forceinline__ unsigned tf_slot_off(unsigned cid) {
+  const unsigned slot = cid & 3u;
+  return (cid >> 31) ? (unsigned)TF_OFF_WR + slot * TF_SLOT_R : (unsigned)TF_OFF_W + slot * 16384u;
+}
+__device__ __forceinline__ unsigned tf_wfull_bar(unsigned sm_u32, unsigned cid) {
+  const unsigned idx = cid & 0x7fffffffu;
+  return sm_u32 + TF_OFF_BARS + ((((idx >> 2) & 1u) ? TF_WFULL1 : 0u) + (cid >> 31) * 4u + (idx & 3u)) * 8u;
+}
+__device__ __forceinline__ unsigned tf_wfull_parity(unsigned cid) { return ((cid & 0x7fffffffu) >> 3) & 1u; }
+__device__ __forceinline__ unsigned tf_wfree_idx(unsigned cid) { return 8u + (cid >> 31) * 4u + (cid & 3u); }
+#else
+__device__ __forceinline__ unsigned tf_slot_off(unsigned cid) { return (unsigned)TF_OFF_W + (cid % TF_NSLOT) * TF_SLOT; }
 __device__ __forceinline__ unsigned tf_wfull_bar(unsigned sm_u32, unsigned ci) {
   const unsigned u = ci / TF_NSLOT, slot = ci - u * TF_NSLOT;
   return sm_u32 + TF_OFF_BARS + ((u & 1u) ? (TF_WFULL1 + slot) : slot) * 8u;
 }
 __device__ __forceinline__ unsigned tf_wfull_parity(unsigned ci) { return ((ci / TF_NSLOT) >> 1) & 1u; }
+__device__ __forceinline__ unsigned tf_wfree_idx(unsigned cid) { return 8u + cid % TF_NSLOT; }
+#endif
 
 // One weight chunk (4 K steps): wait for it, issue its 4 MMAs D[128 x N] += A . B^T, release its FIFO slot.  A real
 // function: the issuing warps are bound by the length of their own instruction stream (every MMA costs ~17 instructions
 // of descriptor arithmetic, register -> uniform-register moves and the per-thread issue loop), one copy keeps it short
 // and in the instruction cache.  d_tmem: accumulator address; b_addr: B operand of the chunk's first K step.
-__device__ __noinline__ void tf_issue_chunk(unsigned ci, uint32_t a_step, uint32_t d_tmem, uint32_t idesc, uint32_t b_addr,
+__device__ __noinline__ void tf_issue_chunk(unsigned ci, unsigned cid, uint32_t a_step, uint32_t d_tmem, uint32_t idesc, uint32_t b_addr,
                                             uint32_t b_step, uint32_t sm_u32, uint32_t elected, int* err, bool have_weights, unsigned* turn_ptr) {
-  // ci counts quarter-tiles (4 instructions); the FIFO chunk that holds it is ci / TF_CPW, at sub-position ci % TF_CPW
-  const unsigned chunk = ci / TF_CPW, sub = ci - chunk * TF_CPW;
-  const unsigned slot = chunk % TF_NSLOT;
+  // ci: position in the issue sequence of the step chain (orders the reproducible mode); cid: the quarter-tile's place in
+  // the weight FIFO(s): the chunk that holds it is cid / TF_CPW, at sub-position cid % TF_CPW
+#ifdef TF_FIFO2
+  const unsigned chunk = cid, sub = 0u;
+#else
+  const unsigned chunk = cid / TF_CPW, sub = cid - chunk * TF_CPW;
+#endif
   if (!have_weights) tf_wait(tf_wfull_bar(sm_u32, chunk), tf_wfull_parity(chunk), err);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (elected) {
-    uint64_t da = tf_desc(sm_u32 + TF_OFF_W + slot * TF_SLOT + sub * 4u * a_step);
+    uint64_t da = tf_desc(sm_u32 + tf_slot_off(chunk) + sub * 4u * a_step);
     uint64_t db = tf_desc(b_addr);
     const uint64_t sa = (uint64_t)(a_step >> 4), sb = (uint64_t)(b_step >> 4);
     // The chunks of a chain accumulate into one TMEM tile from four different threads, and float32 accumulation depends
@@ -239,7 +272,7 @@ __device__ __noinline__ void tf_issue_chunk(unsigned ci, uint32_t a_step, uint32
       da += sa; db += sb;
     }
     if (turn) *turn = ci + 1u;
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sm_u32 + TF_OFF_BARS + (8u + slot) * 8u) : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sm_u32 + TF_OFF_BARS + tf_wfree_idx(chunk) * 8u) : "memory");
   }
   __syncwarp();
 }
@@ -345,6 +378,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
 #pragma unroll
   for (int i = 0; i < 12; ++i) pf[i] = 0;
   long long pf_t = 0;
+  // event trace of ONE time step (VQWN_PROFILE=1, step p.t0 + 300 of CTA 0 of cluster 0): lane 0 of every warp appends
+  // (clock << 16 | event << 8 | layer) to its row of p.prof[256 + warp * TF_TRACE_N ...]; tools/tcf_trace.py prints it
+  int tr_n = 0;
+  bool tracing = false;
+#define TF_TR(ev, l_) do { if (PROF && tracing && lane == 0 && tr_n < TF_TRACE_N) { \
+    p.prof[256 + warp * TF_TRACE_N + tr_n] = (clock64() << 16) | ((long long)(ev) << 8) | (long long)(l_); ++tr_n; } } while (0)
 #define TF_PF_START() do { if (prof) pf_t = clock64(); } while (0)
 #define TF_PF_ADD(i) do { if (prof) { const long long n_ = clock64(); pf[(i)] += n_ - pf_t; pf_t = n_; } } while (0)
 #ifdef TF_DEBUG_MARKS
@@ -406,15 +445,31 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   // this warp's chunk(s) of a chain of `nch` chunks (4 or 8) of `rows`-row tiles that starts at FIFO position ci0: chunk
   // iss (and 4 + iss).  The chunks of a chain go to the four issuing warps: MMAs of different threads are not ordered, so
   // every chain ACCUMULATES - the epilogue that reads an accumulator leaves it zeroed.
-  auto consume = [&](unsigned ci0, int nch, int rows, uint32_t d_col, bool n64, uint32_t b_addr, uint32_t b_step, bool have_weights = false) {
+  // FIFO positions: one sequence (cid = ci), or per class with TF_FIFO2 (cb: 16 KB chunks of the gate / tap tiles, cr: the
+  // others); a chain takes its `nch` places with take(class, nch)
+  unsigned cb = 0u, cr = 0u;
+  auto take = [&](unsigned ci_now, int cls, unsigned nch) -> unsigned {
+#ifdef TF_FIFO2
+    unsigned r;
+    if (cls) { r = 0x80000000u | cr; cr += nch; } else { r = cb; cb += nch; }
+    return r;
+#else
+    return ci_now;
+#endif
+  };
+  auto consume = [&](unsigned ci0, unsigned cid0, int nch, int rows, uint32_t d_col, bool n64, uint32_t b_addr, uint32_t b_step, bool have_weights = false) {
     const uint32_t id = n64 ? idesc64 : idesc32;
-    tf_issue_chunk(ci0 + iss, (uint32_t)rows * 32u, tmem + d_col, id, b_addr + 4u * iss * b_step, b_step, sm_u32, elected, p.err, have_weights, turn_s);
+    tf_issue_chunk(ci0 + iss, cid0 + iss, (uint32_t)rows * 32u, tmem + d_col, id, b_addr + 4u * iss * b_step, b_step, sm_u32, elected, p.err, have_weights, turn_s);
     if (nch == 8)
-      tf_issue_chunk(ci0 + 4u + iss, (uint32_t)rows * 32u, tmem + d_col, id, b_addr + 4u * (4u + iss) * b_step, b_step, sm_u32, elected, p.err, false, turn_s);
+      tf_issue_chunk(ci0 + 4u + iss, cid0 + 4u + iss, (uint32_t)rows * 32u, tmem + d_col, id, b_addr + 4u * (4u + iss) * b_step, b_step, sm_u32, elected, p.err, false, turn_s);
   };
   // the weight chunk of the chain that is waiting for a gather: checked BEFORE the gather wait, off the critical path
-  auto weights_ready = [&](unsigned ci0) {
-    const unsigned c_ = (ci0 + iss) / TF_CPW;
+  auto weights_ready = [&](unsigned cid0) {
+#ifdef TF_FIFO2
+    const unsigned c_ = cid0 + iss;
+#else
+    const unsigned c_ = (cid0 + iss) / TF_CPW;
+#endif
     tf_wait(tf_wfull_bar(sm_u32, c_), tf_wfull_parity(c_), p.err);
   };
   auto wait_b1 = [&](int par) {
@@ -436,21 +491,44 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   const bool tloader = (lane == 0) && (warp == 10);
   unsigned long long wpol = 0;
   if (wloader) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(wpol));
-  auto load_chunks = [&](int nch, int bytes) {
+#ifdef TF_FIFO2
+  // a lane loads the chunks of ITS class only (cls == wmine); li and woff are the lane's position in its class and stream
+  const uint8_t* const wsrc2 = wmine ? p.wstream + (size_t)TF_CS * tf_big_bytes(L) + (size_t)rank * tf_small_bytes(L)
+                                     : p.wstream + (size_t)rank * tf_big_bytes(L);
+  auto load_chunks = [&](int nch, int bytes, unsigned cls = 0u) {
+    if (cls != wmine) return;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      const unsigned cid = (cls << 31) | li;
+      if (li >= 4u) tf_wait(sm_u32 + TF_OFF_BARS + tf_wfree_idx(cid) * 8u, ((li >> 2) - 1u) & 1u, p.err);
+      const unsigned fb = tf_wfull_bar(sm_u32, cid);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((unsigned)bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                   ::"r"(sm_u32 + tf_slot_off(cid)), "l"(wsrc2 + woff), "r"(bytes), "r"(fb), "l"(wpol) : "memory");
+      li += 1;
+      woff += (size_t)bytes;
+    }
+  };
+#else
+  auto load_chunks = [&](int nch, int bytes, unsigned cls = 0u) {
+    (void)cls;
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
       const unsigned slot = li % TF_NSLOT;
       if ((slot % NLOADERS) == wmine) {
         if (li >= TF_NSLOT) tf_wait(f32_smem_u32(&wfree[slot]), ((li / TF_NSLOT) - 1u) & 1u, p.err);
+        TF_TR(20, li & 255u);
         const unsigned fb = tf_wfull_bar(sm_u32, li);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((unsigned)bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                      ::"r"(sm_u32 + TF_OFF_W + slot * TF_SLOT), "l"(wsrc + woff), "r"(bytes), "r"(fb), "l"(wpol) : "memory");
+        TF_TR(21, li & 255u);
       }
       li += 1;
       woff += (size_t)bytes;
     }
   };
+#endif
   // tap loader (warp 6 lane 0)
   unsigned ph_tapfree = 0u;
   auto load_taps = [&](int l, long long t) {
@@ -466,7 +544,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   if (issuer) {
     wait_bar(tapbar, ph_tap);
     operand_fence();
-    consume(0u, 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
+    consume(0u, take(0u, 0, 4u), 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
     commit_to(tapfree);
   }
   TF_MARK(1);
@@ -480,6 +558,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
     const bool more = (t + 1 < p.t0 + p.T);
     t_mark = t - p.t0;
     TF_MARK(2);
+    tracing = PROF && p.prof != nullptr && blockIdx.x == 0 && p.cluster0 == 0 && (t - p.t0) == 300;
+    TF_TR(1, 0);
     TF_PF_START();
     // ================================================================ all threads: frame change -> condition table
     if (frame_t != cond_frame) {
@@ -623,13 +703,22 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       // the epilogue publishes only after it has read (and zeroed) the accumulators of the previous stage.  The one
       // exception is the tail's skip chain (e2done).
       unsigned ci = 4u + (unsigned)(t - p.t0) * (12u * (unsigned)L + 16u);       // chunks consumed before this step
+      cb = 4u + (unsigned)(t - p.t0) * (8u * (unsigned)L);                       // TF_FIFO2: the same, per class
+      cr = (unsigned)(t - p.t0) * (4u * (unsigned)L + 16u);
 #pragma unroll 1
       for (int l = 0; l < L; ++l) {
         const int par = l & 1;
         const uint32_t b1a = sm_u32 + TF_OFF_B1 + par * TF_PAIR;
         TF_MARK(100 + l);
-        weights_ready(ci);
+#ifdef TF_ORDER_RA
+        const unsigned cid0 = take(ci, l > 0 ? 1 : 0, 4u);      // the stage's first chain: residual + skip (gate for layer 0)
+#else
+        const unsigned cid0 = take(ci, 0, 4u);                  // the stage's first chain: the gate tile
+#endif
+        weights_ready(cid0);
+        TF_TR(2, l);
         wait_b1(par);
+        TF_TR(3, l);
         // next use of this parity's barrier: stage l + 2 (gate + layer input, 32 KB); else the tail's gate (parity L & 1,
         // 16 KB), postprocess2's input (the other parity if it is 1, 32 KB), or the next step's stage 0 (16 KB)
         if (lane == 0 && iss == 0)
@@ -639,28 +728,32 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         // residual + skip chain first: its result x_l is the LATER of the two hand-offs of the stage (it is published
         // behind the gate epilogue) and its operand gate_{l-1} is in the same gather
         if (l > 0) {
-          consume(ci, 4, 96, ACCR, false, b1a, 2 * TF_BLK, true);               // residual + skip rows of layer l-1 x gate_{l-1}
+          consume(ci, cid0, 4, 96, ACCR, false, b1a, 2 * TF_BLK, true);         // residual + skip rows of layer l-1 x gate_{l-1}
           commit_to(accB);
           ci += 4u;
         }
-        consume(ci, 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, l == 0);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
+        consume(ci, l == 0 ? cid0 : take(ci, 0, 4u), 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, l == 0);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
         commit_to(accA);
         ci += 4u;
 #else
-        consume(ci, 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, true);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
+        consume(ci, cid0, 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, true);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
         commit_to(accA);
+        TF_TR(4, l);
         ci += 4u;
         if (l > 0) {
-          consume(ci, 4, 96, ACCR, false, b1a, 2 * TF_BLK);                     // residual + skip rows of layer l-1 x gate_{l-1}
+          consume(ci, take(ci, 1, 4u), 4, 96, ACCR, false, b1a, 2 * TF_BLK);    // residual + skip rows of layer l-1 x gate_{l-1}
           commit_to(accB);
+          TF_TR(5, l);
           ci += 4u;
         }
 #endif
         if (l + 1 < L) {
           wait_bar(tapbar, ph_tap);
+          TF_TR(6, l);
           operand_fence();
-          consume(ci, 4, 128, par ? ACC0 : ACC1, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);      // taps of layer l+1
+          consume(ci, take(ci, 0, 4u), 4, 128, par ? ACC0 : ACC1, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);      // taps of layer l+1
           commit_to(tapfree);
+          TF_TR(7, l);
           ci += 4u;
         }
       }
@@ -673,7 +766,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         if (lane == 0 && iss == 0) mbar_expect(&b1bar[par], par == 1 ? 2 * TF_CS * TF_BLK : TF_CS * TF_BLK);
         wait_bar(e2done, ph_e2);       // the residual / skip epilogue of layer L-2 has read ACCR (nothing it publishes is waited for)
         operand_fence();
-        consume(ci, 4, 96, ACCR, false, sm_u32 + TF_OFF_B1 + par * TF_PAIR, 2 * TF_BLK);
+        consume(ci, take(ci, 1, 4u), 4, 96, ACCR, false, sm_u32 + TF_OFF_B1 + par * TF_PAIR, 2 * TF_BLK);
         commit_to(accB);
         ci += 4u;
         cl_arrive();
@@ -681,7 +774,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         wait_bar(xsbar, ph_xs);
         if (lane == 0 && iss == 0) mbar_expect(xsbar, 2 * TF_CS * TF_BLK);
         operand_fence();
-        consume(ci, 8, 64, ACCP1, false, sm_u32 + TF_OFF_B2, TF_BLK);
+        consume(ci, take(ci, 1, 8u), 8, 64, ACCP1, false, sm_u32 + TF_OFF_B2, TF_BLK);
         commit_to(accA);
         commit_to(tapfree);
         ci += 8u;
@@ -691,14 +784,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         wait_b1(1);
         if (lane == 0 && iss == 0) mbar_expect(&b1bar[1], 2 * TF_CS * TF_BLK);      // stage 1 of the next step
         operand_fence();
-        consume(ci, 8, 32, ACCP2, false, sm_u32 + TF_OFF_B1 + TF_PAIR, TF_BLK);
+        consume(ci, take(ci, 1, 8u), 8, 32, ACCP2, false, sm_u32 + TF_OFF_B1 + TF_PAIR, TF_BLK);
         commit_to(accA);
         ci += 8u;
         TF_MARK(154);
         if (more) {
           wait_bar(tapbar, ph_tap);
           operand_fence();
-          consume(ci, 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
+          consume(ci, take(ci, 0, 4u), 4, 128, ACC0, true, sm_u32 + TF_OFF_B2, 2 * TF_BLK);
           commit_to(tapfree);
         }
       }
@@ -724,6 +817,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         const float bres = (warp == 0 && !dead) ? __ldg(p.layers[lr].bres + 16 * rank + (lane & 15)) : 0.f;
         const long long r0_ = prof ? clock64() : 0;
         wait_bar(accB, ph_accB);
+        TF_TR(13, lr);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const long long r1_ = prof ? clock64() : 0;
         if (warp < 3 && !(dead && warp == 0)) {
@@ -763,6 +857,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           uint8_t* g2 = pair_block(ln, t + 2 * dn) + rank * 2 * TF_BLK + TF_BLK;
           const bool needed = (ln + 1 < L);
           publish(stg + TF_BLK, g1, g2, 1, TF_OFF_B1 + ((ln + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK + TF_BLK, needed ? &b1bar[(ln + 1) & 1] : nullptr);
+          TF_TR(14, lr);
         } else if (warp == 1 || warp == 2) {
           // lanes 32-63: skip rows hi, lanes 64-95: skip rows lo of channel 32 rank + lane
 #pragma unroll
@@ -779,6 +874,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         if (l < L) {
         // ---------------------------------------------------------------- gate of layer l
         wait_bar(accA, ph_accA);
+        TF_TR(10, l);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef TF_ORDER_RA
         asm volatile("bar.sync 2, 128;" ::: "memory");       // warp 3 has published the previous gate: the staging buffer is free
@@ -827,6 +923,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           }
         }
         TF_PF_ADD(2);
+        TF_TR(11, l);
         asm volatile("bar.sync 2, 128;" ::: "memory");
         // gate_l: first input of stage l+1's stacked pair (and of the last layer's skip rows in the tail)
         // (warp 3 publishes; warp 0 goes straight on to the residual rows - the layer input it produces is the later of the
@@ -834,6 +931,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         if (warp == 3)
           publish(stg, gst + TF_GST_XG + (l & 1) * TF_CS * TF_BLK + rank * TF_BLK, nullptr, 1,
                   TF_OFF_B1 + ((l + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK, &b1bar[(l + 1) & 1]);
+        TF_TR(12, l);
         TF_PF_ADD(3);
         }
         // ---------------------------------------------------------------- residual + skip of layer l-1 (l = L: the tail's
@@ -955,7 +1053,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           const int nch = (k == 4 || k == 5) ? 8 : 4;
           TF_MARK(300 + op);
           const int bytes = (k == K_RES || k == 3) ? TF_CHUNK_R : (k == 4 ? TF_CHUNK_P1 : (k == 5 ? TF_CHUNK_P2 : TF_CHUNK_A));
-          load_chunks(nch / TF_CPW, bytes * TF_CPW);
+          load_chunks(nch / TF_CPW, bytes * TF_CPW, (bytes == TF_CHUNK_A) ? 0u : 1u);
         }
         if (more) { woff = 0; load_chunks(8 / TF_CPW, TF_CHUNK_A * TF_CPW); }           // T_0 and A_0 of the next step
       }
@@ -964,7 +1062,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         for (int l = 0; l + 1 < L; ++l) {
           TF_MARK(400 + l);
           wait_bar(tapfree, ph_tapfree);       // the previous pair block (layer l's taps) has been consumed
+          TF_TR(30, l);
           load_taps(l + 1, t);
+          TF_TR(31, l);
         }
         wait_bar(tapfree, ph_tapfree);         // layer L-1's taps consumed: B2 now receives postprocess1's input
         wait_bar(tapfree, ph_tapfree);         // postprocess1 consumed it
