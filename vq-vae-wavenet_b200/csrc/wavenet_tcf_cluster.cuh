@@ -38,6 +38,12 @@ constexpr int TF_NISSUE = 4;
 constexpr int TF_NS = 16;                  // streams per cluster (at most)
 constexpr int TF_R = 256, TF_G = 256, TF_S = 512, TF_Q = 256, TF_C = 128, TF_PK = 32;
 constexpr int TF_MAXL = 64;
+// order of a stage's two chains on the tensor pipe: residual + skip of layer l-1 first, then the gate of layer l (default,
+// -4 % per step: x_l reaches the cluster ~1.4k cycles into the stage and the gate path alone is critical); -DTF_ORDER_GA
+// restores gate first (the round-2 default until the end of the round)
+#if !defined(TF_ORDER_GA) && !defined(TF_ORDER_RA)
+#define TF_ORDER_RA 1
+#endif
 constexpr int TF_TRACE_N = 320;            // trace events per warp (profile build)
 constexpr int TF_BLK = 1024;               // one K step (16 channels) of a 32-row activation operand
 constexpr int TF_PAIR = TF_CS * 2 * TF_BLK;    // N-stacked operand, K = 256: [16 senders][first | second][1 KB] = 32 KB
@@ -730,10 +736,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
         if (l > 0) {
           consume(ci, cid0, 4, 96, ACCR, false, b1a, 2 * TF_BLK, true);         // residual + skip rows of layer l-1 x gate_{l-1}
           commit_to(accB);
+          TF_TR(5, l);
           ci += 4u;
         }
         consume(ci, l == 0 ? cid0 : take(ci, 0, 4u), 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, l == 0);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
         commit_to(accA);
+        TF_TR(4, l);
         ci += 4u;
 #else
         consume(ci, cid0, 4, 128, par ? ACC1 : ACC0, true, b1a, 2 * TF_BLK, true);   // [P_l | W2_l] x [gate_{l-1} | x_{l-1}] on top of the taps
