@@ -592,6 +592,14 @@ int launch_tcf(vqwn_handle* h, int mode, long long T, const float* cond, long lo
   p.skf_k = h->tc_skf_k; p.skf_b = h->tc_skf_b;
   p.wstream = h->wtf;
   p.flags = h->tc_reproducible ? 1 : 0;
+  {
+    // weight tiles of the first N stages ask to stay in the L2 (evict_last), the rest stream (evict_first); VQWN_TC_L2_LAYERS
+    int keep = TF_L2_KEEP_LAYERS;
+    if (const char* e = getenv("VQWN_TC_L2_LAYERS")) keep = atoi(e);
+    if (keep < 0) keep = 0;
+    if (keep > 255) keep = 255;
+    p.flags |= keep << 8;
+  }
   p.post1_lc = h->post1_w + (size_t)h->S * h->S;
   p.post1_b = TP(h, "decoder/postprocess1/bias"); p.post2_b = TP(h, "decoder/postprocess2/bias");
   size_t off = 0;

@@ -44,6 +44,7 @@ constexpr int TF_MAXL = 64;
 #if !defined(TF_ORDER_GA) && !defined(TF_ORDER_RA)
 #define TF_ORDER_RA 1
 #endif
+constexpr int TF_L2_KEEP_LAYERS = 255;     // default: every stage's weight tiles ask to stay in the L2 (see the loader lanes)
 constexpr int TF_TRACE_N = 320;            // trace events per warp (profile build)
 constexpr int TF_BLK = 1024;               // one K step (16 channels) of a 32-row activation operand
 constexpr int TF_PAIR = TF_CS * 2 * TF_BLK;    // N-stacked operand, K = 256: [16 senders][first | second][1 KB] = 32 KB
@@ -122,7 +123,7 @@ struct TfParams {
   const double* uniforms;
   unsigned long long seed;
   int b_offset;                            // global index of stream 0 (sharded runs): keys the seeded generator
-  int flags;                               // bit 0: reproducible accumulation order (issuing warps take turns)
+  int flags;                               // bit 0: reproducible accumulation order (issuing warps take turns); bits 8-15: stages whose weight tiles ask to stay in the L2
   float* audio_out;
   int* idx_out;
   float* logits_out;
@@ -495,8 +496,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   const bool wloader = (lane == 0) && (warp == 8 || warp == 9);
   const unsigned wmine = (warp == 9) ? 1u : 0u;
   const bool tloader = (lane == 0) && (warp == 10);
-  unsigned long long wpol = 0;
-  if (wloader) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(wpol));
+  // L2 policy of the weight copies: the tiles of the first `keep_layers` stages are kept (evict_last), the others stream
+  // (evict_first).  All clusters read the same 88 MB once per time step - a cyclic pattern larger than the part of the L2
+  // that keeps it, i.e. no tile survives until the next step if all of them ask to stay; a subset that fits does.
+  unsigned long long wpol_keep = 0, wpol_stream = 0, wpol = 0;
+  const int keep_layers = (p.flags >> 8) & 0xff;
+  if (wloader) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(wpol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(wpol_stream));
+    wpol = keep_layers > 0 ? wpol_keep : wpol_stream;
+  }
 #ifdef TF_FIFO2
   // a lane loads the chunks of ITS class only (cls == wmine); li and woff are the lane's position in its class and stream
   const uint8_t* const wsrc2 = wmine ? p.wstream + (size_t)TF_CS * tf_big_bytes(L) + (size_t)rank * tf_small_bytes(L)
@@ -1061,8 +1070,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
           const int nch = (k == 4 || k == 5) ? 8 : 4;
           TF_MARK(300 + op);
           const int bytes = (k == K_RES || k == 3) ? TF_CHUNK_R : (k == 4 ? TF_CHUNK_P1 : (k == 5 ? TF_CHUNK_P2 : TF_CHUNK_A));
+          wpol = (l < keep_layers) ? wpol_keep : wpol_stream;
           load_chunks(nch / TF_CPW, bytes * TF_CPW, (bytes == TF_CHUNK_A) ? 0u : 1u);
         }
+        wpol = keep_layers > 0 ? wpol_keep : wpol_stream;
         if (more) { woff = 0; load_chunks(8 / TF_CPW, TF_CHUNK_A * TF_CPW); }           // T_0 and A_0 of the next step
       }
       if (tloader) {
