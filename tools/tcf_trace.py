@@ -3,7 +3,7 @@ On the GPU box:  VQWN_PROFILE=1 VQWN_TRACE_FILE=gpurun_out/tcf_trace.txt python 
 Here:            python tools/tcf_trace.py gpurun_out/tcf_trace.txt [first_layer last_layer]
 events: 1 step start | issuing warps 4-7: 2 first-chain weights ready, 3 gather complete, 4 gate chain issued, 5 residual +
 skip chain issued, 6 taps landed, 7 tap chain issued | epilogue warps: 10 gate accumulator ready, 11 gate epilogue done,
-12 gate slice published (warp 3), 13 residual + skip accumulator ready, 14 x published (warp 0) | loader lanes 8-9: 20 slot
+12 gate slice published (warp 3), 13 residual + skip accumulator ready, 14 x staged (warp 0), 15 x published (warp 11) | loader lanes 8-9: 20 slot
 free for chunk n, 21 chunk n requested | tap loader: 30 pair buffer free, 31 pair block requested"""
 import sys
 from collections import defaultdict
@@ -13,7 +13,7 @@ t0 = min(r[3] for r in rows)
 l0 = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 l1 = int(sys.argv[3]) if len(sys.argv) > 3 else 13
 names = {2: "weights ready", 3: "gather complete", 4: "gate chain issued", 5: "res+skip chain issued", 6: "taps landed", 7: "tap chain issued",
-         10: "accA ready", 11: "gate epilogue done", 12: "gate published", 13: "accB ready", 14: "x published"}
+         10: "accA ready", 11: "gate epilogue done", 12: "gate published", 13: "accB ready", 14: "x staged", 15: "x published"}
 by_layer = defaultdict(list)
 for w, e, l, c in rows:
     if e in names:

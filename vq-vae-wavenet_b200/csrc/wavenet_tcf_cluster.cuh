@@ -71,8 +71,8 @@ __host__ __device__ constexpr size_t tf_small_bytes(int L) { return (size_t)L * 
 constexpr int TF_OFF_W = 0;                                  // weight FIFO
 constexpr int TF_OFF_B1 = TF_OFF_W + TF_NSLOT * TF_SLOT;     // [2][gate | layer input] operands, by stage parity
 constexpr int TF_OFF_B2 = TF_OFF_B1 + 2 * TF_PAIR;           // [tap t-d | tap t-2d] operand; postprocess1 input
-constexpr int TF_OFF_STG = TF_OFF_B2 + TF_PAIR;              // publish staging: 2 blocks
-constexpr int TF_OFF_HIST = TF_OFF_STG + 2 * TF_BLK;         // [16][32] fp32 network-input history ring (remote-written)
+constexpr int TF_OFF_STG = TF_OFF_B2 + TF_PAIR;              // publish staging: 2 blocks + 2 layer-input blocks (by layer parity)
+constexpr int TF_OFF_HIST = TF_OFF_STG + 4 * TF_BLK;         // [16][32] fp32 network-input history ring (remote-written)
 constexpr int TF_OFF_LOG = TF_OFF_HIST + TF_NS * TF_PK * 4;  // [256] fp32 logits of this CTA's stream (remote-written)
 constexpr int TF_OFF_US = TF_OFF_LOG + TF_Q * 4;             // [16][32] history in tap order     } 8 KB of CTA-local scratch,
 constexpr int TF_OFF_CUR0 = TF_OFF_US + TF_NS * TF_PK * 4;   // [16 ch][16] fp32 FIR output       } aliased by the condition
@@ -863,17 +863,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
             const float r = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             const float nv = cur[j] + (r + bres);                                // wavenet.py:145
             cur[j] = nv;
-            tf_st_split(stg + TF_BLK, 8 * q + j, i, nv);
+            tf_st_split(stg + (2 + (lr & 1)) * TF_BLK, 8 * q + j, i, nv);
           }
-          __syncwarp();
-          // layer lr+1's input of this step: stored once per tap position of its dilation ring (push_ops); the first
-          // copy is also the source of the hand-off to the cluster (second operand of stage lr+2's stacked pair)
-          const int ln = lr + 1;
-          const int dn = p.layers[ln].d;
-          uint8_t* g1 = pair_block(ln, t + dn) + rank * 2 * TF_BLK;
-          uint8_t* g2 = pair_block(ln, t + 2 * dn) + rank * 2 * TF_BLK + TF_BLK;
-          const bool needed = (ln + 1 < L);
-          publish(stg + TF_BLK, g1, g2, 1, TF_OFF_B1 + ((ln + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK + TF_BLK, needed ? &b1bar[(ln + 1) & 1] : nullptr);
+          // warp 11 publishes the staged slice (ring stores + hand-off, below): warp 0 goes straight on to the gate
+          // epilogue.  The staging block alternates by layer parity: block lr & 1 is rewritten at layer lr + 2, whose
+          // residual chain needed the cluster-wide gather of x_{lr+1}, i.e. warp 11 has published x_lr before.
+          __threadfence_block();
+          asm volatile("bar.arrive 4, 64;" ::: "memory");
           TF_TR(14, lr);
         } else if (warp == 1 || warp == 2) {
           // lanes 32-63: skip rows hi, lanes 64-95: skip rows lo of channel 32 rank + lane
@@ -1053,7 +1049,24 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
       // ============================================================== loader warps: 8 / 9 (lane 0) weight stream, 10 (lane 0) taps
       // their part of the step's ring stores is done: arrive at the step's cluster barrier first - the MMA warps wait on it
       // in the tail while the weight FIFO is still being fed
-      cl_arrive();
+      if (warp != 11) cl_arrive();
+      else {
+        // warp 11: publish x_{lr+1} = layer lr+1's input of this step, staged by warp 0's residual epilogue: stored once per
+        // tap position of its dilation ring (push_ops); the first copy is also the source of the hand-off to the cluster
+        // (second operand of stage lr+2's stacked pair).  Its ring stores precede its arrival at the step's cluster barrier.
+#pragma unroll 1
+        for (int lr = 0; lr + 1 < L; ++lr) {
+          asm volatile("bar.sync 4, 64;" ::: "memory");
+          const int ln = lr + 1;
+          const int dn = p.layers[ln].d;
+          uint8_t* g1 = pair_block(ln, t + dn) + rank * 2 * TF_BLK;
+          uint8_t* g2 = pair_block(ln, t + 2 * dn) + rank * 2 * TF_BLK + TF_BLK;
+          const bool needed = (ln + 1 < L);
+          publish(stg + (2 + (lr & 1)) * TF_BLK, g1, g2, 1, TF_OFF_B1 + ((ln + 1) & 1) * TF_PAIR + rank * 2 * TF_BLK + TF_BLK, needed ? &b1bar[(ln + 1) & 1] : nullptr);
+          TF_TR(15, lr);
+        }
+        cl_arrive();
+      }
       if (wloader) {
         // the same chain order as the MMA warps' (op = 3 l + k, tail 3 L ..); the first gate tile of a step was requested
         // at the end of the previous one, and this step ends with the next step's T_0 and A_0 (stream offset wraps to 0)
