@@ -171,7 +171,7 @@ __device__ __forceinline__ void tf_mbar_arrive(unsigned long long* bar) {
 
 // one copy of the bounded wait loop for the whole kernel: the three warp roles run disjoint code and share the
 // instruction cache, every inlined copy costs all of them
-__device__ __noinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* err) {
+__device__ __noinline__ void tf_wait_slow(unsigned bar_addr, unsigned parity, int* err) {
   unsigned long long t_start = 0;
   bool noted = false;
 #pragma unroll 1
@@ -201,6 +201,20 @@ __device__ __noinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* er
   if (atomicCAS(err, 0, 2) == 0) { err[1] = (int)bar_addr; err[2] = (int)parity; err[3] = (int)threadIdx.x; err[4] = (int)blockIdx.x; }
   __threadfence_system();
   __trap();
+}
+// The wait every role uses: a short polling loop INLINE, the bounded loop above only when that runs out.  A call of the
+// non-inlined function costs ~290 cycles even when the phase has long completed (measured in the loader lanes with
+// -DTF_WAIT_COST: call 352 - 64 cycles of trace overhead, the bare instruction 115 - 64) - the caller saves and restores
+// its live registers around the call - and a stage's critical path goes through four or five waits.
+__device__ __forceinline__ void tf_wait(unsigned bar_addr, unsigned parity, int* err) {
+#pragma unroll 1
+  for (int i = 0; i < 256; ++i) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  tf_wait_slow(bar_addr, parity, err);
 }
 
 // Weight FIFO barriers and parity waits.  An mbarrier parity wait is valid only while the waiter is at most one phase
@@ -531,8 +545,20 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
     for (int c = 0; c < nch; ++c) {
       const unsigned slot = li % TF_NSLOT;
       if ((slot % NLOADERS) == wmine) {
+        TF_TR(22, li & 255u);
         if (li >= TF_NSLOT) tf_wait(f32_smem_u32(&wfree[slot]), ((li / TF_NSLOT) - 1u) & 1u, p.err);
         TF_TR(20, li & 255u);
+#ifdef TF_WAIT_COST
+        if (PROF && li >= TF_NSLOT) {       // calibration: the same wait again (fast path), then two back-to-back trace events
+          tf_wait(f32_smem_u32(&wfree[slot]), ((li / TF_NSLOT) - 1u) & 1u, p.err);
+          TF_TR(23, li & 255u);
+          TF_TR(24, li & 255u);
+          unsigned ok_;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                       : "=r"(ok_) : "r"(f32_smem_u32(&wfree[slot])), "r"(((li / TF_NSLOT) - 1u) & 1u) : "memory");
+          if (ok_) TF_TR(25, li & 255u);
+        }
+#endif
         const unsigned fb = tf_wfull_bar(sm_u32, li);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((unsigned)bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
