@@ -44,6 +44,11 @@ constexpr int TF_MAXL = 64;
 #if !defined(TF_ORDER_GA) && !defined(TF_ORDER_RA)
 #define TF_ORDER_RA 1
 #endif
+#ifdef TF_ISSUE_CALL
+#define TF_ISSUE_INLINE __noinline__
+#else
+#define TF_ISSUE_INLINE __forceinline__
+#endif
 constexpr int TF_L2_KEEP_LAYERS = 255;     // default: every stage's weight tiles ask to stay in the L2 (see the loader lanes)
 constexpr int TF_TRACE_N = 320;            // trace events per warp (profile build)
 constexpr int TF_BLK = 1024;               // one K step (16 channels) of a 32-row activation operand
@@ -263,7 +268,7 @@ __device__ __forceinline__ unsigned tf_wfree_idx(unsigned cid) { return 8u + cid
 // function: the issuing warps are bound by the length of their own instruction stream (every MMA costs ~17 instructions
 // of descriptor arithmetic, register -> uniform-register moves and the per-thread issue loop), one copy keeps it short
 // and in the instruction cache.  d_tmem: accumulator address; b_addr: B operand of the chunk's first K step.
-__device__ __noinline__ void tf_issue_chunk(unsigned ci, unsigned cid, uint32_t a_step, uint32_t d_tmem, uint32_t idesc, uint32_t b_addr,
+__device__ TF_ISSUE_INLINE void tf_issue_chunk(unsigned ci, unsigned cid, uint32_t a_step, uint32_t d_tmem, uint32_t idesc, uint32_t b_addr,
                                             uint32_t b_step, uint32_t sm_u32, uint32_t elected, int* err, bool have_weights, unsigned* turn_ptr) {
   // ci: position in the issue sequence of the step chain (orders the reproducible mode); cid: the quarter-tile's place in
   // the weight FIFO(s): the chunk that holds it is cid / TF_CPW, at sub-position cid % TF_CPW
