@@ -303,7 +303,7 @@ __device__ TF_ISSUE_INLINE void tf_issue_chunk(unsigned ci, unsigned cid, uint32
   __syncwarp();
 }
 // the barrier fires when every MMA this thread has issued so far has completed
-__device__ __noinline__ void tf_commit(uint32_t bar_addr, uint32_t elected) {
+__device__ TF_ISSUE_INLINE void tf_commit(uint32_t bar_addr, uint32_t elected) {
   if (elected)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
   __syncwarp();
