@@ -314,7 +314,10 @@ __device__ TF_ISSUE_INLINE void tf_commit(uint32_t bar_addr, uint32_t elected) {
 template <bool PROF>
 __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfParams p_in) {
   extern __shared__ __align__(1024) uint8_t sm[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the warp index goes through a shuffle so that the compiler knows it (and the FIFO positions, slot addresses and MMA
+  // descriptors derived from it) is uniform across the warp: uniform registers instead of per-MMA register -> uniform-register
+  // transfer loops in the issuing warps
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   TfLayerDev* const layers_s = reinterpret_cast<TfLayerDev*>(sm + TF_OFF_LAYERS);
   for (int i = tid; i < p_in.L * (int)(sizeof(TfLayerDev) / 4); i += TF_THREADS)
     reinterpret_cast<uint32_t*>(layers_s)[i] = reinterpret_cast<const uint32_t*>(p_in.layers)[i];
