@@ -38,7 +38,7 @@ QUEUE_BYTES_PER_SAMPLE = 92160 + 512 + 4
 # dram read + write per time step at 64 streams, from the committed ncu --set full captures of the same kernels
 # (profiles/): not measured by this run, hence "from_profile" in the line
 # wavenet_tcf_cluster: profiles/r2_tcf_full_summary.txt, T = 64 launch: 4.664 GB read + 0.477 GB written
-NCU_DRAM_BYTES_PER_STEP = {"wavenet_fp32_cluster": 85.3e6, "wavenet_tcf_cluster": (4.669908e9 + 478.939648e6) / 64}
+NCU_DRAM_BYTES_PER_STEP = {"wavenet_fp32_cluster": 85.3e6, "wavenet_tcf_cluster": (4.491718e9 + 477.902336e6) / 64}
 METRIC = "generated audio samples/sec"
 DTYPE = {"fp32": "f32", "tc": "bf16x2-split (hi+lo operands, f32 accumulate, f32-grade)", "bf16": "bf16 (f32 accumulate)"}
 
