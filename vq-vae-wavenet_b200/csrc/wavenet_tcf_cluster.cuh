@@ -279,6 +279,14 @@ __device__ TF_ISSUE_INLINE void tf_issue_chunk(unsigned ci, unsigned cid, uint32
 #endif
   if (!have_weights) tf_wait(tf_wfull_bar(sm_u32, chunk), tf_wfull_parity(chunk), err);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef TF_ELECT_AT_SITE
+  // a fresh elect.sync at the site: the compiler may know that exactly one lane runs the block
+  {
+    uint32_t e_;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(e_));
+    elected = e_;
+  }
+#endif
   if (elected) {
     uint64_t da = tf_desc(sm_u32 + tf_slot_off(chunk) + sub * 4u * a_step);
     uint64_t db = tf_desc(b_addr);
