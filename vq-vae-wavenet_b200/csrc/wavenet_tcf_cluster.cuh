@@ -12,7 +12,8 @@
 //     expanded once, W2_l x_l = W2_l x_{l-1} + (W2_l Wres_{l-1}) gate_{l-1} + W2_l bres_{l-1}, with P_l = W2_l Wres_{l-1}
 //     premultiplied on the host side (float64) and the bias term folded into the gated bias.  gate_{l-1} and x_{l-1}
 //     arrive together (both come out of stage l-1), so stage l needs ONE all-gather: [gate_{l-1} | x_{l-1}];
-//   * an MMA of this size occupies the tensor pipe for ~64 cycles whatever M <= 128 and N <= 128 are (tools/r2_probe.cu),
+//   * an MMA of this size costs its issuing thread ~64 cycles whatever M <= 128 and N <= 128 are (tools/r2_probe.cu; most
+//     of it is the descriptor transfer loop ptxas emits per instruction, the pipe itself is busy ~26 cycles: DESIGN.md 8),
 //     so work is packed per instruction, not per FLOP: the activation operand stacks TWO inputs along N (64 columns), the
 //     weight tile puts the rows that multiply the first input in lanes 0-15 and those for the second in lanes 16-31 of
 //     every TMEM lane quarter: [P_l | W2_l] x [gate_{l-1} | x_{l-1}] is 16 instructions, both older taps
@@ -33,7 +34,7 @@
 namespace vqwn {
 
 constexpr int TF_CS = 16;
-constexpr int TF_THREADS = 384;           // warps 0-3 epilogue | 4-7 MMA issue | 8-9 weight loaders | 10 tap loader | 11 idle
+constexpr int TF_THREADS = 384;           // warps 0-3 epilogue | 4-7 MMA issue | 8-9 weight loaders | 10 tap loader | 11 layer-input publisher
 constexpr int TF_NISSUE = 4;
 constexpr int TF_NS = 16;                  // streams per cluster (at most)
 constexpr int TF_R = 256, TF_G = 256, TF_S = 512, TF_Q = 256, TF_C = 128, TF_PK = 32;
@@ -264,10 +265,11 @@ __device__ __forceinline__ unsigned tf_wfull_parity(unsigned ci) { return ((ci /
 __device__ __forceinline__ unsigned tf_wfree_idx(unsigned cid) { return 8u + cid % TF_NSLOT; }
 #endif
 
-// One weight chunk (4 K steps): wait for it, issue its 4 MMAs D[128 x N] += A . B^T, release its FIFO slot.  A real
-// function: the issuing warps are bound by the length of their own instruction stream (every MMA costs ~17 instructions
-// of descriptor arithmetic, register -> uniform-register moves and the per-thread issue loop), one copy keeps it short
-// and in the instruction cache.  d_tmem: accumulator address; b_addr: B operand of the chunk's first K step.
+// One weight chunk (4 K steps): wait for it, issue its 4 MMAs D[128 x N] += A . B^T, release its FIFO slot.  Inline
+// (TF_ISSUE_INLINE): as a call it kept the three roles' code small, but every call cost more than the instruction
+// fetches it saved (90.6 -> 86.1 us per step).  Every MMA costs ~17 instructions of descriptor arithmetic, register ->
+// uniform-register moves and the per-thread issue loop; -DTF_ELECT_AT_SITE removes most of them.
+// d_tmem: accumulator address; b_addr: B operand of the chunk's first K step.
 __device__ TF_ISSUE_INLINE void tf_issue_chunk(unsigned ci, unsigned cid, uint32_t a_step, uint32_t d_tmem, uint32_t idesc, uint32_t b_addr,
                                             uint32_t b_step, uint32_t sm_u32, uint32_t elected, int* err, bool have_weights, unsigned* turn_ptr) {
   // ci: position in the issue sequence of the step chain (orders the reproducible mode); cid: the quarter-tile's place in
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) wavenet_tcf_cluster(const TfPar
   // loader lanes (warp 8 lane 0: even FIFO slots, warp 9 lane 0: odd slots): chunks issued so far, stream position
   unsigned li = 0;
   size_t woff = 0;
-  // (three loader lanes - warp 11 added, slot s owned by lane s mod 3 - measured no faster: 99.3 us against 98.6; the
+  // (three loader lanes - slot s owned by lane s mod 3 - measured no faster, twice: 99.3 us against 98.6, and 93.6 against 90.6; the
   // feed is bound by bytes in flight, not by the issue rate of the loader lanes)
   constexpr unsigned NLOADERS = 2;
   const bool wloader = (lane == 0) && (warp == 8 || warp == 9);
