@@ -314,6 +314,13 @@ __device__ TF_ISSUE_INLINE void tf_issue_chunk(unsigned ci, unsigned cid, uint32
 }
 // the barrier fires when every MMA this thread has issued so far has completed
 __device__ TF_ISSUE_INLINE void tf_commit(uint32_t bar_addr, uint32_t elected) {
+#ifdef TF_ELECT_AT_SITE
+  {
+    uint32_t e_;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(e_));
+    elected = e_;
+  }
+#endif
   if (elected)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
   __syncwarp();
